@@ -1,0 +1,138 @@
+/*
+ * pvk.h -- C ABI of the B200-native phase-vocoder kernels (libpvk.so).
+ *
+ * The reference (goiosunsw/PyPeVoc) is pure Python and has no FFI / plugin boundary for
+ * this path; its interface is the Python class pypevoc.PV (pypevoc/PVAnalysis.py:71-417)
+ * and pypevoc.SinSum (:797-1111).  Every entry point below names the reference method it
+ * replaces; pypevoc_b200/pv.py is the Python host side that mirrors those classes and
+ * reaches these symbols through ctypes (see INTEGRATION.md for the binding a PyPeVoc
+ * maintainer would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all data pointers are DEVICE pointers (cudaMalloc /
+ *     torch tensor .data_ptr()) on the current device unless named host_*.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL =
+ *     legacy default stream) and keeps no global state besides a thread-local error
+ *     string; re-entrant across streams and devices.
+ *   - the library never allocates user-visible memory: outputs and scratch are caller
+ *     provided, scratch sizes come from the *_bytes() queries.
+ *   - return value 0 = ok; non-zero = error, text in pvk_last_error().  Nothing throws.
+ */
+#ifndef PVK_H_
+#define PVK_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PVK_OK 0
+#define PVK_ERR_ARG 1
+#define PVK_ERR_CUDA 2
+
+#define PVK_MIN_NFFT 64
+#define PVK_MAX_NFFT 8192
+#define PVK_MAX_NPKS 1024
+
+/* ABI version (bumped on any signature change). */
+int pvk_version(void);
+
+/* Thread-local text of the last error on this thread ("" if none). */
+const char *pvk_last_error(void);
+
+/* ------------------------------------------------------------------ analysis
+ * Replaces PV.run_pv / PV.calc_pv_frame / PV.calc_fft_frame / PV.dphase2freq
+ * (PVAnalysis.py:133-264) and the PeakFinder calls they make (PeakFinder.py:35-74,
+ * 113-134,155-194).
+ */
+
+/* Bytes of device scratch pvk_analyze_init() fills with twiddle tables for `nfft`. */
+int64_t pvk_analyze_tables_bytes(int nfft);
+
+/* Fill `tables` (pvk_analyze_tables_bytes(nfft) bytes) once per (device, nfft). */
+int pvk_analyze_init(int nfft, void *tables, void *stream);
+
+/*
+ * Analyse `nframes` frames of each of `nclips` signals.
+ *
+ *   x            fp32 samples; clip c starts at x + c*clip_stride and holds nsamp samples
+ *   win_scaled   nfft floats: wind(nfft) / wfact          (PVAnalysis.py:97-102,157)
+ *   fbin, wfbin  nfft doubles each, computed by the host with the reference's own numpy
+ *                expressions                              (PVAnalysis.py:114-118)
+ *   dt, fstep    hop/sr and sr/nfft                       (PVAnalysis.py:105-108)
+ *   pkthresh     PeakFinder minrattomax                   (PVAnalysis.py:175)
+ *   frame0       local index of the first frame to emit: output row r is the frame that
+ *                starts at sample (frame0 + r)*hop of its clip
+ *   prev_zero    1: the frame before `frame0` is the all-zero spectrum PV starts from
+ *                (PVAnalysis.py:121); 0: frame0-1 (>= 0) is recomputed as warm-up
+ *                (segment sharding)
+ *   run_frames   frames one CTA walks through (0 = library default)
+ *
+ * Outputs, in the reference's own layout (PVAnalysis.py:226-264): float64
+ * [nclips, nframes, npks] zero padded f / mag / ph / realph / binno, plus npk int32
+ * [nclips, nframes] (valid entries per row) and totalmag float64 [nclips, nframes].
+ * spec_out (optional, may be NULL): complex64 [nclips, nframes, nfft/2] =
+ * calc_fft_frame(pos)[:nfft/2] (PVAnalysis.py:150-158,169) as (re, im) float pairs.
+ */
+int pvk_analyze(const float *x, int64_t nclips, int64_t clip_stride, int64_t nsamp,
+                const float *win_scaled, const double *fbin, const double *wfbin,
+                const void *tables, int nfft, int hop, int npks, double pkthresh,
+                double dt, double fstep, int64_t frame0, int64_t nframes, int prev_zero,
+                int run_frames, double *f, double *mag, double *ph, double *realph,
+                double *binno, int32_t *npk, double *totalmag, float *spec_out,
+                void *stream);
+
+/* ------------------------------------------------------------------ tracking
+ * Replaces PV.toSinSum -> SinSum.add_frame (PVAnalysis.py:299-322,871-957).
+ *
+ * Input: f, mag float64 [nclips, nframes, npks] (any zero padded rows in the reference
+ * layout; a slot is a point iff f > 0 and mag > 0, :876).
+ * Output: tid int32 [nclips, nframes, npks] track id per slot (-1 = not a point), ids
+ * numbered per clip in add_empty_partial call order (:819-830); tstart / tlen int32
+ * [nclips, max_tracks] first frame and number of frames per track; ntracks int32 [nclips].
+ * prev_f / prev_mag / prev_tid (optional, [nclips, npks]): the peak row preceding frame 0
+ * of this shard with its already-assigned ids (segment sharding); NULL = nothing before.
+ */
+int64_t pvk_track_workspace_bytes(int64_t nclips, int64_t nframes, int npks);
+
+int pvk_track(const double *f, const double *mag, int64_t nclips, int64_t nframes, int npks,
+              double maxpitchjmp, int32_t *tid, int32_t *link, int32_t *tstart,
+              int32_t *tlen, int32_t *ntracks, int64_t max_tracks, void *workspace,
+              int64_t workspace_bytes, void *stream);
+
+/* Pack per-track value runs (= RegPartial.f/mag/ph/realph lists, :616-626) from the frame
+ * tables: toff int64 [ntracks+1] exclusive offsets (computed here), packed float64 arrays
+ * of length sum(tlen).  Single clip. */
+int pvk_track_pack(const double *f, const double *mag, const double *ph, const double *realph,
+                   const int32_t *tid, int64_t nframes, int npks, const int32_t *tstart,
+                   const int32_t *tlen, int64_t ntracks, int64_t *toff, double *pf,
+                   double *pmag, double *pph, double *prealph, void *workspace,
+                   int64_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------ resynthesis
+ * Replaces SinSum.synth -> RegPartial.synth (PVAnalysis.py:1053-1070,684-756),
+ * phase_preserve=True path.
+ *
+ *   tstart/tlen/toff + packed pf/pmag/prealph   the tracks (all ntracks; tracks shorter
+ *                                               than minframes are skipped, :1061)
+ *   sr, hop      synthesis sample rate and hop (may differ from analysis hop)
+ *   nfft, hop_an analysis parameters the SinSum was built with (:824-825,1055)
+ *   out          float64 [nout], nout = (max_end+2)*hop + int(edge*hop*nfft/hop_an/2)
+ *                (:1059,1070); fully written (zeros where no track sounds)
+ *   block0/nblocks  render output blocks [block0, block0+nblocks) of `hop` samples only
+ *                (multi-GPU: each rank renders a disjoint block range); nblocks<0 = all
+ */
+int64_t pvk_resynth_workspace_bytes(int64_t ntracks, int64_t nblocks_total);
+
+int pvk_resynth(const int32_t *tstart, const int32_t *tlen, const int64_t *toff,
+                const double *pf, const double *pmag, const double *prealph,
+                int64_t ntracks, double sr, int hop, int nfft, int hop_an, double edge,
+                int minframes, double *out, int64_t nout, int64_t block0, int64_t nblocks,
+                void *workspace, int64_t workspace_bytes, int64_t *partial_samples,
+                void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PVK_H_ */

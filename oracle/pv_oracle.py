@@ -127,7 +127,7 @@ def dphase2freq(dph, bins, tb):
 
 
 def analyze(x, sr, nfft=1024, hop=None, npks=20, pkthresh=0.005, wind=np.hanning,
-            fft_dtype=np.float64, spectra=False, margins=False):
+            fft_dtype=np.float64, spectra=False, margins=False, fx_given=None, old0=None):
     """``PV(...).run_pv()`` (PVAnalysis.py:72-131,150-264).
 
     Returns a dict with the reference's attributes: ``f mag ph realph binno`` float64
@@ -135,6 +135,12 @@ def analyze(x, sr, nfft=1024, hop=None, npks=20, pkthresh=0.005, wind=np.hanning
     (valid entries per row).  ``fft_dtype=np.float32`` emulates a single-precision FFT
     (feasibility probe only).  ``spectra=True`` adds ``fx`` ``[nframes, nfft/2]``
     (``calc_fft_frame(pos)[:nfft/2]``, :150-158,169).
+
+    ``fx_given`` (complex64 ``[nframes, nfft/2]``): skip the FFT and run everything after
+    PVAnalysis.py:169 on these spectra, with ``famp`` formed in float32 as
+    ``sqrt(re*re + im*im)`` exactly like the CUDA kernel -- used to check the kernel's
+    integer / per-peak logic bit-for-bit on the kernel's own spectrum.  ``old0`` replaces
+    the all-zero spectrum before frame 0 (segment warm-up).
     """
     x = np.array(x, dtype=np.float64)
     nsamp = len(x)
@@ -143,8 +149,8 @@ def analyze(x, sr, nfft=1024, hop=None, npks=20, pkthresh=0.005, wind=np.hanning
         hop = int(nfft / 2)
     tb = pv_tables(sr, nfft, hop, wind)
     win, wfact, fstep = tb["win"], tb["wfact"], tb["fstep"]
-    old = np.zeros(nfft2)                                  # :121 (real zeros)
-    nfr = n_frames(nsamp, nfft, hop)
+    old = np.zeros(nfft2) if old0 is None else np.asarray(old0, dtype=np.complex128)   # :121
+    nfr = n_frames(nsamp, nfft, hop) if fx_given is None else len(fx_given)
     K = npks
     out = {k: np.zeros((nfr, K)) for k in ("f", "mag", "ph", "realph", "binno")}
     npk = np.zeros(nfr, dtype=np.int32)
@@ -154,14 +160,19 @@ def analyze(x, sr, nfft=1024, hop=None, npks=20, pkthresh=0.005, wind=np.hanning
     with np.errstate(all="ignore"):
         for j in range(nfr):
             pos = j * hop
-            xw = x[pos:pos + nfft] * win                   # :155-156
-            if fft_dtype == np.float32:
-                spec = np.fft.fft(xw.astype(np.float32)).astype(np.complex128)
+            if fx_given is not None:
+                g = np.asarray(fx_given[j], dtype=np.complex64)
+                fx = g.astype(np.complex128)
+                famp = np.sqrt(g.real * g.real + g.imag * g.imag).astype(np.float64)   # float32 ops
             else:
-                spec = np.fft.fft(xw)
-            fx = (spec / wfact)[:nfft2]                    # :157,169
+                xw = x[pos:pos + nfft] * win               # :155-156
+                if fft_dtype == np.float32:
+                    spec = np.fft.fft(xw.astype(np.float32)).astype(np.complex128)
+                else:
+                    spec = np.fft.fft(xw)
+                fx = (spec / wfact)[:nfft2]                # :157,169
+                famp = abs(fx)                             # :173
             frat = fx / old                                # :171
-            famp = abs(fx)                                 # :173
             bins = peak_pick(famp, K, pkthresh)            # :175-178
             if margins:
                 marg[j] = peak_margin(famp, K, pkthresh)

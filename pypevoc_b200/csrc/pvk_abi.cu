@@ -1,0 +1,19 @@
+// pvk_abi.cu -- error reporting and version of the C ABI (include/pvk.h).
+#include <stdarg.h>
+
+#include "pvk_common.cuh"
+
+namespace pvk {
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace pvk
+
+extern "C" int pvk_version(void) { return 1; }
+
+extern "C" const char *pvk_last_error(void) { return pvk::g_err; }

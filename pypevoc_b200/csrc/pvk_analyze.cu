@@ -1,0 +1,691 @@
+// pvk_analyze.cu -- fused phase-vocoder analysis kernel for sm_100a.
+//
+// One CTA walks a run of consecutive STFT frames of one signal.  Per frame, without ever
+// leaving shared memory / registers:
+//   1. framing + windowing: the hop-strided frame is read straight from the signal with
+//      coalesced 64-bit loads (re-reads of the nfft-hop overlap hit L1/L2, HBM sees each
+//      sample about once) and multiplied by win/wfact            (PVAnalysis.py:155-157)
+//   2. real FFT of nfft points as a complex Stockham FFT of M = nfft/2 points (radix-16/8/4
+//      register butterflies, padded shared-memory exchanges) plus an in-place untangle step
+//      that yields bins 0..M-1 = fx[:nfft/2]                     (PVAnalysis.py:157,169)
+//   3. peak picking on |fx| with PeakFinder's exact semantics: local maxima, strict
+//      threshold, top-npks by (value desc, bin asc) through an exact radix select on the
+//      fp32 bit pattern, ascending-bin order, +-5-bin salience filter
+//                                                (PeakFinder.py:57-70,155-194,113-134)
+//   4. per-peak epilogue in fp64 with the reference's operation order: phase, phase
+//      difference against the previous frame's spectrum (kept in the other half of a
+//      shared-memory double buffer), dphase2freq, 3-bin magnitude, realph, freq>0 filter
+//                                                (PVAnalysis.py:133-147,187-207)
+//   5. zero padded float64 rows in the reference's layout        (PVAnalysis.py:226-245)
+// Not a dense contraction: no tensor cores.  fp32 FFT, fp64 only per peak.
+#include "pvk_common.cuh"
+
+namespace pvk {
+
+#define PADC(i) ((i) + ((i) >> 4))
+
+struct AParams {
+  const float *x;
+  int64_t clip_stride;
+  const float *win;
+  const float2 *tables;
+  const double *fbin;
+  const double *wfbin;
+  int hop, npks;
+  double pkthresh, dt, fstep;
+  int64_t frame0, nframes;
+  int prev_zero, run;
+  int64_t nruns;
+  double *f, *mag, *ph, *realph, *binno;
+  int32_t *npk;
+  double *totalmag;
+  float2 *spec_out;
+};
+
+template <int LOGM> struct Plan {
+  static constexpr int M = 1 << LOGM;
+  static constexpr int LOGT = LOGM <= 8 ? 5 : (LOGM <= 10 ? 6 : LOGM - 4);
+  static constexpr int T = 1 << LOGT;
+  static constexpr int LP0 = LOGM - LOGT;
+  static constexpr int LP = LP0 < 2 ? 2 : (LP0 > 4 ? 4 : LP0);
+  static constexpr int NPASS = (LOGM + LP - 1) / LP;
+  __host__ __device__ static constexpr int lr(int q) { return q < NPASS - 1 ? LP : LOGM - LP * (NPASS - 1); }
+  __host__ __device__ static constexpr int lp(int q) { return q * LP; }
+  __host__ __device__ static constexpr int tw_off(int q) {
+    int o = 0;
+    for (int i = 1; i < q; ++i) o += ((1 << lr(i)) - 1) << lp(i);
+    return o;
+  }
+  static constexpr int TW_TOTAL = tw_off(NPASS);
+  static constexpr int MP = M + (M >> 4) + 1;
+  static constexpr int MW = M >= 32 ? M / 32 : 1;
+  static constexpr int NW = T / 32;
+};
+
+// ------------------------------------------------------------------ small DFTs
+template <int LR> __host__ __device__ constexpr int brev(int s) {
+  int r = 0;
+  for (int b = 0; b < LR; ++b) r |= ((s >> b) & 1) << (LR - 1 - b);
+  return r;
+}
+
+// d * W_16^e, W_16 = exp(-2*pi*i/16), e in [0,8)
+__device__ __forceinline__ float2 mul_w16(float2 d, int e) {
+  const float C8 = 0.70710678118654752440f, C1 = 0.92387953251128675613f, S1 = 0.38268343236508977173f;
+  switch (e) {
+    case 0: return d;
+    case 4: return make_float2(d.y, -d.x);
+    case 2: return make_float2((d.x + d.y) * C8, (d.y - d.x) * C8);
+    case 6: return make_float2((d.y - d.x) * C8, -(d.x + d.y) * C8);
+    case 1: return make_float2(d.x * C1 + d.y * S1, d.y * C1 - d.x * S1);
+    case 3: return make_float2(d.x * S1 + d.y * C1, d.y * S1 - d.x * C1);
+    case 5: return make_float2(d.y * C1 - d.x * S1, -d.y * S1 - d.x * C1);
+    default: return make_float2(d.y * S1 - d.x * C1, -d.y * C1 - d.x * S1);  // e == 7
+  }
+}
+
+// in-register DFT of R = 2^LR points, radix-2 DIF stages; result V[s] ends up in u[brev(s)]
+template <int LR> __device__ __forceinline__ void dft_dif(float2 *u) {
+  constexpr int R = 1 << LR;
+#pragma unroll
+  for (int h = R / 2; h >= 1; h >>= 1) {
+#pragma unroll
+    for (int g = 0; g < R; g += 2 * h) {
+#pragma unroll
+      for (int j = 0; j < h; ++j) {
+        float2 a = u[g + j], b = u[g + j + h];
+        u[g + j] = make_float2(a.x + b.x, a.y + b.y);
+        float2 d = make_float2(a.x - b.x, a.y - b.y);
+        u[g + j + h] = mul_w16(d, j * (8 / h));
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 w) {
+  return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
+}
+
+// ------------------------------------------------------------------ FFT passes
+template <int LOGM, int Q> struct Pass {
+  using P = Plan<LOGM>;
+  static __device__ __forceinline__ void run(const float2 *__restrict__ twp, float2 *buf) {
+    constexpr int M = P::M, T = P::T;
+    constexpr int LR = P::lr(Q), R = 1 << LR, LPQ = P::lp(Q), PP = 1 << LPQ;
+    constexpr int NBF = M >> LR, NB = (NBF + T - 1) / T;
+    constexpr int OFF = P::tw_off(Q);
+    const int tid = threadIdx.x;
+    float2 u[NB][R];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const int i = tid + b * T;
+      if (NBF >= T || i < NBF) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) u[b][r] = buf[PADC(i + r * NBF)];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const int i = tid + b * T;
+      if (NBF >= T || i < NBF) {
+        const int k = i & (PP - 1);
+        const int j = ((i - k) << LR) + k;
+#pragma unroll
+        for (int r = 1; r < R; ++r) u[b][r] = cmul(u[b][r], __ldg(twp + OFF + (r - 1) * PP + k));
+        dft_dif<LR>(u[b]);
+#pragma unroll
+        for (int s = 0; s < R; ++s) buf[PADC(j + s * PP)] = u[b][brev<LR>(s)];
+      }
+    }
+    __syncthreads();
+    if constexpr (Q + 1 < P::NPASS) Pass<LOGM, Q + 1>::run(twp, buf);
+  }
+};
+
+// complex FFT of the windowed frame, packed z[m] = (x[2m], x[2m+1]); natural order in buf
+template <int LOGM>
+__device__ __forceinline__ void fft_frame(const float *__restrict__ xf, bool al8,
+                                          const float *__restrict__ win,
+                                          const float2 *__restrict__ twp, float2 *buf) {
+  using P = Plan<LOGM>;
+  constexpr int M = P::M, T = P::T;
+  constexpr int LR = P::lr(0), R = 1 << LR;
+  constexpr int NBF = M >> LR, NB = (NBF + T - 1) / T;
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    const int i = tid + b * T;
+    if (NBF >= T || i < NBF) {
+      float2 u[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int m = i + r * NBF;
+        float2 xv;
+        if (al8) xv = __ldg(reinterpret_cast<const float2 *>(xf) + m);
+        else { xv.x = __ldg(xf + 2 * m); xv.y = __ldg(xf + 2 * m + 1); }
+        const float2 wv = __ldg(reinterpret_cast<const float2 *>(win) + m);
+        u[r] = make_float2(xv.x * wv.x, xv.y * wv.y);
+      }
+      dft_dif<LR>(u);
+#pragma unroll
+      for (int s = 0; s < R; ++s) buf[PADC(i * R + s)] = u[brev<LR>(s)];
+    }
+  }
+  __syncthreads();
+  if constexpr (P::NPASS > 1) Pass<LOGM, 1>::run(twp, buf);
+}
+
+// ------------------------------------------------------------------ per-peak epilogue
+struct PeakVals { double f, mag, ph, realph; };
+
+// PVAnalysis.py:188-207 + dphase2freq :133-147, in fp64 and in the reference's operation
+// order (explicit _rn intrinsics: no FMA contraction where rounding decides ties).
+__device__ __forceinline__ bool peak_epilogue(int k, int M, const float2 *cur, const float2 *prev,
+                                              const float *famp, const double *__restrict__ fbin,
+                                              const double *__restrict__ wfbin, double dt,
+                                              double fstep, PeakVals &o) {
+  const float2 c = cur[PADC(k)], p = prev[PADC(k)];
+  const double re = c.x, im = c.y, ore = p.x, oim = p.y;
+  const double thisph = atan2(im, re);                       // np.angle(fx[nbin]) :188
+  // frat = fx / oldfft (:171): numpy's complex128 division (Smith), incl. the x/0 case
+  double qr, qi;
+  const double ar = fabs(ore), ai = fabs(oim);
+  if (ar >= ai) {
+    if (ar == 0.0 && ai == 0.0) {
+      qr = re / ar; qi = im / ar;                            // (+-inf | nan, +-inf | nan)
+    } else {
+      const double rat = oim / ore, scl = 1.0 / (ore + oim * rat);
+      qr = (re + im * rat) * scl; qi = (im - re * rat) * scl;
+    }
+  } else {
+    const double rat = ore / oim, scl = 1.0 / (oim + ore * rat);
+    qr = (re * rat + im) * scl; qi = (im * rat - re) * scl;
+  }
+  const double dph = atan2(qi, qr);                          // np.angle(frat[nbin]) :190
+  const double PI2 = 6.283185307179586;
+  const double fb = __ldg(fbin + k);
+  const double base = __dadd_rn(dph, __ldg(wfbin + k));      // :140
+  double bf = 0.0, bdf = 0.0, ba = 0.0;
+#pragma unroll
+  for (int m = 0; m < 3; ++m) {
+    const double dphw = __dadd_rn(base, m == 0 ? -PI2 : (m == 1 ? 0.0 : PI2));
+    const double fq = __ddiv_rn(__ddiv_rn(dphw, dt), PI2);   // :142
+    const double df = __dsub_rn(fb, fq);                     // :144
+    const double a = fabs(df);
+    if (m == 0 || a < ba) { bf = fq; bdf = df; ba = a; }     // np.argmin: first minimum, nan sticks
+  }
+  // mag = sqrt(sum(famp[max(nbin-1,1) : min(nbin+1,len)+1]**2)), left to right :197-199
+  const double a0 = famp[k];
+  double s = a0 * a0;
+  if (k - 1 >= 1) { const double am = famp[k - 1]; s = am * am + s; }
+  if (k + 1 <= M - 1) { const double ap = famp[k + 1]; s = s + ap * ap; }
+  o.f = bf;
+  o.mag = sqrt(s);
+  o.ph = thisph;
+  o.realph = __dadd_rn(thisph, __ddiv_rn(__dmul_rn(3.141592653589793, bdf), fstep));   // :207
+  return bf > 0.0;                                           // :193 (drops nan too)
+}
+
+// ------------------------------------------------------------------ the kernel
+template <int LOGM> struct Smem {
+  using P = Plan<LOGM>;
+  static constexpr int OFF_BUF0 = 0;
+  static constexpr int OFF_BUF1 = OFF_BUF0 + P::MP * 8;
+  static constexpr int OFF_FAMP = OFF_BUF1 + P::MP * 8;
+  static constexpr int OFF_SKEY = OFF_FAMP + P::M * 4;
+  static constexpr int OFF_MC = OFF_SKEY + P::M * 4;        // candidate mask
+  static constexpr int OFF_MA = OFF_MC + P::MW * 4;         // key above boundary bucket
+  static constexpr int OFF_MB = OFF_MA + P::MW * 4;         // key inside boundary bucket
+  static constexpr int OFF_MS = OFF_MB + P::MW * 4;         // selected
+  static constexpr int OFF_MK = OFF_MS + P::MW * 4;         // kept after salience
+  static constexpr int OFF_WCNT = OFF_MK + P::MW * 4;
+  static constexpr int OFF_WBASE = OFF_WCNT + P::MW * 4;
+  static constexpr int OFF_HIST = OFF_WBASE + (P::MW + 1) * 4;
+  static constexpr int OFF_RED = (OFF_HIST + 256 * 4 + 7) / 8 * 8;   // doubles: 8 sums
+  static constexpr int OFF_REDF = OFF_RED + 8 * 8;                   // floats: 8 min, 8 max
+  static constexpr int OFF_REDU = OFF_REDF + 16 * 4;                 // uints: 8 cnt, 8 kmin, 8 kmax
+  static constexpr int OFF_BC = OFF_REDU + 24 * 4;                   // 8 broadcast ints
+  static constexpr int OFF_PK = OFF_BC + 8 * 4;                      // npks ints
+  static int bytes(int npks) { return OFF_PK + npks * 4; }
+};
+
+// exclusive scan of cnt[0..n) into base[0..n], total in base[n]; executed by warp 0 only
+__device__ __forceinline__ void warp0_excl_scan(const int *cnt, int *base, int n) {
+  const int lane = lane_id();
+  int carry = 0;
+  for (int s = 0; s < n; s += 32) {
+    const int i = s + lane;
+    const int v = i < n ? cnt[i] : 0;
+    const int inc = warp_scan_incl(v);
+    if (i < n) base[i] = carry + inc - v;
+    carry += __shfl_sync(FULL, inc, 31);
+  }
+  if (lane == 0) base[n] = carry;
+}
+
+template <int LOGM>
+__global__ void __launch_bounds__(Plan<LOGM>::T) analyze_kernel(AParams prm) {
+  using P = Plan<LOGM>;
+  using S = Smem<LOGM>;
+  constexpr int M = P::M, T = P::T, MW = P::MW, NW = P::NW, N = 2 * M;
+  constexpr int NIT = M / T;
+  PVK_SMEM(smem);
+  float2 *bufs[2] = {reinterpret_cast<float2 *>(smem + S::OFF_BUF0),
+                     reinterpret_cast<float2 *>(smem + S::OFF_BUF1)};
+  float *famp = reinterpret_cast<float *>(smem + S::OFF_FAMP);
+  unsigned *skey = reinterpret_cast<unsigned *>(smem + S::OFF_SKEY);
+  unsigned *maskC = reinterpret_cast<unsigned *>(smem + S::OFF_MC);
+  unsigned *maskA = reinterpret_cast<unsigned *>(smem + S::OFF_MA);
+  unsigned *maskB = reinterpret_cast<unsigned *>(smem + S::OFF_MB);
+  unsigned *maskS = reinterpret_cast<unsigned *>(smem + S::OFF_MS);
+  unsigned *maskK = reinterpret_cast<unsigned *>(smem + S::OFF_MK);
+  int *wcnt = reinterpret_cast<int *>(smem + S::OFF_WCNT);
+  int *wbase = reinterpret_cast<int *>(smem + S::OFF_WBASE);
+  int *hist = reinterpret_cast<int *>(smem + S::OFF_HIST);
+  double *redd = reinterpret_cast<double *>(smem + S::OFF_RED);
+  float *redf = reinterpret_cast<float *>(smem + S::OFF_REDF);
+  unsigned *redu = reinterpret_cast<unsigned *>(smem + S::OFF_REDU);
+  int *bc = reinterpret_cast<int *>(smem + S::OFF_BC);
+  int *pk = reinterpret_cast<int *>(smem + S::OFF_PK);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t clip = blockIdx.x / prm.nruns;
+  const int64_t run = blockIdx.x % prm.nruns;
+  const int64_t r0 = run * prm.run;
+  const int64_t r1 = (r0 + prm.run < prm.nframes) ? r0 + prm.run : prm.nframes;
+  const float *xc = prm.x + clip * prm.clip_stride;
+  const float2 *twp = prm.tables;
+  const float2 *twr = prm.tables + P::TW_TOTAL;
+  const int K = prm.npks;
+
+  // ---- previous spectrum of the first row of this run
+  {
+    float2 *pb = bufs[(r0 & 1) ^ 1];
+    if (r0 == 0 && prm.prev_zero) {
+      for (int i = tid; i < P::MP; i += T) pb[i] = make_float2(0.f, 0.f);
+      __syncthreads();
+    } else {
+      const int64_t s0 = (prm.frame0 + r0 - 1) * (int64_t)prm.hop;
+      const float *xf = xc + s0;
+      const bool al8 = ((reinterpret_cast<uintptr_t>(xf) & 7) == 0);
+      fft_frame<LOGM>(xf, al8, prm.win, twp, pb);
+      // untangle only (no magnitudes needed)
+      for (int k = tid; k < M / 2; k += T) {
+        if (k == 0) {
+          const float2 z0 = pb[PADC(0)], zh = pb[PADC(M / 2)];
+          pb[PADC(0)] = make_float2(z0.x + z0.y, 0.f);
+          pb[PADC(M / 2)] = make_float2(zh.x, -zh.y);
+        } else {
+          const float2 a = pb[PADC(k)], bq = pb[PADC(M - k)];
+          const float2 e = make_float2(0.5f * (a.x + bq.x), 0.5f * (a.y - bq.y));
+          const float2 o = make_float2(0.5f * (a.y + bq.y), -0.5f * (a.x - bq.x));
+          const float2 wo = cmul(o, __ldg(twr + k));
+          pb[PADC(k)] = make_float2(e.x + wo.x, e.y + wo.y);
+          pb[PADC(M - k)] = make_float2(e.x - wo.x, -(e.y - wo.y));
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  for (int64_t r = r0; r < r1; ++r) {
+    float2 *cur = bufs[r & 1];
+    const float2 *prev = bufs[(r & 1) ^ 1];
+    const int64_t row = clip * prm.nframes + r;
+    const float *xf = xc + (prm.frame0 + r) * (int64_t)prm.hop;
+    const bool al8 = ((reinterpret_cast<uintptr_t>(xf) & 7) == 0);
+    fft_frame<LOGM>(xf, al8, prm.win, twp, cur);
+
+    // ---- untangle -> fx[0..M), |fx|, min / max / sum of squares
+    float lmin = 3.402823466e+38f, lmax = 0.f, lsum = 0.f;
+    float2 *so = prm.spec_out ? prm.spec_out + row * M : nullptr;
+    for (int k = tid; k < M / 2; k += T) {
+      float2 xa, xb;
+      if (k == 0) {
+        const float2 z0 = cur[PADC(0)], zh = cur[PADC(M / 2)];
+        xa = make_float2(z0.x + z0.y, 0.f);
+        xb = make_float2(zh.x, -zh.y);
+      } else {
+        const float2 a = cur[PADC(k)], bq = cur[PADC(M - k)];
+        const float2 e = make_float2(0.5f * (a.x + bq.x), 0.5f * (a.y - bq.y));
+        const float2 o = make_float2(0.5f * (a.y + bq.y), -0.5f * (a.x - bq.x));
+        const float2 wo = cmul(o, __ldg(twr + k));
+        xa = make_float2(e.x + wo.x, e.y + wo.y);
+        xb = make_float2(e.x - wo.x, -(e.y - wo.y));
+      }
+      const int kb = (k == 0) ? M / 2 : M - k;
+      cur[PADC(k)] = xa;
+      cur[PADC(kb)] = xb;
+      // |fx| without FMA contraction: bit-identical to float32 numpy sqrt(re*re + im*im)
+      const float aa = sqrtf(__fadd_rn(__fmul_rn(xa.x, xa.x), __fmul_rn(xa.y, xa.y)));
+      const float ab = sqrtf(__fadd_rn(__fmul_rn(xb.x, xb.x), __fmul_rn(xb.y, xb.y)));
+      famp[k] = aa;
+      famp[kb] = ab;
+      if (so) { so[k] = xa; so[kb] = xb; }
+      lmin = fminf(lmin, fminf(aa, ab));
+      lmax = fmaxf(lmax, fmaxf(aa, ab));
+      lsum += aa * aa + ab * ab;
+    }
+    {
+      const float wmin = warp_min(lmin), wmax = warp_max(lmax);
+      const double wsum = warp_sum((double)lsum);
+      if (lane == 0) { redf[warp] = wmin; redf[8 + warp] = wmax; redd[warp] = wsum; }
+    }
+    __syncthreads();
+    float miny = redf[0], ymax = redf[8];
+    double sumsq = redd[0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) {
+      miny = fminf(miny, redf[w]);
+      ymax = fmaxf(ymax, redf[8 + w]);
+      sumsq += redd[w];
+    }
+    // PeakFinder.__init__ :57-70 and findpos :164,174
+    const double miny_d = (double)miny;
+    double minamp = (double)ymax * prm.pkthresh;
+    if (minamp == 0.0) minamp = miny_d;
+    const double th = minamp - miny_d;
+
+    // ---- candidates: interior local maxima above threshold (or everything when th < 0)
+    {
+      unsigned wc = 0, kmin = 0xffffffffu, kmax = 0u;
+#pragma unroll 4
+      for (int n = 0; n < NIT; ++n) {
+        const int k = tid + n * T;
+        const bool interior = (k >= 1) && (k <= M - 2);
+        const float y = famp[k];
+        const float yl = famp[interior ? k - 1 : k], yr = famp[interior ? k + 1 : k];
+        const bool ispk = interior && (yl < y) && (y >= yr);
+        bool c;
+        if (ispk) c = ((double)y - miny_d) > th;
+        else c = interior && (th < 0.0);
+        const unsigned key = ispk ? __float_as_uint(y) : 0u;
+        skey[k] = key;
+        const unsigned m = __ballot_sync(FULL, c);
+        if (lane == 0) maskC[k >> 5] = m;
+        wc += __popc(m);
+        if (c) { kmin = key < kmin ? key : kmin; kmax = key > kmax ? key : kmax; }
+      }
+      kmin = warp_umin(kmin);
+      kmax = warp_umax(kmax);
+      if (lane == 0) { redu[warp] = wc; redu[8 + warp] = kmin; redu[16 + warp] = kmax; }
+    }
+    __syncthreads();
+    int C = 0;
+    unsigned lo = 0xffffffffu, hi = 0u;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      C += (int)redu[w];
+      lo = redu[8 + w] < lo ? redu[8 + w] : lo;
+      hi = redu[16 + w] > hi ? redu[16 + w] : hi;
+    }
+
+    // ---- top-K by (key desc, bin asc): exact radix select of the K-th largest key
+    const unsigned *selmask = maskC;
+    if (C > K) {
+      int rr = K;
+      for (int level = 0; level < 4; ++level) {
+        const unsigned range = hi - lo;
+        const int bl = 32 - __clz((int)range);
+        const int sh = bl > 8 ? bl - 8 : 0;
+        for (int h = tid; h < 256; h += T) hist[h] = 0;
+        __syncthreads();
+#pragma unroll 4
+        for (int n = 0; n < NIT; ++n) {
+          const int k = tid + n * T;
+          if ((maskC[k >> 5] >> (k & 31)) & 1u) {
+            const unsigned key = skey[k];
+            if (key >= lo && key <= hi) atomicAdd(&hist[(key - lo) >> sh], 1);
+          }
+        }
+        __syncthreads();
+        if (warp == 0) {
+          int c[8], s = 0;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) { c[q] = hist[255 - 8 * lane - q]; s += c[q]; }
+          const int incl = warp_scan_incl(s);
+          int above = incl - s;
+          if (above < rr && rr <= incl) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              if (above < rr && rr <= above + c[q]) { bc[0] = 255 - 8 * lane - q; bc[1] = above; bc[2] = c[q]; }
+              above += c[q];
+            }
+          }
+        }
+        __syncthreads();
+        const int b = bc[0], nabove = bc[1], cb = bc[2];
+        lo = lo + ((unsigned)b << sh);
+        const unsigned hi2 = lo + ((1u << sh) - 1u);
+        hi = hi2 < hi ? hi2 : hi;
+        rr -= nabove;
+        if (cb == rr || sh == 0) break;
+      }
+      // selected = key above the boundary bucket, or among the first rr (by bin) inside it
+#pragma unroll 4
+      for (int n = 0; n < NIT; ++n) {
+        const int k = tid + n * T;
+        const bool c = (maskC[k >> 5] >> (k & 31)) & 1u;
+        const unsigned key = skey[k];
+        const unsigned mA = __ballot_sync(FULL, c && key > hi);
+        const unsigned mB = __ballot_sync(FULL, c && key >= lo && key <= hi);
+        if (lane == 0) { maskA[k >> 5] = mA; maskB[k >> 5] = mB; wcnt[k >> 5] = __popc(mB); }
+      }
+      __syncthreads();
+      if (warp == 0) warp0_excl_scan(wcnt, wbase, MW);
+      __syncthreads();
+#pragma unroll 4
+      for (int n = 0; n < NIT; ++n) {
+        const int k = tid + n * T;
+        const int wd = k >> 5;
+        const unsigned mA = maskA[wd], mB = maskB[wd], bit = 1u << (k & 31);
+        const bool s = (mA & bit) || ((mB & bit) && (wbase[wd] + __popc(mB & (bit - 1u)) < rr));
+        const unsigned mS = __ballot_sync(FULL, s);
+        if (lane == 0) maskS[wd] = mS;
+      }
+      __syncthreads();
+      selmask = maskS;
+    }
+
+    // ---- salience filter, rad = 5 (PeakFinder.py:113-134 as called at PVAnalysis.py:177)
+#pragma unroll 4
+    for (int n = 0; n < NIT; ++n) {
+      const int k = tid + n * T;
+      bool keep = false;
+      if ((selmask[k >> 5] >> (k & 31)) & 1u) {
+        const float y = famp[k];
+        const int a = k - 5 > 1 ? k - 5 : 1, b = k + 5 < M - 1 ? k + 5 : M - 1;
+        keep = true;
+        for (int m = a; m <= b; ++m) keep = keep && !(famp[m] > y);
+      }
+      const unsigned mk = __ballot_sync(FULL, keep);
+      if (lane == 0) { maskK[k >> 5] = mk; wcnt[k >> 5] = __popc(mk); }
+    }
+    __syncthreads();
+    if (warp == 0) warp0_excl_scan(wcnt, wbase, MW);
+    __syncthreads();
+    const int nk = wbase[MW];
+#pragma unroll 4
+    for (int n = 0; n < NIT; ++n) {
+      const int k = tid + n * T;
+      const unsigned mk = maskK[k >> 5], bit = 1u << (k & 31);
+      if (mk & bit) pk[wbase[k >> 5] + __popc(mk & (bit - 1u))] = k;
+    }
+    __syncthreads();
+
+    // ---- per-peak epilogue, freq > 0 filter, ordered write of the zero padded row
+    const int64_t ob = row * K;
+    int outbase = 0;
+    for (int p0 = 0; p0 < nk; p0 += T) {
+      const int p = p0 + tid;
+      PeakVals v;
+      bool valid = false;
+      int k = 0;
+      if (p < nk) {
+        k = pk[p];
+        valid = peak_epilogue(k, M, cur, prev, famp, prm.fbin, prm.wfbin, prm.dt, prm.fstep, v);
+      }
+      const unsigned mv = __ballot_sync(FULL, valid);
+      if (lane == 0) wcnt[warp] = __popc(mv);
+      __syncthreads();
+      int wb = 0, tot = 0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) { const int c = wcnt[w]; wb += (w < warp) ? c : 0; tot += c; }
+      if (valid) {
+        const int64_t pos = ob + outbase + wb + __popc(mv & lanemask_lt());
+        prm.f[pos] = v.f; prm.mag[pos] = v.mag; prm.ph[pos] = v.ph;
+        prm.realph[pos] = v.realph; prm.binno[pos] = (double)k;
+      }
+      outbase += tot;
+      __syncthreads();
+    }
+    for (int p = outbase + tid; p < K; p += T) {
+      prm.f[ob + p] = 0.0; prm.mag[ob + p] = 0.0; prm.ph[ob + p] = 0.0;
+      prm.realph[ob + p] = 0.0; prm.binno[ob + p] = 0.0;
+    }
+    if (tid == 0) {
+      prm.npk[row] = outbase;
+      prm.totalmag[row] = sqrt(sumsq);                       // PVAnalysis.py:210
+    }
+    __syncthreads();   // prev buffer is overwritten by the next frame's FFT
+  }
+  (void)N;
+}
+
+// ------------------------------------------------------------------ twiddle tables
+template <int LOGM> __global__ void tables_kernel(float2 *tab) {
+  using P = Plan<LOGM>;
+  constexpr int M = P::M;
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;
+  for (int q = 1; q < P::NPASS; ++q) {
+    const int R = 1 << P::lr(q), PP = 1 << P::lp(q), off = P::tw_off(q);
+    for (int e = gt; e < (R - 1) * PP; e += gs) {
+      const int r = e / PP + 1, k = e % PP;
+      double s, c;
+      sincospi(-2.0 * (double)k * (double)r / (double)(PP * R), &s, &c);
+      tab[off + e] = make_float2((float)c, (float)s);
+    }
+  }
+  for (int k = gt; k < M / 2; k += gs) {
+    double s, c;
+    sincospi(-(double)k / (double)M, &s, &c);   // exp(-2*pi*i*k/N), N = 2M
+    tab[P::TW_TOTAL + k] = make_float2((float)c, (float)s);
+  }
+}
+
+template <int LOGM> static int64_t tables_bytes_t() { return (int64_t)(Plan<LOGM>::TW_TOTAL + Plan<LOGM>::M / 2) * 8; }
+
+template <int LOGM> static int launch_tables(void *tables, void *stream) {
+  PVK_LAUNCH(tables_kernel<LOGM>, dim3(8), dim3(128), 0, stream, reinterpret_cast<float2 *>(tables));
+  PVK_CHECK_LAUNCH("pvk_analyze_init");
+  return PVK_OK;
+}
+
+template <int LOGM> static int launch_analyze(const AParams &prm, int64_t nclips, void *stream) {
+  using P = Plan<LOGM>;
+  const int smem = Smem<LOGM>::bytes(prm.npks);
+  if (smem > 48 * 1024) {
+    if (PVK_SET_SMEM(analyze_kernel<LOGM>, smem) != 0) {
+      set_error("pvk_analyze: cannot reserve %d bytes of shared memory", smem);
+      return PVK_ERR_CUDA;
+    }
+  }
+  const int64_t nblk = nclips * prm.nruns;
+  PVK_REQUIRE(nblk < (int64_t)2147483647, "pvk_analyze: grid too large (%lld CTAs)", (long long)nblk);
+  PVK_LAUNCH(analyze_kernel<LOGM>, dim3((unsigned)nblk), dim3(P::T), smem, stream, prm);
+  PVK_CHECK_LAUNCH("pvk_analyze");
+  return PVK_OK;
+}
+
+static int log2_exact(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return (1 << l) == v ? l : -1;
+}
+
+#define PVK_DISPATCH_LOGM(logm, CALL)                                                      \
+  switch (logm) {                                                                          \
+    case 5: return CALL(5);                                                                \
+    case 6: return CALL(6);                                                                \
+    case 7: return CALL(7);                                                                \
+    case 8: return CALL(8);                                                                \
+    case 9: return CALL(9);                                                                \
+    case 10: return CALL(10);                                                              \
+    case 11: return CALL(11);                                                              \
+    case 12: return CALL(12);                                                              \
+    default: break;                                                                        \
+  }
+
+}  // namespace pvk
+
+using namespace pvk;
+
+extern "C" int64_t pvk_analyze_tables_bytes(int nfft) {
+  const int l = log2_exact(nfft);
+  if (l < 0 || nfft < PVK_MIN_NFFT || nfft > PVK_MAX_NFFT) return -1;
+#define CALL(L) tables_bytes_t<L>()
+  PVK_DISPATCH_LOGM(l - 1, CALL)
+#undef CALL
+  return -1;
+}
+
+extern "C" int pvk_analyze_init(int nfft, void *tables, void *stream) {
+  const int l = log2_exact(nfft);
+  PVK_REQUIRE(l >= 0 && nfft >= PVK_MIN_NFFT && nfft <= PVK_MAX_NFFT,
+              "pvk_analyze_init: nfft=%d must be a power of two in [%d, %d]", nfft, PVK_MIN_NFFT, PVK_MAX_NFFT);
+  PVK_REQUIRE(tables != nullptr, "pvk_analyze_init: tables is NULL");
+#define CALL(L) launch_tables<L>(tables, stream)
+  PVK_DISPATCH_LOGM(l - 1, CALL)
+#undef CALL
+  return PVK_ERR_ARG;
+}
+
+extern "C" int pvk_analyze(const float *x, int64_t nclips, int64_t clip_stride, int64_t nsamp,
+                           const float *win_scaled, const double *fbin, const double *wfbin,
+                           const void *tables, int nfft, int hop, int npks, double pkthresh,
+                           double dt, double fstep, int64_t frame0, int64_t nframes, int prev_zero,
+                           int run_frames, double *f, double *mag, double *ph, double *realph,
+                           double *binno, int32_t *npk, double *totalmag, float *spec_out,
+                           void *stream) {
+  const int l = log2_exact(nfft);
+  PVK_REQUIRE(l >= 0 && nfft >= PVK_MIN_NFFT && nfft <= PVK_MAX_NFFT,
+              "pvk_analyze: nfft=%d must be a power of two in [%d, %d]", nfft, PVK_MIN_NFFT, PVK_MAX_NFFT);
+  PVK_REQUIRE(hop >= 1, "pvk_analyze: hop=%d must be >= 1", hop);
+  PVK_REQUIRE(npks >= 1 && npks <= PVK_MAX_NPKS, "pvk_analyze: npks=%d must be in [1, %d]", npks, PVK_MAX_NPKS);
+  PVK_REQUIRE(nclips >= 0 && nframes >= 0, "pvk_analyze: negative sizes");
+  PVK_REQUIRE(frame0 >= 0 && (prev_zero || frame0 >= 1),
+              "pvk_analyze: frame0=%lld needs a warm-up frame (frame0 >= 1) unless prev_zero", (long long)frame0);
+  if (nclips == 0 || nframes == 0) return PVK_OK;
+  PVK_REQUIRE((frame0 + nframes - 1) * (int64_t)hop + nfft <= nsamp,
+              "pvk_analyze: last frame ends at sample %lld > nsamp=%lld",
+              (long long)((frame0 + nframes - 1) * (int64_t)hop + nfft), (long long)nsamp);
+  PVK_REQUIRE(x && win_scaled && fbin && wfbin && tables && f && mag && ph && realph && binno && npk && totalmag,
+              "pvk_analyze: NULL pointer argument");
+  PVK_REQUIRE((reinterpret_cast<uintptr_t>(win_scaled) & 7) == 0, "pvk_analyze: win_scaled must be 8-byte aligned");
+  AParams prm;
+  prm.x = x; prm.clip_stride = clip_stride; prm.win = win_scaled;
+  prm.tables = reinterpret_cast<const float2 *>(tables);
+  prm.fbin = fbin; prm.wfbin = wfbin; prm.hop = hop; prm.npks = npks;
+  prm.pkthresh = pkthresh; prm.dt = dt; prm.fstep = fstep;
+  prm.frame0 = frame0; prm.nframes = nframes; prm.prev_zero = prev_zero ? 1 : 0;
+  int run = run_frames;
+  if (run <= 0) {
+    // enough CTAs for a few waves over 148 SMs, while keeping the 1-frame warm-up small
+    const int64_t total = nclips * nframes;
+    int64_t r = (total + 8191) / 8192;
+    if (r < 16) r = 16;
+    if (r > 128) r = 128;
+    run = (int)r;
+  }
+  if (run > nframes) run = (int)nframes;
+  prm.run = run;
+  prm.nruns = (nframes + run - 1) / run;
+  prm.f = f; prm.mag = mag; prm.ph = ph; prm.realph = realph; prm.binno = binno;
+  prm.npk = npk; prm.totalmag = totalmag;
+  prm.spec_out = reinterpret_cast<float2 *>(spec_out);
+#define CALL(L) launch_analyze<L>(prm, nclips, stream)
+  PVK_DISPATCH_LOGM(l - 1, CALL)
+#undef CALL
+  return PVK_ERR_ARG;
+}

@@ -1,0 +1,88 @@
+"""TEST INFRASTRUCTURE ONLY -- drive tests/emu/libpvk_emu.so (the kernels compiled for the
+CPU SIMT emulator) through the same C ABI, with numpy arrays standing in for device memory.
+Used to debug kernel logic on the GPU-less build container; the real parity tests are the
+``-m gpu`` ones that go through pypevoc_b200 -> libpvk.so on the B200."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from pypevoc_b200 import _lib as binding
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "libpvk_emu.so")
+
+
+def build(force=False):
+    srcs = [os.path.join(HERE, f) for f in ("cuda_emu.h", "cuda_emu.cc")]
+    csrc = os.path.join(os.path.dirname(os.path.dirname(HERE)), "pypevoc_b200", "csrc")
+    srcs += [os.path.join(csrc, f) for f in os.listdir(csrc)]
+    srcs.append(os.path.join(os.path.dirname(os.path.dirname(HERE)), "include", "pvk.h"))
+    if force or not os.path.isfile(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in srcs):
+        subprocess.check_call([os.path.join(HERE, "build_emu.sh")], stdout=subprocess.DEVNULL)
+    return SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = binding.declare(C.CDLL(build()), strict=False)
+    return _lib
+
+
+def ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def check(st):
+    if st != 0:
+        raise RuntimeError("emu libpvk: %s" % lib().pvk_last_error().decode())
+
+
+def host_tables(sr, nfft, hop, wind=np.hanning):
+    """Same expressions as PV.__init__ (PVAnalysis.py:97-118)."""
+    win = wind(nfft)
+    wfact = np.sqrt(sum(win ** 2) * nfft) / 2.0
+    fstep = float(sr) / float(nfft)
+    dt = float(hop) / float(sr)
+    fbin = np.arange(float(nfft)) * fstep
+    pi2 = 2.0 * np.pi
+    wfbin = np.round(pi2 * fbin * dt / pi2) * pi2
+    return dict(win_scaled=np.ascontiguousarray((win / wfact).astype(np.float32)), fbin=fbin,
+                wfbin=wfbin, dt=dt, fstep=fstep, wfact=wfact)
+
+
+def analyze(x, sr, nfft, hop, npks, pkthresh=0.005, nclips=1, frame0=0, nframes=None,
+            prev_zero=1, run_frames=0, spectra=False, wind=np.hanning):
+    L = lib()
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    if x.ndim == 1:
+        x = x[None, :]
+    nclips, nsamp = x.shape
+    tb = host_tables(sr, nfft, hop, wind)
+    if nframes is None:
+        span = nsamp - nfft
+        nframes = 0 if span <= 0 else -(-span // hop)
+        nframes -= frame0
+    tbytes = L.pvk_analyze_tables_bytes(nfft)
+    assert tbytes > 0
+    tables = np.zeros(tbytes, dtype=np.uint8)
+    check(L.pvk_analyze_init(nfft, ptr(tables), None))
+    shp = (nclips, nframes, npks)
+    out = {k: np.full(shp, np.nan) for k in ("f", "mag", "ph", "realph", "binno")}
+    npk = np.full((nclips, nframes), -7, dtype=np.int32)
+    totalmag = np.full((nclips, nframes), np.nan)
+    spec = np.zeros((nclips, nframes, nfft // 2, 2), dtype=np.float32) if spectra else None
+    check(L.pvk_analyze(ptr(x), nclips, x.strides[0] // 4, nsamp, ptr(tb["win_scaled"]), ptr(tb["fbin"]),
+                        ptr(tb["wfbin"]), ptr(tables), nfft, hop, npks, pkthresh, tb["dt"], tb["fstep"],
+                        frame0, nframes, prev_zero, run_frames, ptr(out["f"]), ptr(out["mag"]),
+                        ptr(out["ph"]), ptr(out["realph"]), ptr(out["binno"]), ptr(npk), ptr(totalmag),
+                        ptr(spec), None))
+    out.update(npk=npk, totalmag=totalmag, nframes=nframes)
+    if spectra:
+        out["fx"] = spec[..., 0] + 1j * spec[..., 1]
+    return out
