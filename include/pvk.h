@@ -86,50 +86,52 @@ int pvk_analyze(const float *x, int64_t nclips, int64_t clip_stride, int64_t nsa
 /* ------------------------------------------------------------------ tracking
  * Replaces PV.toSinSum -> SinSum.add_frame (PVAnalysis.py:299-322,871-957).
  *
- * Input: f, mag float64 [nclips, nframes, npks] (any zero padded rows in the reference
- * layout; a slot is a point iff f > 0 and mag > 0, :876).
- * Output: tid int32 [nclips, nframes, npks] track id per slot (-1 = not a point), ids
- * numbered per clip in add_empty_partial call order (:819-830); tstart / tlen int32
- * [nclips, max_tracks] first frame and number of frames per track; ntracks int32 [nclips].
- * prev_f / prev_mag / prev_tid (optional, [nclips, npks]): the peak row preceding frame 0
- * of this shard with its already-assigned ids (segment sharding); NULL = nothing before.
+ * Input: f, mag float64 [nclips, nframes, npks] (rows in the reference layout; a slot is a
+ * point iff f > 0 and mag > 0, :876).
+ * Output:
+ *   link  int32 [nclips, nframes, npks]: column of the continued peak in the previous frame
+ *         (>= 0), -1 = not a point, <= -2 = starts a new partial (rank -2-link among the
+ *         frame's new partials in processing order, :941)
+ *   tid   int32 [nclips, nframes, npks]: track (partial) id per slot, -1 = not a point; ids
+ *         numbered per clip in add_empty_partial call order (:819-830), i.e. the index of
+ *         the partial in the reference's ss.partial list
+ *   ntracks int32 [nclips]: number of partials per clip
  */
 int64_t pvk_track_workspace_bytes(int64_t nclips, int64_t nframes, int npks);
 
 int pvk_track(const double *f, const double *mag, int64_t nclips, int64_t nframes, int npks,
-              double maxpitchjmp, int32_t *tid, int32_t *link, int32_t *tstart,
-              int32_t *tlen, int32_t *ntracks, int64_t max_tracks, void *workspace,
-              int64_t workspace_bytes, void *stream);
+              double maxpitchjmp, int32_t *tid, int32_t *link, int32_t *ntracks,
+              void *workspace, int64_t workspace_bytes, void *stream);
 
-/* Pack per-track value runs (= RegPartial.f/mag/ph/realph lists, :616-626) from the frame
- * tables: toff int64 [ntracks+1] exclusive offsets (computed here), packed float64 arrays
- * of length sum(tlen).  Single clip. */
+/* Pack per-track value runs (= RegPartial.f/mag/ph/realph lists, :616-626, with
+ * start_idx = tstart, :598) from the frame tables of ONE clip.  ntracks must be the value
+ * pvk_track reported.  Outputs: tstart / tlen int32 [ntracks] (= ss.st and
+ * ss.end - ss.st + 1, :827-828,950), toff int64 [ntracks+1] exclusive offsets, packed
+ * float64 arrays of length sum(tlen) (pph may be NULL). */
 int pvk_track_pack(const double *f, const double *mag, const double *ph, const double *realph,
-                   const int32_t *tid, int64_t nframes, int npks, const int32_t *tstart,
-                   const int32_t *tlen, int64_t ntracks, int64_t *toff, double *pf,
-                   double *pmag, double *pph, double *prealph, void *workspace,
-                   int64_t workspace_bytes, void *stream);
+                   const int32_t *tid, const int32_t *link, int64_t nframes, int npks,
+                   int64_t ntracks, int32_t *tstart, int32_t *tlen, int64_t *toff, double *pf,
+                   double *pmag, double *pph, double *prealph, void *stream);
 
 /* ------------------------------------------------------------------ resynthesis
  * Replaces SinSum.synth -> RegPartial.synth (PVAnalysis.py:1053-1070,684-756),
- * phase_preserve=True path.
+ * phase_preserve=True path, for ONE clip.
  *
- *   tstart/tlen/toff + packed pf/pmag/prealph   the tracks (all ntracks; tracks shorter
- *                                               than minframes are skipped, :1061)
- *   sr, hop      synthesis sample rate and hop (may differ from analysis hop)
+ *   tid [nframes, npks]                  track id per frame slot (pvk_track)
+ *   tstart/tlen/toff, pf/pmag/prealph    the packed partials (pvk_track_pack); partials
+ *                                        shorter than minframes are skipped (:1061)
+ *   sr, hop      synthesis sample rate and hop (hop may differ from the analysis hop)
  *   nfft, hop_an analysis parameters the SinSum was built with (:824-825,1055)
  *   out          float64 [nout], nout = (max_end+2)*hop + int(edge*hop*nfft/hop_an/2)
- *                (:1059,1070); fully written (zeros where no track sounds)
- *   block0/nblocks  render output blocks [block0, block0+nblocks) of `hop` samples only
- *                (multi-GPU: each rank renders a disjoint block range); nblocks<0 = all
+ *                (:1059,1070); every sample of the rendered block range is written
+ *                (zeros where no partial sounds)
+ *   block0, nblocks  render output blocks [block0, block0+nblocks) of `hop` samples
+ *                (multi-GPU: each rank renders a disjoint block range); nblocks < 0 = all
  */
-int64_t pvk_resynth_workspace_bytes(int64_t ntracks, int64_t nblocks_total);
-
-int pvk_resynth(const int32_t *tstart, const int32_t *tlen, const int64_t *toff,
-                const double *pf, const double *pmag, const double *prealph,
-                int64_t ntracks, double sr, int hop, int nfft, int hop_an, double edge,
+int pvk_resynth(const int32_t *tid, int64_t nframes, int npks, const int32_t *tstart,
+                const int32_t *tlen, const int64_t *toff, const double *pf, const double *pmag,
+                const double *prealph, double sr, int hop, int nfft, int hop_an, double edge,
                 int minframes, double *out, int64_t nout, int64_t block0, int64_t nblocks,
-                void *workspace, int64_t workspace_bytes, int64_t *partial_samples,
                 void *stream);
 
 #ifdef __cplusplus

@@ -23,12 +23,10 @@ SIGNATURES = {
     "pvk_analyze": (_i, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _i, _i, _i, _d, _d, _d, _i64, _i64,
                          _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "pvk_track_workspace_bytes": (_i64, [_i64, _i64, _i]),
-    "pvk_track": (_i, [_p, _p, _i64, _i64, _i, _d, _p, _p, _p, _p, _p, _i64, _p, _i64, _p]),
-    "pvk_track_pack": (_i, [_p, _p, _p, _p, _p, _i64, _i, _p, _p, _i64, _p, _p, _p, _p, _p, _p,
-                            _i64, _p]),
-    "pvk_resynth_workspace_bytes": (_i64, [_i64, _i64]),
-    "pvk_resynth": (_i, [_p, _p, _p, _p, _p, _p, _i64, _d, _i, _i, _i, _d, _i, _p, _i64, _i64,
-                         _i64, _p, _i64, _p, _p]),
+    "pvk_track": (_i, [_p, _p, _i64, _i64, _i, _d, _p, _p, _p, _p, _i64, _p]),
+    "pvk_track_pack": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _i64, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "pvk_resynth": (_i, [_p, _i64, _i, _p, _p, _p, _p, _p, _p, _d, _i, _i, _i, _d, _i, _p, _i64, _i64,
+                         _i64, _p]),
 }
 
 

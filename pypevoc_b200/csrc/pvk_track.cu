@@ -1,0 +1,399 @@
+// pvk_track.cu -- partial tracking (PV.toSinSum -> SinSum.add_frame, PVAnalysis.py:299-322,
+// 871-957) as a handful of small GPU kernels.
+//
+// The reference's greedy match of frame j against frame j-1 depends on those two peak rows
+// only, so tracking splits into
+//   link     one warp per frame pair: peaks of frame j in descending magnitude each take the
+//            nearest still-unused peak of frame j-1 (|17.312*(fc/fp-1)| < maxpitchjmp,
+//            :914-928) or start a new partial (:941)
+//   scan     exclusive scan of new-partial counts -> ids in add_empty_partial call order (:819-830)
+//   resolve  continued peaks inherit the id of their predecessor: chunk-local propagation,
+//            a short sequential pass over chunk boundaries, final fix-up
+//   pack     per-track runs (= RegPartial.f/mag/ph/realph lists, :616-626) for resynthesis
+// Exact magnitude ties inside one frame (measure zero for real signals) are ordered by column
+// (current frame: higher column first, previous frame: lower column first); the reference's
+// order there comes from numpy's unstable argsort and python's tuple sort on track index.
+#include "pvk_common.cuh"
+
+namespace pvk {
+
+constexpr int LINK_NONE = -1;    // slot is not a point
+// link <= -2: new partial, rank among the frame's new partials = -2 - link
+constexpr int TRACK_CHUNK = 128; // frames per chain-resolution chunk
+
+// ------------------------------------------------------------------ link
+__global__ void track_link_kernel(const double *__restrict__ f, const double *__restrict__ mag,
+                                  int64_t nrows, int64_t F, int K, double maxjump,
+                                  int32_t *__restrict__ link, int32_t *__restrict__ newcount) {
+  PVK_SMEM(smem);
+  const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per_warp = K * (4 * 8 + 2 * 2);
+  unsigned char *base = smem + (size_t)warp * ((per_warp + 15) / 16 * 16);
+  double *cf = reinterpret_cast<double *>(base);
+  double *cm = cf + K;
+  double *pf = cm + K;
+  double *pm = pf + K;
+  short *ord = reinterpret_cast<short *>(pm + K);
+  short *prank = ord + K;
+
+  for (int64_t row = (int64_t)blockIdx.x * W + warp; row < nrows; row += (int64_t)gridDim.x * W) {
+    const int64_t j = row % F;
+    const bool has_prev = j > 0;
+    int chi = 0, phi = 0;   // 1 + highest valid column of current / previous row
+    for (int i = lane; i < K; i += 32) {
+      const double a = f[row * K + i], b = mag[row * K + i];
+      cf[i] = a; cm[i] = b;
+      const bool v = a > 0.0 && b > 0.0;                        // :876
+      if (v) chi = i + 1; else link[row * K + i] = LINK_NONE;
+      if (has_prev) {
+        const double c = f[(row - 1) * K + i], d = mag[(row - 1) * K + i];
+        pf[i] = c; pm[i] = d;
+        if (c > 0.0 && d > 0.0) phi = i + 1;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      chi = max(chi, __shfl_xor_sync(FULL, chi, o));
+      phi = max(phi, __shfl_xor_sync(FULL, phi, o));
+    }
+    __syncwarp();
+    // order of the current peaks: magnitude descending (:874-875)
+    int nc = 0;
+    for (int i0 = 0; i0 < chi; i0 += 32) {
+      const int i = i0 + lane;
+      const double mi = i < chi ? cm[i] : 0.0;
+      const bool vi = i < chi && cf[i] > 0.0 && mi > 0.0;
+      int r = 0;
+      if (vi) {
+        for (int i2 = 0; i2 < chi; ++i2) {
+          const double m2 = cm[i2];
+          const bool v2 = cf[i2] > 0.0 && m2 > 0.0;
+          r += (v2 && (m2 > mi || (m2 == mi && i2 > i))) ? 1 : 0;
+        }
+        ord[r] = (short)i;
+      }
+      nc += __popc(__ballot_sync(FULL, vi));
+    }
+    // rank of the previous peaks in descending magnitude (:891-900)
+    for (int i0 = 0; i0 < phi; i0 += 32) {
+      const int i = i0 + lane;
+      if (i < phi) {
+        const double mi = pm[i];
+        int r = 0;
+        if (pf[i] > 0.0 && mi > 0.0) {
+          for (int i2 = 0; i2 < phi; ++i2) {
+            const double m2 = pm[i2];
+            const bool v2 = pf[i2] > 0.0 && m2 > 0.0;
+            r += (v2 && (m2 > mi || (m2 == mi && i2 < i))) ? 1 : 0;
+          }
+        }
+        prank[i] = (short)r;
+      }
+    }
+    __syncwarp();
+    // greedy nearest-frequency match (:903-950)
+    unsigned usedmask = 0;
+    int nnew = 0;
+    for (int t = 0; t < nc; ++t) {
+      const int c = ord[t];
+      const double fc = cf[c];
+      double bd = 1e300;
+      int br = 0x7fffffff, bp = -1;
+      for (int p = lane, q = 0; p < phi; p += 32, ++q) {
+        const double pfv = pf[p];
+        if (pfv > 0.0 && pm[p] > 0.0 && !((usedmask >> q) & 1u)) {
+          // abs(17.312*(fc/pf - 1.0)): dpitch2st :62-68 as called at :914
+          const double d = fabs(__dmul_rn(17.312, __dsub_rn(__ddiv_rn(fc, pfv), 1.0)));
+          const int r = prank[p];
+          if (d < bd || (d == bd && r < br)) { bd = d; br = r; bp = p; }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        const double od = __shfl_xor_sync(FULL, bd, o);
+        const int orr = __shfl_xor_sync(FULL, br, o), op = __shfl_xor_sync(FULL, bp, o);
+        if (od < bd || (od == bd && orr < br)) { bd = od; br = orr; bp = op; }
+      }
+      int lk;
+      if (bp >= 0 && bd < maxjump) {                            // :923
+        lk = bp;
+        if ((bp & 31) == lane) usedmask |= 1u << (bp >> 5);
+      } else {
+        lk = -2 - nnew;                                         // add_empty_partial :941
+        ++nnew;
+      }
+      if (lane == 0) link[row * K + c] = lk;
+    }
+    if (lane == 0) newcount[row] = nnew;
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------ per-clip exclusive scan
+__global__ void track_scan_kernel(const int32_t *__restrict__ newcount, int32_t *__restrict__ base,
+                                  int32_t *__restrict__ ntracks, int64_t F) {
+  PVK_SMEM(smem);
+  int *wsum = reinterpret_cast<int *>(smem);
+  int &carry_s = wsum[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NWARP = blockDim.x >> 5;
+  const int64_t clip = blockIdx.x;
+  const int32_t *in = newcount + clip * F;
+  int32_t *out = base + clip * F;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int64_t s = 0; s < F; s += blockDim.x) {
+    const int64_t i = s + tid;
+    const int v = i < F ? in[i] : 0;
+    const int inc = warp_scan_incl(v);
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    int woff = 0, tot = 0;
+    for (int w = 0; w < NWARP; ++w) { const int x = wsum[w]; woff += (w < warp) ? x : 0; tot += x; }
+    const int carry = carry_s;
+    if (i < F) out[i] = carry + woff + inc - v;
+    __syncthreads();
+    if (tid == 0) carry_s = carry + tot;
+    __syncthreads();
+  }
+  if (tid == 0) ntracks[clip] = carry_s;
+}
+
+// ------------------------------------------------------------------ chain resolution
+// tid values while unresolved: >= 0 final id; -1 not a point; <= -2: descends from column
+// (-2 - v) of the first row of this chunk, whose own id is not known yet.
+__global__ void track_chunk_kernel(const int32_t *__restrict__ link, const int32_t *__restrict__ base,
+                                   int64_t F, int K, int64_t nchunks, int32_t *__restrict__ tid) {
+  PVK_SMEM(smem);
+  int *prevrow = reinterpret_cast<int *>(smem);
+  const int64_t clip = blockIdx.x / nchunks, ch = blockIdx.x % nchunks;
+  const int64_t j0 = ch * TRACK_CHUNK, j1 = (j0 + TRACK_CHUNK < F) ? j0 + TRACK_CHUNK : F;
+  const int c = threadIdx.x;
+  const bool act = c < K;
+  int lk_next = act ? link[(clip * F + j0) * K + c] : LINK_NONE;
+  for (int64_t j = j0; j < j1; ++j) {
+    const int64_t row = clip * F + j;
+    const int lk = lk_next;
+    if (j + 1 < j1 && act) lk_next = link[(row + 1) * K + c];
+    int v;
+    if (lk == LINK_NONE) v = -1;
+    else if (lk <= -2) v = base[row] + (-2 - lk);
+    else if (j == j0) v = -2 - c;
+    else v = prevrow[lk];
+    __syncthreads();
+    if (act) { prevrow[c] = v; tid[row * K + c] = v; }
+    __syncthreads();
+  }
+}
+
+// G[ch][c] for the first row of chunk ch >= 1: what the continued peak points at in chunk ch-1
+__global__ void track_boundary_kernel(const int32_t *__restrict__ link, const int32_t *__restrict__ tid,
+                                      int64_t F, int K, int64_t nchunks, int64_t nclips,
+                                      int32_t *__restrict__ G) {
+  const int64_t n = nclips * nchunks * K;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % K);
+    const int64_t cc = e / K, ch = cc % nchunks, clip = cc / nchunks;
+    const int64_t row = clip * F + ch * TRACK_CHUNK;
+    int v = tid[row * K + c];
+    if (v <= -2) {                      // continued from the previous chunk's last row
+      const int lk = link[row * K + c];
+      v = tid[(row - 1) * K + lk];      // >= 0 final, or <= -2: first-row column of chunk ch-1
+    }
+    G[e] = v;
+  }
+}
+
+// sequential over the chunks of one clip; G becomes the final ids of every chunk's first row
+__global__ void track_stitch_kernel(int32_t *__restrict__ G, int K, int64_t nchunks) {
+  PVK_SMEM(smem);
+  int *fprev = reinterpret_cast<int *>(smem);
+  const int64_t clip = blockIdx.x;
+  int32_t *g = G + clip * nchunks * K;
+  const int c = threadIdx.x;
+  const bool act = c < K;
+  int v_next = act && nchunks > 0 ? g[c] : -1;
+  for (int64_t ch = 0; ch < nchunks; ++ch) {
+    int v = v_next;
+    if (ch + 1 < nchunks && act) v_next = g[(ch + 1) * K + c];
+    if (v <= -2) v = fprev[-2 - v];
+    __syncthreads();
+    if (act) { fprev[c] = v; g[ch * K + c] = v; }
+    __syncthreads();
+  }
+}
+
+__global__ void track_fix_kernel(int32_t *__restrict__ tid, const int32_t *__restrict__ G, int64_t F,
+                                 int K, int64_t nchunks, int64_t nclips) {
+  const int64_t n = nclips * F * K;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int v = tid[e];
+    if (v <= -2) {
+      const int64_t row = e / K, clip = row / F, ch = (row % F) / TRACK_CHUNK;
+      tid[e] = G[(clip * nchunks + ch) * K + (-2 - v)];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ pack
+__global__ void pack_count_kernel(const int32_t *__restrict__ tid, const int32_t *__restrict__ link,
+                                  int64_t F, int K, int32_t *__restrict__ tstart, int32_t *__restrict__ tlen) {
+  const int64_t n = F * K;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int v = tid[e];
+    if (v >= 0) {
+      atomicAdd(&tlen[v], 1);
+      if (link[e] <= -2) tstart[v] = (int32_t)(e / K);
+    }
+  }
+}
+
+// single-CTA exclusive scan int32 -> int64 (ntracks + 1 outputs)
+__global__ void pack_scan_kernel(const int32_t *__restrict__ tlen, int64_t n, int64_t *__restrict__ toff) {
+  PVK_SMEM(smem);
+  long long *wsum = reinterpret_cast<long long *>(smem);
+  long long &carry_s = wsum[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NWARP = blockDim.x >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int64_t s = 0; s < n; s += blockDim.x) {
+    const int64_t i = s + tid;
+    const long long v = i < n ? tlen[i] : 0;
+    long long inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long t = __shfl_up_sync(FULL, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    long long woff = 0, tot = 0;
+    for (int w = 0; w < NWARP; ++w) { const long long x = wsum[w]; woff += (w < warp) ? x : 0; tot += x; }
+    const long long carry = carry_s;
+    if (i < n) toff[i] = carry + woff + inc - v;
+    __syncthreads();
+    if (tid == 0) carry_s = carry + tot;
+    __syncthreads();
+  }
+  if (tid == 0) toff[n] = carry_s;
+}
+
+__global__ void pack_scatter_kernel(const double *__restrict__ f, const double *__restrict__ mag,
+                                    const double *__restrict__ ph, const double *__restrict__ realph,
+                                    const int32_t *__restrict__ tid, int64_t F, int K,
+                                    const int32_t *__restrict__ tstart, const int64_t *__restrict__ toff,
+                                    double *__restrict__ pf, double *__restrict__ pmag,
+                                    double *__restrict__ pph, double *__restrict__ prealph) {
+  const int64_t n = F * K;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int v = tid[e];
+    if (v >= 0) {
+      const int64_t pos = toff[v] + (e / K - tstart[v]);
+      pf[pos] = f[e]; pmag[pos] = mag[e];
+      if (pph) pph[pos] = ph[e];
+      prealph[pos] = realph[e];
+    }
+  }
+}
+
+static inline int grid_for(int64_t n, int block) {
+  int64_t g = (n + block - 1) / block;
+  const int64_t cap = 148 * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace pvk
+
+using namespace pvk;
+
+extern "C" int64_t pvk_track_workspace_bytes(int64_t nclips, int64_t nframes, int npks) {
+  if (nclips < 0 || nframes < 0 || npks < 1) return -1;
+  const int64_t rows = nclips * nframes;
+  const int64_t nchunks = (nframes + TRACK_CHUNK - 1) / TRACK_CHUNK;
+  return align_up(rows * 4, 256) * 2 + align_up(nclips * nchunks * npks * 4, 256) + 256;
+}
+
+extern "C" int pvk_track(const double *f, const double *mag, int64_t nclips, int64_t nframes, int npks,
+                         double maxpitchjmp, int32_t *tid, int32_t *link, int32_t *ntracks,
+                         void *workspace, int64_t workspace_bytes, void *stream) {
+  PVK_REQUIRE(npks >= 1 && npks <= PVK_MAX_NPKS, "pvk_track: npks=%d must be in [1, %d]", npks, PVK_MAX_NPKS);
+  PVK_REQUIRE(nclips >= 0 && nframes >= 0, "pvk_track: negative sizes");
+  PVK_REQUIRE(ntracks != nullptr, "pvk_track: ntracks is NULL");
+  if (nclips == 0) return PVK_OK;
+  if (nframes == 0) {
+    cudaMemsetAsync(ntracks, 0, (size_t)nclips * 4, (cudaStream_t)stream);
+    return PVK_OK;
+  }
+  PVK_REQUIRE(f && mag && tid && link && workspace, "pvk_track: NULL pointer argument");
+  PVK_REQUIRE(workspace_bytes >= pvk_track_workspace_bytes(nclips, nframes, npks),
+              "pvk_track: workspace too small (%lld < %lld bytes)", (long long)workspace_bytes,
+              (long long)pvk_track_workspace_bytes(nclips, nframes, npks));
+  PVK_REQUIRE(nclips * nframes * (int64_t)npks < (int64_t)2147483647,
+              "pvk_track: nclips*nframes*npks must be < 2^31");
+  const int K = npks;
+  const int64_t rows = nclips * nframes;
+  const int64_t nchunks = (nframes + TRACK_CHUNK - 1) / TRACK_CHUNK;
+  unsigned char *ws = reinterpret_cast<unsigned char *>(workspace);
+  int32_t *newcount = reinterpret_cast<int32_t *>(ws);
+  int32_t *base = reinterpret_cast<int32_t *>(ws + align_up(rows * 4, 256));
+  int32_t *G = reinterpret_cast<int32_t *>(ws + 2 * align_up(rows * 4, 256));
+
+  {  // link: one warp per frame pair
+    const int per_warp = (K * (4 * 8 + 2 * 2) + 15) / 16 * 16;
+    int W = 160 * 1024 / per_warp;
+    if (W > 8) W = 8;
+    if (W < 1) W = 1;
+    const int smem = W * per_warp;
+    if (smem > 48 * 1024) {
+      if (PVK_SET_SMEM(track_link_kernel, smem) != 0) {
+        set_error("pvk_track: cannot reserve %d bytes of shared memory", smem);
+        return PVK_ERR_CUDA;
+      }
+    }
+    int64_t g = (rows + W - 1) / W;
+    if (g > 148 * 64) g = 148 * 64;
+    PVK_LAUNCH(track_link_kernel, dim3((unsigned)g), dim3(W * 32), smem, stream, f, mag, rows, nframes, K,
+               maxpitchjmp, link, newcount);
+    PVK_CHECK_LAUNCH("pvk_track(link)");
+  }
+  PVK_LAUNCH(track_scan_kernel, dim3((unsigned)nclips), dim3(1024), 33 * 4, stream, newcount, base, ntracks, nframes);
+  PVK_CHECK_LAUNCH("pvk_track(scan)");
+  const int cb = (K + 31) / 32 * 32;
+  PVK_LAUNCH(track_chunk_kernel, dim3((unsigned)(nclips * nchunks)), dim3(cb), (size_t)K * 4, stream, link, base,
+             nframes, K, nchunks, tid);
+  PVK_CHECK_LAUNCH("pvk_track(chunk)");
+  if (nchunks > 1) {
+    PVK_LAUNCH(track_boundary_kernel, dim3(grid_for(nclips * nchunks * K, 256)), dim3(256), 0, stream, link, tid,
+               nframes, K, nchunks, nclips, G);
+    PVK_CHECK_LAUNCH("pvk_track(boundary)");
+    PVK_LAUNCH(track_stitch_kernel, dim3((unsigned)nclips), dim3(cb), (size_t)K * 4, stream, G, K, nchunks);
+    PVK_CHECK_LAUNCH("pvk_track(stitch)");
+    PVK_LAUNCH(track_fix_kernel, dim3(grid_for(rows * K, 256)), dim3(256), 0, stream, tid, G, nframes, K, nchunks,
+               nclips);
+    PVK_CHECK_LAUNCH("pvk_track(fix)");
+  }
+  return PVK_OK;
+}
+
+extern "C" int pvk_track_pack(const double *f, const double *mag, const double *ph, const double *realph,
+                              const int32_t *tid, const int32_t *link, int64_t nframes, int npks,
+                              int64_t ntracks, int32_t *tstart, int32_t *tlen, int64_t *toff, double *pf,
+                              double *pmag, double *pph, double *prealph, void *stream) {
+  PVK_REQUIRE(npks >= 1 && nframes >= 0 && ntracks >= 0, "pvk_track_pack: bad sizes");
+  PVK_REQUIRE(toff != nullptr, "pvk_track_pack: toff is NULL");
+  if (ntracks == 0 || nframes == 0) {
+    cudaMemsetAsync(toff, 0, 8 * (size_t)(ntracks + 1), (cudaStream_t)stream);
+    return PVK_OK;
+  }
+  PVK_REQUIRE(f && mag && realph && tid && link && tstart && tlen && pf && pmag && prealph,
+              "pvk_track_pack: NULL pointer argument");
+  const int64_t n = nframes * npks;
+  cudaMemsetAsync(tlen, 0, 4 * (size_t)ntracks, (cudaStream_t)stream);
+  PVK_LAUNCH(pack_count_kernel, dim3(grid_for(n, 256)), dim3(256), 0, stream, tid, link, nframes, npks, tstart, tlen);
+  PVK_CHECK_LAUNCH("pvk_track_pack(count)");
+  PVK_LAUNCH(pack_scan_kernel, dim3(1), dim3(1024), 33 * 8, stream, tlen, ntracks, toff);
+  PVK_CHECK_LAUNCH("pvk_track_pack(scan)");
+  PVK_LAUNCH(pack_scatter_kernel, dim3(grid_for(n, 256)), dim3(256), 0, stream, f, mag, ph, realph, tid, nframes,
+             npks, tstart, toff, pf, pmag, pph, prealph);
+  PVK_CHECK_LAUNCH("pvk_track_pack(scatter)");
+  return PVK_OK;
+}

@@ -86,3 +86,60 @@ def analyze(x, sr, nfft, hop, npks, pkthresh=0.005, nclips=1, frame0=0, nframes=
     if spectra:
         out["fx"] = spec[..., 0] + 1j * spec[..., 1]
     return out
+
+
+def track(f, mag, maxpitchjmp=0.5):
+    """pvk_track on host arrays; f, mag [F, K] or [nclips, F, K]."""
+    L = lib()
+    f = np.ascontiguousarray(f, dtype=np.float64)
+    mag = np.ascontiguousarray(mag, dtype=np.float64)
+    if f.ndim == 2:
+        f, mag = f[None], mag[None]
+    nclips, F, K = f.shape
+    tid = np.full((nclips, F, K), -99, dtype=np.int32)
+    link = np.full((nclips, F, K), -99, dtype=np.int32)
+    ntracks = np.full(nclips, -1, dtype=np.int32)
+    wsb = L.pvk_track_workspace_bytes(nclips, F, K)
+    ws = np.zeros(max(wsb, 8), dtype=np.uint8)
+    check(L.pvk_track(ptr(f), ptr(mag), nclips, F, K, maxpitchjmp, ptr(tid), ptr(link), ptr(ntracks),
+                      ptr(ws), wsb, None))
+    return dict(tid=tid, link=link, ntracks=ntracks)
+
+
+def track_pack(f, mag, ph, realph, tid, link, ntracks):
+    """pvk_track_pack for one clip ([F, K] arrays)."""
+    L = lib()
+    F, K = f.shape
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (f, mag, ph, realph)]
+    tid = np.ascontiguousarray(tid, dtype=np.int32)
+    link = np.ascontiguousarray(link, dtype=np.int32)
+    npts = int((tid >= 0).sum())
+    tstart = np.full(max(ntracks, 1), -1, dtype=np.int32)
+    tlen = np.full(max(ntracks, 1), -1, dtype=np.int32)
+    toff = np.full(ntracks + 1, -1, dtype=np.int64)
+    packed = [np.full(max(npts, 1), np.nan) for _ in range(4)]
+    check(L.pvk_track_pack(ptr(arrs[0]), ptr(arrs[1]), ptr(arrs[2]), ptr(arrs[3]), ptr(tid), ptr(link), F, K,
+                           ntracks, ptr(tstart), ptr(tlen), ptr(toff), ptr(packed[0]), ptr(packed[1]),
+                           ptr(packed[2]), ptr(packed[3]), None))
+    return dict(tstart=tstart[:ntracks], tlen=tlen[:ntracks], toff=toff, pf=packed[0][:npts],
+                pmag=packed[1][:npts], pph=packed[2][:npts], prealph=packed[3][:npts])
+
+
+def resynth(tid, pk, sr, hop, nfft, hop_an, edge=1.0, minframes=3, block0=0, nblocks=-1, nout=None):
+    """pvk_resynth for one clip: tid [F, K], pk = dict from track_pack."""
+    L = lib()
+    tid = np.ascontiguousarray(tid, dtype=np.int32)
+    F, K = tid.shape
+    nt = len(pk["tstart"])
+    max_end = int((pk["tstart"] + pk["tlen"] - 1).max()) if nt else -1
+    dfr = 1.0 / (hop_an / float(nfft)) / 2.0
+    E = int(dfr * hop * edge)
+    if nout is None:
+        nout = (max_end + 2) * hop + E
+    out = np.full(nout, np.nan)
+    ts = np.ascontiguousarray(pk["tstart"], dtype=np.int32)
+    tl = np.ascontiguousarray(pk["tlen"], dtype=np.int32)
+    check(L.pvk_resynth(ptr(tid), F, K, ptr(ts), ptr(tl), ptr(pk["toff"]), ptr(pk["pf"]), ptr(pk["pmag"]),
+                        ptr(pk["prealph"]), float(sr), int(hop), int(nfft), int(hop_an), float(edge),
+                        int(minframes), ptr(out), nout, block0, nblocks, None))
+    return out
