@@ -1,0 +1,723 @@
+"""Host side of the B200 phase vocoder: drop-in mirrors of ``pypevoc.PV`` and
+``pypevoc.SinSum`` (reference pypevoc/PVAnalysis.py:71-417, 585-756, 797-1111).
+
+Same constructor arguments, method names, attribute names, array shapes and dtypes as the
+reference, so code written against ``pypevoc.PVAnalysis.PV`` runs unchanged:
+
+    from pypevoc_b200 import PV
+    pv = PV(sig, sr, nfft=2048, hop=512, npks=50); pv.run_pv()
+    pv.f, pv.mag, pv.ph, pv.realph, pv.binno     # float64 [nframes, npks], zero padded
+    ss = pv.toSinSum(); w = ss.synth(sr, pv.hop)
+
+All arithmetic of the hot path runs in libpvk.so (hand written sm_100a kernels) through the
+C ABI of include/pvk.h; torch is used only for device memory, streams and copies.  There is
+no CPU fallback: without a CUDA device or without the built extension every compute call
+raises.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+pi2 = 2.0 * np.pi
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _device(device=None):
+    if not torch.cuda.is_available():
+        raise RuntimeError("pypevoc_b200 needs a CUDA device (B200); there is no CPU fallback")
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device(device)
+
+
+class Progress(object):
+    """Minimal stand-in for pypevoc.ProgressDisplay.Progress (ProgressDisplay.py:58-117):
+    the GPU path finishes in one launch, so only completion is reported."""
+
+    def __init__(self, end=100):
+        self.end = end
+        self.value = 0
+
+    def update(self, value):
+        self.value = value
+
+
+_table_cache = {}
+
+
+def _analysis_tables(nfft, dev):
+    """Twiddle tables of libpvk for (device, nfft), built once by pvk_analyze_init."""
+    key = (dev.index, nfft)
+    tab = _table_cache.get(key)
+    if tab is None:
+        L = _lib.lib()
+        nbytes = L.pvk_analyze_tables_bytes(nfft)
+        if nbytes <= 0:
+            raise ValueError("nfft=%r is not supported by the CUDA kernels: it must be a power of two "
+                             "in [64, 8192]" % (nfft,))
+        tab = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.pvk_analyze_init(nfft, _ptr(tab), _stream()), "pvk_analyze_init")
+        _table_cache[key] = tab
+    return tab
+
+
+def n_frames(nsamp, nfft, hop):
+    """Number of iterations of run_pv's ``while curpos < nsamp - nfft`` (PVAnalysis.py:223-225)."""
+    span = nsamp - nfft
+    return 0 if span <= 0 else -(-span // hop)
+
+
+def host_tables(sr, nfft, hop, wind=np.hanning):
+    """Window / normalisation / per-bin tables, evaluated on the host with the reference's own
+    numpy expressions (PVAnalysis.py:97-118) so that the unwrapping constants are bit-identical."""
+    win = wind(nfft)
+    wsum = sum(win)
+    wsum2 = sum(win ** 2)
+    wfact = np.sqrt(wsum2 * nfft) / 2.0
+    fstep = float(sr) / float(nfft)
+    dt = float(hop) / float(sr)
+    fbin = np.arange(float(nfft)) * fstep
+    dthetabin = pi2 * fbin * dt
+    wfbin = np.round(dthetabin / pi2) * pi2
+    return dict(win=win, wsum=wsum, wsum2=wsum2, wfact=wfact, fstep=fstep, dt=dt, fbin=fbin, wfbin=wfbin)
+
+
+def analyze_device(xd, sr, nfft, hop, npks, pkthresh, tb, frame0=0, nframes=None, prev_zero=True,
+                   run_frames=0, spectra=False, out=None):
+    """Launch pvk_analyze on a device signal.
+
+    ``xd``: float32 CUDA tensor, ``[nsamp]`` or ``[nclips, nsamp]``.  Returns a dict of device
+    tensors ``f mag ph realph binno`` (float64 ``[nclips, nframes, npks]``), ``npk`` (int32),
+    ``totalmag`` (float64) and optionally ``fx`` (complex64 ``[nclips, nframes, nfft/2]``).
+    Asynchronous on the current stream.
+    """
+    L = _lib.lib()
+    if xd.dim() == 1:
+        xd = xd.unsqueeze(0)
+    assert xd.dtype == torch.float32 and xd.is_cuda and xd.stride(1) == 1
+    dev = xd.device
+    nclips, nsamp = xd.shape
+    if nframes is None:
+        nframes = max(n_frames(nsamp, nfft, hop) - frame0, 0)
+    key = ("dev", dev.index)
+    if key not in tb:
+        tb[key] = dict(
+            win=torch.from_numpy(np.ascontiguousarray((tb["win"] / tb["wfact"]).astype(np.float32))).to(dev),
+            fbin=torch.from_numpy(np.ascontiguousarray(tb["fbin"], dtype=np.float64)).to(dev),
+            wfbin=torch.from_numpy(np.ascontiguousarray(tb["wfbin"], dtype=np.float64)).to(dev))
+    dtb = tb[key]
+    tables = _analysis_tables(nfft, dev)
+    if out is None:
+        out = {}
+        for k in ("f", "mag", "ph", "realph", "binno"):
+            out[k] = torch.empty((nclips, nframes, npks), dtype=torch.float64, device=dev)
+        out["npk"] = torch.empty((nclips, nframes), dtype=torch.int32, device=dev)
+        out["totalmag"] = torch.empty((nclips, nframes), dtype=torch.float64, device=dev)
+    spec = torch.empty((nclips, nframes, nfft // 2), dtype=torch.complex64, device=dev) if spectra else None
+    with torch.cuda.device(dev):
+        _lib.check(L.pvk_analyze(
+            _ptr(xd), nclips, xd.stride(0), nsamp, _ptr(dtb["win"]), _ptr(dtb["fbin"]), _ptr(dtb["wfbin"]),
+            _ptr(tables), int(nfft), int(hop), int(npks), float(pkthresh), float(tb["dt"]), float(tb["fstep"]),
+            int(frame0), int(nframes), 1 if prev_zero else 0, int(run_frames),
+            _ptr(out["f"]), _ptr(out["mag"]), _ptr(out["ph"]), _ptr(out["realph"]), _ptr(out["binno"]),
+            _ptr(out["npk"]), _ptr(out["totalmag"]), _ptr(spec), _stream()), "pvk_analyze")
+    if spectra:
+        out["fx"] = spec
+    return out
+
+
+def track_device(fd, magd, maxpitchjmp=0.5):
+    """pvk_track on device tables ``[nclips, F, K]`` (or ``[F, K]``); returns device ``tid``,
+    ``link`` (int32, same shape) and ``ntracks`` (int32 ``[nclips]``).  Asynchronous."""
+    L = _lib.lib()
+    squeeze = fd.dim() == 2
+    if squeeze:
+        fd, magd = fd.unsqueeze(0), magd.unsqueeze(0)
+    assert fd.dtype == torch.float64 and fd.is_contiguous() and magd.is_contiguous()
+    dev = fd.device
+    nclips, F, K = fd.shape
+    tid = torch.empty((nclips, F, K), dtype=torch.int32, device=dev)
+    link = torch.empty((nclips, F, K), dtype=torch.int32, device=dev)
+    ntracks = torch.empty((nclips,), dtype=torch.int32, device=dev)
+    wsb = L.pvk_track_workspace_bytes(nclips, F, K)
+    ws = torch.empty(max(int(wsb), 8), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.pvk_track(_ptr(fd), _ptr(magd), nclips, F, K, float(maxpitchjmp), _ptr(tid), _ptr(link),
+                               _ptr(ntracks), _ptr(ws), int(wsb), _stream()), "pvk_track")
+    if squeeze:
+        tid, link = tid[0], link[0]
+    return dict(tid=tid, link=link, ntracks=ntracks)
+
+
+def pack_device(fd, magd, phd, realphd, tid, link, ntracks):
+    """pvk_track_pack for one clip (``[F, K]`` device tables, ``ntracks`` python int)."""
+    L = _lib.lib()
+    dev = fd.device
+    F, K = fd.shape
+    npts = int((tid >= 0).sum().item()) if F * K else 0
+    nt = int(ntracks)
+    tstart = torch.empty((max(nt, 1),), dtype=torch.int32, device=dev)
+    tlen = torch.empty((max(nt, 1),), dtype=torch.int32, device=dev)
+    toff = torch.empty((nt + 1,), dtype=torch.int64, device=dev)
+    packed = [torch.empty((max(npts, 1),), dtype=torch.float64, device=dev) for _ in range(4)]
+    with torch.cuda.device(dev):
+        _lib.check(L.pvk_track_pack(_ptr(fd), _ptr(magd), _ptr(phd), _ptr(realphd), _ptr(tid), _ptr(link), F, K, nt,
+                                    _ptr(tstart), _ptr(tlen), _ptr(toff), _ptr(packed[0]), _ptr(packed[1]),
+                                    _ptr(packed[2]), _ptr(packed[3]), _stream()), "pvk_track_pack")
+    return dict(tstart=tstart[:nt], tlen=tlen[:nt], toff=toff, pf=packed[0][:npts], pmag=packed[1][:npts],
+                pph=packed[2][:npts], prealph=packed[3][:npts], npts=npts)
+
+
+def synth_geometry(max_end, hop, nfft, hop_an, edge=1.0):
+    """Output length of SinSum.synth (PVAnalysis.py:1055-1059,1070) and the edge length."""
+    dfr = nfft / hop_an / 2.
+    edgsamp = int(edge * hop * dfr)
+    return (max_end + 2) * hop + edgsamp, edgsamp
+
+
+def resynth_device(tid, pk, sr, hop, nfft, hop_an, edge=1.0, minframes=3, max_end=None, block0=0,
+                   nblocks=-1, out=None):
+    """pvk_resynth for one clip; returns the float64 device signal (asynchronous)."""
+    L = _lib.lib()
+    dev = tid.device
+    F, K = tid.shape
+    if max_end is None:
+        max_end = int((pk["tstart"] + pk["tlen"] - 1).max().item()) if len(pk["tstart"]) else -1
+    nout, _ = synth_geometry(max_end, hop, nfft, hop_an, edge)
+    if out is None:
+        out = torch.empty((nout,), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.pvk_resynth(_ptr(tid), F, K, _ptr(pk["tstart"]), _ptr(pk["tlen"]), _ptr(pk["toff"]),
+                                 _ptr(pk["pf"]), _ptr(pk["pmag"]), _ptr(pk["prealph"]), float(sr), int(hop),
+                                 int(nfft), int(hop_an), float(edge), int(minframes), _ptr(out), int(nout),
+                                 int(block0), int(nblocks), _stream()), "pvk_resynth")
+    return out
+
+
+# =========================================================================== PV
+class PV(object):
+    def __init__(self, x, sr, nfft=1024, hop=None, npks=20, pkthresh=0.005, wind=np.hanning,
+                 progress=True, device=None):
+        '''
+        Phase vocoder object (GPU).  Arguments as pypevoc.PV (PVAnalysis.py:72-82):
+            * sr   = Sampling rate
+            * nfft = Number of points in FFT analysis window (power of two, 64..8192)
+            * hop  = Number of points between FFT windows (default nfft/2)
+            * npks = Maximum number of peaks at each frame
+            * pkthresh = Threshold of peak amplitude relative of maximum
+            * wind = window callable evaluated on the host (default np.hanning)
+        x may be a sequence, a numpy array or a torch tensor (CPU or CUDA); the kernels work
+        on its float32 rounding.  ``device`` selects the GPU (default: current device).
+        '''
+        self._dev = _device(device if device is not None else (x.device if torch.is_tensor(x) and x.is_cuda else None))
+        if torch.is_tensor(x):
+            xd = x.detach()
+            if xd.dim() != 1:
+                raise ValueError("PV expects a 1-D signal")
+            self._xd = xd.to(device=self._dev, dtype=torch.float32).contiguous()
+            self._x_host = None
+        else:
+            xh = np.array(x)
+            if xh.ndim != 1:
+                raise ValueError("PV expects a 1-D signal")
+            self._x_host = xh
+            x32 = np.ascontiguousarray(xh, dtype=np.float32)
+            self._xd = torch.from_numpy(x32).to(self._dev, non_blocking=False)
+        self.nsamp = int(self._xd.shape[0])
+        self.sr = sr
+        self.nfft = nfft
+        self.nfft2 = int(nfft / 2)
+        if hop is None:
+            self.hop = int(self.nfft / 2)
+        else:
+            self.hop = hop
+        if int(self.hop) != self.hop or self.hop < 1:
+            raise ValueError("hop must be a positive integer")
+        self.hop = int(self.hop)
+        if int(npks) < 1 or int(npks) > 1024:
+            raise ValueError("npks must be in [1, 1024]")
+        self.peakthresh = pkthresh
+        self.npeaks = int(npks)
+        self.nframes = 0
+        if nfft < 64 or nfft > 8192 or (nfft & (nfft - 1)) != 0:
+            raise ValueError("nfft=%r is not supported by the CUDA kernels: it must be a power of two "
+                             "in [64, 8192]" % (nfft,))
+
+        self._tb = host_tables(sr, nfft, self.hop, wind)
+        self.win = self._tb["win"]
+        self.wsum = self._tb["wsum"]
+        self.wsum2 = self._tb["wsum2"]
+        self.wfact = self._tb["wfact"]
+        self.fstep = self._tb["fstep"]
+        self.dt = self._tb["dt"]
+        self.fbin = self._tb["fbin"]
+        self.wfbin = self._tb["wfbin"]
+        # the reference carries the previous frame here (PVAnalysis.py:121,209); the GPU path
+        # keeps it in shared memory, so this stays the initial all-zero spectrum
+        self.oldfft = np.zeros(self.nfft2)
+
+        self._host = {"t": [], "f": [], "ph": [], "mag": []}
+        self._devout = None
+        if progress:
+            self.progress = Progress(end=self.nsamp)
+        else:
+            self.progress = None
+
+    # -- lazily materialised host arrays (float64, the reference's layout) ------------
+    def _get(self, name):
+        if name not in self._host:
+            if self._devout is None:
+                raise AttributeError(name)
+            self._host[name] = self._fetch(name)
+        return self._host[name]
+
+    def _fetch(self, name):
+        d = self._devout
+        if name == "totalmag":
+            return [v for v in d["totalmag"][0].cpu().numpy()]
+        if self.nframes == 0:
+            return np.array([])
+        return d[name][0].cpu().numpy()
+
+    def _prop(name):  # noqa: N805
+        def g(self):
+            return self._get(name)
+
+        def s(self, value):
+            self._host[name] = value
+        return property(g, s)
+
+    f = _prop("f")
+    mag = _prop("mag")
+    ph = _prop("ph")
+    realph = _prop("realph")
+    binno = _prop("binno")
+    totalmag = _prop("totalmag")
+    t = _prop("t")
+    del _prop
+
+    @property
+    def x(self):
+        if self._x_host is None:
+            self._x_host = self._xd.cpu().numpy()
+        return self._x_host
+
+    @property
+    def device_tables(self):
+        """Device tensors of the last run_pv: f mag ph realph binno [nframes, npks] float64,
+        npk int32 [nframes], totalmag float64 [nframes]."""
+        if self._devout is None:
+            raise RuntimeError("run_pv() has not been called")
+        return {k: v[0] for k, v in self._devout.items()}
+
+    # -- analysis ----------------------------------------------------------------------
+    def run_pv(self, run_frames=0):
+        """STFT + peak picking + instantaneous frequency for every frame (PVAnalysis.py:213-264)
+        in one kernel launch.  Results appear as the reference's attributes ``f mag ph realph
+        binno`` (float64 ``[nframes, npks]``), ``t``, ``nframes``, ``totalmag`` (list)."""
+        self._devout = analyze_device(self._xd, self.sr, self.nfft, self.hop, self.npeaks, self.peakthresh,
+                                      self._tb, run_frames=run_frames)
+        self.nframes = int(self._devout["f"].shape[1])
+        self._host = {}
+        self._host["t"] = (np.arange(self.nframes) * self.hop + self.nfft / 2.0) / self.sr   # :247
+        if self.progress:
+            self.progress.update(self.nsamp)
+
+    def dphase2freq(self, dph, nbin):
+        '''"instantaneous frequency" for the phase difference dph at bin nbin (host helper with
+        the reference's arithmetic, PVAnalysis.py:133-147; the kernels do this per peak on the GPU)'''
+        dphw = dph + self.wfbin[nbin] + pi2 * np.arange(-1, 2)
+        freq = dphw / self.dt / pi2
+        df = self.fbin[nbin] - freq
+        ii = np.argmin(abs(df))
+        return freq[ii], df[ii]
+
+    def calc_fft_frame(self, pos):
+        '''FFT frame at sample pos, all nfft bins, normalised by wfact (PVAnalysis.py:150-158).
+        Convenience accessor (computed on the device with torch.fft in float64); run_pv does
+        not use it.'''
+        seg = self._xd[pos:pos + self.nfft].to(torch.float64)
+        w = torch.from_numpy(np.asarray(self.win, dtype=np.float64)).to(self._dev)
+        return (torch.fft.fft(seg * w) / self.wfact).cpu().numpy()
+
+    def calc_pv_frame(self, pos):
+        '''PV peaks of the frame at sample ``pos`` with the frame at ``pos - hop`` as previous
+        frame (all-zero spectrum if pos < hop), like the reference when called in run order
+        (PVAnalysis.py:160-211).  Returns lists f, mag, ph, realph, binno and totalmag.'''
+        if pos + self.nfft > self.nsamp:
+            raise ValueError("frame exceeds the signal")
+        if pos >= self.hop:
+            seg = self._xd[pos - self.hop:pos + self.nfft]
+            o = analyze_device(seg, self.sr, self.nfft, self.hop, self.npeaks, self.peakthresh, self._tb,
+                               frame0=1, nframes=1, prev_zero=False)
+        else:
+            seg = self._xd[pos:pos + self.nfft]
+            o = analyze_device(seg, self.sr, self.nfft, self.hop, self.npeaks, self.peakthresh, self._tb,
+                               frame0=0, nframes=1, prev_zero=True)
+        n = int(o["npk"][0, 0].item())
+        vals = [o[k][0, 0, :n].cpu().numpy().tolist() for k in ("f", "mag", "ph", "realph", "binno")]
+        return vals[0], vals[1], vals[2], vals[3], [int(b) for b in vals[4]], float(o["totalmag"][0, 0].item())
+
+    # -- tracking ----------------------------------------------------------------------
+    def toSinSum(self, maxpitchjmp=0.5):
+        '''
+        Convert to Sine sum (PVAnalysis.py:299-322): greedy frame-to-frame partial tracking on
+        the GPU.  As in the reference the argument is not forwarded: add_frame's default
+        maxpitchjmp=0.5 semitones is what is applied (PVAnalysis.py:320-321,871).
+        '''
+        if self._devout is None:
+            raise RuntimeError("run_pv() has not been called")
+        ss = SinSum(self.sr, nfft=self.nfft, hop=self.hop, device=self._dev)
+        d = self.device_tables
+        ss._set_device_tables(d["f"], d["mag"], d["ph"], d["realph"])
+        return ss
+
+    # -- consumers (host side views over the peak tables, PVAnalysis.py:324-417) ---------
+    def plot_time_freq(self, colors=True, ax=None):
+        import pylab as pl
+        if ax is None:
+            fig, allax = pl.subplots(1)
+            ax = allax
+        t = np.outer(self.t, np.ones(self.npeaks))
+        if colors:
+            ax.scatter(t, self.f, s=6, c=20 * np.log10(self.mag), lw=0)
+        else:
+            ax.scatter(t, self.f, s=100 + 20 * np.log10(self.mag), lw=0)
+        pl.xlabel('Time (s)')
+        pl.ylabel('Frequency (Hz)')
+        return ax
+
+    def plot_time_mag(self):
+        import pylab as pl
+        pl.figure()
+        t = np.outer(self.t, np.ones(self.npeaks))
+        pl.scatter(t, 20 * np.log10(self.mag), s=10, c=self.f, lw=0, norm=pl.matplotlib.colors.LogNorm())
+        pl.xlabel('Time (s)')
+        pl.ylabel('Magnitude (dB)')
+        cs = pl.colorbar()
+        cs.set_label('Frequency (Hz)')
+        return pl.gca()
+
+    def get_time_vector(self):
+        return self.t
+
+    def get_sample_vector(self):
+        return (self.t * self.sr).astype('int')
+
+    def calc_f0(self, fmin=50, fmax=10000, thr=0.1):
+        """Lowest-frequency strong peak of every frame (PVAnalysis.py:371-391), vectorised."""
+        f, mag = self.f, self.mag
+        if f.ndim != 2:
+            self.fundamental_idx = np.zeros(0, dtype='i')
+            return np.zeros(0)
+        maxmag = np.max(mag, axis=1, keepdims=True)
+        ok = (f > fmin) & (f < fmax) & (mag > maxmag * thr)
+        cand = np.where(ok, f, np.inf)
+        im = np.argmin(cand, axis=1)
+        has = ok.any(axis=1)
+        im = np.where(has, im, 0).astype('i')
+        fm = np.where(has, f[np.arange(f.shape[0]), im], 0.0)
+        self.fundamental_idx = im
+        return fm
+
+    @property
+    def fundamental_frequency(self):
+        try:
+            return self.f[np.arange(self.f.shape[0]), self.fundamental_idx]
+        except AttributeError:
+            return self.calc_f0()
+
+    @property
+    def fundamental_magnitude(self):
+        try:
+            return self.mag[np.arange(self.f.shape[0]), self.fundamental_idx]
+        except AttributeError:
+            self.calc_f0()
+            return self.mag[np.arange(self.f.shape[0]), self.fundamental_idx]
+
+    @property
+    def partial_sum_magnitude(self):
+        return np.sqrt(np.sum(self.mag ** 2, axis=1))
+
+    @property
+    def partial_magnitude_ratio(self):
+        return self.partial_sum_magnitude / self.totalmag
+
+
+# =========================================================================== partials
+class RegPartial(object):
+    """A quasi-sinusoidal partial with homogeneous sampling (PVAnalysis.py:585-626): view of
+    one track of a SinSum.  ``f mag ph realph`` are float64 numpy arrays (the reference keeps
+    python lists of the same values)."""
+
+    def __init__(self, istart, pdict=None, overlap=0.5, fstep=None):
+        self.start_idx = istart
+        self.overlap = overlap
+        self.fstep = fstep
+        if pdict is None:
+            self.f, self.mag, self.ph, self.realph = [], [], [], []
+        else:
+            self.f = pdict['f']
+            self.mag = pdict['mag']
+            self.ph = pdict['ph']
+            self.realph = pdict.get('realph', pdict['ph'])
+
+    def get_freq_at_frame(self, fr):
+        relidx = fr - self.start_idx
+        return self.f[relidx] if relidx >= 0 else np.nan
+
+    def get_mag_at_frame(self, fr):
+        relidx = fr - self.start_idx
+        return self.mag[relidx] if relidx >= 0 else np.nan
+
+    def synth(self, sr, hop, edge=.5, device=None):
+        """Render this partial alone on the GPU (PVAnalysis.py:684-756); returns
+        ``(signal, start_sample)`` like the reference: the signal starts ``edgsam`` samples
+        before sample ``start_idx*hop``."""
+        dev = _device(device)
+        nfr = len(self.f)
+        if self.fstep is None:
+            raise ValueError("RegPartial.synth on the GPU needs fstep (phase correction, :715)")
+        # the kernel is parameterised like SinSum (nfft, analysis hop): fstep = sr/nfft (:825),
+        # overlap = hop_an/nfft (:824)
+        nfft_eff = float(sr) / float(self.fstep)
+        hop_an = self.overlap * nfft_eff
+        if abs(nfft_eff - round(nfft_eff)) > 1e-6 or abs(hop_an - round(hop_an)) > 1e-6:
+            raise ValueError("fstep / overlap must correspond to integer nfft and analysis hop")
+        nfft_eff, hop_an = int(round(nfft_eff)), int(round(hop_an))
+        dfr = 1. / self.overlap / 2.
+        edgsam = int(dfr * hop * edge)
+        dE = -(-edgsam // hop)
+        rows = nfr + dE
+        tid = -torch.ones((rows, 1), dtype=torch.int32, device=dev)
+        tid[dE:dE + nfr, 0] = 0
+        as_t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)  # noqa: E731
+        pk = dict(tstart=torch.tensor([dE], dtype=torch.int32, device=dev),
+                  tlen=torch.tensor([nfr], dtype=torch.int32, device=dev),
+                  toff=torch.tensor([0, nfr], dtype=torch.int64, device=dev),
+                  pf=as_t(self.f), pmag=as_t(self.mag), prealph=as_t(self.realph))
+        out = resynth_device(tid, pk, sr, hop, nfft_eff, hop_an, edge=edge, minframes=1, max_end=dE + nfr - 1)
+        s0 = dE * hop - edgsam
+        sig = out[s0:s0 + hop * nfr + 2 * edgsam].cpu().numpy()
+        return sig, int(self.start_idx * hop - edgsam)
+
+
+class _PartialList(object):
+    """Lazy ``ss.partial``: RegPartial views created from the packed track arrays on access."""
+
+    def __init__(self, ss):
+        self._ss = ss
+
+    def __len__(self):
+        return self._ss._ntracks()
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(len(self)))]
+        n = len(self)
+        if i < 0:
+            i += n
+        if i < 0 or i >= n:
+            raise IndexError(i)
+        h = self._ss._host_tracks()
+        a, b = int(h["toff"][i]), int(h["toff"][i + 1])
+        return RegPartial(int(h["tstart"][i]),
+                          dict(f=h["pf"][a:b], mag=h["pmag"][a:b], ph=h["pph"][a:b], realph=h["prealph"][a:b]),
+                          overlap=self._ss.hop / float(self._ss.nfft), fstep=self._ss.sr / float(self._ss.nfft))
+
+    def __iter__(self):
+        for i in range(len(self)):
+            yield self[i]
+
+
+class SinSum(object):
+    def __init__(self, sr, nfft=1024, hop=512, device=None):
+        '''
+        Sine sum object (PVAnalysis.py:797-817): a sound decomposed in a sum of quasi-sine
+        waves.  Tracking (add_frame) and resynthesis (synth) run on the GPU.
+            * sr   = Sampling rate
+            * nfft = Number of points in FFT analysis window
+            * hop  = Number of points between FFT windows
+        '''
+        self.nfft = nfft
+        self.hop = hop
+        self.sr = sr
+        self._dev = _device(device)
+        self._rows = {}          # host rows handed to add_frame: fr -> (f, mag, ph, realph)
+        self._tables = None      # device f, mag, ph, realph [F, K]
+        self._trk = None         # device tid, link, ntracks
+        self._pk = None          # device packed tracks
+        self._hosttrk = None
+        self._maxpitchjmp = 0.5
+
+    # -- construction ------------------------------------------------------------------
+    def _set_device_tables(self, f, mag, ph, realph):
+        self._tables = dict(f=f.contiguous(), mag=mag.contiguous(), ph=ph.contiguous(), realph=realph.contiguous())
+        self._rows = None
+        self._trk = self._pk = self._hosttrk = None
+
+    def add_frame(self, fr, f, mag, ph, realph=None, maxpitchjmp=0.5):
+        """Add the peaks of frame ``fr`` (PVAnalysis.py:871-957).  Rows are collected on the host;
+        the greedy linking itself runs on the GPU, over all frames at once, the next time the
+        partials are needed (links depend on adjacent frame pairs only)."""
+        if self._rows is None:
+            raise RuntimeError("this SinSum was built from device tables; add_frame is not available")
+        f = np.asarray(f, dtype=np.float64)
+        mag = np.asarray(mag, dtype=np.float64)
+        ph = np.asarray(ph, dtype=np.float64)
+        realph = ph if realph is None else np.asarray(realph, dtype=np.float64)
+        self._rows[int(fr)] = (f, mag, ph, realph)
+        self._maxpitchjmp = maxpitchjmp
+        self._tables = self._trk = self._pk = self._hosttrk = None
+
+    def _ensure_tables(self):
+        if self._tables is None:
+            if not self._rows:
+                z = torch.zeros((0, 1), dtype=torch.float64, device=self._dev)
+                self._tables = dict(f=z, mag=z.clone(), ph=z.clone(), realph=z.clone())
+                return
+            F = max(self._rows) + 1
+            K = max(len(r[0]) for r in self._rows.values())
+            host = np.zeros((4, F, K))
+            for fr, row in self._rows.items():
+                for q in range(4):
+                    host[q, fr, :len(row[q])] = row[q]
+            d = torch.from_numpy(host).to(self._dev)
+            self._tables = dict(f=d[0], mag=d[1], ph=d[2], realph=d[3])
+
+    def _ensure_tracks(self):
+        self._ensure_tables()
+        if self._trk is None:
+            t = self._tables
+            if t["f"].shape[0] == 0:
+                self._trk = dict(tid=torch.zeros((0, 1), dtype=torch.int32, device=self._dev), link=None, ntracks=0)
+            else:
+                tr = track_device(t["f"], t["mag"], self._maxpitchjmp)
+                tr["ntracks"] = int(tr["ntracks"][0].item())
+                self._trk = tr
+        return self._trk
+
+    def _ensure_packed(self):
+        tr = self._ensure_tracks()
+        if self._pk is None:
+            t = self._tables
+            if tr["ntracks"] == 0:
+                e = torch.zeros((0,), dtype=torch.float64, device=self._dev)
+                self._pk = dict(tstart=torch.zeros((0,), dtype=torch.int32, device=self._dev),
+                                tlen=torch.zeros((0,), dtype=torch.int32, device=self._dev),
+                                toff=torch.zeros((1,), dtype=torch.int64, device=self._dev),
+                                pf=e, pmag=e, pph=e, prealph=e, npts=0)
+            else:
+                self._pk = pack_device(t["f"], t["mag"], t["ph"], t["realph"], tr["tid"], tr["link"], tr["ntracks"])
+        return self._pk
+
+    def _ntracks(self):
+        return self._ensure_tracks()["ntracks"]
+
+    def _host_tracks(self):
+        if self._hosttrk is None:
+            pk = self._ensure_packed()
+            self._hosttrk = {k: pk[k].cpu().numpy() for k in ("tstart", "tlen", "toff", "pf", "pmag", "pph", "prealph")}
+        return self._hosttrk
+
+    # -- the reference's attributes ------------------------------------------------------
+    @property
+    def partial(self):
+        return _PartialList(self)
+
+    @property
+    def st(self):
+        return self._host_tracks()["tstart"].astype(np.int64).tolist()
+
+    @property
+    def end(self):
+        h = self._host_tracks()
+        return (h["tstart"].astype(np.int64) + h["tlen"] - 1).tolist()
+
+    @property
+    def track_ids(self):
+        """int32 numpy [nframes, npks]: index into ``partial`` for every peak slot (-1 = none)."""
+        return self._ensure_tracks()["tid"].cpu().numpy()
+
+    @property
+    def device_tracks(self):
+        """Device tensors: tid, link [F, K]; tstart, tlen, toff; packed pf pmag pph prealph."""
+        d = dict(self._ensure_packed())
+        d.update(tid=self._trk["tid"], link=self._trk["link"])
+        return d
+
+    # -- resynthesis ---------------------------------------------------------------------
+    def synth(self, sr, hop, edge=1.0, minframes=3, phase_preserve=True, to_host=True):
+        """Overlap-add resynthesis of all partials with >= minframes frames
+        (PVAnalysis.py:1053-1070) in one kernel launch; float64 ``[(max(end)+2)*hop + edgsamp]``.
+        ``to_host=False`` returns the CUDA tensor instead of a numpy array."""
+        if not phase_preserve:
+            raise NotImplementedError("phase_preserve=False calls RegPartial.synth_no_phase, which is "
+                                      "broken in the reference (PVAnalysis.py:665); not provided")
+        if int(hop) != hop:
+            raise TypeError("hop must be an integer number of samples")
+        pk = self._ensure_packed()
+        tr = self._trk
+        if tr["ntracks"] == 0:
+            raise ValueError("max() arg is an empty sequence")     # what the reference raises (:1059)
+        out = resynth_device(tr["tid"], pk, sr, int(hop), self.nfft, self.hop, edge=edge, minframes=minframes)
+        return out.cpu().numpy() if to_host else out
+
+    def partial_samples(self, hop, edge=1.0, minframes=3):
+        """Work units of synth(): sum over rendered partials of hop*nfr + 2*edgsam."""
+        h = self._host_tracks()
+        dfr = self.nfft / self.hop / 2.
+        e = int(dfr * hop * edge)
+        tl = h["tlen"][h["tlen"] >= minframes].astype(np.int64)
+        return int((tl * hop + 2 * e).sum())
+
+    # -- summaries (PVAnalysis.py:960-994,1072-1111) ---------------------------------------
+    def get_partials_idx_at_frame(self, fr):
+        h = self._host_tracks()
+        s = h["tstart"].astype(np.int64)
+        return np.flatnonzero((fr >= s) & (fr <= s + h["tlen"] - 1))
+
+    def get_partials_at_frame(self, fr):
+        return [self.partial[int(i)] for i in self.get_partials_idx_at_frame(fr)]
+
+    def get_partials_idx_ending_at_frame(self, fr):
+        h = self._host_tracks()
+        s = h["tstart"].astype(np.int64)
+        return np.flatnonzero((fr >= s) & (fr == s + h["tlen"] - 1))
+
+    def _track_means(self, key):
+        h = self._host_tracks()
+        if len(h["tlen"]) == 0:
+            return np.zeros(0)
+        return np.add.reduceat(h[key], h["toff"][:-1]) / h["tlen"]
+
+    def get_avfreq(self):
+        return self._track_means("pf")
+
+    def get_avmag(self):
+        return self._track_means("pmag")
+
+    def get_summary(self, minlen=10):
+        h = self._host_tracks()
+        sel = np.flatnonzero(h["tlen"] > minlen)
+        psum = np.zeros(len(sel), dtype=[('idx', 'i4'), ('n', 'i4'), ('f', 'f4'), ('mag', 'f4')])
+        psum['idx'] = sel
+        psum['n'] = h["tlen"][sel]
+        psum['f'] = self.get_avfreq()[sel]
+        psum['mag'] = self.get_avmag()[sel]
+        psum.sort(order='mag')
+        return psum
+
+    def get_nframes(self):
+        return max(self.end)

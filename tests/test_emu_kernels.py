@@ -1,0 +1,91 @@
+"""CPU: the CUDA sources compiled for the SIMT emulator (tests/emu) reproduce the reference.
+
+This runs the *same kernel code* as the GPU (tests/emu/cuda_emu.h turns threads into fibers)
+through the same C ABI, so kernel logic regressions are caught on the GPU-less build
+container.  It is test infrastructure: the product never loads the emulator library, and
+the parity tests proper are the ``-m gpu`` ones."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+
+from oracle import pv_oracle as orc
+from golden_util import CASES, case_golden, case_signal, pv_kwargs
+import parity_util as pu
+
+eh = pytest.importorskip("emu_harness")
+
+FAST = ["two_sines", "readme_vibrato", "noisy_odd_hop", "cfg3_clip", "cfg5_like"]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _build():
+    eh.build()
+
+
+@pytest.mark.parametrize("name", FAST)
+def test_emu_analysis_vs_reference_golden(name):
+    x, sr = case_signal(name)
+    kw = pv_kwargs(name)
+    hop = kw["hop"] or kw["nfft"] // 2
+    g = case_golden(name)
+    o = eh.analyze(x, sr, kw["nfft"], hop, kw["npks"], spectra=True)
+    got = {k: o[k][0] for k in ("f", "mag", "ph", "realph", "binno", "totalmag", "npk")}
+    ref = {k: g[k] for k in ("f", "mag", "ph", "realph", "binno", "totalmag")}
+    pu.compare_analysis(got, ref, sr, kw["nfft"])
+    oo = orc.analyze(np.zeros(1), sr, nfft=kw["nfft"], hop=hop, npks=kw["npks"], fx_given=o["fx"][0].astype(np.complex64))
+    pu.compare_exact_on_spectrum(got, oo)
+
+
+@pytest.mark.parametrize("name", FAST)
+def test_emu_tracking_and_resynthesis_vs_reference_golden(name):
+    g = case_golden(name)
+    _, sr = case_signal(name)
+    kw = pv_kwargs(name)
+    tr = eh.track(g["f"], g["mag"])
+    assert np.array_equal(tr["tid"][0], g["tid"])
+    nt = int(tr["ntracks"][0])
+    pk = eh.track_pack(g["f"], g["mag"], g["ph"], g["realph"], tr["tid"][0], tr["link"][0], nt)
+    assert np.array_equal(pk["tstart"], g["st"])
+    assert np.array_equal(pk["tstart"] + pk["tlen"] - 1, g["end"])
+    for h in CASES[name]["synth_hops"]:
+        w = eh.resynth(tr["tid"][0], pk, sr, h, kw["nfft"], int(g["hop"]))
+        ref = g["synth_%d" % h]
+        assert w.shape == ref.shape
+        assert pu.snr_db(w, ref) > 110.0
+
+
+def test_emu_degenerate_and_select_paths():
+    rng = np.random.RandomState(3)
+    sr = 44100
+    cases = []
+    cases.append((rng.randn(2048 * 4).astype(np.float32), 2048, 1024, 50, 0.005))    # C > K: radix select
+    cases.append((rng.randn(1024 * 4).astype(np.float32), 1024, 512, 3, 0.0))
+    z = np.zeros(1024 * 4, dtype=np.float32); cases.append((z, 1024, 256, 20, 0.005))
+    imp = np.zeros(1024 * 4, dtype=np.float32); imp[1500] = 1.0; cases.append((imp, 1024, 256, 20, 0.005))
+    flat = np.zeros(256 * 4, dtype=np.float32); flat[300] = 1.0; flat[301] = 1e-4; cases.append((flat, 256, 64, 5, 0.5))
+    tr_ = np.zeros(512 * 6, dtype=np.float32); tr_[::32] = 1.0; cases.append((tr_, 512, 128, 30, 0.005))
+    for x, nfft, hop, npks, th in cases:
+        o = eh.analyze(x, sr, nfft, hop, npks, pkthresh=th, spectra=True)
+        got = {k: o[k][0] for k in ("f", "mag", "ph", "realph", "binno", "totalmag", "npk")}
+        oo = orc.analyze(np.zeros(1), sr, nfft=nfft, hop=hop, npks=npks, pkthresh=th,
+                         fx_given=o["fx"][0].astype(np.complex64))
+        pu.compare_exact_on_spectrum(got, oo)
+
+
+def test_emu_segment_warmup_and_batch():
+    from pypevoc_b200 import signals
+    x = signals.harm(44100, 0.4, 220, 90, 0.5, 0.01, 1)
+    full = eh.analyze(x, 44100, 2048, 256, 60)
+    seg = eh.analyze(x[6 * 256:], 44100, 2048, 256, 60, frame0=1, prev_zero=0)
+    for k in ("f", "mag", "ph", "realph", "binno", "npk", "totalmag"):
+        assert np.array_equal(full[k][0][7:], seg[k][0]), k
+    clips = np.stack([x[:12000], x[3000:15000], np.zeros(12000, dtype=np.float32)])
+    b = eh.analyze(clips, 44100, 1024, 256, 20, run_frames=5)
+    for i in range(3):
+        one = eh.analyze(clips[i], 44100, 1024, 256, 20)
+        for k in ("f", "binno", "npk"):
+            assert np.array_equal(one[k][0], b[k][i])
