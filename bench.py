@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py -- phase-vocoder hot path on B200: STFT frames/s + resynthesis partial-samples/s.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json): the 10-minute mono 44.1 kHz synthetic harmonic tone + noise of
+configs[1], analysed with the parameters the metric is quoted on (nfft=2048, hop=512,
+npks=50), followed by tracking and full resynthesis.  One "step" = one pass of the whole hot
+path (PV.run_pv -> toSinSum -> SinSum.synth) over that signal.
+
+  value      frames / step time with the signal already resident in HBM (kernel path)
+  e2e        same metric through the public API with HOST buffers: pinned host signal -> H2D
+             -> PV.run_pv -> toSinSum -> synth -> D2H of the peak tables and the signal
+  roofline   the step's dominant kernel against the measured HBM copy peak
+  cpu_baseline  the numpy oracle (port of the reference's algorithm) on one host core, on a
+             bounded prefix of the same samples
+N > 1 is weak scaling: every rank owns its own hop-aligned 10-minute segment of an N x 10
+minute signal (one warm-up frame + nfft-hop halo on the left), links its frames locally and
+one all_gather stitches the track tables; no collective inside analysis or resynthesis.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CFG = dict(sr=44100, seconds=600, nfft=2048, hop=512, npks=50, pkthresh=0.005,
+           f0=110.0, nharm=150, p=0.5, sigma=0.01, seed=2)
+METRIC = "STFT frames/sec (nfft=2048,hop=512,npks=50) + resynth partial-samples/sec"
+WORKLOAD = ("10 min mono 44.1 kHz synthetic harmonic tone+noise (configs[1] signal), metric parameters "
+            "nfft=2048 hop=512 npks=50, analysis + tracking + full resynthesis")
+MY_LAUNCHES_PER_STEP = 11   # analyze 1, track 6 (link scan chunk boundary stitch fix), pack 3, resynth 1
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return json.load(fh), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = "/tmp/pvk_clocks_%d_%d.csv" % (os.getpid(), index)
+
+    def start(self):
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+            self.fh.close()
+            sm, smax, reasons = [], [], set()
+            for line in open(self.path):
+                p = [s.strip() for s in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1])); smax.append(float(p[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            if sm:
+                # "under load": samples in the upper half of the observed range
+                hi = [v for v in sm if v >= 0.5 * max(sm)]
+                out = {"sm_mhz": float(np.median(hi)), "sm_max_mhz": float(max(smax)),
+                       "reasons": sorted(reasons), "samples": len(sm)}
+            os.unlink(self.path)
+        except Exception:
+            pass
+        return out
+
+
+# --------------------------------------------------------------------------- GPU arm
+def gpu_main(args):
+    import torch
+    import torch.distributed as dist
+    from pypevoc_b200 import PV, signals
+    from pypevoc_b200 import pv as P
+    from pypevoc_b200 import dist as D
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    c = CFG
+    sr, nfft, hop, npks = c["sr"], c["nfft"], c["hop"], c["npks"]
+    nsamp_seg = sr * c["seconds"]
+
+    # ---- synthetic signal: rank r owns frames [r*Fseg, (r+1)*Fseg) of an N*10-minute signal
+    plans = D.plan_segments(world * nsamp_seg, nfft, hop, world)
+    plan = dict(plans[rank], all=plans)
+    xd = signals.harm_torch(sr, plan["nsamp"], c["f0"], c["nharm"], c["p"], c["sigma"], c["seed"], dev,
+                            t0_samples=plan["sample0"], scale=0.25)
+    tb = P.host_tables(sr, nfft, hop)
+    F = plan["j1"] - plan["j0"]                      # own frames (the overlap row is not counted)
+    frames_total = plan["frames_total"]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    state = {}
+
+    def step(timed=None):
+        """One pass of the hot path over this rank's segment (device resident)."""
+        e = [ev() for _ in range(5)] if timed is not None else None
+        if e: e[0].record()
+        a = P.analyze_device(xd, sr, nfft, hop, npks, c["pkthresh"], tb, frame0=plan["frame0"],
+                             nframes=plan["nframes"], prev_zero=plan["prev_zero"])
+        if e: e[1].record()
+        trk = D.track_segment(a, plan, world)            # link + ids (+ the one all_gather when world > 1)
+        if e: e[2].record()
+        pk = P.pack_device(trk["f"], trk["mag"], trk["ph"], trk["realph"], trk["tid"], None, trk["ntracks"])
+        max_end = int((pk["tstart"] + pk["tlen"] - 1).max().item()) if trk["ntracks"] else -1
+        if e: e[3].record()
+        nout, _ = P.synth_geometry(max_end, hop, nfft, hop)
+        nb = trk["nblocks"]
+        if world > 1 and rank == world - 1:
+            nb = -(-nout // hop) - trk["block0"]         # the last rank also renders the tail
+        w = P.resynth_device(trk["tid"], pk, sr, hop, nfft, hop, max_end=max_end, block0=trk["block0"], nblocks=nb)
+        if e: e[4].record()
+        state.update(a=a, trk=trk, pk=pk, w=w, max_end=max_end)
+        if timed is not None:
+            timed.append(e)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    timed = []
+    for _ in range(args.steps):
+        flush.fill_(1)                                   # L2 flush between timed iterations
+        step(timed)
+    barrier()
+    clocks = sampler.stop()
+    st = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(4)] for e in timed])   # ms per stage
+    ms_step_local = float(st.sum(axis=1).mean())
+    t = torch.tensor([ms_step_local] + st.mean(axis=0).tolist(), device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step, ms_an, ms_trk, ms_pack, ms_syn = [float(v) for v in t.tolist()]
+
+    tl = state["pk"]["tlen"].cpu().numpy().astype(np.int64)       # global table when world > 1
+    _, E = P.synth_geometry(state["max_end"], hop, nfft, hop)
+    psamp_total = float((tl[tl >= 3] * hop + 2 * E).sum())
+    psamp_local = psamp_total / world
+
+    # ---- end to end through the public API with host buffers (pinned), per rank
+    e2e = None
+    if not args.no_e2e:
+        xh = torch.empty(plan["nsamp"], dtype=torch.float32).pin_memory()
+        xh.copy_(xd)
+        hostbuf = {}
+        times = []
+
+        def e2e_step():
+            t0 = time.perf_counter()
+            if world == 1:
+                pv = PV(xh, sr, nfft=nfft, hop=hop, npks=npks, pkthresh=c["pkthresh"], progress=False, device=dev)
+                pv.run_pv()
+                ss = pv.toSinSum()
+                wd = ss.synth(sr, hop, to_host=False)
+                nb = pv.fetch_into(hostbuf, extra={"w": wd})
+            else:
+                spv = D.ShardedPV(xh, sr, world * nsamp_seg, nfft=nfft, hop=hop, npks=npks, pkthresh=c["pkthresh"],
+                                  rank=rank, world=world, device=dev)
+                spv.run_pv()
+                ss = spv.toSinSum()
+                wd = spv.synth_local(ss)
+                nb = spv.pv.fetch_into(hostbuf, extra={"w": wd})
+            torch.cuda.synchronize()
+            return time.perf_counter() - t0, nb
+        for _ in range(2):
+            e2e_step()
+        for _ in range(max(2, min(args.steps, 5))):
+            flush.fill_(1)
+            barrier()
+            dt, nb = e2e_step()
+            times.append(dt)
+        tt = torch.tensor([float(np.mean(times)), float(nb), float(xh.numel() * 4)], device=dev, dtype=torch.float64)
+        if world > 1:
+            tmax = tt.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+            tt[0] = tmax[0]
+        e2e = {"value": frames_total / float(tt[0].item()), "unit": "frames/s",
+               "h2d_bytes_per_step": int(tt[2].item()), "d2h_bytes_per_step": int(tt[1].item()),
+               "ms_per_step": 1e3 * float(tt[0].item()),
+               "note": "PV(pinned host signal).run_pv -> toSinSum -> synth -> fetch_into(pinned): "
+                       "f/mag/ph/realph/binno/totalmag float64 tables + float64 resynthesis; host wall clock, "
+                       "max over ranks"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk_, how = peaks()
+    hbm = float(pk_["hbm_gbs"])
+    alg_an = (4 * hop + 20 * npks + 8) * F                       # bytes per launch
+    pbar = psamp_local / max(1.0, float(state["w"].numel()))
+    alg_syn = (16.0 / hop + 4.0 / max(pbar, 1e-9)) * psamp_local
+    roof_an = {"kernel": "analyze_kernel<10>", "bound": "hbm", "achieved": alg_an / (ms_an * 1e-3) / 1e9, "peak": hbm,
+               "unit": "GB/s", "frac": alg_an / (ms_an * 1e-3) / 1e9 / hbm, "traffic": _traffic("analyze"),
+               "ms": ms_an, "alg_bytes_per_launch": alg_an, "peak_source": how,
+               "note": "fused framing+FFT+peak-pick+IF is shared-memory / issue bound, see DESIGN.md"}
+    roof_syn = {"kernel": "resynth_kernel", "bound": "hbm", "achieved": alg_syn / (ms_syn * 1e-3) / 1e9, "peak": hbm,
+                "unit": "GB/s", "frac": alg_syn / (ms_syn * 1e-3) / 1e9 / hbm, "traffic": _traffic("resynth"),
+                "ms": ms_syn, "alg_bytes_per_launch": alg_syn, "peak_source": how,
+                "partial_samples_per_s": psamp_local / (ms_syn * 1e-3),
+                "note": "compute bound by construction (FP64 phase + MUFU cos per partial-sample), see DESIGN.md"}
+    dominant = roof_an if ms_an >= ms_syn else roof_syn
+    line = {
+        "metric": METRIC, "value": frames_total / (ms_step * 1e-3), "unit": "frames/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 FFT, f64 per-peak/phase",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sr": sr, "seconds_per_gpu": c["seconds"], "nfft": nfft, "hop": hop,
+                   "npks": npks, "frames_per_gpu": F, "frames_total": frames_total,
+                   "partial_samples_total": psamp_total, "tracks_rank0": int(state["trk"]["ntracks"]),
+                   "l2": "256 MiB buffer written between timed steps; per-step CUDA events on the launch stream",
+                   "parallelism": "segment-sharded x%d (hop-aligned, 1 warm-up frame + nfft-hop halo)" % world},
+        "stages": {"analysis_ms": ms_an, "tracking_ms": ms_trk, "pack_ms": ms_pack, "resynth_ms": ms_syn,
+                   "analysis_frames_per_s": frames_total / (ms_an * 1e-3),
+                   "resynth_partial_samples_per_s": psamp_total / (ms_syn * 1e-3)},
+        "roofline": dominant, "roofline_analysis": roof_an, "roofline_resynth": roof_syn,
+        "clocks": clocks, "gpu_launches": MY_LAUNCHES_PER_STEP * args.steps,
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(xd[:sr * args.cpu_seconds + nfft].cpu().numpy(), 1)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _traffic(which):
+    """DRAM bytes per launch from the committed ncu capture (profiles/traffic.json), else null."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            return json.load(fh).get(which)
+    except Exception:
+        return None
+
+
+# --------------------------------------------------------------------------- CPU arms
+def _oracle_pipeline(x):
+    """analysis -> tracking -> resynthesis with the numpy oracle; returns (frames, partial-samples, stage times)."""
+    from oracle import pv_oracle as orc
+    c = CFG
+    t0 = time.perf_counter()
+    o = orc.analyze(x, c["sr"], nfft=c["nfft"], hop=c["hop"], npks=c["npks"], pkthresh=c["pkthresh"])
+    t1 = time.perf_counter()
+    tr = orc.track(o["f"], o["mag"])
+    parts = orc.partials_from_tracks(tr, o["f"], o["mag"], o["ph"], o["realph"])
+    t2 = time.perf_counter()
+    orc.synth(parts, c["sr"], c["hop"], c["nfft"], c["hop"])
+    t3 = time.perf_counter()
+    ps = orc.partial_samples(parts, c["hop"], c["nfft"], c["hop"])
+    return o["nframes"], ps, (t1 - t0, t2 - t1, t3 - t2)
+
+
+def _worker(args):
+    seed_off, nsamp = args
+    from pypevoc_b200 import signals
+    c = CFG
+    x = signals.harm(c["sr"], nsamp / float(c["sr"]), c["f0"], c["nharm"], c["p"], c["sigma"], c["seed"] + seed_off)
+    import warnings
+    warnings.simplefilter("ignore")
+    t0 = time.perf_counter()
+    fr, ps, st = _oracle_pipeline(x)
+    return fr, ps, st, time.perf_counter() - t0
+
+
+def cpu_baseline(x, cores):
+    import warnings
+    warnings.simplefilter("ignore")
+    t0 = time.perf_counter()
+    fr, ps, st = _oracle_pipeline(x)
+    dt = time.perf_counter() - t0
+    return {"value": fr / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": "first %.0f s of the same samples (%d frames): numpy oracle analyze+track+synth" % (len(x) / CFG["sr"], fr),
+            "analysis_frames_per_s": fr / st[0], "tracking_s": st[1],
+            "resynth_partial_samples_per_s": ps / st[2]}
+
+
+def reference_main(args):
+    """--impl reference: the reference's CPU algorithm (numpy oracle port; the Python reference
+    itself cannot travel to the GPU box) on all host cores, one disjoint segment per process."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    seg = CFG["sr"] * args.ref_seconds + CFG["nfft"]
+    ctx = mp.get_context("fork")
+    times, frames = [], 0
+    with ctx.Pool(cores) as pool:
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            res = pool.map(_worker, [(100 * it + i, seg) for i in range(cores)])
+            dt = time.perf_counter() - t0
+            if it >= args.warmup:
+                times.append(max(r[3] for r in res))
+                frames = sum(r[0] for r in res)
+    ms = 1e3 * float(np.mean(times))
+    val = frames / (ms * 1e-3)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": "%d processes x %d s segments per step" % (cores, args.ref_seconds)},
+            "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": "port",
+                             "sample": "%d disjoint %d s segments of the workload signal per step, one process per core, "
+                                       "numpy oracle analyze+track+synth" % (cores, args.ref_seconds)},
+            "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=int, default=15)
+    ap.add_argument("--ref-seconds", type=int, default=8)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_main(args)
+    else:
+        gpu_main(args)
+
+
+if __name__ == "__main__":
+    main()

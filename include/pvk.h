@@ -109,7 +109,7 @@ int pvk_track(const double *f, const double *mag, int64_t nclips, int64_t nframe
  * ss.end - ss.st + 1, :827-828,950), toff int64 [ntracks+1] exclusive offsets, packed
  * float64 arrays of length sum(tlen) (pph may be NULL). */
 int pvk_track_pack(const double *f, const double *mag, const double *ph, const double *realph,
-                   const int32_t *tid, const int32_t *link, int64_t nframes, int npks,
+                   const int32_t *tid, int64_t nframes, int npks,
                    int64_t ntracks, int32_t *tstart, int32_t *tlen, int64_t *toff, double *pf,
                    double *pmag, double *pph, double *prealph, void *stream);
 
@@ -122,11 +122,12 @@ int pvk_track_pack(const double *f, const double *mag, const double *ph, const d
  *                                        shorter than minframes are skipped (:1061)
  *   sr, hop      synthesis sample rate and hop (hop may differ from the analysis hop)
  *   nfft, hop_an analysis parameters the SinSum was built with (:824-825,1055)
- *   out          float64 [nout], nout = (max_end+2)*hop + int(edge*hop*nfft/hop_an/2)
- *                (:1059,1070); every sample of the rendered block range is written
- *                (zeros where no partial sounds)
+ *   nout         length of the whole signal, (max_end+2)*hop + int(edge*hop*nfft/hop_an/2)
+ *                (:1059,1070)
  *   block0, nblocks  render output blocks [block0, block0+nblocks) of `hop` samples
  *                (multi-GPU: each rank renders a disjoint block range); nblocks < 0 = all
+ *   out          float64; out[0] is sample block0*hop; every sample of the rendered block
+ *                range below nout is written (zeros where no partial sounds)
  */
 int pvk_resynth(const int32_t *tid, int64_t nframes, int npks, const int32_t *tstart,
                 const int32_t *tlen, const int64_t *toff, const double *pf, const double *pmag,

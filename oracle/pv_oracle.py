@@ -220,6 +220,9 @@ def track(f, mag, maxpitchjmp=0.5):
     ``link`` int32 ``[F, K]`` (column of the continued peak in frame j-1, -1 = new /
     none), ``st``, ``end`` (first / last frame per track, :827-828,950).
     Track ids are numbered in ``add_empty_partial`` call order (:819-830).
+
+    Exact ties: see the comment at the argsort below (current frame) -- previous-frame ties
+    keep the reference's deterministic (magnitude, track index) descending order (:893).
     """
     f = np.asarray(f, dtype=np.float64)
     mag = np.asarray(mag, dtype=np.float64)
@@ -229,7 +232,12 @@ def track(f, mag, maxpitchjmp=0.5):
     link = -np.ones((F, K), dtype=np.int32)
     st, end = [], []
     for fr in range(F):
-        idx = np.argsort(mag[fr])[::-1]                                   # :874-875
+        # :874-875.  The reference calls np.argsort(mag)[::-1] with numpy's default *unstable*
+        # sort, so the order of peaks whose magnitudes are exactly equal (e.g. the 1e-17 hash
+        # of a frame leaving digital silence) depends on the numpy build / CPU SIMD dispatch.
+        # The oracle pins that one undefined case to "reversed stable sort" (= what numpy's
+        # insertion sort gives for <= 16 entries): among exact ties the higher column first.
+        idx = np.argsort(mag[fr], kind="stable")[::-1]
         idx = idx[np.logical_and(f[fr][idx] > 0, mag[fr][idx] > 0)]       # :876
         if fr > 0:
             pcols = np.flatnonzero(tid[fr - 1] >= 0)                      # partials ending at fr-1 (:887,984-994)

@@ -24,7 +24,7 @@ SIGNATURES = {
                          _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "pvk_track_workspace_bytes": (_i64, [_i64, _i64, _i]),
     "pvk_track": (_i, [_p, _p, _i64, _i64, _i, _d, _p, _p, _p, _p, _i64, _p]),
-    "pvk_track_pack": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _i64, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "pvk_track_pack": (_i, [_p, _p, _p, _p, _p, _i64, _i, _i64, _p, _p, _p, _p, _p, _p, _p, _p]),
     "pvk_resynth": (_i, [_p, _i64, _i, _p, _p, _p, _p, _p, _p, _d, _i, _i, _i, _d, _i, _p, _i64, _i64,
                          _i64, _p]),
 }

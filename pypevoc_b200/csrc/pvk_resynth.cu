@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(256) resynth_kernel(RParams p) {
     for (int m = 0; m < R_S; ++m) {
       const int q = q0 + tid + m * BD;
       const int64_t n = nbase + q;
-      if (q < h && n < p.nout) p.out[n] = tot[m];
+      if (q < h && n < p.nout) p.out[n - p.block0 * (int64_t)h] = tot[m];
     }
   }
 }

@@ -235,14 +235,14 @@ __global__ void track_fix_kernel(int32_t *__restrict__ tid, const int32_t *__res
 }
 
 // ------------------------------------------------------------------ pack
-__global__ void pack_count_kernel(const int32_t *__restrict__ tid, const int32_t *__restrict__ link,
-                                  int64_t F, int K, int32_t *__restrict__ tstart, int32_t *__restrict__ tlen) {
+__global__ void pack_count_kernel(const int32_t *__restrict__ tid, int64_t F, int K,
+                                  int32_t *__restrict__ tstart, int32_t *__restrict__ tlen) {
   const int64_t n = F * K;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
     const int v = tid[e];
     if (v >= 0) {
       atomicAdd(&tlen[v], 1);
-      if (link[e] <= -2) tstart[v] = (int32_t)(e / K);
+      atomicMin(&tstart[v], (int32_t)(e / K));
     }
   }
 }
@@ -375,7 +375,7 @@ extern "C" int pvk_track(const double *f, const double *mag, int64_t nclips, int
 }
 
 extern "C" int pvk_track_pack(const double *f, const double *mag, const double *ph, const double *realph,
-                              const int32_t *tid, const int32_t *link, int64_t nframes, int npks,
+                              const int32_t *tid, int64_t nframes, int npks,
                               int64_t ntracks, int32_t *tstart, int32_t *tlen, int64_t *toff, double *pf,
                               double *pmag, double *pph, double *prealph, void *stream) {
   PVK_REQUIRE(npks >= 1 && nframes >= 0 && ntracks >= 0, "pvk_track_pack: bad sizes");
@@ -384,11 +384,12 @@ extern "C" int pvk_track_pack(const double *f, const double *mag, const double *
     cudaMemsetAsync(toff, 0, 8 * (size_t)(ntracks + 1), (cudaStream_t)stream);
     return PVK_OK;
   }
-  PVK_REQUIRE(f && mag && realph && tid && link && tstart && tlen && pf && pmag && prealph,
+  PVK_REQUIRE(f && mag && realph && tid && tstart && tlen && pf && pmag && prealph,
               "pvk_track_pack: NULL pointer argument");
   const int64_t n = nframes * npks;
   cudaMemsetAsync(tlen, 0, 4 * (size_t)ntracks, (cudaStream_t)stream);
-  PVK_LAUNCH(pack_count_kernel, dim3(grid_for(n, 256)), dim3(256), 0, stream, tid, link, nframes, npks, tstart, tlen);
+  cudaMemsetAsync(tstart, 0x7f, 4 * (size_t)ntracks, (cudaStream_t)stream);   // 0x7f7f7f7f: "no frame yet"
+  PVK_LAUNCH(pack_count_kernel, dim3(grid_for(n, 256)), dim3(256), 0, stream, tid, nframes, npks, tstart, tlen);
   PVK_CHECK_LAUNCH("pvk_track_pack(count)");
   PVK_LAUNCH(pack_scan_kernel, dim3(1), dim3(1024), 33 * 8, stream, tlen, ntracks, toff);
   PVK_CHECK_LAUNCH("pvk_track_pack(scan)");

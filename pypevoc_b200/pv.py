@@ -160,7 +160,7 @@ def track_device(fd, magd, maxpitchjmp=0.5):
     return dict(tid=tid, link=link, ntracks=ntracks)
 
 
-def pack_device(fd, magd, phd, realphd, tid, link, ntracks):
+def pack_device(fd, magd, phd, realphd, tid, link, ntracks):   # link: unused, kept for call sites
     """pvk_track_pack for one clip (``[F, K]`` device tables, ``ntracks`` python int)."""
     L = _lib.lib()
     dev = fd.device
@@ -172,7 +172,7 @@ def pack_device(fd, magd, phd, realphd, tid, link, ntracks):
     toff = torch.empty((nt + 1,), dtype=torch.int64, device=dev)
     packed = [torch.empty((max(npts, 1),), dtype=torch.float64, device=dev) for _ in range(4)]
     with torch.cuda.device(dev):
-        _lib.check(L.pvk_track_pack(_ptr(fd), _ptr(magd), _ptr(phd), _ptr(realphd), _ptr(tid), _ptr(link), F, K, nt,
+        _lib.check(L.pvk_track_pack(_ptr(fd), _ptr(magd), _ptr(phd), _ptr(realphd), _ptr(tid), F, K, nt,
                                     _ptr(tstart), _ptr(tlen), _ptr(toff), _ptr(packed[0]), _ptr(packed[1]),
                                     _ptr(packed[2]), _ptr(packed[3]), _stream()), "pvk_track_pack")
     return dict(tstart=tstart[:nt], tlen=tlen[:nt], toff=toff, pf=packed[0][:npts], pmag=packed[1][:npts],
@@ -195,8 +195,10 @@ def resynth_device(tid, pk, sr, hop, nfft, hop_an, edge=1.0, minframes=3, max_en
     if max_end is None:
         max_end = int((pk["tstart"] + pk["tlen"] - 1).max().item()) if len(pk["tstart"]) else -1
     nout, _ = synth_geometry(max_end, hop, nfft, hop_an, edge)
+    nblk = -(-nout // hop)
+    nb = nblk - block0 if nblocks < 0 else nblocks
     if out is None:
-        out = torch.empty((nout,), dtype=torch.float64, device=dev)
+        out = torch.empty((max(min(nb * hop, nout - block0 * hop), 0),), dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
         _lib.check(L.pvk_resynth(_ptr(tid), F, K, _ptr(pk["tstart"]), _ptr(pk["tlen"]), _ptr(pk["toff"]),
                                  _ptr(pk["pf"]), _ptr(pk["pmag"]), _ptr(pk["prealph"]), float(sr), int(hop),
@@ -225,7 +227,7 @@ class PV(object):
             xd = x.detach()
             if xd.dim() != 1:
                 raise ValueError("PV expects a 1-D signal")
-            self._xd = xd.to(device=self._dev, dtype=torch.float32).contiguous()
+            self._xd = xd.to(device=self._dev, dtype=torch.float32, non_blocking=True).contiguous()
             self._x_host = None
         else:
             xh = np.array(x)
@@ -320,6 +322,29 @@ class PV(object):
         if self._devout is None:
             raise RuntimeError("run_pv() has not been called")
         return {k: v[0] for k, v in self._devout.items()}
+
+    def fetch_into(self, hostbuf, extra=None):
+        """Copy the peak tables of the last run_pv (and any ``extra`` device tensors) into
+        reusable pinned host tensors kept in the dict ``hostbuf`` (allocated on first use), with
+        asynchronous copies on the current stream; the caller synchronises.  The tables become
+        this object's ``f mag ph realph binno totalmag`` attributes (numpy views of the pinned
+        buffers, valid until the next fetch_into with the same ``hostbuf``).  Returns the number
+        of bytes copied device -> host."""
+        src = {k: self._devout[k][0] for k in ("f", "mag", "ph", "realph", "binno", "totalmag")}
+        if extra:
+            src.update(extra)
+        nbytes = 0
+        for k, t in src.items():
+            hb = hostbuf.get(k)
+            if hb is None or hb.shape != t.shape or hb.dtype != t.dtype:
+                hb = torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=True)
+                hostbuf[k] = hb
+            hb.copy_(t, non_blocking=True)
+            nbytes += t.numel() * t.element_size()
+        for k in ("f", "mag", "ph", "realph", "binno"):
+            self._host[k] = hostbuf[k].numpy() if self.nframes else np.array([])
+        self._host["totalmag"] = hostbuf["totalmag"].numpy()
+        return nbytes
 
     # -- analysis ----------------------------------------------------------------------
     def run_pv(self, run_frames=0):
@@ -566,6 +591,11 @@ class SinSum(object):
         self._tables = dict(f=f.contiguous(), mag=mag.contiguous(), ph=ph.contiguous(), realph=realph.contiguous())
         self._rows = None
         self._trk = self._pk = self._hosttrk = None
+
+    def _set_device_tracks(self, tid, link, ntracks):
+        """Adopt precomputed track ids (sharded runs: ids made global by the all_gather)."""
+        self._trk = dict(tid=tid.contiguous(), link=link, ntracks=int(ntracks))
+        self._pk = self._hosttrk = None
 
     def add_frame(self, fr, f, mag, ph, realph=None, maxpitchjmp=0.5):
         """Add the peaks of frame ``fr`` (PVAnalysis.py:871-957).  Rows are collected on the host;

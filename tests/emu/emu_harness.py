@@ -106,19 +106,18 @@ def track(f, mag, maxpitchjmp=0.5):
     return dict(tid=tid, link=link, ntracks=ntracks)
 
 
-def track_pack(f, mag, ph, realph, tid, link, ntracks):
+def track_pack(f, mag, ph, realph, tid, link, ntracks):   # link unused (kept for call sites)
     """pvk_track_pack for one clip ([F, K] arrays)."""
     L = lib()
     F, K = f.shape
     arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (f, mag, ph, realph)]
     tid = np.ascontiguousarray(tid, dtype=np.int32)
-    link = np.ascontiguousarray(link, dtype=np.int32)
     npts = int((tid >= 0).sum())
     tstart = np.full(max(ntracks, 1), -1, dtype=np.int32)
     tlen = np.full(max(ntracks, 1), -1, dtype=np.int32)
     toff = np.full(ntracks + 1, -1, dtype=np.int64)
     packed = [np.full(max(npts, 1), np.nan) for _ in range(4)]
-    check(L.pvk_track_pack(ptr(arrs[0]), ptr(arrs[1]), ptr(arrs[2]), ptr(arrs[3]), ptr(tid), ptr(link), F, K,
+    check(L.pvk_track_pack(ptr(arrs[0]), ptr(arrs[1]), ptr(arrs[2]), ptr(arrs[3]), ptr(tid), F, K,
                            ntracks, ptr(tstart), ptr(tlen), ptr(toff), ptr(packed[0]), ptr(packed[1]),
                            ptr(packed[2]), ptr(packed[3]), None))
     return dict(tstart=tstart[:ntracks], tlen=tlen[:ntracks], toff=toff, pf=packed[0][:npts],
@@ -136,7 +135,9 @@ def resynth(tid, pk, sr, hop, nfft, hop_an, edge=1.0, minframes=3, block0=0, nbl
     E = int(dfr * hop * edge)
     if nout is None:
         nout = (max_end + 2) * hop + E
-    out = np.full(nout, np.nan)
+    nblk = -(-nout // hop)
+    nb = nblk - block0 if nblocks < 0 else nblocks
+    out = np.full(min(nb * hop, nout - block0 * hop), np.nan)
     ts = np.ascontiguousarray(pk["tstart"], dtype=np.int32)
     tl = np.ascontiguousarray(pk["tlen"], dtype=np.int32)
     check(L.pvk_resynth(ptr(tid), F, K, ptr(ts), ptr(tl), ptr(pk["toff"]), ptr(pk["pf"]), ptr(pk["pmag"]),
