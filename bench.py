@@ -32,11 +32,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# signal: SURVEY 8d "metric" recipe (f0 = 220 Hz so that harmonics are > 5 bins apart at
+# nfft 2048 and survive the salience filter: ~40 peaks per frame), 10 minutes long
 CFG = dict(sr=44100, seconds=600, nfft=2048, hop=512, npks=50, pkthresh=0.005,
-           f0=110.0, nharm=150, p=0.5, sigma=0.01, seed=2)
+           f0=220.0, nharm=90, p=0.5, sigma=0.01, seed=1)
 METRIC = "STFT frames/sec (nfft=2048,hop=512,npks=50) + resynth partial-samples/sec"
-WORKLOAD = ("10 min mono 44.1 kHz synthetic harmonic tone+noise (configs[1] signal), metric parameters "
-            "nfft=2048 hop=512 npks=50, analysis + tracking + full resynthesis")
+WORKLOAD = ("10 min mono 44.1 kHz synthetic harmonic tone+noise (configs[1] length; 220 Hz, 90 harmonics, "
+            "sigma 0.01), metric parameters nfft=2048 hop=512 npks=50, analysis + tracking + full resynthesis")
 MY_LAUNCHES_PER_STEP = 11   # analyze 1, track 6 (link scan chunk boundary stitch fix), pack 3, resynth 1
 
 

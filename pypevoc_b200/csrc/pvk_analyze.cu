@@ -116,6 +116,17 @@ template <int LOGM, int Q> struct Pass {
     constexpr int OFF = P::tw_off(Q);
     const int tid = threadIdx.x;
     float2 u[NB][R];
+    float2 tw[NB][R - 1];
+    // twiddles first: their (L1-resident) loads overlap the shared-memory reads and the barrier
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const int i = tid + b * T;
+      if (NBF >= T || i < NBF) {
+        const int k = i & (PP - 1);
+#pragma unroll
+        for (int r = 1; r < R; ++r) tw[b][r - 1] = __ldg(twp + OFF + (r - 1) * PP + k);
+      }
+    }
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
       const int i = tid + b * T;
@@ -132,7 +143,7 @@ template <int LOGM, int Q> struct Pass {
         const int k = i & (PP - 1);
         const int j = ((i - k) << LR) + k;
 #pragma unroll
-        for (int r = 1; r < R; ++r) u[b][r] = cmul(u[b][r], __ldg(twp + OFF + (r - 1) * PP + k));
+        for (int r = 1; r < R; ++r) u[b][r] = cmul(u[b][r], tw[b][r - 1]);
         dft_dif<LR>(u[b]);
 #pragma unroll
         for (int s = 0; s < R; ++s) buf[PADC(j + s * PP)] = u[b][brev<LR>(s)];
@@ -233,21 +244,19 @@ template <int LOGM> struct Smem {
   static constexpr int OFF_BUF0 = 0;
   static constexpr int OFF_BUF1 = OFF_BUF0 + P::MP * 8;
   static constexpr int OFF_FAMP = OFF_BUF1 + P::MP * 8;
-  static constexpr int OFF_SKEY = OFF_FAMP + P::M * 4;
-  static constexpr int OFF_MC = OFF_SKEY + P::M * 4;        // candidate mask
-  static constexpr int OFF_MA = OFF_MC + P::MW * 4;         // key above boundary bucket
-  static constexpr int OFF_MB = OFF_MA + P::MW * 4;         // key inside boundary bucket
-  static constexpr int OFF_MS = OFF_MB + P::MW * 4;         // selected
-  static constexpr int OFF_MK = OFF_MS + P::MW * 4;         // kept after salience
-  static constexpr int OFF_WCNT = OFF_MK + P::MW * 4;
+  static constexpr int OFF_CKEY = OFF_FAMP + P::M * 4;       // candidate keys (compact, bin order)
+  static constexpr int OFF_MC = OFF_CKEY + P::M * 4;         // candidate mask words
+  static constexpr int OFF_WCNT = OFF_MC + P::MW * 4;
   static constexpr int OFF_WBASE = OFF_WCNT + P::MW * 4;
   static constexpr int OFF_HIST = OFF_WBASE + (P::MW + 1) * 4;
   static constexpr int OFF_RED = (OFF_HIST + 256 * 4 + 7) / 8 * 8;   // doubles: 8 sums
   static constexpr int OFF_REDF = OFF_RED + 8 * 8;                   // floats: 8 min, 8 max
   static constexpr int OFF_REDU = OFF_REDF + 16 * 4;                 // uints: 8 cnt, 8 kmin, 8 kmax
   static constexpr int OFF_BC = OFF_REDU + 24 * 4;                   // 8 broadcast ints
-  static constexpr int OFF_PK = OFF_BC + 8 * 4;                      // npks ints
-  static int bytes(int npks) { return OFF_PK + npks * 4; }
+  static constexpr int OFF_WS = OFF_BC + 8 * 4;                      // 2 x (2 x 8) warp sums
+  static constexpr int OFF_CBIN = OFF_WS + 32 * 4;                   // candidate bins (uint16, compact)
+  static constexpr int OFF_PK = OFF_CBIN + P::M * 2;                 // 2 x npks uint16
+  static int bytes(int npks) { return OFF_PK + 2 * ((npks + 7) / 8 * 8) * 2; }
 };
 
 // exclusive scan of cnt[0..n) into base[0..n], total in base[n]; executed by warp 0 only
@@ -264,6 +273,23 @@ __device__ __forceinline__ void warp0_excl_scan(const int *cnt, int *base, int n
   if (lane == 0) base[n] = carry;
 }
 
+// Ordered compaction of a list processed in rounds of blockDim threads: position of this
+// thread's entry among the flagged ones (valid if flag), running total in `base`.
+// wsum: 2 x NW ints, double buffered by round parity -> one barrier per round.
+template <int NW>
+__device__ __forceinline__ int round_pos(bool flag, int *wsum, int round, int &base) {
+  const unsigned m = __ballot_sync(FULL, flag);
+  int *ws = wsum + (round & 1) * NW;
+  if (lane_id() == 0) ws[warp_id()] = __popc(m);
+  __syncthreads();
+  int wb = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) { const int c = ws[w]; wb += (w < warp_id()) ? c : 0; tot += c; }
+  const int pos = base + wb + __popc(m & lanemask_lt());
+  base += tot;
+  return pos;
+}
+
 template <int LOGM>
 __global__ void __launch_bounds__(Plan<LOGM>::T) analyze_kernel(AParams prm) {
   using P = Plan<LOGM>;
@@ -274,12 +300,8 @@ __global__ void __launch_bounds__(Plan<LOGM>::T) analyze_kernel(AParams prm) {
   float2 *bufs[2] = {reinterpret_cast<float2 *>(smem + S::OFF_BUF0),
                      reinterpret_cast<float2 *>(smem + S::OFF_BUF1)};
   float *famp = reinterpret_cast<float *>(smem + S::OFF_FAMP);
-  unsigned *skey = reinterpret_cast<unsigned *>(smem + S::OFF_SKEY);
+  unsigned *ckey = reinterpret_cast<unsigned *>(smem + S::OFF_CKEY);
   unsigned *maskC = reinterpret_cast<unsigned *>(smem + S::OFF_MC);
-  unsigned *maskA = reinterpret_cast<unsigned *>(smem + S::OFF_MA);
-  unsigned *maskB = reinterpret_cast<unsigned *>(smem + S::OFF_MB);
-  unsigned *maskS = reinterpret_cast<unsigned *>(smem + S::OFF_MS);
-  unsigned *maskK = reinterpret_cast<unsigned *>(smem + S::OFF_MK);
   int *wcnt = reinterpret_cast<int *>(smem + S::OFF_WCNT);
   int *wbase = reinterpret_cast<int *>(smem + S::OFF_WBASE);
   int *hist = reinterpret_cast<int *>(smem + S::OFF_HIST);
@@ -287,7 +309,11 @@ __global__ void __launch_bounds__(Plan<LOGM>::T) analyze_kernel(AParams prm) {
   float *redf = reinterpret_cast<float *>(smem + S::OFF_REDF);
   unsigned *redu = reinterpret_cast<unsigned *>(smem + S::OFF_REDU);
   int *bc = reinterpret_cast<int *>(smem + S::OFF_BC);
-  int *pk = reinterpret_cast<int *>(smem + S::OFF_PK);
+  int *wsA = reinterpret_cast<int *>(smem + S::OFF_WS);
+  int *wsB = wsA + 16;
+  unsigned short *cbin = reinterpret_cast<unsigned short *>(smem + S::OFF_CBIN);
+  unsigned short *pk1 = reinterpret_cast<unsigned short *>(smem + S::OFF_PK);
+  unsigned short *pk2 = pk1 + (prm.npks + 7) / 8 * 8;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t clip = blockIdx.x / prm.nruns;
@@ -387,10 +413,13 @@ __global__ void __launch_bounds__(Plan<LOGM>::T) analyze_kernel(AParams prm) {
     if (minamp == 0.0) minamp = miny_d;
     const double th = minamp - miny_d;
 
-    // ---- candidates: interior local maxima above threshold (or everything when th < 0)
+    // ---- candidates: interior local maxima above threshold (or everything when th < 0),
+    //      compacted in bin order into (cbin, ckey)
+    unsigned keyr[NIT];
+    unsigned mybits = 0;
     {
       unsigned wc = 0, kmin = 0xffffffffu, kmax = 0u;
-#pragma unroll 4
+#pragma unroll
       for (int n = 0; n < NIT; ++n) {
         const int k = tid + n * T;
         const bool interior = (k >= 1) && (k <= M - 2);
@@ -401,11 +430,11 @@ __global__ void __launch_bounds__(Plan<LOGM>::T) analyze_kernel(AParams prm) {
         if (ispk) c = ((double)y - miny_d) > th;
         else c = interior && (th < 0.0);
         const unsigned key = ispk ? __float_as_uint(y) : 0u;
-        skey[k] = key;
+        keyr[n] = key;
         const unsigned m = __ballot_sync(FULL, c);
-        if (lane == 0) maskC[k >> 5] = m;
+        if (lane == 0) { maskC[k >> 5] = m; wcnt[k >> 5] = __popc(m); }
         wc += __popc(m);
-        if (c) { kmin = key < kmin ? key : kmin; kmax = key > kmax ? key : kmax; }
+        if (c) { mybits |= 1u << n; kmin = key < kmin ? key : kmin; kmax = key > kmax ? key : kmax; }
       }
       kmin = warp_umin(kmin);
       kmax = warp_umax(kmax);
@@ -420,24 +449,34 @@ __global__ void __launch_bounds__(Plan<LOGM>::T) analyze_kernel(AParams prm) {
       lo = redu[8 + w] < lo ? redu[8 + w] : lo;
       hi = redu[16 + w] > hi ? redu[16 + w] : hi;
     }
+    if (warp == 0) warp0_excl_scan(wcnt, wbase, MW);
+    __syncthreads();
+#pragma unroll
+    for (int n = 0; n < NIT; ++n) {
+      if ((mybits >> n) & 1u) {
+        const int k = tid + n * T;
+        const int pos = wbase[k >> 5] + __popc(maskC[k >> 5] & lanemask_lt());
+        cbin[pos] = (unsigned short)k;
+        ckey[pos] = keyr[n];
+      }
+    }
+    __syncthreads();
 
     // ---- top-K by (key desc, bin asc): exact radix select of the K-th largest key
-    const unsigned *selmask = maskC;
+    const unsigned short *sel = cbin;
+    int ns = C;
     if (C > K) {
       int rr = K;
+      bool exact_ties = false;
       for (int level = 0; level < 4; ++level) {
         const unsigned range = hi - lo;
         const int bl = 32 - __clz((int)range);
         const int sh = bl > 8 ? bl - 8 : 0;
         for (int h = tid; h < 256; h += T) hist[h] = 0;
         __syncthreads();
-#pragma unroll 4
-        for (int n = 0; n < NIT; ++n) {
-          const int k = tid + n * T;
-          if ((maskC[k >> 5] >> (k & 31)) & 1u) {
-            const unsigned key = skey[k];
-            if (key >= lo && key <= hi) atomicAdd(&hist[(key - lo) >> sh], 1);
-          }
+        for (int e = tid; e < C; e += T) {
+          const unsigned key = ckey[e];
+          if (key >= lo && key <= hi) atomicAdd(&hist[(key - lo) >> sh], 1);
         }
         __syncthreads();
         if (warp == 0) {
@@ -460,64 +499,54 @@ __global__ void __launch_bounds__(Plan<LOGM>::T) analyze_kernel(AParams prm) {
         const unsigned hi2 = lo + ((1u << sh) - 1u);
         hi = hi2 < hi ? hi2 : hi;
         rr -= nabove;
-        if (cb == rr || sh == 0) break;
+        if (cb == rr) break;
+        if (sh == 0) { exact_ties = true; break; }
       }
-      // selected = key above the boundary bucket, or among the first rr (by bin) inside it
-#pragma unroll 4
-      for (int n = 0; n < NIT; ++n) {
-        const int k = tid + n * T;
-        const bool c = (maskC[k >> 5] >> (k & 31)) & 1u;
-        const unsigned key = skey[k];
-        const unsigned mA = __ballot_sync(FULL, c && key > hi);
-        const unsigned mB = __ballot_sync(FULL, c && key >= lo && key <= hi);
-        if (lane == 0) { maskA[k >> 5] = mA; maskB[k >> 5] = mB; wcnt[k >> 5] = __popc(mB); }
+      // selected = key above the boundary bucket, or inside it (only its first rr entries in bin
+      // order when the bucket is a run of exactly equal keys); compacted in bin order into pk1
+      int base = 0, tbase = 0;
+      for (int e0 = 0, round = 0; e0 < C; e0 += T, ++round) {
+        const int e = e0 + tid;
+        const unsigned key = e < C ? ckey[e] : 0u;
+        const bool inA = e < C && key > hi;
+        const bool inB = e < C && key >= lo && key <= hi;
+        bool s = inA || inB;
+        if (exact_ties) {
+          const int tpos = round_pos<NW>(inB, wsA, round, tbase);
+          s = inA || (inB && tpos < rr);
+        }
+        const int pos = round_pos<NW>(s, wsB, round, base);
+        if (s) pk1[pos] = cbin[e];
       }
+      sel = pk1;
+      ns = K;
       __syncthreads();
-      if (warp == 0) warp0_excl_scan(wcnt, wbase, MW);
-      __syncthreads();
-#pragma unroll 4
-      for (int n = 0; n < NIT; ++n) {
-        const int k = tid + n * T;
-        const int wd = k >> 5;
-        const unsigned mA = maskA[wd], mB = maskB[wd], bit = 1u << (k & 31);
-        const bool s = (mA & bit) || ((mB & bit) && (wbase[wd] + __popc(mB & (bit - 1u)) < rr));
-        const unsigned mS = __ballot_sync(FULL, s);
-        if (lane == 0) maskS[wd] = mS;
-      }
-      __syncthreads();
-      selmask = maskS;
     }
 
-    // ---- salience filter, rad = 5 (PeakFinder.py:113-134 as called at PVAnalysis.py:177)
-#pragma unroll 4
-    for (int n = 0; n < NIT; ++n) {
-      const int k = tid + n * T;
+    // ---- salience filter, rad = 5 (PeakFinder.py:113-134 as called at PVAnalysis.py:177), one
+    //      thread per selected peak; survivors compacted in bin order into pk2
+    int nk = 0;
+    for (int e0 = 0, round = 0; e0 < ns; e0 += T, ++round) {
+      const int e = e0 + tid;
       bool keep = false;
-      if ((selmask[k >> 5] >> (k & 31)) & 1u) {
+      int k = 0;
+      if (e < ns) {
+        k = sel[e];
         const float y = famp[k];
         const int a = k - 5 > 1 ? k - 5 : 1, b = k + 5 < M - 1 ? k + 5 : M - 1;
         keep = true;
         for (int m = a; m <= b; ++m) keep = keep && !(famp[m] > y);
       }
-      const unsigned mk = __ballot_sync(FULL, keep);
-      if (lane == 0) { maskK[k >> 5] = mk; wcnt[k >> 5] = __popc(mk); }
+      const int pos = round_pos<NW>(keep, wsA, round, nk);
+      if (keep) pk2[pos] = (unsigned short)k;
     }
     __syncthreads();
-    if (warp == 0) warp0_excl_scan(wcnt, wbase, MW);
-    __syncthreads();
-    const int nk = wbase[MW];
-#pragma unroll 4
-    for (int n = 0; n < NIT; ++n) {
-      const int k = tid + n * T;
-      const unsigned mk = maskK[k >> 5], bit = 1u << (k & 31);
-      if (mk & bit) pk[wbase[k >> 5] + __popc(mk & (bit - 1u))] = k;
-    }
-    __syncthreads();
+    const unsigned short *pk = pk2;
 
     // ---- per-peak epilogue, freq > 0 filter, ordered write of the zero padded row
     const int64_t ob = row * K;
     int outbase = 0;
-    for (int p0 = 0; p0 < nk; p0 += T) {
+    for (int p0 = 0, round = 0; p0 < nk; p0 += T, ++round) {
       const int p = p0 + tid;
       PeakVals v;
       bool valid = false;
@@ -526,19 +555,11 @@ __global__ void __launch_bounds__(Plan<LOGM>::T) analyze_kernel(AParams prm) {
         k = pk[p];
         valid = peak_epilogue(k, M, cur, prev, famp, prm.fbin, prm.wfbin, prm.dt, prm.fstep, v);
       }
-      const unsigned mv = __ballot_sync(FULL, valid);
-      if (lane == 0) wcnt[warp] = __popc(mv);
-      __syncthreads();
-      int wb = 0, tot = 0;
-#pragma unroll
-      for (int w = 0; w < NW; ++w) { const int c = wcnt[w]; wb += (w < warp) ? c : 0; tot += c; }
+      const int64_t pos = ob + round_pos<NW>(valid, wsB, round, outbase);
       if (valid) {
-        const int64_t pos = ob + outbase + wb + __popc(mv & lanemask_lt());
         prm.f[pos] = v.f; prm.mag[pos] = v.mag; prm.ph[pos] = v.ph;
         prm.realph[pos] = v.realph; prm.binno[pos] = (double)k;
       }
-      outbase += tot;
-      __syncthreads();
     }
     for (int p = outbase + tid; p < K; p += T) {
       prm.f[ob + p] = 0.0; prm.mag[ob + p] = 0.0; prm.ph[ob + p] = 0.0;

@@ -32,7 +32,7 @@ struct RParams {
   int64_t nout, block0;
 };
 
-constexpr int R_S = 4;      // samples per thread per pass
+constexpr int R_S = 8;      // samples per thread per pass
 
 // np.interp(n, h*(a + arange(nfr)), v) for integer n >= 0 (:701-702), clamped at both ends
 __device__ __forceinline__ double interp_at(const double *__restrict__ v, int nfr, double a, int h, double n) {
@@ -80,17 +80,13 @@ __device__ __forceinline__ double cum_cycles(const Lin2 &L, double sr, int q) {
   return s0 + (L.c1 * (qd - qk) + L.s1 * ((qd * (qd - 1.0)) - (qk * (qk - 1.0))) * 0.5) / sr;
 }
 
-// shared-memory item table (struct of arrays, one entry per row slot)
-struct Items {
-  double *A0, *B0, *C0, *A1, *B1, *C1;
-  float *m0c, *m0s, *m1c, *m1s, *einv;
-  int *qk, *qkm, *qa, *qb, *eoff, *type;
-  __device__ void carve(unsigned char *p, int K) {
-    A0 = reinterpret_cast<double *>(p); B0 = A0 + K; C0 = B0 + K; A1 = C0 + K; B1 = A1 + K; C1 = B1 + K;
-    m0c = reinterpret_cast<float *>(C1 + K); m0s = m0c + K; m1c = m0s + K; m1s = m1c + K; einv = m1s + K;
-    qk = reinterpret_cast<int *>(einv + K); qkm = qk + K; qa = qkm + K; qb = qa + K; eoff = qb + K; type = eoff + K;
-  }
-  static int bytes(int K) { return K * (6 * 8 + 5 * 4 + 6 * 4); }
+// one sinusoid segment that sounds in the block: phase polynomial (cycles) and linear
+// amplitude, each with one knot; 96 bytes, read back with six 128-bit shared loads
+struct __align__(16) Item {
+  double A0, B0, C0, A1, B1, C1;     // theta(q) = A + B q + C q^2, set 1 for q >= qk
+  float m0c, m0s, m1c, m1s;          // amp(q)   = c + s q,         set 1 for q >= qkm
+  int qk, qkm, qa, qb;               // knots and valid sample range [qa, qb)
+  int eoff; float einv; int type; int pad;   // fade envelope: cos(pi*(q+eoff)*einv)
 };
 
 constexpr int IT_NONE = 0, IT_BODY = 1, IT_HEAD = 2, IT_TAIL = 3;
@@ -98,140 +94,158 @@ constexpr double INV_2PI = 0.15915494309189535;
 constexpr double TWO_PI = 6.283185307179586;
 constexpr double PI_D = 3.141592653589793;
 
+// turn slot c of frame row r into the segment that sounds in block b (type IT_NONE if none)
+__device__ __forceinline__ void make_item(const RParams &p, int64_t b, int64_t r, int c, Item &it) {
+  const int h = p.h, E = p.E;
+  const double sr = p.sr;
+  it.type = IT_NONE;
+  const int v = p.tid[r * p.K + c];
+  if (v < 0) return;
+  const int nfr = p.tlen[v];
+  if (nfr < p.minframes) return;                                   // :1061
+  const int s = p.tstart[v];
+  const int ii = (int)(r - s);
+  int type = IT_NONE;
+  if (r == b) type = IT_BODY;
+  else if (r > b && ii == 0) type = IT_HEAD;
+  else if (r < b && ii == nfr - 1) type = IT_TAIL;
+  if (type == IT_NONE) return;
+  const int64_t o = p.toff[v];
+  const double *tf = p.pf + o, *tm = p.pmag + o, *tr = p.prealph + o;
+  const double af = p.dfr + 0.5, am = p.dfr;                        // knot offsets of :701 / :702
+  if (type == IT_BODY) {
+    const Lin2 Lf = interp_block(tf, nfr, ii, af, h);
+    const double fb0 = interp_at(tf, nfr, af, h, (double)h * ii);
+    const double fb1 = interp_at(tf, nfr, af, h, (double)h * (ii + 1));
+    const double phcor = PI_D * (fb1 - fb0) / p.fstep / 2.0;        // :715
+    const double th0 = (tr[ii] + phcor) * INV_2PI;                  // :721
+    double dphc = 0.0;
+    if (ii < nfr - 1) {
+      const double fb2 = interp_at(tf, nfr, af, h, (double)h * (ii + 2));
+      const double phcornext = PI_D * (fb2 - fb1) / p.fstep / 2.0;  // :717-718
+      const double phend = TWO_PI * cum_cycles(Lf, sr, h - 1) + (tr[ii] + phcor) + TWO_PI * fb1 / sr;   // :726
+      double mm = fmod(tr[ii + 1] + phcornext - phend + PI_D, TWO_PI);   // np.mod :727
+      if (mm < 0.0) mm += TWO_PI;
+      dphc = (mm - PI_D) * INV_2PI / (double)h;                     // :728-729, per sample, cycles
+    }
+    const double qk = (double)Lf.qk;
+    it.A0 = th0;
+    it.B0 = (Lf.c0 - 0.5 * Lf.s0) / sr + dphc;
+    it.C0 = 0.5 * Lf.s0 / sr;
+    it.A1 = th0 + (Lf.c0 * qk + Lf.s0 * (qk * (qk - 1.0)) * 0.5) / sr
+                - (Lf.c1 * qk + Lf.s1 * (qk * (qk - 1.0)) * 0.5) / sr;
+    it.B1 = (Lf.c1 - 0.5 * Lf.s1) / sr + dphc;
+    it.C1 = 0.5 * Lf.s1 / sr;
+    it.qk = Lf.qk;
+    const Lin2 Lm = interp_block(tm, nfr, ii, am, h);
+    it.m0c = (float)Lm.c0; it.m0s = (float)Lm.s0;
+    it.m1c = (float)Lm.c1; it.m1s = (float)Lm.s1;
+    it.qkm = Lm.qk;
+    it.qa = 0; it.qb = h;
+    it.eoff = 0; it.einv = 0.f;
+  } else if (type == IT_HEAD) {
+    // head sample qh = q + off, off = (b - s)*h + E; valid 0 <= qh < E   (:740-745)
+    const int64_t off = (b - (int64_t)s) * h + E;
+    const double fc = tf[0] / sr;
+    const int qa = (int)(off < 0 ? -off : 0);
+    int64_t qb = (int64_t)E - off;
+    if (qb > h) qb = h;
+    if (qb <= qa) return;
+    it.A0 = tr[0] * INV_2PI - fc * (double)((int64_t)E - off);
+    it.B0 = fc; it.C0 = 0.0;
+    it.A1 = it.A0; it.B1 = fc; it.C1 = 0.0;
+    it.qk = h;
+    const float m0 = (float)interp_at(tm, nfr, am, h, 0.0);         // msig[0] :742
+    it.m0c = m0; it.m0s = 0.f; it.m1c = m0; it.m1s = 0.f; it.qkm = h;
+    it.qa = qa; it.qb = (int)qb;
+    it.eoff = (int)off; it.einv = (float)(1.0 / (double)E);
+  } else {
+    // tail sample qt = q + off, off = (b - s - nfr)*h; valid 0 <= qt < E   (:748-751)
+    const int64_t off = (b - (int64_t)s - nfr) * h;
+    const int il = nfr - 1;
+    int64_t qb = (int64_t)E - off;
+    if (qb > h) qb = h;
+    if (qb <= 0) return;
+    const Lin2 Lf = interp_block(tf, nfr, il, af, h);
+    const double fb0 = interp_at(tf, nfr, af, h, (double)h * il);
+    const double fb1 = interp_at(tf, nfr, af, h, (double)h * (il + 1));
+    const double phcor = PI_D * (fb1 - fb0) / p.fstep / 2.0;
+    const double thl = (tr[il] + phcor) * INV_2PI + cum_cycles(Lf, sr, h - 1);   // ph[-1] :750
+    const double fc = tf[il] / sr;
+    it.A0 = thl + fc * (double)(off + 1);
+    it.B0 = fc; it.C0 = 0.0;
+    it.A1 = it.A0; it.B1 = fc; it.C1 = 0.0;
+    it.qk = h;
+    const float m0 = (float)interp_at(tm, nfr, am, h, (double)h * nfr);   // msig[hop*nfr] :748
+    it.m0c = m0; it.m0s = 0.f; it.m1c = m0; it.m1s = 0.f; it.qkm = h;
+    it.qa = 0; it.qb = (int)qb;
+    it.eoff = (int)off; it.einv = (float)(1.0 / (double)E);
+  }
+  it.type = type;
+  it.pad = 0;
+}
+
 __global__ void __launch_bounds__(256) resynth_kernel(RParams p) {
   PVK_SMEM(smem);
-  Items it;
-  it.carve(smem, p.K);
-  const int tid = threadIdx.x, BD = blockDim.x;
+  Item *items = reinterpret_cast<Item *>(smem);
+  int *wsum = reinterpret_cast<int *>(smem + (size_t)p.K * sizeof(Item));   // 2 x 8 warp sums
+  const int tid = threadIdx.x, BD = blockDim.x, NWARP = BD >> 5;
+  const int lane = tid & 31, warp = tid >> 5;
   const int64_t b = p.block0 + blockIdx.x;
-  const int h = p.h, K = p.K, E = p.E;
-  const double sr = p.sr;
+  const int h = p.h, K = p.K;
   const int64_t nbase = b * (int64_t)h;
+  int round = 0;
 
   for (int q0 = 0; q0 < h; q0 += R_S * BD) {
-    double tot[R_S];
+    double tot[R_S], qd[R_S];
 #pragma unroll
-    for (int m = 0; m < R_S; ++m) tot[m] = 0.0;
+    for (int m = 0; m < R_S; ++m) { tot[m] = 0.0; qd[m] = (double)(q0 + tid + m * BD); }
 
     for (int64_t r = b - p.dE; r <= b + p.dE; ++r) {
       if (r < 0 || r >= p.F) continue;                       // uniform
-      // ---- stage the items of row r (one thread per slot)
-      for (int c = tid; c < K; c += BD) {
-        int type = IT_NONE;
-        const int v = p.tid[r * K + c];
-        if (v >= 0) {
-          const int nfr = p.tlen[v];
-          const int s = p.tstart[v];
-          const int ii = (int)(r - s);
-          if (nfr >= p.minframes) {                          // :1061
-            if (r == b) type = IT_BODY;
-            else if (r > b && ii == 0) type = IT_HEAD;
-            else if (r < b && ii == nfr - 1) type = IT_TAIL;
-          }
-          if (type != IT_NONE) {
-            const int64_t o = p.toff[v];
-            const double *tf = p.pf + o, *tm = p.pmag + o, *tr = p.prealph + o;
-            const double af = p.dfr + 0.5, am = p.dfr;       // knot offsets of :701 / :702
-            if (type == IT_BODY) {
-              const Lin2 Lf = interp_block(tf, nfr, ii, af, h);
-              const double fb0 = interp_at(tf, nfr, af, h, (double)h * ii);
-              const double fb1 = interp_at(tf, nfr, af, h, (double)h * (ii + 1));
-              const double phcor = PI_D * (fb1 - fb0) / p.fstep / 2.0;          // :715
-              const double th0 = (tr[ii] + phcor) * INV_2PI;                    // :721
-              double dphc = 0.0;
-              if (ii < nfr - 1) {
-                const double fb2 = interp_at(tf, nfr, af, h, (double)h * (ii + 2));
-                const double phcornext = PI_D * (fb2 - fb1) / p.fstep / 2.0;    // :717-718
-                const double phend = TWO_PI * cum_cycles(Lf, sr, h - 1) + (tr[ii] + phcor) + TWO_PI * fb1 / sr;   // :726
-                double mm = fmod(tr[ii + 1] + phcornext - phend + PI_D, TWO_PI);   // np.mod :727
-                if (mm < 0.0) mm += TWO_PI;
-                dphc = (mm - PI_D) * INV_2PI / (double)h;                       // :728-729, per sample, cycles
-              }
-              const double qk = (double)Lf.qk;
-              it.A0[c] = th0;
-              it.B0[c] = (Lf.c0 - 0.5 * Lf.s0) / sr + dphc;
-              it.C0[c] = 0.5 * Lf.s0 / sr;
-              it.A1[c] = th0 + (Lf.c0 * qk + Lf.s0 * (qk * (qk - 1.0)) * 0.5) / sr
-                             - (Lf.c1 * qk + Lf.s1 * (qk * (qk - 1.0)) * 0.5) / sr;
-              it.B1[c] = (Lf.c1 - 0.5 * Lf.s1) / sr + dphc;
-              it.C1[c] = 0.5 * Lf.s1 / sr;
-              it.qk[c] = Lf.qk;
-              const Lin2 Lm = interp_block(tm, nfr, ii, am, h);
-              it.m0c[c] = (float)Lm.c0; it.m0s[c] = (float)Lm.s0;
-              it.m1c[c] = (float)Lm.c1; it.m1s[c] = (float)Lm.s1;
-              it.qkm[c] = Lm.qk;
-              it.qa[c] = 0; it.qb[c] = h;
-              it.eoff[c] = 0; it.einv[c] = 0.f;
-            } else if (type == IT_HEAD) {
-              // head sample qh = q + off, off = (b - s)*h + E; valid 0 <= qh < E   (:740-745)
-              const int64_t off = (b - (int64_t)s) * h + E;
-              const double fc = tf[0] / sr;
-              int qa = (int)(off < 0 ? -off : 0);
-              int64_t qb = (int64_t)E - off;
-              if (qb > h) qb = h;
-              if (qb <= qa) type = IT_NONE;
-              it.A0[c] = tr[0] * INV_2PI - fc * (double)((int64_t)E - off);
-              it.B0[c] = fc; it.C0[c] = 0.0;
-              it.A1[c] = it.A0[c]; it.B1[c] = fc; it.C1[c] = 0.0;
-              it.qk[c] = h;
-              const float m0 = (float)interp_at(tm, nfr, am, h, 0.0);           // msig[0] :742
-              it.m0c[c] = m0; it.m0s[c] = 0.f; it.m1c[c] = m0; it.m1s[c] = 0.f; it.qkm[c] = h;
-              it.qa[c] = qa; it.qb[c] = (int)qb;
-              it.eoff[c] = (int)off; it.einv[c] = (float)(1.0 / (double)E);
-            } else {
-              // tail sample qt = q + off, off = (b - s - nfr)*h; valid 0 <= qt < E   (:748-751)
-              const int64_t off = (b - (int64_t)s - nfr) * h;
-              const int il = nfr - 1;
-              const Lin2 Lf = interp_block(tf, nfr, il, af, h);
-              const double fb0 = interp_at(tf, nfr, af, h, (double)h * il);
-              const double fb1 = interp_at(tf, nfr, af, h, (double)h * (il + 1));
-              const double phcor = PI_D * (fb1 - fb0) / p.fstep / 2.0;
-              const double thl = (tr[il] + phcor) * INV_2PI + cum_cycles(Lf, sr, h - 1);   // ph[-1] :750
-              const double fc = tf[il] / sr;
-              int qa = 0;
-              int64_t qb = (int64_t)E - off;
-              if (qb > h) qb = h;
-              if (qb <= qa) type = IT_NONE;
-              it.A0[c] = thl + fc * (double)(off + 1);
-              it.B0[c] = fc; it.C0[c] = 0.0;
-              it.A1[c] = it.A0[c]; it.B1[c] = fc; it.C1[c] = 0.0;
-              it.qk[c] = h;
-              const float m0 = (float)interp_at(tm, nfr, am, h, (double)h * nfr);   // msig[hop*nfr] :748
-              it.m0c[c] = m0; it.m0s[c] = 0.f; it.m1c[c] = m0; it.m1s[c] = 0.f; it.qkm[c] = h;
-              it.qa[c] = qa; it.qb[c] = (int)qb;
-              it.eoff[c] = (int)off; it.einv[c] = (float)(1.0 / (double)E);
-            }
-          }
-        }
-        it.type[c] = type;
+      // ---- stage the segments of row r, compacted in slot order (deterministic sum order)
+      int nit = 0;
+      for (int c0 = 0; c0 < K; c0 += BD, ++round) {
+        const int c = c0 + tid;
+        Item it;
+        it.type = IT_NONE;
+        if (c < K) make_item(p, b, r, c, it);
+        const bool on = it.type != IT_NONE;
+        const unsigned mk = __ballot_sync(FULL, on);
+        int *ws = wsum + (round & 1) * 8;
+        if (lane == 0) ws[warp] = __popc(mk);
+        __syncthreads();
+        int wb = 0, tt = 0;
+        for (int w = 0; w < NWARP; ++w) { const int x = ws[w]; wb += (w < warp) ? x : 0; tt += x; }
+        if (on) items[nit + wb + __popc(mk & lanemask_lt())] = it;
+        nit += tt;
       }
+      if (nit == 0) continue;                                // uniform: nothing of this row sounds here
       __syncthreads();
-      // ---- render: every thread adds all items of this row to its samples
+      // ---- render: every thread adds all segments of this row to its samples
       float acc[R_S];
 #pragma unroll
       for (int m = 0; m < R_S; ++m) acc[m] = 0.f;
-      for (int c = 0; c < K; ++c) {
-        const int type = it.type[c];
-        if (type == IT_NONE) continue;                       // uniform (shared-memory broadcast)
-        const double A0 = it.A0[c], B0 = it.B0[c], C0 = it.C0[c];
-        const double A1 = it.A1[c], B1 = it.B1[c], C1 = it.C1[c];
-        const float m0c = it.m0c[c], m0s = it.m0s[c], m1c = it.m1c[c], m1s = it.m1s[c];
-        const int qk = it.qk[c], qkm = it.qkm[c], qa = it.qa[c], qb = it.qb[c];
-        const int eoff = it.eoff[c];
-        const float einv = it.einv[c];
+      for (int c = 0; c < nit; ++c) {
+        const double2 *pd = reinterpret_cast<const double2 *>(&items[c]);
+        const double2 d0 = pd[0], d1 = pd[1], d2 = pd[2];    // A0 B0 | C0 A1 | B1 C1
+        const float4 mf = *reinterpret_cast<const float4 *>(&items[c].m0c);
+        const int4 qi = *reinterpret_cast<const int4 *>(&items[c].qk);
+        const int4 ei = *reinterpret_cast<const int4 *>(&items[c].eoff);
+        const int type = ei.z;
+        const float einv = __int_as_float(ei.y);
 #pragma unroll
         for (int m = 0; m < R_S; ++m) {
           const int q = q0 + tid + m * BD;
-          if (q >= qa && q < qb) {
-            const double qd = (double)q;
-            const bool s1 = q >= qk;
-            const double th = fma(fma(s1 ? C1 : C0, qd, s1 ? B1 : B0), qd, s1 ? A1 : A0);
+          if (q >= qi.z && q < qi.w) {
+            const bool s1 = q >= qi.x;
+            const double th = fma(fma(s1 ? d2.y : d1.x, qd[m], s1 ? d2.x : d0.y), qd[m], s1 ? d1.y : d0.x);
             const float fr = (float)(th - rint(th));         // exact range reduction, [-0.5, 0.5]
             const float cs = __cosf(6.283185307179586f * fr);
             const float qf = (float)q;
-            float am = (q >= qkm) ? fmaf(m1s, qf, m1c) : fmaf(m0s, qf, m0c);
+            float am = (q >= qi.y) ? fmaf(mf.w, qf, mf.z) : fmaf(mf.y, qf, mf.x);
             if (type != IT_BODY) {
-              const float ce = __cosf(3.14159265358979f * (float)(q + eoff) * einv);
+              const float ce = __cosf(3.14159265358979f * (float)(q + ei.x) * einv);
               am *= (type == IT_HEAD) ? 0.5f * (1.f - ce) : 0.5f * (1.f + ce);
             }
             acc[m] = fmaf(am, cs, acc[m]);
@@ -287,7 +301,7 @@ extern "C" int pvk_resynth(const int32_t *tid, int64_t nframes, int npks, const 
   int bd = ((hop + R_S - 1) / R_S + 31) / 32 * 32;
   if (bd > 256) bd = 256;
   if (bd < 32) bd = 32;
-  const int smem = Items::bytes(npks);
+  const int smem = npks * (int)sizeof(Item) + 64;
   if (smem > 48 * 1024) {
     if (PVK_SET_SMEM(resynth_kernel, smem) != 0) {
       set_error("pvk_resynth: cannot reserve %d bytes of shared memory", smem);

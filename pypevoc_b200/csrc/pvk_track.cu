@@ -247,18 +247,21 @@ __global__ void pack_count_kernel(const int32_t *__restrict__ tid, int64_t F, in
   }
 }
 
-// single-CTA exclusive scan int32 -> int64 (ntracks + 1 outputs)
+// single-CTA exclusive scan int32 -> int64 (ntracks + 1 outputs), 8 elements per thread per tile
 __global__ void pack_scan_kernel(const int32_t *__restrict__ tlen, int64_t n, int64_t *__restrict__ toff) {
   PVK_SMEM(smem);
   long long *wsum = reinterpret_cast<long long *>(smem);
   long long &carry_s = wsum[32];
+  constexpr int E = 8;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NWARP = blockDim.x >> 5;
   if (tid == 0) carry_s = 0;
   __syncthreads();
-  for (int64_t s = 0; s < n; s += blockDim.x) {
-    const int64_t i = s + tid;
-    const long long v = i < n ? tlen[i] : 0;
-    long long inc = v;
+  for (int64_t s = 0; s < n; s += (int64_t)blockDim.x * E) {
+    const int64_t i0 = s + (int64_t)tid * E;
+    long long v[E], loc = 0;
+#pragma unroll
+    for (int j = 0; j < E; ++j) { v[j] = (i0 + j < n) ? tlen[i0 + j] : 0; loc += v[j]; }
+    long long inc = loc;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const long long t = __shfl_up_sync(FULL, inc, o);
@@ -269,7 +272,9 @@ __global__ void pack_scan_kernel(const int32_t *__restrict__ tlen, int64_t n, in
     long long woff = 0, tot = 0;
     for (int w = 0; w < NWARP; ++w) { const long long x = wsum[w]; woff += (w < warp) ? x : 0; tot += x; }
     const long long carry = carry_s;
-    if (i < n) toff[i] = carry + woff + inc - v;
+    long long run = carry + woff + inc - loc;
+#pragma unroll
+    for (int j = 0; j < E; ++j) { if (i0 + j < n) toff[i0 + j] = run; run += v[j]; }
     __syncthreads();
     if (tid == 0) carry_s = carry + tot;
     __syncthreads();

@@ -30,9 +30,10 @@
 struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 struct uint3 { unsigned x, y, z; };
 struct float2 { float x, y; };
-struct double2 { double x, y; };
+struct __attribute__((aligned(16))) double2 { double x, y; };
 struct int2 { int x, y; };
-struct float4 { float x, y, z, w; };
+struct __attribute__((aligned(16))) float4 { float x, y, z, w; };
+struct __attribute__((aligned(16))) int4 { int x, y, z, w; };
 static inline float2 make_float2(float a, float b) { float2 r; r.x = a; r.y = b; return r; }
 static inline double2 make_double2(double a, double b) { double2 r; r.x = a; r.y = b; return r; }
 static inline int2 make_int2(int a, int b) { int2 r; r.x = a; r.y = b; return r; }
