@@ -185,6 +185,12 @@ __device__ __forceinline__ void make_item(const RParams &p, int64_t b, int64_t r
   it.pad = 0;
 }
 
+// Thread t renders the R_S consecutive samples q = qs .. qs+R_S-1 of the block.  Fast path (a
+// partial body whose phase / amplitude knots do not fall inside the thread's samples, i.e.
+// practically always): the phase polynomial is evaluated once in fp64 at qs, reduced to
+// [-0.5, 0.5] cycles, and advanced over the R_S samples as an fp32 quadratic in radians
+// (|increment| < 4 cycles, so fp32 keeps ~3e-7 cycles); one MUFU cosine per partial-sample.
+// Slow path (fade-in / fade-out segments, knots inside the chunk): fp64 per sample.
 __global__ void __launch_bounds__(256) resynth_kernel(RParams p) {
   PVK_SMEM(smem);
   Item *items = reinterpret_cast<Item *>(smem);
@@ -194,12 +200,15 @@ __global__ void __launch_bounds__(256) resynth_kernel(RParams p) {
   const int64_t b = p.block0 + blockIdx.x;
   const int h = p.h, K = p.K;
   const int64_t nbase = b * (int64_t)h;
+  const float TWO_PI_F = 6.283185307179586f;
   int round = 0;
 
   for (int q0 = 0; q0 < h; q0 += R_S * BD) {
-    double tot[R_S], qd[R_S];
+    const int qs = q0 + tid * R_S;
+    const double qsd = (double)qs;
+    double tot[R_S];
 #pragma unroll
-    for (int m = 0; m < R_S; ++m) { tot[m] = 0.0; qd[m] = (double)(q0 + tid + m * BD); }
+    for (int m = 0; m < R_S; ++m) tot[m] = 0.0;
 
     for (int64_t r = b - p.dE; r <= b + p.dE; ++r) {
       if (r < 0 || r >= p.F) continue;                       // uniform
@@ -230,25 +239,46 @@ __global__ void __launch_bounds__(256) resynth_kernel(RParams p) {
         const double2 *pd = reinterpret_cast<const double2 *>(&items[c]);
         const double2 d0 = pd[0], d1 = pd[1], d2 = pd[2];    // A0 B0 | C0 A1 | B1 C1
         const float4 mf = *reinterpret_cast<const float4 *>(&items[c].m0c);
-        const int4 qi = *reinterpret_cast<const int4 *>(&items[c].qk);
-        const int4 ei = *reinterpret_cast<const int4 *>(&items[c].eoff);
+        const int4 qi = *reinterpret_cast<const int4 *>(&items[c].qk);      // qk qkm qa qb
+        const int4 ei = *reinterpret_cast<const int4 *>(&items[c].eoff);    // eoff einv type pad
         const int type = ei.z;
-        const float einv = __int_as_float(ei.y);
+        const bool fast = (type == IT_BODY) && (qs + R_S <= h) &&
+                          (qs + R_S <= qi.x || qs >= qi.x) && (qs + R_S <= qi.y || qs >= qi.y);
+        if (fast) {
+          const bool s1 = qs >= qi.x;
+          const double A = s1 ? d1.y : d0.x, B = s1 ? d2.x : d0.y, C = s1 ? d2.y : d1.x;
+          double th = fma(fma(C, qsd, B), qsd, A);           // cycles at the first sample
+          th -= rint(th);
+          const double bq = fma(2.0 * C, qsd, B);            // d theta / dq at qs (cycles per sample)
+          const float t0 = TWO_PI_F * (float)th, t1 = TWO_PI_F * (float)bq, t2 = TWO_PI_F * (float)C;
+          const bool a1 = qs >= qi.y;
+          const float as = a1 ? mf.w : mf.y;
+          const float a0 = fmaf(as, (float)qs, a1 ? mf.z : mf.x);
 #pragma unroll
-        for (int m = 0; m < R_S; ++m) {
-          const int q = q0 + tid + m * BD;
-          if (q >= qi.z && q < qi.w) {
-            const bool s1 = q >= qi.x;
-            const double th = fma(fma(s1 ? d2.y : d1.x, qd[m], s1 ? d2.x : d0.y), qd[m], s1 ? d1.y : d0.x);
-            const float fr = (float)(th - rint(th));         // exact range reduction, [-0.5, 0.5]
-            const float cs = __cosf(6.283185307179586f * fr);
-            const float qf = (float)q;
-            float am = (q >= qi.y) ? fmaf(mf.w, qf, mf.z) : fmaf(mf.y, qf, mf.x);
-            if (type != IT_BODY) {
-              const float ce = __cosf(3.14159265358979f * (float)(q + ei.x) * einv);
-              am *= (type == IT_HEAD) ? 0.5f * (1.f - ce) : 0.5f * (1.f + ce);
+          for (int m = 0; m < R_S; ++m) {
+            const float fm = (float)m;
+            const float cs = __cosf(fmaf(fmaf(t2, fm, t1), fm, t0));
+            acc[m] = fmaf(fmaf(as, fm, a0), cs, acc[m]);
+          }
+        } else {
+          const float einv = __int_as_float(ei.y);
+#pragma unroll
+          for (int m = 0; m < R_S; ++m) {
+            const int q = qs + m;
+            if (q >= qi.z && q < qi.w) {
+              const double qd = (double)q;
+              const bool s1 = q >= qi.x;
+              const double th = fma(fma(s1 ? d2.y : d1.x, qd, s1 ? d2.x : d0.y), qd, s1 ? d1.y : d0.x);
+              const float fr = (float)(th - rint(th));       // exact range reduction, [-0.5, 0.5]
+              const float cs = __cosf(TWO_PI_F * fr);
+              const float qf = (float)q;
+              float am = (q >= qi.y) ? fmaf(mf.w, qf, mf.z) : fmaf(mf.y, qf, mf.x);
+              if (type != IT_BODY) {
+                const float ce = __cosf(3.14159265358979f * (float)(q + ei.x) * einv);
+                am *= (type == IT_HEAD) ? 0.5f * (1.f - ce) : 0.5f * (1.f + ce);
+              }
+              acc[m] = fmaf(am, cs, acc[m]);
             }
-            acc[m] = fmaf(am, cs, acc[m]);
           }
         }
       }
@@ -258,7 +288,7 @@ __global__ void __launch_bounds__(256) resynth_kernel(RParams p) {
     }
 #pragma unroll
     for (int m = 0; m < R_S; ++m) {
-      const int q = q0 + tid + m * BD;
+      const int q = qs + m;
       const int64_t n = nbase + q;
       if (q < h && n < p.nout) p.out[n - p.block0 * (int64_t)h] = tot[m];
     }
