@@ -42,9 +42,18 @@ struct AParams {
   float2 *spec_out;
 };
 
+// tuning knobs (compile time): PVK_TSHIFT = log2 of extra threads per frame for nfft >= 1024,
+// PVK_TWREG = 1 keeps the inter-pass twiddles of a thread in registers across the frame loop
+#ifndef PVK_TSHIFT
+#define PVK_TSHIFT 0
+#endif
+#ifndef PVK_TWREG
+#define PVK_TWREG 0
+#endif
+
 template <int LOGM> struct Plan {
   static constexpr int M = 1 << LOGM;
-  static constexpr int LOGT = LOGM <= 8 ? 5 : (LOGM <= 10 ? 6 : LOGM - 4);
+  static constexpr int LOGT = LOGM <= 8 ? 5 : (LOGM <= 9 ? 6 : (LOGM <= 10 ? 6 : LOGM - 4) + PVK_TSHIFT);
   static constexpr int T = 1 << LOGT;
   static constexpr int LP0 = LOGM - LOGT;
   static constexpr int LP = LP0 < 2 ? 2 : (LP0 > 4 ? 4 : LP0);
@@ -57,6 +66,16 @@ template <int LOGM> struct Plan {
     return o;
   }
   static constexpr int TW_TOTAL = tw_off(NPASS);
+  // register-resident twiddles: NB_q * (R_q - 1) per pass q >= 1
+  __host__ __device__ static constexpr int twr_off(int q) {
+    int o = 0;
+    for (int i = 1; i < q; ++i) {
+      const int nbf = M >> lr(i);
+      o += ((nbf + T - 1) / T) * ((1 << lr(i)) - 1);
+    }
+    return o;
+  }
+  static constexpr int TWR_TOTAL = twr_off(NPASS) > 0 ? twr_off(NPASS) : 1;
   static constexpr int MP = M + (M >> 4) + 1;
   static constexpr int MW = M >= 32 ? M / 32 : 1;
   static constexpr int NW = T / 32;
@@ -109,24 +128,45 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 w) {
 // ------------------------------------------------------------------ FFT passes
 template <int LOGM, int Q> struct Pass {
   using P = Plan<LOGM>;
-  static __device__ __forceinline__ void run(const float2 *__restrict__ twp, float2 *buf) {
-    constexpr int M = P::M, T = P::T;
-    constexpr int LR = P::lr(Q), R = 1 << LR, LPQ = P::lp(Q), PP = 1 << LPQ;
-    constexpr int NBF = M >> LR, NB = (NBF + T - 1) / T;
-    constexpr int OFF = P::tw_off(Q);
+  static constexpr int M = P::M, T = P::T;
+  static constexpr int LR = P::lr(Q), R = 1 << LR, LPQ = P::lp(Q), PP = 1 << LPQ;
+  static constexpr int NBF = M >> LR, NB = (NBF + T - 1) / T;
+  static constexpr int OFF = P::tw_off(Q), OFFR = P::twr_off(Q);
+
+  // twiddles of this thread for pass Q and all later passes -> treg
+  static __device__ __forceinline__ void load_tw(const float2 *__restrict__ twp, float2 *treg) {
     const int tid = threadIdx.x;
-    float2 u[NB][R];
-    float2 tw[NB][R - 1];
-    // twiddles first: their (L1-resident) loads overlap the shared-memory reads and the barrier
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
       const int i = tid + b * T;
       if (NBF >= T || i < NBF) {
         const int k = i & (PP - 1);
 #pragma unroll
-        for (int r = 1; r < R; ++r) tw[b][r - 1] = __ldg(twp + OFF + (r - 1) * PP + k);
+        for (int r = 1; r < R; ++r) treg[OFFR + b * (R - 1) + r - 1] = __ldg(twp + OFF + (r - 1) * PP + k);
       }
     }
+    if constexpr (Q + 1 < P::NPASS) Pass<LOGM, Q + 1>::load_tw(twp, treg);
+  }
+
+  static __device__ __forceinline__ void run(const float2 *__restrict__ twp, const float2 *treg, float2 *buf) {
+    const int tid = threadIdx.x;
+    float2 u[NB][R];
+#if !PVK_TWREG
+    // twiddles first: their loads overlap the shared-memory reads and the barrier
+    float2 tloc[NB * (R - 1) > 0 ? NB * (R - 1) : 1];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const int i = tid + b * T;
+      if (NBF >= T || i < NBF) {
+        const int k = i & (PP - 1);
+#pragma unroll
+        for (int r = 1; r < R; ++r) tloc[b * (R - 1) + r - 1] = __ldg(twp + OFF + (r - 1) * PP + k);
+      }
+    }
+    const float2 *tw = tloc;
+#else
+    const float2 *tw = treg + OFFR;
+#endif
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
       const int i = tid + b * T;
@@ -143,14 +183,14 @@ template <int LOGM, int Q> struct Pass {
         const int k = i & (PP - 1);
         const int j = ((i - k) << LR) + k;
 #pragma unroll
-        for (int r = 1; r < R; ++r) u[b][r] = cmul(u[b][r], tw[b][r - 1]);
+        for (int r = 1; r < R; ++r) u[b][r] = cmul(u[b][r], tw[b * (R - 1) + r - 1]);
         dft_dif<LR>(u[b]);
 #pragma unroll
         for (int s = 0; s < R; ++s) buf[PADC(j + s * PP)] = u[b][brev<LR>(s)];
       }
     }
     __syncthreads();
-    if constexpr (Q + 1 < P::NPASS) Pass<LOGM, Q + 1>::run(twp, buf);
+    if constexpr (Q + 1 < P::NPASS) Pass<LOGM, Q + 1>::run(twp, treg, buf);
   }
 };
 
@@ -158,7 +198,7 @@ template <int LOGM, int Q> struct Pass {
 template <int LOGM>
 __device__ __forceinline__ void fft_frame(const float *__restrict__ xf, bool al8,
                                           const float *__restrict__ win,
-                                          const float2 *__restrict__ twp, float2 *buf) {
+                                          const float2 *__restrict__ twp, const float2 *treg, float2 *buf) {
   using P = Plan<LOGM>;
   constexpr int M = P::M, T = P::T;
   constexpr int LR = P::lr(0), R = 1 << LR;
@@ -184,7 +224,7 @@ __device__ __forceinline__ void fft_frame(const float *__restrict__ xf, bool al8
     }
   }
   __syncthreads();
-  if constexpr (P::NPASS > 1) Pass<LOGM, 1>::run(twp, buf);
+  if constexpr (P::NPASS > 1) Pass<LOGM, 1>::run(twp, treg, buf);
 }
 
 // ------------------------------------------------------------------ per-peak epilogue
@@ -325,6 +365,11 @@ __global__ void __launch_bounds__(Plan<LOGM>::T) analyze_kernel(AParams prm) {
   const float2 *twr = prm.tables + P::TW_TOTAL;
   const int K = prm.npks;
 
+  float2 treg[P::TWR_TOTAL];
+#if PVK_TWREG
+  if constexpr (P::NPASS > 1) Pass<LOGM, 1>::load_tw(twp, treg);
+#endif
+
   // ---- previous spectrum of the first row of this run
   {
     float2 *pb = bufs[(r0 & 1) ^ 1];
@@ -335,7 +380,7 @@ __global__ void __launch_bounds__(Plan<LOGM>::T) analyze_kernel(AParams prm) {
       const int64_t s0 = (prm.frame0 + r0 - 1) * (int64_t)prm.hop;
       const float *xf = xc + s0;
       const bool al8 = ((reinterpret_cast<uintptr_t>(xf) & 7) == 0);
-      fft_frame<LOGM>(xf, al8, prm.win, twp, pb);
+      fft_frame<LOGM>(xf, al8, prm.win, twp, treg, pb);
       // untangle only (no magnitudes needed)
       for (int k = tid; k < M / 2; k += T) {
         if (k == 0) {
@@ -361,7 +406,7 @@ __global__ void __launch_bounds__(Plan<LOGM>::T) analyze_kernel(AParams prm) {
     const int64_t row = clip * prm.nframes + r;
     const float *xf = xc + (prm.frame0 + r) * (int64_t)prm.hop;
     const bool al8 = ((reinterpret_cast<uintptr_t>(xf) & 7) == 0);
-    fft_frame<LOGM>(xf, al8, prm.win, twp, cur);
+    fft_frame<LOGM>(xf, al8, prm.win, twp, treg, cur);
 
     // ---- untangle -> fx[0..M), |fx|, min / max / sum of squares
     float lmin = 3.402823466e+38f, lmax = 0.f, lsum = 0.f;

@@ -22,6 +22,110 @@ constexpr int LINK_NONE = -1;    // slot is not a point
 constexpr int TRACK_CHUNK = 128; // frames per chain-resolution chunk
 
 // ------------------------------------------------------------------ link
+// Shared by both link kernels: load the two peak rows of one frame pair into the warp's shared
+// memory (invalid slots get magnitude -1), order the current peaks by descending magnitude
+// (ord) and rank the previous ones (prank).  Returns nc; chi / phi = 1 + highest valid column.
+__device__ __forceinline__ int link_prepare(const double *__restrict__ f, const double *__restrict__ mag,
+                                            int64_t row, bool has_prev, int K, int32_t *__restrict__ link,
+                                            double *cf, double *cm, double *pf, double *pm, short *ord,
+                                            short *prank, int &chi_out, int &phi_out) {
+  const int lane = threadIdx.x & 31;
+  int chi = 0, phi = 0;
+  for (int i = lane; i < K; i += 32) {
+    const double a = f[row * K + i], b = mag[row * K + i];
+    const bool v = a > 0.0 && b > 0.0;                        // :876
+    cf[i] = a; cm[i] = v ? b : -1.0;
+    if (v) chi = i + 1; else link[row * K + i] = LINK_NONE;
+    if (has_prev) {
+      const double c = f[(row - 1) * K + i], d = mag[(row - 1) * K + i];
+      const bool vp = c > 0.0 && d > 0.0;
+      pf[i] = c; pm[i] = vp ? d : -1.0;
+      if (vp) phi = i + 1;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    chi = max(chi, __shfl_xor_sync(FULL, chi, o));
+    phi = max(phi, __shfl_xor_sync(FULL, phi, o));
+  }
+  __syncwarp();
+  // order of the current peaks: magnitude descending (:874-875)
+  int nc = 0;
+  for (int i0 = 0; i0 < chi; i0 += 32) {
+    const int i = i0 + lane;
+    const double mi = i < chi ? cm[i] : -1.0;
+    const bool vi = mi > 0.0;
+    if (vi) {
+      int r = 0;
+      for (int i2 = 0; i2 < chi; ++i2) {
+        const double m2 = cm[i2];
+        r += (m2 > mi || (m2 == mi && i2 > i)) ? 1 : 0;
+      }
+      ord[r] = (short)i;
+    }
+    nc += __popc(__ballot_sync(FULL, vi));
+  }
+  // rank of the previous peaks in descending magnitude (:891-900)
+  for (int i = lane; i < phi; i += 32) {
+    const double mi = pm[i];
+    int r = 0;
+    if (mi > 0.0) {
+      for (int i2 = 0; i2 < phi; ++i2) {
+        const double m2 = pm[i2];
+        r += (m2 > mi || (m2 == mi && i2 < i)) ? 1 : 0;
+      }
+    }
+    prank[i] = (short)r;
+  }
+  __syncwarp();
+  chi_out = chi; phi_out = phi;
+  return nc;
+}
+
+// abs(17.312*(fc/pf - 1.0)): dpitch2st :62-68 as called at :914
+__device__ __forceinline__ double stonediff(double fc, double pfv) {
+  return fabs(__dmul_rn(17.312, __dsub_rn(__ddiv_rn(fc, pfv), 1.0)));
+}
+
+// The reference's loop, one current peak at a time (:903-950); the whole warp scans the previous
+// row for the nearest unused peak.  Works for any K <= 1024.  Returns the number of new partials.
+__device__ __forceinline__ int link_greedy_generic(const double *cf, const double *pf, const double *pm,
+                                                   const short *ord, const short *prank, int nc, int phi,
+                                                   double maxjump, int32_t *__restrict__ link_row) {
+  const int lane = threadIdx.x & 31;
+  unsigned usedmask = 0;
+  int nnew = 0;
+  for (int t = 0; t < nc; ++t) {
+    const int c = ord[t];
+    const double fc = cf[c];
+    double bd = 1e300;
+    int br = 0x7fffffff, bp = -1;
+    for (int p = lane, q = 0; p < phi; p += 32, ++q) {
+      if (pm[p] > 0.0 && !((usedmask >> q) & 1u)) {
+        const double d = stonediff(fc, pf[p]);
+        const int r = prank[p];
+        if (d < bd || (d == bd && r < br)) { bd = d; br = r; bp = p; }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      const double od = __shfl_xor_sync(FULL, bd, o);
+      const int orr = __shfl_xor_sync(FULL, br, o), op = __shfl_xor_sync(FULL, bp, o);
+      if (od < bd || (od == bd && orr < br)) { bd = od; br = orr; bp = op; }
+    }
+    int lk;
+    if (bp >= 0 && bd < maxjump) {                              // :923
+      lk = bp;
+      if ((bp & 31) == lane) usedmask |= 1u << (bp >> 5);
+    } else {
+      lk = -2 - nnew;                                           // add_empty_partial :941
+      ++nnew;
+    }
+    if (lane == 0) link_row[c] = lk;
+  }
+  return nnew;
+}
+
 __global__ void track_link_kernel(const double *__restrict__ f, const double *__restrict__ mag,
                                   int64_t nrows, int64_t F, int K, double maxjump,
                                   int32_t *__restrict__ link, int32_t *__restrict__ newcount) {
@@ -35,94 +139,145 @@ __global__ void track_link_kernel(const double *__restrict__ f, const double *__
   double *pm = pf + K;
   short *ord = reinterpret_cast<short *>(pm + K);
   short *prank = ord + K;
+  for (int64_t row = (int64_t)blockIdx.x * W + warp; row < nrows; row += (int64_t)gridDim.x * W) {
+    int chi, phi;
+    const int nc = link_prepare(f, mag, row, (row % F) > 0, K, link, cf, cm, pf, pm, ord, prank, chi, phi);
+    const int nnew = link_greedy_generic(cf, pf, pm, ord, prank, nc, phi, maxjump, link + row * K);
+    if (lane == 0) newcount[row] = nnew;
+    __syncwarp();
+  }
+}
+
+// Fast link for K <= 32*S (S = slots per lane).  Same result as the generic loop, different
+// schedule: every lane owns the current peaks t = lane + 32*s (t = position in the descending
+// magnitude order), collects the few previous peaks within maxpitchjmp of it (cheap fp64
+// pre-test, exact distance only for survivors), then all peaks propose their nearest unused
+// candidate at once.  A proposal is final when no peak earlier in the order proposed the same
+// previous peak AND every earlier peak is final too, i.e. the longest conflict-free prefix of
+// the order is committed per round (an earlier peak can never be affected by a later one, and
+// removing somebody else's target from the unused set does not change one's own arg-min).
+constexpr int LINK_NC = 8;   // candidates kept per current peak; overflow -> generic loop for that row
+
+template <int S>
+__global__ void track_link_fast_kernel(const double *__restrict__ f, const double *__restrict__ mag,
+                                       int64_t nrows, int64_t F, int K, double maxjump,
+                                       int32_t *__restrict__ link, int32_t *__restrict__ newcount) {
+  PVK_SMEM(smem);
+  constexpr int KM = 32 * S;
+  const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int PER_WARP = KM * 4 * 8 + KM * LINK_NC * 8 + KM * 4 + KM * 2 * 2 + KM * LINK_NC * 2 * 2 + 16;
+  unsigned char *base = smem + (size_t)warp * PER_WARP;
+  double *cf = reinterpret_cast<double *>(base);
+  double *cm = cf + KM;
+  double *pf = cm + KM;
+  double *pm = pf + KM;
+  double *cand_d = pm + KM;                                       // [LINK_NC][S][32]
+  int *winner = reinterpret_cast<int *>(cand_d + KM * LINK_NC);   // [KM]
+  unsigned *usedw = reinterpret_cast<unsigned *>(winner + KM);    // [4]
+  short *ord = reinterpret_cast<short *>(usedw + 4);
+  short *prank = ord + KM;
+  short *cand_p = prank + KM;                                     // [LINK_NC][S][32]
+  short *cand_r = cand_p + KM * LINK_NC;
+  const double eps2 = maxjump / 17.312 * (1.0 + 1e-6);
 
   for (int64_t row = (int64_t)blockIdx.x * W + warp; row < nrows; row += (int64_t)gridDim.x * W) {
-    const int64_t j = row % F;
-    const bool has_prev = j > 0;
-    int chi = 0, phi = 0;   // 1 + highest valid column of current / previous row
-    for (int i = lane; i < K; i += 32) {
-      const double a = f[row * K + i], b = mag[row * K + i];
-      cf[i] = a; cm[i] = b;
-      const bool v = a > 0.0 && b > 0.0;                        // :876
-      if (v) chi = i + 1; else link[row * K + i] = LINK_NONE;
-      if (has_prev) {
-        const double c = f[(row - 1) * K + i], d = mag[(row - 1) * K + i];
-        pf[i] = c; pm[i] = d;
-        if (c > 0.0 && d > 0.0) phi = i + 1;
-      }
-    }
+    int chi, phi;
+    const int nc = link_prepare(f, mag, row, (row % F) > 0, K, link, cf, cm, pf, pm, ord, prank, chi, phi);
+    int32_t *lrow = link + row * K;
+    // ---- candidate lists
+    int ncand[S], cidx[S];
+    bool overflow = false;
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-      chi = max(chi, __shfl_xor_sync(FULL, chi, o));
-      phi = max(phi, __shfl_xor_sync(FULL, phi, o));
-    }
-    __syncwarp();
-    // order of the current peaks: magnitude descending (:874-875)
-    int nc = 0;
-    for (int i0 = 0; i0 < chi; i0 += 32) {
-      const int i = i0 + lane;
-      const double mi = i < chi ? cm[i] : 0.0;
-      const bool vi = i < chi && cf[i] > 0.0 && mi > 0.0;
-      int r = 0;
-      if (vi) {
-        for (int i2 = 0; i2 < chi; ++i2) {
-          const double m2 = cm[i2];
-          const bool v2 = cf[i2] > 0.0 && m2 > 0.0;
-          r += (v2 && (m2 > mi || (m2 == mi && i2 > i))) ? 1 : 0;
-        }
-        ord[r] = (short)i;
-      }
-      nc += __popc(__ballot_sync(FULL, vi));
-    }
-    // rank of the previous peaks in descending magnitude (:891-900)
-    for (int i0 = 0; i0 < phi; i0 += 32) {
-      const int i = i0 + lane;
-      if (i < phi) {
-        const double mi = pm[i];
-        int r = 0;
-        if (pf[i] > 0.0 && mi > 0.0) {
-          for (int i2 = 0; i2 < phi; ++i2) {
-            const double m2 = pm[i2];
-            const bool v2 = pf[i2] > 0.0 && m2 > 0.0;
-            r += (v2 && (m2 > mi || (m2 == mi && i2 < i))) ? 1 : 0;
+    for (int s = 0; s < S; ++s) {
+      const int t = lane + 32 * s;
+      ncand[s] = 0; cidx[s] = 0;
+      if (t < nc) {
+        const int c = ord[t];
+        cidx[s] = c;
+        const double fc = cf[c];
+        for (int p = 0; p < phi; ++p) {
+          const double pfv = pf[p];
+          if (pm[p] > 0.0 && fabs(fc - pfv) < eps2 * pfv) {
+            const double d = stonediff(fc, pfv);
+            if (d < maxjump) {                                    // :923: only these can ever match
+              if (ncand[s] < LINK_NC) {
+                const int o = (ncand[s] * S + s) * 32 + lane;
+                cand_p[o] = (short)p; cand_d[o] = d; cand_r[o] = prank[p];
+              }
+              ++ncand[s];
+            }
           }
         }
-        prank[i] = (short)r;
+        overflow = overflow || ncand[s] > LINK_NC;
       }
     }
+    if (__any_sync(FULL, overflow)) {                             // rare: keep exactness via the generic loop
+      const int nnew = link_greedy_generic(cf, pf, pm, ord, prank, nc, phi, maxjump, lrow);
+      if (lane == 0) newcount[row] = nnew;
+      __syncwarp();
+      continue;
+    }
+    // ---- propose / commit rounds
+    if (lane < 4) usedw[lane] = 0u;
+    int res[S];                                                   // -3 unresolved, -2 new, >= 0 matched column
+#pragma unroll
+    for (int s = 0; s < S; ++s) res[s] = (lane + 32 * s < nc) ? -3 : -4;
     __syncwarp();
-    // greedy nearest-frequency match (:903-950)
-    unsigned usedmask = 0;
-    int nnew = 0;
-    for (int t = 0; t < nc; ++t) {
-      const int c = ord[t];
-      const double fc = cf[c];
-      double bd = 1e300;
-      int br = 0x7fffffff, bp = -1;
-      for (int p = lane, q = 0; p < phi; p += 32, ++q) {
-        const double pfv = pf[p];
-        if (pfv > 0.0 && pm[p] > 0.0 && !((usedmask >> q) & 1u)) {
-          // abs(17.312*(fc/pf - 1.0)): dpitch2st :62-68 as called at :914
-          const double d = fabs(__dmul_rn(17.312, __dsub_rn(__ddiv_rn(fc, pfv), 1.0)));
-          const int r = prank[p];
-          if (d < bd || (d == bd && r < br)) { bd = d; br = r; bp = p; }
+    for (;;) {
+      for (int p = lane; p < phi; p += 32) winner[p] = 0x7fffffff;
+      __syncwarp();
+      int prop[S];
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        prop[s] = -1;
+        if (res[s] == -3) {
+          double bd = 1e300;
+          int br = 0x7fffffff;
+          for (int n = 0; n < ncand[s]; ++n) {
+            const int o = (n * S + s) * 32 + lane;
+            const int p = cand_p[o];
+            if (!((usedw[p >> 5] >> (p & 31)) & 1u)) {
+              const double d = cand_d[o];
+              const int r = cand_r[o];
+              if (d < bd || (d == bd && r < br)) { bd = d; br = r; prop[s] = p; }
+            }
+          }
+          if (prop[s] >= 0) atomicMin(&winner[prop[s]], lane + 32 * s);
         }
       }
+      __syncwarp();
+      // first loser in the order
+      int L = nc;
 #pragma unroll
-      for (int o = 16; o >= 1; o >>= 1) {
-        const double od = __shfl_xor_sync(FULL, bd, o);
-        const int orr = __shfl_xor_sync(FULL, br, o), op = __shfl_xor_sync(FULL, bp, o);
-        if (od < bd || (od == bd && orr < br)) { bd = od; br = orr; bp = op; }
+      for (int s = S - 1; s >= 0; --s) {
+        const bool lose = res[s] == -3 && prop[s] >= 0 && winner[prop[s]] != lane + 32 * s;
+        const unsigned m = __ballot_sync(FULL, lose);
+        if (m) L = 32 * s + __ffs((int)m) - 1;
       }
-      int lk;
-      if (bp >= 0 && bd < maxjump) {                            // :923
-        lk = bp;
-        if ((bp & 31) == lane) usedmask |= 1u << (bp >> 5);
-      } else {
-        lk = -2 - nnew;                                         // add_empty_partial :941
-        ++nnew;
+      bool pending = false;
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        if (res[s] == -3) {
+          if (lane + 32 * s < L) {
+            res[s] = prop[s] >= 0 ? prop[s] : -2;
+            if (prop[s] >= 0) atomicOr(&usedw[prop[s] >> 5], 1u << (prop[s] & 31));
+          } else {
+            pending = true;
+          }
+        }
       }
-      if (lane == 0) link[row * K + c] = lk;
+      __syncwarp();
+      if (!__any_sync(FULL, pending)) break;
+    }
+    // ---- new partials are numbered in processing order (:941)
+    int nnew = 0;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const bool isnew = res[s] == -2;
+      const unsigned m = __ballot_sync(FULL, isnew);
+      if (res[s] >= 0) lrow[cidx[s]] = res[s];
+      else if (isnew) lrow[cidx[s]] = -2 - (nnew + __popc(m & lanemask_lt()));
+      nnew += __popc(m);
     }
     if (lane == 0) newcount[row] = nnew;
     __syncwarp();
@@ -135,22 +290,27 @@ __global__ void track_scan_kernel(const int32_t *__restrict__ newcount, int32_t 
   PVK_SMEM(smem);
   int *wsum = reinterpret_cast<int *>(smem);
   int &carry_s = wsum[32];
+  constexpr int E = 8;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NWARP = blockDim.x >> 5;
   const int64_t clip = blockIdx.x;
   const int32_t *in = newcount + clip * F;
   int32_t *out = base + clip * F;
   if (tid == 0) carry_s = 0;
   __syncthreads();
-  for (int64_t s = 0; s < F; s += blockDim.x) {
-    const int64_t i = s + tid;
-    const int v = i < F ? in[i] : 0;
-    const int inc = warp_scan_incl(v);
+  for (int64_t s = 0; s < F; s += (int64_t)blockDim.x * E) {
+    const int64_t i0 = s + (int64_t)tid * E;
+    int v[E], loc = 0;
+#pragma unroll
+    for (int j = 0; j < E; ++j) { v[j] = (i0 + j < F) ? in[i0 + j] : 0; loc += v[j]; }
+    const int inc = warp_scan_incl(loc);
     if (lane == 31) wsum[warp] = inc;
     __syncthreads();
     int woff = 0, tot = 0;
     for (int w = 0; w < NWARP; ++w) { const int x = wsum[w]; woff += (w < warp) ? x : 0; tot += x; }
     const int carry = carry_s;
-    if (i < F) out[i] = carry + woff + inc - v;
+    int run = carry + woff + inc - loc;
+#pragma unroll
+    for (int j = 0; j < E; ++j) { if (i0 + j < F) out[i0 + j] = run; run += v[j]; }
     __syncthreads();
     if (tid == 0) carry_s = carry + tot;
     __syncthreads();
@@ -235,15 +395,29 @@ __global__ void track_fix_kernel(int32_t *__restrict__ tid, const int32_t *__res
 }
 
 // ------------------------------------------------------------------ pack
+// Every thread walks one column over a strip of PACK_STRIP consecutive frames and merges runs of
+// equal ids (a partial usually stays in its column for a while) before touching the per-track
+// counters: ~PACK_STRIP x fewer atomics than one per point.
+constexpr int PACK_STRIP = 64;
 __global__ void pack_count_kernel(const int32_t *__restrict__ tid, int64_t F, int K,
                                   int32_t *__restrict__ tstart, int32_t *__restrict__ tlen) {
-  const int64_t n = F * K;
+  const int64_t nstrips = (F + PACK_STRIP - 1) / PACK_STRIP;
+  const int64_t n = nstrips * K;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
-    const int v = tid[e];
-    if (v >= 0) {
-      atomicAdd(&tlen[v], 1);
-      atomicMin(&tstart[v], (int32_t)(e / K));
+    const int c = (int)(e % K);
+    const int64_t j0 = (e / K) * PACK_STRIP;
+    const int64_t j1 = j0 + PACK_STRIP < F ? j0 + PACK_STRIP : F;
+    int cur = -1, cnt = 0;
+    int64_t first = 0;
+    for (int64_t j = j0; j < j1; ++j) {
+      const int v = tid[j * K + c];
+      if (v != cur) {
+        if (cur >= 0) { atomicAdd(&tlen[cur], cnt); atomicMin(&tstart[cur], (int32_t)first); }
+        cur = v; cnt = 0; first = j;
+      }
+      ++cnt;
     }
+    if (cur >= 0) { atomicAdd(&tlen[cur], cnt); atomicMin(&tstart[cur], (int32_t)first); }
   }
 }
 
@@ -343,21 +517,45 @@ extern "C" int pvk_track(const double *f, const double *mag, int64_t nclips, int
   int32_t *G = reinterpret_cast<int32_t *>(ws + 2 * align_up(rows * 4, 256));
 
   {  // link: one warp per frame pair
-    const int per_warp = (K * (4 * 8 + 2 * 2) + 15) / 16 * 16;
-    int W = 160 * 1024 / per_warp;
-    if (W > 8) W = 8;
-    if (W < 1) W = 1;
-    const int smem = W * per_warp;
-    if (smem > 48 * 1024) {
-      if (PVK_SET_SMEM(track_link_kernel, smem) != 0) {
-        set_error("pvk_track: cannot reserve %d bytes of shared memory", smem);
-        return PVK_ERR_CUDA;
+    int64_t g;
+    if (K <= 128) {
+      const int S = K <= 32 ? 1 : (K <= 64 ? 2 : 4);
+      const int KM = 32 * S;
+      const int per_warp = KM * 4 * 8 + KM * LINK_NC * 8 + KM * 4 + KM * 2 * 2 + KM * LINK_NC * 2 * 2 + 16;
+      const int W = S == 4 ? 4 : 8;
+      const int smem = W * per_warp;
+      g = (rows + W - 1) / W;
+      if (g > 148 * 64) g = 148 * 64;
+#define PVK_LINK_FAST(SS)                                                                          \
+      do {                                                                                           \
+        if (smem > 48 * 1024 && PVK_SET_SMEM(track_link_fast_kernel<SS>, smem) != 0) {              \
+          set_error("pvk_track: cannot reserve %d bytes of shared memory", smem);                    \
+          return PVK_ERR_CUDA;                                                                       \
+        }                                                                                            \
+        PVK_LAUNCH(track_link_fast_kernel<SS>, dim3((unsigned)g), dim3(W * 32), smem, stream, f, mag, rows, \
+                   nframes, K, maxpitchjmp, link, newcount);                                         \
+      } while (0)
+      if (S == 1) PVK_LINK_FAST(1);
+      else if (S == 2) PVK_LINK_FAST(2);
+      else PVK_LINK_FAST(4);
+#undef PVK_LINK_FAST
+    } else {
+      const int per_warp = (K * (4 * 8 + 2 * 2) + 15) / 16 * 16;
+      int W = 160 * 1024 / per_warp;
+      if (W > 8) W = 8;
+      if (W < 1) W = 1;
+      const int smem = W * per_warp;
+      if (smem > 48 * 1024) {
+        if (PVK_SET_SMEM(track_link_kernel, smem) != 0) {
+          set_error("pvk_track: cannot reserve %d bytes of shared memory", smem);
+          return PVK_ERR_CUDA;
+        }
       }
+      g = (rows + W - 1) / W;
+      if (g > 148 * 64) g = 148 * 64;
+      PVK_LAUNCH(track_link_kernel, dim3((unsigned)g), dim3(W * 32), smem, stream, f, mag, rows, nframes, K,
+                 maxpitchjmp, link, newcount);
     }
-    int64_t g = (rows + W - 1) / W;
-    if (g > 148 * 64) g = 148 * 64;
-    PVK_LAUNCH(track_link_kernel, dim3((unsigned)g), dim3(W * 32), smem, stream, f, mag, rows, nframes, K,
-               maxpitchjmp, link, newcount);
     PVK_CHECK_LAUNCH("pvk_track(link)");
   }
   PVK_LAUNCH(track_scan_kernel, dim3((unsigned)nclips), dim3(1024), 33 * 4, stream, newcount, base, ntracks, nframes);
@@ -394,7 +592,8 @@ extern "C" int pvk_track_pack(const double *f, const double *mag, const double *
   const int64_t n = nframes * npks;
   cudaMemsetAsync(tlen, 0, 4 * (size_t)ntracks, (cudaStream_t)stream);
   cudaMemsetAsync(tstart, 0x7f, 4 * (size_t)ntracks, (cudaStream_t)stream);   // 0x7f7f7f7f: "no frame yet"
-  PVK_LAUNCH(pack_count_kernel, dim3(grid_for(n, 256)), dim3(256), 0, stream, tid, nframes, npks, tstart, tlen);
+  PVK_LAUNCH(pack_count_kernel, dim3(grid_for((nframes + PACK_STRIP - 1) / PACK_STRIP * npks, 128)), dim3(128), 0,
+             stream, tid, nframes, npks, tstart, tlen);
   PVK_CHECK_LAUNCH("pvk_track_pack(count)");
   PVK_LAUNCH(pack_scan_kernel, dim3(1), dim3(1024), 33 * 8, stream, tlen, ntracks, toff);
   PVK_CHECK_LAUNCH("pvk_track_pack(scan)");

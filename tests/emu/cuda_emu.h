@@ -163,6 +163,7 @@ static inline float atomicAdd(float *p, float v) { float o = *p; *p = o + v; ret
 static inline double atomicAdd(double *p, double v) { double o = *p; *p = o + v; return o; }
 template <class T> static inline T atomicMax(T *p, T v) { T o = *p; while (o < v && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {} return o; }
 template <class T> static inline T atomicMin(T *p, T v) { T o = *p; while (o > v && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {} return o; }
+template <class T> static inline T atomicOr(T *p, T v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 template <class T> static inline T atomicExch(T *p, T v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
 template <class T> static inline T atomicCAS(T *p, T c, T v) { __atomic_compare_exchange_n(p, &c, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED); return c; }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
