@@ -39,7 +39,6 @@ CFG = dict(sr=44100, seconds=600, nfft=2048, hop=512, npks=50, pkthresh=0.005,
 METRIC = "STFT frames/sec (nfft=2048,hop=512,npks=50) + resynth partial-samples/sec"
 WORKLOAD = ("10 min mono 44.1 kHz synthetic harmonic tone+noise (configs[1] length; 220 Hz, 90 harmonics, "
             "sigma 0.01), metric parameters nfft=2048 hop=512 npks=50, analysis + tracking + full resynthesis")
-MY_LAUNCHES_PER_STEP = 11   # analyze 1, track 6 (link scan chunk boundary stitch fix), pack 3, resynth 1
 
 
 def peaks():
@@ -166,11 +165,14 @@ def gpu_main(args):
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
+    from pypevoc_b200 import _lib
+    launches0 = int(_lib.lib().pvk_launch_count())
     timed = []
     for _ in range(args.steps):
         flush.fill_(1)                                   # L2 flush between timed iterations
         step(timed)
     barrier()
+    launches = int(_lib.lib().pvk_launch_count()) - launches0     # libpvk kernels launched by the timed steps
     clocks = sampler.stop()
     st = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(4)] for e in timed])   # ms per stage
     ms_step_local = float(st.sum(axis=1).mean())
@@ -261,7 +263,7 @@ def gpu_main(args):
                    "analysis_frames_per_s": frames_total / (ms_an * 1e-3),
                    "resynth_partial_samples_per_s": psamp_total / (ms_syn * 1e-3)},
         "roofline": dominant, "roofline_analysis": roof_an, "roofline_resynth": roof_syn,
-        "clocks": clocks, "gpu_launches": MY_LAUNCHES_PER_STEP * args.steps,
+        "clocks": clocks, "gpu_launches": launches,
     }
     if e2e is not None:
         line["e2e"] = e2e

@@ -41,6 +41,9 @@ int pvk_version(void);
 /* Thread-local text of the last error on this thread ("" if none). */
 const char *pvk_last_error(void);
 
+/* Number of kernels this library has launched in this process so far (diagnostics / benchmarks). */
+int64_t pvk_launch_count(void);
+
 /* ------------------------------------------------------------------ analysis
  * Replaces PV.run_pv / PV.calc_pv_frame / PV.calc_fft_frame / PV.dphase2freq
  * (PVAnalysis.py:133-264) and the PeakFinder calls they make (PeakFinder.py:35-74,
@@ -118,7 +121,7 @@ int pvk_track_pack(const double *f, const double *mag, const double *ph, const d
  * phase_preserve=True path, for ONE clip.
  *
  *   tid [nframes, npks]                  track id per frame slot (pvk_track)
- *   tstart/tlen/toff, pf/pmag/prealph    the packed partials (pvk_track_pack); partials
+ *   ntracks, tstart/tlen/toff, pf/pmag/prealph   the packed partials (pvk_track_pack); partials
  *                                        shorter than minframes are skipped (:1061)
  *   sr, hop      synthesis sample rate and hop (hop may differ from the analysis hop)
  *   nfft, hop_an analysis parameters the SinSum was built with (:824-825,1055)
@@ -128,11 +131,19 @@ int pvk_track_pack(const double *f, const double *mag, const double *ph, const d
  *                (multi-GPU: each rank renders a disjoint block range); nblocks < 0 = all
  *   out          float64; out[0] is sample block0*hop; every sample of the rendered block
  *                range below nout is written (zeros where no partial sounds)
+ *   workspace    scratch: start / end slot masks and fade parameters of the rendered
+ *                partials plus the staged per-block coefficients of one chunk of blocks.
+ *                pvk_resynth_workspace_bytes() gives the recommended size (chunks of up to
+ *                32768 blocks); any size that holds the fixed part and one block works,
+ *                smaller workspaces only mean more, smaller launches.
  */
-int pvk_resynth(const int32_t *tid, int64_t nframes, int npks, const int32_t *tstart,
-                const int32_t *tlen, const int64_t *toff, const double *pf, const double *pmag,
-                const double *prealph, double sr, int hop, int nfft, int hop_an, double edge,
-                int minframes, double *out, int64_t nout, int64_t block0, int64_t nblocks,
+int64_t pvk_resynth_workspace_bytes(int64_t nframes, int npks, int64_t ntracks, int64_t nblocks);
+
+int pvk_resynth(const int32_t *tid, int64_t nframes, int npks, int64_t ntracks,
+                const int32_t *tstart, const int32_t *tlen, const int64_t *toff, const double *pf,
+                const double *pmag, const double *prealph, double sr, int hop, int nfft,
+                int hop_an, double edge, int minframes, double *out, int64_t nout,
+                int64_t block0, int64_t nblocks, void *workspace, int64_t workspace_bytes,
                 void *stream);
 
 #ifdef __cplusplus

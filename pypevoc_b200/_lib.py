@@ -19,6 +19,7 @@ _d = C.c_double
 SIGNATURES = {
     "pvk_version": (_i, []),
     "pvk_last_error": (C.c_char_p, []),
+    "pvk_launch_count": (_i64, []),
     "pvk_analyze_tables_bytes": (_i64, [_i]),
     "pvk_analyze_init": (_i, [_i, _p, _p]),
     "pvk_analyze": (_i, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _i, _i, _i, _d, _d, _d, _i64, _i64,
@@ -26,8 +27,9 @@ SIGNATURES = {
     "pvk_track_workspace_bytes": (_i64, [_i64, _i64, _i]),
     "pvk_track": (_i, [_p, _p, _i64, _i64, _i, _d, _p, _p, _p, _p, _i64, _p]),
     "pvk_track_pack": (_i, [_p, _p, _p, _p, _p, _i64, _i, _i64, _p, _p, _p, _p, _p, _p, _p, _p]),
-    "pvk_resynth": (_i, [_p, _i64, _i, _p, _p, _p, _p, _p, _p, _d, _i, _i, _i, _d, _i, _p, _i64, _i64,
-                         _i64, _p]),
+    "pvk_resynth_workspace_bytes": (_i64, [_i64, _i, _i64, _i64]),
+    "pvk_resynth": (_i, [_p, _i64, _i, _i64, _p, _p, _p, _p, _p, _p, _d, _i, _i, _i, _d, _i, _p, _i64, _i64,
+                         _i64, _p, _i64, _p]),
 }
 
 

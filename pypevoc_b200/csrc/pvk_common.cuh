@@ -16,19 +16,24 @@
 namespace pvk {
 
 void set_error(const char *fmt, ...);
+void count_launch();
 
 #ifdef PVK_EMU
 #define PVK_SMEM(name) unsigned char *name = emu_smem()
 #define PVK_LAUNCH(kernel, grid, block, smem, stream, ...)                                 \
   do {                                                                                     \
     auto _body = [=]() { kernel(__VA_ARGS__); };                                           \
+    pvk::count_launch();                                                                   \
     emu::launch(_body, grid, block, smem);                                                 \
   } while (0)
 #define PVK_SET_SMEM(kernel, bytes) (0)
 #else
 #define PVK_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #define PVK_LAUNCH(kernel, grid, block, smem, stream, ...)                                 \
-  kernel<<<grid, block, smem, (cudaStream_t)(stream)>>>(__VA_ARGS__)
+  do {                                                                                     \
+    pvk::count_launch();                                                                   \
+    kernel<<<grid, block, smem, (cudaStream_t)(stream)>>>(__VA_ARGS__);                    \
+  } while (0)
 #define PVK_SET_SMEM(kernel, bytes)                                                        \
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))
 #endif

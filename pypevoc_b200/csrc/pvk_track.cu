@@ -363,21 +363,29 @@ __global__ void track_boundary_kernel(const int32_t *__restrict__ link, const in
   }
 }
 
-// sequential over the chunks of one clip; G becomes the final ids of every chunk's first row
-__global__ void track_stitch_kernel(int32_t *__restrict__ G, int K, int64_t nchunks) {
+// sequential over the chunks of one clip; G becomes the final ids of every chunk's first row.
+// The table is streamed through shared memory in tiles of `tile` chunks (coalesced loads and
+// stores by the whole CTA); inside a tile the pass runs out of shared memory, one barrier per
+// chunk: an unresolved entry -2-c takes the (already final) id of column c of the chunk before.
+__global__ void __launch_bounds__(1024) track_stitch_kernel(int32_t *__restrict__ G, int K, int64_t nchunks, int tile) {
   PVK_SMEM(smem);
-  int *fprev = reinterpret_cast<int *>(smem);
+  int *gs = reinterpret_cast<int *>(smem);          // [tile + 1][K]; row 0 = last chunk of the previous tile
   const int64_t clip = blockIdx.x;
   int32_t *g = G + clip * nchunks * K;
-  const int c = threadIdx.x;
-  const bool act = c < K;
-  int v_next = act && nchunks > 0 ? g[c] : -1;
-  for (int64_t ch = 0; ch < nchunks; ++ch) {
-    int v = v_next;
-    if (ch + 1 < nchunks && act) v_next = g[(ch + 1) * K + c];
-    if (v <= -2) v = fprev[-2 - v];
+  const int t = threadIdx.x, BD = blockDim.x;
+  for (int64_t c0 = 0; c0 < nchunks; c0 += tile) {
+    const int n = (int)((c0 + tile <= nchunks) ? tile : nchunks - c0);
+    for (int i = t; i < n * K; i += BD) gs[K + i] = g[c0 * K + i];
     __syncthreads();
-    if (act) { fprev[c] = v; g[ch * K + c] = v; }
+    for (int ch = (c0 == 0 ? 1 : 0); ch < n; ++ch) {   // chunk 0 of the clip has no predecessor
+      if (t < K) {
+        const int v = gs[(ch + 1) * K + t];
+        if (v <= -2) gs[(ch + 1) * K + t] = gs[ch * K + (-2 - v)];
+      }
+      __syncthreads();
+    }
+    for (int i = t; i < n * K; i += BD) g[c0 * K + i] = gs[K + i];
+    if (t < K) gs[t] = gs[n * K + t];
     __syncthreads();
   }
 }
@@ -568,7 +576,16 @@ extern "C" int pvk_track(const double *f, const double *mag, int64_t nclips, int
     PVK_LAUNCH(track_boundary_kernel, dim3(grid_for(nclips * nchunks * K, 256)), dim3(256), 0, stream, link, tid,
                nframes, K, nchunks, nclips, G);
     PVK_CHECK_LAUNCH("pvk_track(boundary)");
-    PVK_LAUNCH(track_stitch_kernel, dim3((unsigned)nclips), dim3(cb), (size_t)K * 4, stream, G, K, nchunks);
+    int tile = (96 * 1024) / (K * 4) - 1;                       // <= 96 KB of shared memory
+    if (tile > nchunks) tile = (int)nchunks;
+    if (tile < 1) tile = 1;
+    const int sb = cb > 256 ? cb : 256;
+    const size_t ssm = (size_t)(tile + 1) * K * 4;
+    if (ssm > 48 * 1024 && PVK_SET_SMEM(track_stitch_kernel, (int)ssm) != 0) {
+      set_error("pvk_track: cannot reserve %d bytes of shared memory", (int)ssm);
+      return PVK_ERR_CUDA;
+    }
+    PVK_LAUNCH(track_stitch_kernel, dim3((unsigned)nclips), dim3(sb), ssm, stream, G, K, nchunks, tile);
     PVK_CHECK_LAUNCH("pvk_track(stitch)");
     PVK_LAUNCH(track_fix_kernel, dim3(grid_for(rows * K, 256)), dim3(256), 0, stream, tid, G, nframes, K, nchunks,
                nclips);

@@ -199,11 +199,14 @@ def resynth_device(tid, pk, sr, hop, nfft, hop_an, edge=1.0, minframes=3, max_en
     nb = nblk - block0 if nblocks < 0 else nblocks
     if out is None:
         out = torch.empty((max(min(nb * hop, nout - block0 * hop), 0),), dtype=torch.float64, device=dev)
+    nt = int(pk["tstart"].shape[0])
+    wsb = int(L.pvk_resynth_workspace_bytes(F, K, nt, max(nb, 0)))
+    ws = torch.empty(max(wsb, 8), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(L.pvk_resynth(_ptr(tid), F, K, _ptr(pk["tstart"]), _ptr(pk["tlen"]), _ptr(pk["toff"]),
-                                 _ptr(pk["pf"]), _ptr(pk["pmag"]), _ptr(pk["prealph"]), float(sr), int(hop),
-                                 int(nfft), int(hop_an), float(edge), int(minframes), _ptr(out), int(nout),
-                                 int(block0), int(nblocks), _stream()), "pvk_resynth")
+        _lib.check(L.pvk_resynth(_ptr(tid), F, K, nt, _ptr(pk["tstart"]), _ptr(pk["tlen"]),
+                                 _ptr(pk["toff"]), _ptr(pk["pf"]), _ptr(pk["pmag"]), _ptr(pk["prealph"]), float(sr),
+                                 int(hop), int(nfft), int(hop_an), float(edge), int(minframes), _ptr(out), int(nout),
+                                 int(block0), int(nblocks), _ptr(ws), wsb, _stream()), "pvk_resynth")
     return out
 
 

@@ -124,7 +124,8 @@ def track_pack(f, mag, ph, realph, tid, link, ntracks):   # link unused (kept fo
                 pmag=packed[1][:npts], pph=packed[2][:npts], prealph=packed[3][:npts])
 
 
-def resynth(tid, pk, sr, hop, nfft, hop_an, edge=1.0, minframes=3, block0=0, nblocks=-1, nout=None):
+def resynth(tid, pk, sr, hop, nfft, hop_an, edge=1.0, minframes=3, block0=0, nblocks=-1, nout=None,
+            ws_blocks=None):
     """pvk_resynth for one clip: tid [F, K], pk = dict from track_pack."""
     L = lib()
     tid = np.ascontiguousarray(tid, dtype=np.int32)
@@ -140,7 +141,11 @@ def resynth(tid, pk, sr, hop, nfft, hop_an, edge=1.0, minframes=3, block0=0, nbl
     out = np.full(min(nb * hop, nout - block0 * hop), np.nan)
     ts = np.ascontiguousarray(pk["tstart"], dtype=np.int32)
     tl = np.ascontiguousarray(pk["tlen"], dtype=np.int32)
-    check(L.pvk_resynth(ptr(tid), F, K, ptr(ts), ptr(tl), ptr(pk["toff"]), ptr(pk["pf"]), ptr(pk["pmag"]),
+    wsb = int(L.pvk_resynth_workspace_bytes(F, K, nt, max(nb, 0)))
+    if ws_blocks is not None:       # force chunked rendering: room for ws_blocks blocks only
+        wsb = int(L.pvk_resynth_workspace_bytes(F, K, nt, 0)) + (ws_blocks - 1) * (K * 80 + 4)
+    ws = np.zeros(max(wsb, 8), dtype=np.uint8)
+    check(L.pvk_resynth(ptr(tid), F, K, nt, ptr(ts), ptr(tl), ptr(pk["toff"]), ptr(pk["pf"]), ptr(pk["pmag"]),
                         ptr(pk["prealph"]), float(sr), int(hop), int(nfft), int(hop_an), float(edge),
-                        int(minframes), ptr(out), nout, block0, nblocks, None))
+                        int(minframes), ptr(out), nout, block0, nblocks, ptr(ws), wsb, None))
     return out

@@ -56,6 +56,11 @@ def test_emu_tracking_and_resynthesis_vs_reference_golden(name):
         ref = g["synth_%d" % h]
         assert w.shape == ref.shape
         assert pu.snr_db(w, ref) > 110.0
+        # a small workspace renders the same signal chunk by chunk; a block sub-range matches too
+        w2 = eh.resynth(tr["tid"][0], pk, sr, h, kw["nfft"], int(g["hop"]), ws_blocks=5)
+        assert np.array_equal(w, w2)
+        w3 = eh.resynth(tr["tid"][0], pk, sr, h, kw["nfft"], int(g["hop"]), block0=3, nblocks=4)
+        assert np.array_equal(w[3 * h:7 * h], w3)
 
 
 def test_emu_degenerate_and_select_paths():
@@ -89,3 +94,23 @@ def test_emu_segment_warmup_and_batch():
         one = eh.analyze(clips[i], 44100, 1024, 256, 20)
         for k in ("f", "binno", "npk"):
             assert np.array_equal(one[k][0], b[k][i])
+
+
+def test_emu_track_stitch_across_tiles():
+    """Long partials crossing many 128-frame chunks and more than one shared-memory tile of the
+    stitch pass (npks = 1024 -> 23 chunks per tile), peaks in random slots."""
+    rng = np.random.RandomState(11)
+    F, K = 128 * 30 + 17, 1024
+    f = np.zeros((F, K)); mag = np.zeros((F, K))
+    base = np.array([440.0, 1000.0, 3000.0])
+    for j in range(F):
+        cols = np.sort(rng.choice(K, 3, replace=False))
+        alive = [True, (j // 500) % 2 == 0, j % 97 != 0]       # partial 1 dies / is reborn, 2 has gaps
+        for q in range(3):
+            if alive[q]:
+                f[j, cols[q]] = base[q] * (1 + 0.001 * np.sin(j / 50.0 + q))
+                mag[j, cols[q]] = 0.5 / (q + 1) + 0.01 * rng.rand()
+    o = orc.track(f, mag)
+    tr = eh.track(f, mag)
+    assert np.array_equal(tr["tid"][0], o["tid"])
+    assert int(tr["ntracks"][0]) == len(o["st"])

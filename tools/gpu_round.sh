@@ -16,5 +16,11 @@ ncu --kernel-name-base demangled -k "regex:pvk::analyze_kernel" --set full --clo
     -f -o $OUT/prof_analyze_$TAG python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu > /dev/null 2>&1
 ncu --kernel-name-base demangled -k "regex:pvk::resynth_kernel" --set full --clock-control none --import-source on -s 2 -c 1 \
     -f -o $OUT/prof_resynth_$TAG python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu > /dev/null 2>&1
+if [ "$3" = "more" ]; then
+ncu --kernel-name-base demangled -k "regex:pvk::track_link" --set full --clock-control none --import-source on -s 2 -c 1 \
+    -f -o $OUT/prof_link_$TAG python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu > /dev/null 2>&1
+ncu --kernel-name-base demangled -k "regex:pvk::resynth_prepare" --set full --clock-control none --import-source on -s 2 -c 1 \
+    -f -o $OUT/prof_prepare_$TAG python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu > /dev/null 2>&1
+fi
 ls -la $OUT
 fi
