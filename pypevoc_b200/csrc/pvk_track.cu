@@ -157,6 +157,10 @@ __global__ void track_link_kernel(const double *__restrict__ f, const double *__
 // the order is committed per round (an earlier peak can never be affected by a later one, and
 // removing somebody else's target from the unused set does not change one's own arg-min).
 constexpr int LINK_NC = 8;   // candidates kept per current peak; overflow -> generic loop for that row
+__host__ __device__ constexpr int link_fast_smem_per_warp(int S) {
+  // cf cm pf pm (double) | cand_d | winner | pf32 | usedw | ord prank | cand_p cand_r
+  return 32 * S * 4 * 8 + 32 * S * LINK_NC * 8 + 32 * S * 4 + 32 * S * 4 + 16 + 32 * S * 2 * 2 + 32 * S * LINK_NC * 2 * 2;
+}
 
 template <int S>
 __global__ void track_link_fast_kernel(const double *__restrict__ f, const double *__restrict__ mag,
@@ -165,7 +169,7 @@ __global__ void track_link_fast_kernel(const double *__restrict__ f, const doubl
   PVK_SMEM(smem);
   constexpr int KM = 32 * S;
   const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int PER_WARP = KM * 4 * 8 + KM * LINK_NC * 8 + KM * 4 + KM * 2 * 2 + KM * LINK_NC * 2 * 2 + 16;
+  constexpr int PER_WARP = link_fast_smem_per_warp(S);
   unsigned char *base = smem + (size_t)warp * PER_WARP;
   double *cf = reinterpret_cast<double *>(base);
   double *cm = cf + KM;
@@ -173,18 +177,24 @@ __global__ void track_link_fast_kernel(const double *__restrict__ f, const doubl
   double *pm = pf + KM;
   double *cand_d = pm + KM;                                       // [LINK_NC][S][32]
   int *winner = reinterpret_cast<int *>(cand_d + KM * LINK_NC);   // [KM]
-  unsigned *usedw = reinterpret_cast<unsigned *>(winner + KM);    // [4]
+  float *pf32 = reinterpret_cast<float *>(winner + KM);           // [KM] previous frequencies, -1 = not a point
+  unsigned *usedw = reinterpret_cast<unsigned *>(pf32 + KM);      // [4]
   short *ord = reinterpret_cast<short *>(usedw + 4);
   short *prank = ord + KM;
   short *cand_p = prank + KM;                                     // [LINK_NC][S][32]
   short *cand_r = cand_p + KM * LINK_NC;
-  const double eps2 = maxjump / 17.312 * (1.0 + 1e-6);
+  // fp32 pre-test window: |fc - fp| < eps32 * fp is implied by |17.312 (fc/fp - 1)| < maxjump
+  // (slack 1e-4 relative + 1e-6 absolute >> fp32 rounding of fc and fp); the exact fp64 test
+  // decides among the survivors
+  const float eps32 = (float)(maxjump / 17.312 * (1.0 + 1e-4) + 1e-6);
 
   for (int64_t row = (int64_t)blockIdx.x * W + warp; row < nrows; row += (int64_t)gridDim.x * W) {
     int chi, phi;
     const int nc = link_prepare(f, mag, row, (row % F) > 0, K, link, cf, cm, pf, pm, ord, prank, chi, phi);
     int32_t *lrow = link + row * K;
-    // ---- candidate lists
+    for (int p = lane; p < phi; p += 32) pf32[p] = pm[p] > 0.0 ? (float)pf[p] : -1.f;
+    __syncwarp();
+    // ---- candidate lists: cheap window scan over the previous row, then exact distances
     int ncand[S], cidx[S];
     bool overflow = false;
 #pragma unroll
@@ -194,21 +204,34 @@ __global__ void track_link_fast_kernel(const double *__restrict__ f, const doubl
       if (t < nc) {
         const int c = ord[t];
         cidx[s] = c;
-        const double fc = cf[c];
+        const float fc32 = (float)cf[c];
+        int n = 0;
         for (int p = 0; p < phi; ++p) {
-          const double pfv = pf[p];
-          if (pm[p] > 0.0 && fabs(fc - pfv) < eps2 * pfv) {
-            const double d = stonediff(fc, pfv);
-            if (d < maxjump) {                                    // :923: only these can ever match
-              if (ncand[s] < LINK_NC) {
-                const int o = (ncand[s] * S + s) * 32 + lane;
-                cand_p[o] = (short)p; cand_d[o] = d; cand_r[o] = prank[p];
-              }
-              ++ncand[s];
-            }
+          const float pv = pf32[p];
+          if (fabsf(fc32 - pv) < eps32 * pv) {
+            if (n < LINK_NC) cand_p[(n * S + s) * 32 + lane] = (short)p;
+            ++n;
           }
         }
-        overflow = overflow || ncand[s] > LINK_NC;
+        ncand[s] = n;
+        overflow = overflow || n > LINK_NC;
+      }
+    }
+    if (!__any_sync(FULL, overflow)) {
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const double fc = cf[cidx[s]];
+        int keep = 0;
+        for (int n = 0; n < ncand[s]; ++n) {
+          const int p = cand_p[(n * S + s) * 32 + lane];
+          const double d = stonediff(fc, pf[p]);
+          if (d < maxjump) {                                      // :923: only these can ever match
+            const int o = (keep * S + s) * 32 + lane;
+            cand_p[o] = (short)p; cand_d[o] = d; cand_r[o] = prank[p];
+            ++keep;
+          }
+        }
+        ncand[s] = keep;
       }
     }
     if (__any_sync(FULL, overflow)) {                             // rare: keep exactness via the generic loop
@@ -528,8 +551,7 @@ extern "C" int pvk_track(const double *f, const double *mag, int64_t nclips, int
     int64_t g;
     if (K <= 128) {
       const int S = K <= 32 ? 1 : (K <= 64 ? 2 : 4);
-      const int KM = 32 * S;
-      const int per_warp = KM * 4 * 8 + KM * LINK_NC * 8 + KM * 4 + KM * 2 * 2 + KM * LINK_NC * 2 * 2 + 16;
+      const int per_warp = link_fast_smem_per_warp(S);
       const int W = S == 4 ? 4 : 8;
       const int smem = W * per_warp;
       g = (rows + W - 1) / W;
