@@ -198,10 +198,11 @@ def gpu_main(args):
             t0 = time.perf_counter()
             if world == 1:
                 pv = PV(xh, sr, nfft=nfft, hop=hop, npks=npks, pkthresh=c["pkthresh"], progress=False, device=dev)
-                pv.run_pv()
+                pv.run_pv(hostbuf=hostbuf)                 # upload, analysis and table download overlap
                 ss = pv.toSinSum()
-                wd = ss.synth(sr, hop, to_host=False)
-                nb = pv.fetch_into(hostbuf, extra={"w": wd})
+                w = ss.synth(sr, hop, hostbuf=hostbuf)     # rendering and signal download overlap
+                assert pv.f.shape == (pv.nframes, npks) and w.dtype == np.float64   # host views (synchronises)
+                nb = pv.d2h_bytes + ss.d2h_bytes
             else:
                 spv = D.ShardedPV(xh, sr, world * nsamp_seg, nfft=nfft, hop=hop, npks=npks, pkthresh=c["pkthresh"],
                                   rank=rank, world=world, device=dev)
@@ -226,9 +227,9 @@ def gpu_main(args):
         e2e = {"value": frames_total / float(tt[0].item()), "unit": "frames/s",
                "h2d_bytes_per_step": int(tt[2].item()), "d2h_bytes_per_step": int(tt[1].item()),
                "ms_per_step": 1e3 * float(tt[0].item()),
-               "note": "PV(pinned host signal).run_pv -> toSinSum -> synth -> fetch_into(pinned): "
-                       "f/mag/ph/realph/binno/totalmag float64 tables + float64 resynthesis; host wall clock, "
-                       "max over ranks"}
+               "note": "PV(pinned host signal).run_pv(hostbuf) -> toSinSum -> synth(hostbuf): f/mag/ph/realph/"
+                       "binno/totalmag float64 tables + float64 resynthesis land in pinned host memory (copies "
+                       "overlap the kernels on side streams); host wall clock, max over ranks"}
 
     if rank != 0:
         if world > 1:

@@ -136,6 +136,9 @@ int pvk_track_pack(const double *f, const double *mag, const double *ph, const d
  *                pvk_resynth_workspace_bytes() gives the recommended size (chunks of up to
  *                32768 blocks); any size that holds the fixed part and one block works,
  *                smaller workspaces only mean more, smaller launches.
+ *   reuse_tracks 1: the workspace still holds the masks and fade parameters written by an
+ *                earlier call with the same partials, hop, nfft, hop_an, edge and minframes
+ *                (rendering one signal in several block ranges); 0: compute them
  */
 int64_t pvk_resynth_workspace_bytes(int64_t nframes, int npks, int64_t ntracks, int64_t nblocks);
 
@@ -144,7 +147,7 @@ int pvk_resynth(const int32_t *tid, int64_t nframes, int npks, int64_t ntracks,
                 const double *pmag, const double *prealph, double sr, int hop, int nfft,
                 int hop_an, double edge, int minframes, double *out, int64_t nout,
                 int64_t block0, int64_t nblocks, void *workspace, int64_t workspace_bytes,
-                void *stream);
+                int reuse_tracks, void *stream);
 
 #ifdef __cplusplus
 }

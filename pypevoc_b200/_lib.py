@@ -29,7 +29,7 @@ SIGNATURES = {
     "pvk_track_pack": (_i, [_p, _p, _p, _p, _p, _i64, _i, _i64, _p, _p, _p, _p, _p, _p, _p, _p]),
     "pvk_resynth_workspace_bytes": (_i64, [_i64, _i, _i64, _i64]),
     "pvk_resynth": (_i, [_p, _i64, _i, _i64, _p, _p, _p, _p, _p, _p, _d, _i, _i, _i, _d, _i, _p, _i64, _i64,
-                         _i64, _p, _i64, _p]),
+                         _i64, _p, _i64, _i, _p]),
 }
 
 

@@ -421,7 +421,7 @@ extern "C" int pvk_resynth(const int32_t *tid, int64_t nframes, int npks, int64_
                            const int32_t *tlen, const int64_t *toff, const double *pf, const double *pmag,
                            const double *prealph, double sr, int hop, int nfft, int hop_an, double edge,
                            int minframes, double *out, int64_t nout, int64_t block0, int64_t nblocks,
-                           void *workspace, int64_t workspace_bytes, void *stream) {
+                           void *workspace, int64_t workspace_bytes, int reuse_tracks, void *stream) {
   PVK_REQUIRE(hop >= 1 && nfft >= 1 && hop_an >= 1, "pvk_resynth: hop=%d nfft=%d hop_an=%d must be >= 1", hop, nfft, hop_an);
   PVK_REQUIRE(npks >= 1 && npks <= PVK_MAX_NPKS, "pvk_resynth: npks=%d must be in [1, %d]", npks, PVK_MAX_NPKS);
   PVK_REQUIRE(sr > 0.0 && edge >= 0.0, "pvk_resynth: sr and edge must be positive");
@@ -473,8 +473,8 @@ extern "C" int pvk_resynth(const int32_t *tid, int64_t nframes, int npks, int64_
   int32_t *gcount = reinterpret_cast<int32_t *>(chunk_ws + align_up(cb * npks * (int64_t)sizeof(BodyItem), 256));
   p.mask = mask; p.tfade = tfade; p.gitems = gitems; p.gcount = gcount;
 
-  if (nframes > 0) cudaMemsetAsync(mask, 0, (size_t)(nframes * 2 * p.mwk * 4), (cudaStream_t)stream);
-  if (ntracks > 0 && nframes > 0) {
+  if (nframes > 0 && !reuse_tracks) cudaMemsetAsync(mask, 0, (size_t)(nframes * 2 * p.mwk * 4), (cudaStream_t)stream);
+  if (ntracks > 0 && nframes > 0 && !reuse_tracks) {
     int64_t gsz = (ntracks * 32 + 255) / 256;
     if (gsz > 148 * 16) gsz = 148 * 16;
     p.chunk0 = 0;

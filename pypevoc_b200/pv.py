@@ -40,6 +40,29 @@ def _device(device=None):
     return torch.device(device)
 
 
+_side = {}
+
+
+def _side_streams(dev):
+    """(host->device, device->host) copy streams of a device, created once."""
+    st = _side.get(dev.index)
+    if st is None:
+        st = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+        _side[dev.index] = st
+    return st
+
+
+def _pinned(hostbuf, key, shape, dtype):
+    """Reusable pinned host tensor ``hostbuf[key]`` of at least ``shape`` (first dimension may be
+    larger: buffers are kept across calls and only grow)."""
+    hb = hostbuf.get(key)
+    if (hb is None or hb.dtype != dtype or hb.dim() != len(shape) or tuple(hb.shape[1:]) != tuple(shape[1:])
+            or hb.shape[0] < shape[0]):
+        hb = torch.empty(shape, dtype=dtype, device="cpu", pin_memory=True)
+        hostbuf[key] = hb
+    return hb
+
+
 class Progress(object):
     """Minimal stand-in for pypevoc.ProgressDisplay.Progress (ProgressDisplay.py:58-117):
     the GPU path finishes in one launch, so only completion is reported."""
@@ -187,8 +210,10 @@ def synth_geometry(max_end, hop, nfft, hop_an, edge=1.0):
 
 
 def resynth_device(tid, pk, sr, hop, nfft, hop_an, edge=1.0, minframes=3, max_end=None, block0=0,
-                   nblocks=-1, out=None):
-    """pvk_resynth for one clip; returns the float64 device signal (asynchronous)."""
+                   nblocks=-1, out=None, ws=None, reuse_tracks=False):
+    """pvk_resynth for one clip; returns the float64 device signal (asynchronous).  ``ws``: a
+    workspace tensor to (re)use; ``reuse_tracks``: ``ws`` already holds the per-partial masks and
+    fade parameters of an earlier call with the same tracks and synthesis parameters."""
     L = _lib.lib()
     dev = tid.device
     F, K = tid.shape
@@ -200,14 +225,20 @@ def resynth_device(tid, pk, sr, hop, nfft, hop_an, edge=1.0, minframes=3, max_en
     if out is None:
         out = torch.empty((max(min(nb * hop, nout - block0 * hop), 0),), dtype=torch.float64, device=dev)
     nt = int(pk["tstart"].shape[0])
-    wsb = int(L.pvk_resynth_workspace_bytes(F, K, nt, max(nb, 0)))
-    ws = torch.empty(max(wsb, 8), dtype=torch.uint8, device=dev)
+    if ws is None:
+        ws = resynth_workspace(F, K, nt, nb, dev)
     with torch.cuda.device(dev):
         _lib.check(L.pvk_resynth(_ptr(tid), F, K, nt, _ptr(pk["tstart"]), _ptr(pk["tlen"]),
                                  _ptr(pk["toff"]), _ptr(pk["pf"]), _ptr(pk["pmag"]), _ptr(pk["prealph"]), float(sr),
                                  int(hop), int(nfft), int(hop_an), float(edge), int(minframes), _ptr(out), int(nout),
-                                 int(block0), int(nblocks), _ptr(ws), wsb, _stream()), "pvk_resynth")
+                                 int(block0), int(nblocks), _ptr(ws), int(ws.numel()), 1 if reuse_tracks else 0,
+                                 _stream()), "pvk_resynth")
     return out
+
+
+def resynth_workspace(F, K, ntracks, nblocks, dev):
+    wsb = int(_lib.lib().pvk_resynth_workspace_bytes(int(F), int(K), int(ntracks), max(int(nblocks), 0)))
+    return torch.empty(max(wsb, 8), dtype=torch.uint8, device=dev)
 
 
 # =========================================================================== PV
@@ -226,11 +257,18 @@ class PV(object):
         on its float32 rounding.  ``device`` selects the GPU (default: current device).
         '''
         self._dev = _device(device if device is not None else (x.device if torch.is_tensor(x) and x.is_cuda else None))
+        self._xh_pinned = None
         if torch.is_tensor(x):
             xd = x.detach()
             if xd.dim() != 1:
                 raise ValueError("PV expects a 1-D signal")
-            self._xd = xd.to(device=self._dev, dtype=torch.float32, non_blocking=True).contiguous()
+            if (not xd.is_cuda) and xd.is_pinned() and xd.dtype == torch.float32 and xd.is_contiguous():
+                # pinned host signal: uploaded by run_pv (in chunks that overlap the analysis when a
+                # ``hostbuf`` is given, in one asynchronous copy otherwise)
+                self._xh_pinned = xd
+                self._xd_t = None
+            else:
+                self._xd_t = xd.to(device=self._dev, dtype=torch.float32, non_blocking=True).contiguous()
             self._x_host = None
         else:
             xh = np.array(x)
@@ -238,8 +276,8 @@ class PV(object):
                 raise ValueError("PV expects a 1-D signal")
             self._x_host = xh
             x32 = np.ascontiguousarray(xh, dtype=np.float32)
-            self._xd = torch.from_numpy(x32).to(self._dev, non_blocking=False)
-        self.nsamp = int(self._xd.shape[0])
+            self._xd_t = torch.from_numpy(x32).to(self._dev, non_blocking=False)
+        self.nsamp = int((self._xh_pinned if self._xh_pinned is not None else self._xd_t).shape[0])
         self.sr = sr
         self.nfft = nfft
         self.nfft2 = int(nfft / 2)
@@ -274,12 +312,21 @@ class PV(object):
 
         self._host = {"t": [], "f": [], "ph": [], "mag": []}
         self._devout = None
+        self._hostbuf = None
+        self._d2h_event = None
         if progress:
             self.progress = Progress(end=self.nsamp)
         else:
             self.progress = None
 
     # -- lazily materialised host arrays (float64, the reference's layout) ------------
+    @property
+    def _xd(self):
+        """The float32 device signal (a pinned host input is uploaded on first use)."""
+        if self._xd_t is None:
+            self._xd_t = self._xh_pinned.to(device=self._dev, non_blocking=True)
+        return self._xd_t
+
     def _get(self, name):
         if name not in self._host:
             if self._devout is None:
@@ -289,6 +336,15 @@ class PV(object):
 
     def _fetch(self, name):
         d = self._devout
+        if self._hostbuf is not None and name in ("f", "mag", "ph", "realph", "binno", "totalmag"):
+            # run_pv(hostbuf=...) already streamed the tables into pinned memory
+            if self._d2h_event is not None:
+                self._d2h_event.synchronize()
+                self._d2h_event = None
+            hb = self._hostbuf[name][:self.nframes].numpy()
+            if name == "totalmag":
+                return [v for v in hb]
+            return hb if self.nframes else np.array([])
         if name == "totalmag":
             return [v for v in d["totalmag"][0].cpu().numpy()]
         if self.nframes == 0:
@@ -350,17 +406,77 @@ class PV(object):
         return nbytes
 
     # -- analysis ----------------------------------------------------------------------
-    def run_pv(self, run_frames=0):
+    def run_pv(self, run_frames=0, hostbuf=None, chunks=8):
         """STFT + peak picking + instantaneous frequency for every frame (PVAnalysis.py:213-264)
         in one kernel launch.  Results appear as the reference's attributes ``f mag ph realph
-        binno`` (float64 ``[nframes, npks]``), ``t``, ``nframes``, ``totalmag`` (list)."""
-        self._devout = analyze_device(self._xd, self.sr, self.nfft, self.hop, self.npeaks, self.peakthresh,
-                                      self._tb, run_frames=run_frames)
+        binno`` (float64 ``[nframes, npks]``), ``t``, ``nframes``, ``totalmag`` (list).
+
+        ``hostbuf`` (a dict, reused across calls): stream the tables into pinned host memory
+        while the analysis is still running -- the frames are analysed in ``chunks`` launches, the
+        upload of a pinned host signal, the kernels and the download of finished rows overlap on
+        three streams; the attributes are numpy views of the pinned buffers (valid until the next
+        call with the same ``hostbuf``) and synchronise on first access."""
+        self._hostbuf = None
+        self._d2h_event = None
+        if hostbuf is not None:
+            self._run_pv_streamed(hostbuf, int(chunks), run_frames)
+        else:
+            self._devout = analyze_device(self._xd, self.sr, self.nfft, self.hop, self.npeaks, self.peakthresh,
+                                          self._tb, run_frames=run_frames)
         self.nframes = int(self._devout["f"].shape[1])
         self._host = {}
         self._host["t"] = (np.arange(self.nframes) * self.hop + self.nfft / 2.0) / self.sr   # :247
         if self.progress:
             self.progress.update(self.nsamp)
+
+    def _run_pv_streamed(self, hostbuf, chunks, run_frames):
+        dev, K = self._dev, self.npeaks
+        F = n_frames(self.nsamp, self.nfft, self.hop)
+        cur = torch.cuda.current_stream(dev)
+        h2d, d2h = _side_streams(dev)
+        names = ("f", "mag", "ph", "realph", "binno")
+        with torch.cuda.device(dev):
+            out = {k: torch.empty((1, F, K), dtype=torch.float64, device=dev) for k in names}
+            out["npk"] = torch.empty((1, F), dtype=torch.int32, device=dev)
+            out["totalmag"] = torch.empty((1, F), dtype=torch.float64, device=dev)
+            hb = {k: _pinned(hostbuf, k, (F, K), torch.float64) for k in names}
+            hb["totalmag"] = _pinned(hostbuf, "totalmag", (F,), torch.float64)
+            upload = self._xd_t is None
+            if upload:
+                xd = torch.empty((self.nsamp,), dtype=torch.float32, device=dev)
+                h2d.wait_stream(cur)          # the buffers may be recycled memory still in use on `cur`
+            else:
+                xd = self._xd_t
+            d2h.wait_stream(cur)
+            chunks = max(1, min(chunks, F // 64 if F >= 64 else 1))
+            s_done = 0
+            for i in range(chunks if F else 0):
+                j0, j1 = (F * i) // chunks, (F * (i + 1)) // chunks
+                if upload:
+                    s_end = self.nsamp if i == chunks - 1 else (j1 - 1) * self.hop + self.nfft
+                    with torch.cuda.stream(h2d):
+                        xd[s_done:s_end].copy_(self._xh_pinned[s_done:s_end], non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(h2d)
+                    cur.wait_event(ev)
+                    s_done = s_end
+                view = {k: v[:, j0:j1] for k, v in out.items()}
+                analyze_device(xd, self.sr, self.nfft, self.hop, K, self.peakthresh, self._tb, frame0=j0,
+                               nframes=j1 - j0, prev_zero=(j0 == 0), run_frames=run_frames, out=view)
+                ev2 = torch.cuda.Event()
+                ev2.record(cur)
+                with torch.cuda.stream(d2h):
+                    d2h.wait_event(ev2)
+                    for k in names:
+                        hb[k][j0:j1].copy_(out[k][0, j0:j1], non_blocking=True)
+                    hb["totalmag"][j0:j1].copy_(out["totalmag"][0, j0:j1], non_blocking=True)
+            if upload:
+                self._xd_t = xd
+            self._d2h_event = torch.cuda.Event()
+            self._d2h_event.record(d2h)
+        self._devout = out
+        self._hostbuf = hostbuf
+        self.d2h_bytes = F * (5 * K + 1) * 8
 
     def dphase2freq(self, dph, nbin):
         '''"instantaneous frequency" for the phase difference dph at bin nbin (host helper with
@@ -691,10 +807,13 @@ class SinSum(object):
         return d
 
     # -- resynthesis ---------------------------------------------------------------------
-    def synth(self, sr, hop, edge=1.0, minframes=3, phase_preserve=True, to_host=True):
+    def synth(self, sr, hop, edge=1.0, minframes=3, phase_preserve=True, to_host=True, hostbuf=None, chunks=8):
         """Overlap-add resynthesis of all partials with >= minframes frames
-        (PVAnalysis.py:1053-1070) in one kernel launch; float64 ``[(max(end)+2)*hop + edgsamp]``.
-        ``to_host=False`` returns the CUDA tensor instead of a numpy array."""
+        (PVAnalysis.py:1053-1070); float64 ``[(max(end)+2)*hop + edgsamp]``.
+        ``to_host=False`` returns the CUDA tensor instead of a numpy array.  ``hostbuf`` (a dict,
+        reused across calls): render in ``chunks`` block ranges and download each finished range
+        into the pinned tensor ``hostbuf['w']`` while the next one is rendered; returns a numpy view
+        of it (valid until the next call with the same ``hostbuf``)."""
         if not phase_preserve:
             raise NotImplementedError("phase_preserve=False calls RegPartial.synth_no_phase, which is "
                                       "broken in the reference (PVAnalysis.py:665); not provided")
@@ -704,8 +823,39 @@ class SinSum(object):
         tr = self._trk
         if tr["ntracks"] == 0:
             raise ValueError("max() arg is an empty sequence")     # what the reference raises (:1059)
+        if hostbuf is not None:
+            return self._synth_streamed(pk, tr, sr, int(hop), edge, minframes, hostbuf, int(chunks))
         out = resynth_device(tr["tid"], pk, sr, int(hop), self.nfft, self.hop, edge=edge, minframes=minframes)
         return out.cpu().numpy() if to_host else out
+
+    def _synth_streamed(self, pk, tr, sr, hop, edge, minframes, hostbuf, chunks):
+        dev = self._dev
+        F, K = tr["tid"].shape
+        max_end = int((pk["tstart"] + pk["tlen"] - 1).max().item())
+        nout, _ = synth_geometry(max_end, hop, self.nfft, self.hop, edge)
+        nblk = -(-nout // hop)
+        cur = torch.cuda.current_stream(dev)
+        _, d2h = _side_streams(dev)
+        with torch.cuda.device(dev):
+            out = torch.empty((nout,), dtype=torch.float64, device=dev)
+            hw = _pinned(hostbuf, "w", (nout,), torch.float64)
+            d2h.wait_stream(cur)
+            chunks = max(1, min(chunks, nblk // 64 if nblk >= 64 else 1))
+            ws = resynth_workspace(F, K, int(pk["tstart"].shape[0]), -(-nblk // chunks), dev)
+            for i in range(chunks):
+                b0, b1 = (nblk * i) // chunks, (nblk * (i + 1)) // chunks
+                n0, n1 = b0 * hop, min(b1 * hop, nout)
+                resynth_device(tr["tid"], pk, sr, hop, self.nfft, self.hop, edge=edge, minframes=minframes,
+                               max_end=max_end, block0=b0, nblocks=b1 - b0, out=out[n0:n1], ws=ws, reuse_tracks=i > 0)
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                with torch.cuda.stream(d2h):
+                    d2h.wait_event(ev)
+                    hw[n0:n1].copy_(out[n0:n1], non_blocking=True)
+            d2h.synchronize()
+        self.d2h_bytes = nout * 8
+        self._last_out = out
+        return hw[:nout].numpy()
 
     def partial_samples(self, hop, edge=1.0, minframes=3):
         """Work units of synth(): sum over rendered partials of hop*nfr + 2*edgsam."""

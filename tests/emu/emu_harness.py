@@ -102,7 +102,7 @@ def track(f, mag, maxpitchjmp=0.5):
     wsb = L.pvk_track_workspace_bytes(nclips, F, K)
     ws = np.zeros(max(wsb, 8), dtype=np.uint8)
     check(L.pvk_track(ptr(f), ptr(mag), nclips, F, K, maxpitchjmp, ptr(tid), ptr(link), ptr(ntracks),
-                      ptr(ws), wsb, None))
+                      ptr(ws), wsb, 0, None))
     return dict(tid=tid, link=link, ntracks=ntracks)
 
 
@@ -147,5 +147,5 @@ def resynth(tid, pk, sr, hop, nfft, hop_an, edge=1.0, minframes=3, block0=0, nbl
     ws = np.zeros(max(wsb, 8), dtype=np.uint8)
     check(L.pvk_resynth(ptr(tid), F, K, nt, ptr(ts), ptr(tl), ptr(pk["toff"]), ptr(pk["pf"]), ptr(pk["pmag"]),
                         ptr(pk["prealph"]), float(sr), int(hop), int(nfft), int(hop_an), float(edge),
-                        int(minframes), ptr(out), nout, block0, nblocks, ptr(ws), wsb, None))
+                        int(minframes), ptr(out), nout, block0, nblocks, ptr(ws), wsb, 0, None))
     return out

@@ -288,3 +288,26 @@ def test_full_size_pipeline_properties(pvmod):
     pb = resynth_device(tr["tid"], pk, sr, hop, nfft, hop, block0=cut, nblocks=nblk - cut)
     assert torch.equal(torch.cat([pa, pb]), w1)
     assert torch.isfinite(w1).all() and float(w1.abs().max()) > 0.05
+
+
+def test_streamed_pipeline_equals_plain_calls(pvmod):
+    """run_pv(hostbuf=...) / synth(hostbuf=...) (chunked launches, copies overlapped on side
+    streams, pinned host results) give bit-identical results to the one-launch calls."""
+    from pypevoc_b200 import signals
+    x = signals.harm(44100, 3.0, 220, 90, 0.5, 0.01, 7)
+    sr = 44100
+    pv0 = pvmod.PV(x, sr, nfft=2048, hop=512, npks=50, progress=False)
+    pv0.run_pv()
+    w0 = pv0.toSinSum().synth(sr, 512)
+    xh = torch.from_numpy(x).pin_memory()
+    hb = {}
+    for rep in range(2):                       # second pass reuses the pinned buffers
+        pv1 = pvmod.PV(xh, sr, nfft=2048, hop=512, npks=50, progress=False)
+        pv1.run_pv(hostbuf=hb, chunks=3)
+        ss1 = pv1.toSinSum()
+        w1 = ss1.synth(sr, 512, hostbuf=hb, chunks=3)
+        for k in ("f", "mag", "ph", "realph", "binno"):
+            assert np.array_equal(getattr(pv0, k), getattr(pv1, k)), k
+        assert np.array_equal(np.asarray(pv0.totalmag), np.asarray(pv1.totalmag))
+        assert w1.shape == w0.shape and np.array_equal(w0, w1)
+        assert pv1.d2h_bytes == pv1.nframes * (5 * 50 + 1) * 8 and ss1.d2h_bytes == w1.nbytes
