@@ -648,7 +648,25 @@ template <int LOGM> static int launch_tables(void *tables, void *stream) {
   return PVK_OK;
 }
 
-template <int LOGM> static int launch_analyze(const AParams &prm, int64_t nclips, void *stream) {
+// CTAs of analyze_kernel<LOGM> the current device holds at once (occupancy x SM count)
+template <int LOGM> static int64_t resident_ctas(int smem) {
+#ifdef PVK_EMU
+  (void)smem;
+  return 148 * 7;
+#else
+  int dev = 0, sms = 148, occ = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, analyze_kernel<LOGM>, Plan<LOGM>::T, (size_t)smem) != cudaSuccess ||
+      occ < 1) {
+    cudaGetLastError();
+    occ = 1;
+  }
+  return (int64_t)sms * occ;
+#endif
+}
+
+template <int LOGM> static int launch_analyze(AParams prm, int64_t nclips, int run_frames, void *stream) {
   using P = Plan<LOGM>;
   const int smem = Smem<LOGM>::bytes(prm.npks);
   if (smem > 48 * 1024) {
@@ -657,6 +675,21 @@ template <int LOGM> static int launch_analyze(const AParams &prm, int64_t nclips
       return PVK_ERR_CUDA;
     }
   }
+  int64_t run = run_frames;
+  if (run <= 0) {
+    // The kernel is latency bound (one CTA = one chain of dependent frames), so what matters is
+    // that every resident CTA slot is busy for the same time: size the runs so that the grid is a
+    // whole number of waves, as few as possible (every run pays one warm-up frame), with runs of
+    // 4..256 frames.
+    const int64_t slots = resident_ctas<LOGM>(smem);
+    const int64_t total = nclips * prm.nframes;
+    const int64_t waves = (total + slots * 256 - 1) / (slots * 256);
+    run = (total + slots * waves - 1) / (slots * waves);
+    if (run < 4) run = 4;
+  }
+  if (run > prm.nframes) run = prm.nframes;
+  prm.run = (int)run;
+  prm.nruns = (prm.nframes + run - 1) / run;
   const int64_t nblk = nclips * prm.nruns;
   PVK_REQUIRE(nblk < (int64_t)2147483647, "pvk_analyze: grid too large (%lld CTAs)", (long long)nblk);
   PVK_LAUNCH(analyze_kernel<LOGM>, dim3((unsigned)nblk), dim3(P::T), smem, stream, prm);
@@ -735,22 +768,11 @@ extern "C" int pvk_analyze(const float *x, int64_t nclips, int64_t clip_stride, 
   prm.fbin = fbin; prm.wfbin = wfbin; prm.hop = hop; prm.npks = npks;
   prm.pkthresh = pkthresh; prm.dt = dt; prm.fstep = fstep;
   prm.frame0 = frame0; prm.nframes = nframes; prm.prev_zero = prev_zero ? 1 : 0;
-  int run = run_frames;
-  if (run <= 0) {
-    // enough CTAs for a few waves over 148 SMs, while keeping the 1-frame warm-up small
-    const int64_t total = nclips * nframes;
-    int64_t r = (total + 8191) / 8192;
-    if (r < 16) r = 16;
-    if (r > 128) r = 128;
-    run = (int)r;
-  }
-  if (run > nframes) run = (int)nframes;
-  prm.run = run;
-  prm.nruns = (nframes + run - 1) / run;
+  prm.run = 0; prm.nruns = 0;                              // chosen by launch_analyze
   prm.f = f; prm.mag = mag; prm.ph = ph; prm.realph = realph; prm.binno = binno;
   prm.npk = npk; prm.totalmag = totalmag;
   prm.spec_out = reinterpret_cast<float2 *>(spec_out);
-#define CALL(L) launch_analyze<L>(prm, nclips, stream)
+#define CALL(L) launch_analyze<L>(prm, nclips, run_frames, stream)
   PVK_DISPATCH_LOGM(l - 1, CALL)
 #undef CALL
   return PVK_ERR_ARG;

@@ -41,6 +41,15 @@ def _device(device=None):
 
 
 _side = {}
+TRACE = None     # set to a list to collect (label, cuda event) marks of the streamed pipeline (diagnostics)
+
+
+def _mark(label, stream):
+    if TRACE is not None:
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(stream)
+        TRACE.append((label, ev))
+
 
 
 def _side_streams(dev):
@@ -450,6 +459,7 @@ class PV(object):
             d2h.wait_stream(cur)
             chunks = max(1, min(chunks, F // 64 if F >= 64 else 1))
             s_done = 0
+            _mark("start", cur)
             for i in range(chunks if F else 0):
                 j0, j1 = (F * i) // chunks, (F * (i + 1)) // chunks
                 if upload:
@@ -458,6 +468,7 @@ class PV(object):
                         xd[s_done:s_end].copy_(self._xh_pinned[s_done:s_end], non_blocking=True)
                         ev = torch.cuda.Event()
                         ev.record(h2d)
+                        _mark("h2d %d" % i, h2d)
                     cur.wait_event(ev)
                     s_done = s_end
                 view = {k: v[:, j0:j1] for k, v in out.items()}
@@ -465,11 +476,13 @@ class PV(object):
                                nframes=j1 - j0, prev_zero=(j0 == 0), run_frames=run_frames, out=view)
                 ev2 = torch.cuda.Event()
                 ev2.record(cur)
+                _mark("analysis %d" % i, cur)
                 with torch.cuda.stream(d2h):
                     d2h.wait_event(ev2)
                     for k in names:
                         hb[k][j0:j1].copy_(out[k][0, j0:j1], non_blocking=True)
                     hb["totalmag"][j0:j1].copy_(out["totalmag"][0, j0:j1], non_blocking=True)
+                    _mark("tables d2h %d" % i, d2h)
             if upload:
                 self._xd_t = xd
             self._d2h_event = torch.cuda.Event()
@@ -842,6 +855,7 @@ class SinSum(object):
             d2h.wait_stream(cur)
             chunks = max(1, min(chunks, nblk // 64 if nblk >= 64 else 1))
             ws = resynth_workspace(F, K, int(pk["tstart"].shape[0]), -(-nblk // chunks), dev)
+            _mark("pack done", cur)
             for i in range(chunks):
                 b0, b1 = (nblk * i) // chunks, (nblk * (i + 1)) // chunks
                 n0, n1 = b0 * hop, min(b1 * hop, nout)
@@ -849,9 +863,11 @@ class SinSum(object):
                                max_end=max_end, block0=b0, nblocks=b1 - b0, out=out[n0:n1], ws=ws, reuse_tracks=i > 0)
                 ev = torch.cuda.Event()
                 ev.record(cur)
+                _mark("resynth %d" % i, cur)
                 with torch.cuda.stream(d2h):
                     d2h.wait_event(ev)
                     hw[n0:n1].copy_(out[n0:n1], non_blocking=True)
+                    _mark("w d2h %d" % i, d2h)
             d2h.synchronize()
         self.d2h_bytes = nout * 8
         self._last_out = out
