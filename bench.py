@@ -16,8 +16,9 @@ path (PV.run_pv -> toSinSum -> SinSum.synth) over that signal.
   cpu_baseline  the numpy oracle (port of the reference's algorithm) on one host core, on a
              bounded prefix of the same samples
 N > 1 is weak scaling: every rank owns its own hop-aligned 10-minute segment of an N x 10
-minute signal (one warm-up frame + nfft-hop halo on the left), links its frames locally and
-one all_gather stitches the track tables; no collective inside analysis or resynthesis.
+minute signal (plus a few halo frames either side), analyses, links and resynthesises it from
+local data; a 2K+4-integer all_gather makes the partial numbering global and ONE all_gather
+collects the int32 track table (overlapped with pack + resynthesis).
 """
 import argparse
 import json
@@ -51,6 +52,9 @@ def peaks():
 
 # --------------------------------------------------------------------------- clocks
 class ClockSampler(object):
+    """SM clock and throttle reasons sampled DURING the timed region: an NVML polling thread
+    (2 ms period -- the timed region lasts tens of milliseconds, too short for `nvidia-smi -lms`),
+    with `nvidia-smi` as the fallback when NVML is not importable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -58,19 +62,64 @@ class ClockSampler(object):
     def __init__(self, index):
         self.index = index
         self.proc = None
+        self.thread = None
+        self.samples = []
         self.path = "/tmp/pvk_clocks_%d_%d.csv" % (os.getpid(), index)
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        n = self.nvml
+        bits = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40),
+                ("sw_power_cap", 0x4))
+        while not self._stop:
+            try:
+                clk = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                try:
+                    r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.samples.append((clk, tuple(name for name, b in bits if r & b)))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        if self.nvml is not None:
+            import threading
+            self._stop = False
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.fh = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=self.fh, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.thread is not None:
+            self._stop = True
+            self.thread.join(timeout=1.0)
+            if self.samples:
+                sm = [c for c, _ in self.samples]
+                hi = [v for v in sm if v >= 0.5 * max(sm)]
+                reasons = sorted({r for _, rs in self.samples for r in rs})
+                out = {"sm_mhz": float(np.median(hi)), "sm_max_mhz": self.smax, "reasons": reasons,
+                       "samples": len(sm), "source": "nvml, 2 ms polling during the timed steps"}
+            return out
         if self.proc is None:
             return out
         try:
@@ -90,10 +139,9 @@ class ClockSampler(object):
                     if v.lower().startswith("active"):
                         reasons.add(name)
             if sm:
-                # "under load": samples in the upper half of the observed range
                 hi = [v for v in sm if v >= 0.5 * max(sm)]
                 out = {"sm_mhz": float(np.median(hi)), "sm_max_mhz": float(max(smax)),
-                       "reasons": sorted(reasons), "samples": len(sm)}
+                       "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 20"}
             os.unlink(self.path)
         except Exception:
             pass
@@ -102,6 +150,11 @@ class ClockSampler(object):
 
 # --------------------------------------------------------------------------- GPU arm
 def gpu_main(args):
+    # everything else that writes to fd 1 (NCCL's version banner, library chatter) goes to stderr:
+    # the contract is ONE JSON line on stdout
+    real_stdout = os.dup(1)
+    sys.stdout.flush()
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from pypevoc_b200 import PV, signals
@@ -120,13 +173,14 @@ def gpu_main(args):
     sr, nfft, hop, npks = c["sr"], c["nfft"], c["hop"], c["npks"]
     nsamp_seg = sr * c["seconds"]
 
-    # ---- synthetic signal: rank r owns frames [r*Fseg, (r+1)*Fseg) of an N*10-minute signal
+    # ---- synthetic signal: rank r owns frames [r*Fseg, (r+1)*Fseg) of an N*10-minute signal and
+    #      analyses a window with a few halo rows either side (pypevoc_b200/dist.py)
     plans = D.plan_segments(world * nsamp_seg, nfft, hop, world)
-    plan = dict(plans[rank], all=plans)
+    plan = plans[rank]
     xd = signals.harm_torch(sr, plan["nsamp"], c["f0"], c["nharm"], c["p"], c["sigma"], c["seed"], dev,
                             t0_samples=plan["sample0"], scale=0.25)
     tb = P.host_tables(sr, nfft, hop)
-    F = plan["j1"] - plan["j0"]                      # own frames (the overlap row is not counted)
+    F = plan["nown"]                                 # own frames (halo rows are not counted)
     frames_total = plan["frames_total"]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -140,18 +194,26 @@ def gpu_main(args):
         a = P.analyze_device(xd, sr, nfft, hop, npks, c["pkthresh"], tb, frame0=plan["frame0"],
                              nframes=plan["nframes"], prev_zero=plan["prev_zero"])
         if e: e[1].record()
-        trk = D.track_segment(a, plan, world)            # link + ids (+ the one all_gather when world > 1)
+        tab = {k: a[k][0] for k in ("f", "mag", "ph", "realph")}
+        tr = P.track_device(tab["f"], tab["mag"])        # local link + ids
+        ntl = int(tr["ntracks"][0].item())
+        if world > 1:
+            # global numbering (2K+4-int all_gather) and THE all_gather of the track table (async)
+            st = D.stitch(tr["tid"], plan, plans)
+            _, finish = D.gather_track_table(st["tid_own"], plans, async_op=True)
         if e: e[2].record()
-        pk = P.pack_device(trk["f"], trk["mag"], trk["ph"], trk["realph"], trk["tid"], None, trk["ntracks"])
-        max_end = int((pk["tstart"] + pk["tlen"] - 1).max().item()) if trk["ntracks"] else -1
+        pk = P.pack_device(tab["f"], tab["mag"], tab["ph"], tab["realph"], tr["tid"], None, ntl)
+        if world == 1:
+            st = dict(ntracks=ntl, max_end=int((pk["tstart"] + pk["tlen"] - 1).max().item()) if ntl else -1)
         if e: e[3].record()
-        nout, _ = P.synth_geometry(max_end, hop, nfft, hop)
-        nb = trk["nblocks"]
-        if world > 1 and rank == world - 1:
-            nb = -(-nout // hop) - trk["block0"]         # the last rank also renders the tail
-        w = P.resynth_device(trk["tid"], pk, sr, hop, nfft, hop, max_end=max_end, block0=trk["block0"], nblocks=nb)
+        w = D.resynth_local(tr["tid"], pk, plan, plans, st["max_end"], sr, hop, nfft, hop)
+        if world > 1:
+            table = finish()                             # the gather overlapped pack + resynthesis
+            spans = P.spans_device(table, st["ntracks"]) # first frame / length of every partial
+        else:
+            table, spans = tr["tid"], (pk["tstart"], pk["tlen"])
         if e: e[4].record()
-        state.update(a=a, trk=trk, pk=pk, w=w, max_end=max_end)
+        state.update(a=a, tr=tr, pk=pk, w=w, st=st, table=table, spans=spans)
         if timed is not None:
             timed.append(e)
 
@@ -181,8 +243,8 @@ def gpu_main(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step, ms_an, ms_trk, ms_pack, ms_syn = [float(v) for v in t.tolist()]
 
-    tl = state["pk"]["tlen"].cpu().numpy().astype(np.int64)       # global table when world > 1
-    _, E = P.synth_geometry(state["max_end"], hop, nfft, hop)
+    tl = state["spans"][1].cpu().numpy().astype(np.int64)         # global table (every rank has it)
+    _, E = P.synth_geometry(state["st"]["max_end"], hop, nfft, hop)
     psamp_total = float((tl[tl >= 3] * hop + 2 * E).sum())
     psamp_local = psamp_total / world
 
@@ -206,10 +268,12 @@ def gpu_main(args):
             else:
                 spv = D.ShardedPV(xh, sr, world * nsamp_seg, nfft=nfft, hop=hop, npks=npks, pkthresh=c["pkthresh"],
                                   rank=rank, world=world, device=dev)
-                spv.run_pv()
+                spv.run_pv(hostbuf=hostbuf)
                 ss = spv.toSinSum()
-                wd = spv.synth_local(ss)
-                nb = spv.pv.fetch_into(hostbuf, extra={"w": wd})
+                w, _ = ss.synth_local(hostbuf=hostbuf)
+                tids = ss.device_track_table                 # the gathered track table (stays on the device)
+                assert spv.pv.f.shape[1] == npks and w.dtype == np.float64 and tids.shape[0] == frames_total
+                nb = spv.pv.d2h_bytes + ss.d2h_bytes
             torch.cuda.synchronize()
             return time.perf_counter() - t0, nb
         for _ in range(2):
@@ -257,9 +321,10 @@ def gpu_main(args):
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "sr": sr, "seconds_per_gpu": c["seconds"], "nfft": nfft, "hop": hop,
                    "npks": npks, "frames_per_gpu": F, "frames_total": frames_total,
-                   "partial_samples_total": psamp_total, "tracks_rank0": int(state["trk"]["ntracks"]),
+                   "partial_samples_total": psamp_total, "tracks_total": int(state["st"]["ntracks"]),
                    "l2": "256 MiB buffer written between timed steps; per-step CUDA events on the launch stream",
-                   "parallelism": "segment-sharded x%d (hop-aligned, 1 warm-up frame + nfft-hop halo)" % world},
+                   "parallelism": "segment-sharded x%d (hop-aligned frame ranges + %d/%d halo rows; local "
+                                  "resynthesis, one all_gather of the int32 track table)" % ((world,) + D.halos(nfft, hop))},
         "stages": {"analysis_ms": ms_an, "tracking_ms": ms_trk, "pack_ms": ms_pack, "resynth_ms": ms_syn,
                    "analysis_frames_per_s": frames_total / (ms_an * 1e-3),
                    "resynth_partial_samples_per_s": psamp_total / (ms_syn * 1e-3)},
@@ -270,7 +335,8 @@ def gpu_main(args):
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(xd[:sr * args.cpu_seconds + nfft].cpu().numpy(), 1)
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -106,6 +106,12 @@ int pvk_track(const double *f, const double *mag, int64_t nclips, int64_t nframe
               double maxpitchjmp, int32_t *tid, int32_t *link, int32_t *ntracks,
               void *workspace, int64_t workspace_bytes, void *stream);
 
+/* First frame and length of every partial from a track-id table alone (tstart / tlen int32
+ * [ntracks] = ss.st and ss.end - ss.st + 1, :827-828,950); ids >= ntracks must not occur.  Used
+ * on the gathered global id table of a sharded run. */
+int pvk_track_spans(const int32_t *tid, int64_t nframes, int npks, int64_t ntracks,
+                    int32_t *tstart, int32_t *tlen, void *stream);
+
 /* Pack per-track value runs (= RegPartial.f/mag/ph/realph lists, :616-626, with
  * start_idx = tstart, :598) from the frame tables of ONE clip.  ntracks must be the value
  * pvk_track reported.  Outputs: tstart / tlen int32 [ntracks] (= ss.st and
@@ -115,6 +121,32 @@ int pvk_track_pack(const double *f, const double *mag, const double *ph, const d
                    const int32_t *tid, int64_t nframes, int npks,
                    int64_t ntracks, int32_t *tstart, int32_t *tlen, int64_t *toff, double *pf,
                    double *pmag, double *pph, double *prealph, void *stream);
+
+/* ------------------------------------------------------------------ segment sharding
+ * A long signal split into per-GPU frame ranges is linked per segment (pvk_track on the
+ * segment's window of rows: `own0` halo rows, then `nown` own rows, then more halo rows); these
+ * three calls give the own rows the numbering the unsharded pvk_track would give them
+ * (partials in order of creation, PVAnalysis.py:819-830).  See pypevoc_b200/dist.py.
+ *
+ * pvk_segment_summary: int32 summary[2*npks + 4] of one segment = local ids of the row before
+ *   the first own row (-1 = none) | local ids of the last own row | partials born before the
+ *   own rows | those + partials born in the own rows | global index (j0 + local) of the last own
+ *   row holding a point (-1 = none) | nown.  The summaries of all segments are exchanged with
+ *   one small all_gather.
+ * pvk_segment_resolve: sequential pass over the gathered summaries [world][2*npks + 4] for
+ *   segment `rank`: gidlow[v] = global id of local id v for the partials born before the own
+ *   rows (v < summary[2K]; gidlow and scratch: at least npks * the largest own0 of any segment ints
+ *   each, scratch_ints says how many), params[8] = {global
+ *   id of the first partial born in the own rows, partials born before the own rows, partials
+ *   born in them, total number of partials, global index of the last frame with a point, ...}.
+ * pvk_segment_rename: tid_global[e] for the n = nown*npks slots of the own rows.
+ */
+int pvk_segment_summary(const int32_t *tid, int npks, int64_t own0, int64_t nown, int64_t j0,
+                        int32_t *summary, void *stream);
+int pvk_segment_resolve(const int32_t *summaries, int world, int npks, int rank, int32_t *scratch,
+                        int64_t scratch_ints, int32_t *gidlow, int32_t *params, void *stream);
+int pvk_segment_rename(const int32_t *tid_own, int64_t n, const int32_t *gidlow,
+                       const int32_t *params, int32_t *tid_global, void *stream);
 
 /* ------------------------------------------------------------------ resynthesis
  * Replaces SinSum.synth -> RegPartial.synth (PVAnalysis.py:1053-1070,684-756),

@@ -616,6 +616,21 @@ extern "C" int pvk_track(const double *f, const double *mag, int64_t nclips, int
   return PVK_OK;
 }
 
+extern "C" int pvk_track_spans(const int32_t *tid, int64_t nframes, int npks, int64_t ntracks, int32_t *tstart,
+                               int32_t *tlen, void *stream) {
+  PVK_REQUIRE(npks >= 1 && nframes >= 0 && ntracks >= 0, "pvk_track_spans: bad sizes");
+  if (ntracks == 0) return PVK_OK;
+  PVK_REQUIRE(tstart && tlen, "pvk_track_spans: NULL pointer argument");
+  cudaMemsetAsync(tlen, 0, 4 * (size_t)ntracks, (cudaStream_t)stream);
+  cudaMemsetAsync(tstart, 0x7f, 4 * (size_t)ntracks, (cudaStream_t)stream);   // 0x7f7f7f7f: "no frame yet"
+  if (nframes == 0) return PVK_OK;
+  PVK_REQUIRE(tid != nullptr, "pvk_track_spans: tid is NULL");
+  PVK_LAUNCH(pack_count_kernel, dim3(grid_for((nframes + PACK_STRIP - 1) / PACK_STRIP * npks, 128)), dim3(128), 0,
+             stream, tid, nframes, npks, tstart, tlen);
+  PVK_CHECK_LAUNCH("pvk_track_spans");
+  return PVK_OK;
+}
+
 extern "C" int pvk_track_pack(const double *f, const double *mag, const double *ph, const double *realph,
                               const int32_t *tid, int64_t nframes, int npks,
                               int64_t ntracks, int32_t *tstart, int32_t *tlen, int64_t *toff, double *pf,
@@ -639,5 +654,122 @@ extern "C" int pvk_track_pack(const double *f, const double *mag, const double *
   PVK_LAUNCH(pack_scatter_kernel, dim3(grid_for(n, 256)), dim3(256), 0, stream, f, mag, ph, realph, tid, nframes,
              npks, tstart, toff, pf, pmag, pph, prealph);
   PVK_CHECK_LAUNCH("pvk_track_pack(scatter)");
+  return PVK_OK;
+}
+
+// ------------------------------------------------------------------ segment sharding helpers
+// (pypevoc_b200/dist.py: global numbering of partials that were linked per segment)
+namespace pvk {
+
+// summary[0..K) local ids of the row before the first own row, [K..2K) of the last own row,
+// [2K] nb = partials born before the own rows, [2K+1] nb + n_own, [2K+2] global index of the last
+// own row holding a point, [2K+3] number of own rows.  Pre-set to -1 / 0 by the caller.
+__global__ void segment_summary_kernel(const int32_t *__restrict__ tid, int K, int64_t own0, int64_t nown,
+                                       int64_t j0, int32_t *__restrict__ summary) {
+  const int64_t n = (own0 + nown) * K;
+  int mb = -1, mo = -1, lastrow = -1;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int v = tid[e];
+    const int64_t row = e / K;
+    if (row < own0) mb = max(mb, v);
+    else if (v >= 0) { mo = max(mo, v); lastrow = max(lastrow, (int)(row - own0)); }
+    if (row == own0 - 1) summary[e - row * K] = v;
+    if (row == own0 + nown - 1) summary[K + (e - row * K)] = v;
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    mb = max(mb, __shfl_xor_sync(FULL, mb, o));
+    mo = max(mo, __shfl_xor_sync(FULL, mo, o));
+    lastrow = max(lastrow, __shfl_xor_sync(FULL, lastrow, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (mb >= 0) { atomicMax(&summary[2 * K], mb + 1); atomicMax(&summary[2 * K + 1], mb + 1); }
+    if (mo >= 0) atomicMax(&summary[2 * K + 1], mo + 1);
+    if (lastrow >= 0) atomicMax(&summary[2 * K + 2], (int)(j0 + lastrow));
+  }
+}
+
+// Sequential pass over the ranks (one CTA): global ids of the row before `rank`'s first own row,
+// expressed per local id (gidlow[v] for the local ids v < nb born in the back halo), and
+// params = {base, nb, n_own, total partials, global index of the last frame with a point}.
+__global__ void segment_resolve_kernel(const int32_t *__restrict__ summ, int world, int K, int rank,
+                                       int32_t *__restrict__ inv, int cap, int32_t *__restrict__ gidlow,
+                                       int32_t *__restrict__ params) {
+  PVK_SMEM(smem);
+  int *G = reinterpret_cast<int *>(smem);          // [K] global ids of the previous rank's last own row
+  int *Gn = G + K;
+  const int t = threadIdx.x, BD = blockDim.x;
+  for (int c = t; c < K; c += BD) G[c] = -1;
+  int base = 0, maxend = -1;
+  __syncthreads();
+  for (int g = 0; g < world; ++g) {
+    const int32_t *s = summ + (int64_t)g * (2 * K + 4);
+    const int nb = s[2 * K], nbo = s[2 * K + 1], lastrow = s[2 * K + 2], nown = s[2 * K + 3];
+    if (nown == 0) continue;                        // uniform
+    const int n_own = nbo - nb;
+    for (int c = t; c < K; c += BD) { const int pt = s[c]; if (pt >= 0 && pt < cap) inv[pt] = c; }
+    __syncthreads();
+    if (g == rank) {
+      for (int c = t; c < K; c += BD) { const int pt = s[c]; if (pt >= 0 && pt < cap) gidlow[pt] = G[c]; }
+      if (t == 0) { params[0] = base; params[1] = nb; params[2] = n_own; }
+    }
+    for (int c = t; c < K; c += BD) {
+      const int lt = s[K + c];
+      Gn[c] = lt < 0 ? -1 : (lt >= nb ? base + (lt - nb) : (lt < cap ? G[inv[lt]] : -1));
+    }
+    __syncthreads();
+    for (int c = t; c < K; c += BD) G[c] = Gn[c];
+    base += n_own;
+    maxend = max(maxend, lastrow);
+    __syncthreads();
+  }
+  if (t == 0) { params[3] = base; params[4] = maxend; }
+}
+
+__global__ void segment_rename_kernel(const int32_t *__restrict__ tid_own, int64_t n, const int32_t *__restrict__ gidlow,
+                                      const int32_t *__restrict__ params, int32_t *__restrict__ out) {
+  const int base = params[0], nb = params[1];
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int v = tid_own[e];
+    out[e] = v < 0 ? -1 : (v >= nb ? base + (v - nb) : gidlow[v]);
+  }
+}
+
+}  // namespace pvk
+
+extern "C" int pvk_segment_summary(const int32_t *tid, int npks, int64_t own0, int64_t nown, int64_t j0,
+                                   int32_t *summary, void *stream) {
+  PVK_REQUIRE(npks >= 1 && own0 >= 0 && nown >= 0 && summary, "pvk_segment_summary: bad arguments");
+  const int K = npks;
+  cudaMemsetAsync(summary, 0xff, (size_t)(2 * K) * 4, (cudaStream_t)stream);           // -1
+  const int32_t tail[4] = {0, 0, -1, (int32_t)nown};
+  cudaMemcpyAsync(summary + 2 * K, tail, sizeof(tail), cudaMemcpyHostToDevice, (cudaStream_t)stream);
+  if (nown == 0) return PVK_OK;
+  PVK_REQUIRE(tid != nullptr, "pvk_segment_summary: tid is NULL");
+  PVK_LAUNCH(segment_summary_kernel, dim3(grid_for((own0 + nown) * K, 256)), dim3(256), 0, stream, tid, K, own0, nown,
+             j0, summary);
+  PVK_CHECK_LAUNCH("pvk_segment_summary");
+  return PVK_OK;
+}
+
+extern "C" int pvk_segment_resolve(const int32_t *summaries, int world, int npks, int rank, int32_t *scratch,
+                                   int64_t scratch_ints, int32_t *gidlow, int32_t *params, void *stream) {
+  PVK_REQUIRE(summaries && scratch && gidlow && params && world >= 1 && rank >= 0 && rank < world && npks >= 1,
+              "pvk_segment_resolve: bad arguments");
+  PVK_REQUIRE(scratch_ints >= 1 && scratch_ints < (int64_t)2147483647, "pvk_segment_resolve: bad scratch size");
+  const int bd = npks < 1024 ? (npks + 31) / 32 * 32 : 1024;
+  PVK_LAUNCH(segment_resolve_kernel, dim3(1), dim3(bd), (size_t)npks * 8, stream, summaries, world, npks, rank, scratch,
+             (int)scratch_ints, gidlow, params);
+  PVK_CHECK_LAUNCH("pvk_segment_resolve");
+  return PVK_OK;
+}
+
+extern "C" int pvk_segment_rename(const int32_t *tid_own, int64_t n, const int32_t *gidlow, const int32_t *params,
+                                  int32_t *tid_global, void *stream) {
+  PVK_REQUIRE(n >= 0, "pvk_segment_rename: negative size");
+  if (n == 0) return PVK_OK;
+  PVK_REQUIRE(tid_own && gidlow && params && tid_global, "pvk_segment_rename: NULL pointer argument");
+  PVK_LAUNCH(segment_rename_kernel, dim3(grid_for(n, 256)), dim3(256), 0, stream, tid_own, n, gidlow, params, tid_global);
+  PVK_CHECK_LAUNCH("pvk_segment_rename");
   return PVK_OK;
 }

@@ -1,18 +1,28 @@
 """Segment sharding of one long signal over the GPUs of a box.
 
-One process per GPU (torchrun).  Rank g owns the contiguous, hop-aligned frame range
-[j0, j1) and reads samples [(j0-2)*hop, (j1-1)*hop + nfft): the nfft-hop overlap with its
-right neighbour plus two extra hops on the left, so that it can recompute
-  * frame j0-2 as a pure warm-up (its spectrum feeds the phase difference of frame j0-1) and
-  * frame j0-1 as an *overlap row*: the peak row its own first frame links into -- identical,
-    bit for bit, to the last row of rank g-1 (tests/test_gpu_parity.py::test_segment_sharding).
-Analysis and the frame-pair-local link step then need no communication at all.  Track ids are
-made global by ONE all_gather (NCCL over NVLink) of each rank's peak/track tables: partials
-born in the overlap row are renamed to the id they carry on the left neighbour (same column of
-the same row), the others are offset by the number of partials born on earlier ranks, which
-reproduces the reference's numbering (order of add_empty_partial calls, PVAnalysis.py:819-830).
-Resynthesis is again embarrassingly parallel: every rank renders its own block range from the
-gathered table.
+One process per GPU (torchrun).  Rank g *owns* the contiguous, hop-aligned frame range
+[j0, j1) and analyses a slightly larger *window* of frames [w0, w1) = [j0 - Lb, j1 + Lf):
+
+  * analysis needs the previous frame's spectrum: one extra warm-up frame before w0
+    (recomputed, not emitted), i.e. the rank reads samples [(w0-1)*hop, (w1-1)*hop + nfft);
+  * the link of frame j to frame j-1 depends on those two peak rows only, so local
+    tracking over the window rows reproduces the global links of every own row;
+  * one block of resynthesised samples depends on a few neighbouring frames of each partial that
+    sounds in it: Af + 1 frames back and one frame ahead for the body (PVAnalysis.py:701-736),
+    ceil(dfr*edge) further frames for fade-in heads / fade-out tails of partials that start
+    after / end before the block (:740-751), and `minframes` frames to know that a partial is
+    rendered at all (:1061).  With Lb = dE + max(Af + 2, minframes) and Lf = dE + minframes + 2
+    halo rows the partials cut by the window edges cannot influence an own block, so every rank
+    renders its own block range [j0, j1) from LOCAL tables, bit-identical to the unsharded run.
+
+Hence no collective runs on the hot path.  What has to be global is the numbering of the
+partials (the reference numbers them in order of creation, PVAnalysis.py:819-830): every rank
+contributes 2*K + 4 integers (the local ids in the row before its first own row and in its
+last own row, and how many partials were born before / inside its own rows), one tiny
+all_gather distributes them and each rank renames its own rows.  ONE all_gather over NVLink
+then collects the track table (global ids of every frame, int32 [F, K]); first frame and length
+of every partial follow from it (pvk_track_spans).  The peak tables stay sharded;
+`ShardedSinSum.gather_tables()` collects them on request (second, optional collective).
 """
 import numpy as np
 import torch
@@ -20,133 +30,369 @@ import torch
 from . import pv as P
 
 
-def plan_segments(nsamp_total, nfft, hop, world):
-    """Frame ranges and sample windows of every rank.  Keys: j0, j1 (global frames),
-    sample0 / nsamp (window of the global signal the rank reads), frame0 (local index of the
-    first emitted row), nframes (emitted rows, including the overlap row when has_overlap),
-    prev_zero, has_overlap."""
+def halos(nfft, hop, edge=1.0, minframes=3):
+    """(Lb, Lf): frame rows a rank needs before / after its own range to render its own blocks."""
+    dfr = nfft / float(hop) / 2.
+    Af = int(np.floor(dfr + 0.5))
+    dE = int(np.ceil(dfr * edge))
+    return dE + max(Af + 2, int(minframes)), dE + int(minframes) + 2
+
+
+def plan_segments(nsamp_total, nfft, hop, world, edge=1.0, minframes=3):
+    """Frame ranges and sample windows of every rank.  Keys: j0, j1 (own global frames), w0, w1
+    (window = emitted rows), own0 (local row of j0), nown, sample0 / nsamp (window of the global
+    signal the rank reads), frame0 (local index of the first emitted row), nframes (emitted
+    rows), prev_zero, frames_total."""
     F = P.n_frames(nsamp_total, nfft, hop)
+    Lb, Lf = halos(nfft, hop, edge, minframes)
     plans = []
     shard = F >= 4 * world          # too short to shard: rank 0 takes everything
     for g in range(world):
         j0 = (F * g) // world if shard else (0 if g == 0 else F)
         j1 = (F * (g + 1)) // world if shard else F
         if j1 <= j0:
-            plans.append(dict(rank=g, j0=j0, j1=j1, sample0=0, nsamp=0, frame0=0, nframes=0, prev_zero=True,
-                              has_overlap=False, frames_total=F))
-        elif g == 0:
-            plans.append(dict(rank=g, j0=0, j1=j1, sample0=0, nsamp=(j1 - 1) * hop + nfft, frame0=0, nframes=j1,
-                              prev_zero=True, has_overlap=False, frames_total=F))
+            plans.append(dict(rank=g, j0=j0, j1=j1, w0=j0, w1=j0, own0=0, nown=0, sample0=0, nsamp=0, frame0=0,
+                              nframes=0, prev_zero=True, frames_total=F))
+            continue
+        w0, w1 = max(0, j0 - Lb), min(F, j1 + Lf)
+        if w0 == 0:
+            s0, frame0, prev_zero = 0, 0, True
         else:
-            s0 = (j0 - 2) * hop
-            plans.append(dict(rank=g, j0=j0, j1=j1, sample0=s0, nsamp=(j1 - 1) * hop + nfft - s0, frame0=1,
-                              nframes=j1 - j0 + 1, prev_zero=False, has_overlap=True, frames_total=F))
+            s0, frame0, prev_zero = (w0 - 1) * hop, 1, False
+        plans.append(dict(rank=g, j0=j0, j1=j1, w0=w0, w1=w1, own0=j0 - w0, nown=j1 - j0, sample0=s0,
+                          nsamp=(w1 - 1) * hop + nfft - s0, frame0=frame0, nframes=w1 - w0, prev_zero=prev_zero,
+                          frames_total=F))
     return plans
 
 
-def stitch_ids(tids, ntracks, has_overlap):
-    """Global track ids from per-segment local ids.
+# --------------------------------------------------------------------------- global numbering
+def local_summary(tid_local, plan):
+    """int32 [2K + 4]: local ids of the row before the first own row (-1 = none), local ids of the
+    last own row, nb = partials born before the own rows, n_own = partials born in the own rows,
+    global index of the last own row that holds a point (-1 = none), number of own rows.
+    Local ids count partials in order of creation, so ids born in rows < r are exactly the ids
+    below 1 + max(tid[:r])."""
+    K = tid_local.shape[1]
+    dev = tid_local.device
+    own0, nown = plan["own0"], plan["nown"]
+    out = torch.full((2 * K + 4,), -1, dtype=torch.int32, device=dev)
+    if nown == 0 or tid_local.shape[0] == 0:
+        out[2 * K:] = torch.tensor([0, 0, -1, 0], dtype=torch.int32, device=dev)
+        return out
+    if own0 > 0:
+        out[:K] = tid_local[own0 - 1]
+        nb = tid_local[:own0].max().clamp(min=-1) + 1
+    else:
+        nb = torch.zeros((), dtype=torch.int32, device=dev)
+    own = tid_local[own0:own0 + nown]
+    out[K:2 * K] = own[-1]
+    nbo = torch.maximum(own.max().clamp(min=-1) + 1, nb)
+    rows = torch.nonzero((own >= 0).any(dim=1)).flatten()
+    last = (rows[-1] + plan["j0"]) if rows.numel() else torch.full((), -1, device=dev)
+    out[2 * K] = nb
+    out[2 * K + 1] = nbo - nb
+    out[2 * K + 2] = last
+    out[2 * K + 3] = nown
+    return out
 
-    tids[g]: int tensor [rows_g, K] of local ids (-1 = no point); row 0 is the overlap row
-    when has_overlap[g].  Returns (list of global-id tensors for the OWN rows of every
-    segment, total number of tracks).  Pure torch (runs on CPU tensors too: gloo tests).
-    """
-    out = []
-    base = 0
-    glast = None
-    for g, tid in enumerate(tids):
-        nt = int(ntracks[g])
-        dev = tid.device
-        if tid.shape[0] == 0:
-            out.append(tid)
+
+def resolve_ids(summ_all, K):
+    """Sequential pass over the ranks' summaries (numpy int [world, 2K+4], host): returns
+    (base[g], Gprev[g]) -- global id of the first partial born in rank g's own rows and global
+    ids of the row before its first own row -- plus the total number of partials and the global
+    index of the last frame that holds a point."""
+    world = summ_all.shape[0]
+    base, G = 0, np.full(K, -1, dtype=np.int64)
+    bases, gprevs, max_end = [], [], -1
+    for g in range(world):
+        prev_tid, last_tid = summ_all[g, :K], summ_all[g, K:2 * K]
+        nb, n_own, last_row, nown = (int(v) for v in summ_all[g, 2 * K:2 * K + 4])
+        bases.append(base)
+        gprevs.append(G.copy())
+        if nown == 0:
             continue
-        gid = torch.empty((max(nt, 1),), dtype=torch.int64, device=dev)
-        if has_overlap[g]:
-            row0 = tid[0].long()
-            cols = torch.nonzero(row0 >= 0).flatten()
-            n0 = int(cols.numel())
-            # partials born in the overlap row continue the left neighbour's partials
-            gid[row0[cols]] = glast.to(dev)[cols]
-            own = tid[1:]
-        else:
-            n0 = 0
-            own = tid
-        nnew = nt - n0
-        if nnew > 0:
-            gid[n0:nt] = base + torch.arange(nnew, device=dev)
-        base += nnew
-        ownl = own.long()
-        gown = torch.where(ownl >= 0, gid[ownl.clamp(min=0)], torch.full_like(ownl, -1))
-        out.append(gown.to(torch.int32))
-        if gown.shape[0] > 0:
-            glast = gown[-1].long()
-        else:   # no own rows: the boundary row stays the overlap row's ids
-            glast = torch.where(tid[0].long() >= 0, gid[tid[0].long().clamp(min=0)], torch.full_like(tid[0].long(), -1))
-    return out, base
+        # global ids of this rank's last own row: born in the own rows -> base + rank of birth,
+        # born before them -> the id the partial carries in the row before the first own row
+        Gl = np.full(K, -1, dtype=np.int64)
+        cols = np.flatnonzero(last_tid >= 0)
+        if len(cols):
+            L = last_tid[cols].astype(np.int64)
+            newborn = L >= nb
+            Gl[cols[newborn]] = base + (L[newborn] - nb)
+            old = cols[~newborn]
+            if len(old):
+                inv = np.full(max(nb, 1), -1, dtype=np.int64)      # local id -> column in the previous row
+                pc = np.flatnonzero(prev_tid >= 0)
+                inv[prev_tid[pc]] = pc
+                Gl[old] = G[inv[last_tid[old]]]
+        G = Gl
+        base += n_own
+        max_end = max(max_end, last_row)
+    return bases, gprevs, base, max_end
 
 
-def _pack_bytes(tables, tid, ntracks, rows_max):
-    """One contiguous uint8 buffer per rank: 4 float64 tables + int32 tid, padded to rows_max."""
-    K = tid.shape[1]
-    dev = tid.device
-    rows = tid.shape[0]
-    f64 = torch.zeros((4, rows_max, K), dtype=torch.float64, device=dev)
-    for q, k in enumerate(("f", "mag", "ph", "realph")):
-        f64[q, :rows] = tables[k]
-    i32 = torch.full((rows_max + 1, K), -1, dtype=torch.int32, device=dev)
-    i32[:rows] = tid
-    i32[rows_max, 0] = int(ntracks)
-    i32[rows_max, 1] = rows
-    return torch.cat([f64.view(torch.uint8).flatten(), i32.view(torch.uint8).flatten()])
+def global_ids(tid_local, plan, base, gprev, nb, n_own):
+    """Global ids of the own rows (int32 [nown, K]) from the local ids of the window."""
+    dev = tid_local.device
+    own0, nown = plan["own0"], plan["nown"]
+    own = tid_local[own0:own0 + nown].long()
+    if nown == 0:
+        return own.to(torch.int32)
+    nt = max(int(nb + n_own), 1)
+    gid = torch.full((nt,), -1, dtype=torch.int64, device=dev)
+    if n_own > 0:
+        gid[nb:nb + n_own] = base + torch.arange(n_own, device=dev)
+    if own0 > 0 and nb > 0:
+        prev = tid_local[own0 - 1].long()
+        cols = torch.nonzero(prev >= 0).flatten()
+        gid[prev[cols]] = torch.as_tensor(np.asarray(gprev), dtype=torch.int64, device=dev)[cols]
+    return torch.where(own >= 0, gid[own.clamp(min=0, max=nt - 1)], torch.full_like(own, -1)).to(torch.int32)
 
 
-def _unpack_bytes(buf, rows_max, K):
-    n64 = 4 * rows_max * K * 8
-    f64 = buf[:n64].view(torch.float64).view(4, rows_max, K)
-    i32 = buf[n64:].view(torch.int32).view(rows_max + 1, K)
-    nt, rows = int(i32[rows_max, 0].item()), int(i32[rows_max, 1].item())
-    return {k: f64[q, :rows] for q, k in enumerate(("f", "mag", "ph", "realph"))}, i32[:rows], nt
+def segment_summary_device(tid_local, plan):
+    """pvk_segment_summary of this rank's window (CUDA int32 [2K + 4]); slot 2K+1 holds nb + n_own."""
+    import ctypes as C
+    from . import _lib
+    L = _lib.lib()
+    K = tid_local.shape[1]
+    dev = tid_local.device
+    with torch.cuda.device(dev):
+        mine = torch.empty((2 * K + 4,), dtype=torch.int32, device=dev)
+        _lib.check(L.pvk_segment_summary(C.c_void_p(tid_local.data_ptr()), K, plan["own0"], plan["nown"], plan["j0"],
+                                         C.c_void_p(mine.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                   "pvk_segment_summary")
+    return mine
 
 
-def gather_tables(tables, tid, ntracks, plans, group=None):
-    """The single all_gather: every rank receives every rank's local tables and returns the
-    global frame tables (own rows of all segments, overlap rows dropped) with global ids."""
+def segment_rename_device(tid_local, plan, world, allv, max_own0=None):
+    """pvk_segment_resolve + pvk_segment_rename: global ids of the own rows from the gathered
+    summaries ``allv`` (CUDA int32 [world * (2K + 4)]).  One host read-back (8 ints) at the end."""
+    import ctypes as C
+    from . import _lib
+    L = _lib.lib()
+    K = tid_local.shape[1]
+    dev = tid_local.device
+    own0, nown, g = plan["own0"], plan["nown"], plan["rank"]
+    ptr = lambda t: C.c_void_p(t.data_ptr())                                   # noqa: E731
+    with torch.cuda.device(dev):
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        # the pass walks every segment: scratch must hold the back-halo ids of the largest one
+        cap = max((own0 if max_own0 is None else max_own0) * K, 1)
+        scratch = torch.empty((2, cap), dtype=torch.int32, device=dev)
+        params = torch.zeros((8,), dtype=torch.int32, device=dev)
+        _lib.check(L.pvk_segment_resolve(ptr(allv), world, K, g, ptr(scratch[0]), cap, ptr(scratch[1]), ptr(params),
+                                         stream), "pvk_segment_resolve")
+        own = tid_local[own0:own0 + nown]
+        tid_own = torch.empty_like(own)
+        _lib.check(L.pvk_segment_rename(ptr(own), own.numel(), ptr(scratch[1]), ptr(params), ptr(tid_own), stream),
+                   "pvk_segment_rename")
+        ph = params.cpu().numpy()
+    return dict(tid_own=tid_own, ntracks=int(ph[3]), max_end=int(ph[4]))
+
+
+def _stitch_device(tid_local, plan, plans, group):
+    """stitch() for CUDA tables: summary / resolve / rename run as three small libpvk kernels."""
     import torch.distributed as dist
     world = len(plans)
-    K = tid.shape[1]
-    rows_max = max(p["nframes"] for p in plans)
-    mine = _pack_bytes(tables, tid, ntracks, rows_max)
-    flat = torch.empty((world * mine.numel(),), dtype=torch.uint8, device=mine.device)
-    dist.all_gather_into_tensor(flat, mine, group=group)
-    allb = flat.view(world, mine.numel())
-    segs = [_unpack_bytes(allb[g], rows_max, K) for g in range(world)]
-    gids, ntot = stitch_ids([s[1] for s in segs], [s[2] for s in segs], [p["has_overlap"] for p in plans])
-    glob = {}
-    for k in ("f", "mag", "ph", "realph"):
-        glob[k] = torch.cat([segs[g][0][k][1:] if plans[g]["has_overlap"] else segs[g][0][k] for g in range(world)]).contiguous()
-    glob["tid"] = torch.cat(gids).contiguous()
-    glob["ntracks"] = ntot
-    return glob
+    tid_local = tid_local.contiguous()
+    mine = segment_summary_device(tid_local, plan)
+    if world > 1:
+        allv = torch.empty((world * mine.numel(),), dtype=torch.int32, device=mine.device)
+        dist.all_gather_into_tensor(allv, mine, group=group)
+    else:
+        allv = mine
+    return segment_rename_device(tid_local, plan, world, allv, max(p["own0"] for p in plans))
 
 
-def track_segment(a, plan, world):
-    """Link this rank's rows (first row = overlap row on ranks > 0), then -- when world > 1 --
-    make ids global and assemble the global tables with one all_gather.
+def stitch(tid_local, plan, plans, group=None):
+    """Global numbering of this rank's own rows: one tiny all_gather (2K + 4 ints per rank) and a
+    sequential pass over the ranks.  Returns dict(tid_own int32 [nown, K] global ids, ntracks
+    (total), max_end (global index of the last frame with a point)).  CUDA tables take the libpvk
+    kernels; CPU tensors (gloo tests) the equivalent torch / numpy statement below."""
+    if tid_local.is_cuda:
+        return _stitch_device(tid_local, plan, plans, group)
+    import torch.distributed as dist
+    world = len(plans)
+    K = tid_local.shape[1]
+    mine = local_summary(tid_local, plan)
+    if world > 1:
+        flat = torch.empty((world * mine.numel(),), dtype=torch.int32, device=mine.device)
+        dist.all_gather_into_tensor(flat, mine, group=group)
+        allv = flat.view(world, mine.numel())
+    else:
+        allv = mine.unsqueeze(0)
+    summ = allv.cpu().numpy()
+    bases, gprevs, ntot, max_end = resolve_ids(summ, K)
+    g = plan["rank"]
+    tid_own = global_ids(tid_local, plan, bases[g], gprevs[g], int(summ[g, 2 * K]), int(summ[g, 2 * K + 1]))
+    return dict(tid_own=tid_own, ntracks=ntot, max_end=max_end)
 
-    ``a``: dict from analyze_device (nclips == 1).  Returns dict(f, mag, ph, realph [F*, K],
-    tid, link, ntracks, block0, nblocks): F* = own frames (world == 1) or all frames.
-    """
-    tables = {k: a[k][0] for k in ("f", "mag", "ph", "realph")}
-    tr = P.track_device(tables["f"], tables["mag"])
-    nt = int(tr["ntracks"][0].item())
+
+def gather_track_table(tid_own, plans, group=None, async_op=False):
+    """THE all_gather of the track table: global ids of every frame, int32 [F, K], on every rank.
+    Returns (work handle or None, finish()) -- finish() waits and returns the table."""
+    import torch.distributed as dist
+    world = len(plans)
+    K = tid_own.shape[1]
+    rows_max = max(p["nown"] for p in plans)
+    mine = torch.full((rows_max, K), -1, dtype=torch.int32, device=tid_own.device)
+    mine[:tid_own.shape[0]] = tid_own
     if world == 1:
-        out = dict(tables)
-        out.update(tid=tr["tid"], link=tr["link"], ntracks=nt, block0=0, nblocks=-1)
-        return out
-    plans = plan["all"]
-    glob = gather_tables(tables, tr["tid"], nt, plans)
-    glob.update(link=None, block0=plan["j0"], nblocks=plan["j1"] - plan["j0"])
-    return glob
+        return None, (lambda: tid_own)
+    flat1 = torch.empty((world * rows_max * K,), dtype=torch.int32, device=tid_own.device)
+    work = dist.all_gather_into_tensor(flat1, mine.view(-1), group=group, async_op=async_op)
+    flat = flat1.view(world, rows_max, K)
+
+    def finish():
+        if work is not None:
+            work.wait()
+        return torch.cat([flat[g, :plans[g]["nown"]] for g in range(world)]).contiguous()
+    return work, finish
+
+
+def gather_rows(t_own, plans, group=None):
+    """all_gather of one sharded per-frame table (own rows of every rank, any dtype) -> [F, ...]."""
+    import torch.distributed as dist
+    world = len(plans)
+    if world == 1:
+        return t_own
+    rows_max = max(p["nown"] for p in plans)
+    mine = torch.zeros((rows_max,) + tuple(t_own.shape[1:]), dtype=t_own.dtype, device=t_own.device)
+    mine[:t_own.shape[0]] = t_own
+    flat1 = torch.empty((world * mine.numel(),), dtype=t_own.dtype, device=t_own.device)
+    dist.all_gather_into_tensor(flat1, mine.contiguous().view(-1), group=group)
+    flat = flat1.view((world,) + tuple(mine.shape))
+    return torch.cat([flat[g, :plans[g]["nown"]] for g in range(world)]).contiguous()
+
+
+def render_range(plan, plans, max_end, hop, nfft, hop_an, edge=1.0):
+    """Blocks this rank renders, in global and local (window row) coordinates, and the length of
+    the whole signal: own blocks [j0, j1), clipped to the signal; the rank owning the last frames
+    also renders the blocks after them.  Returns (b0, b1, nout_total)."""
+    nout, _ = P.synth_geometry(max_end, hop, nfft, hop_an, edge)
+    if max_end < 0:
+        return 0, 0, 0
+    nblk = -(-nout // hop)
+    last = max(p["rank"] for p in plans if p["nown"] > 0)
+    b0 = min(plan["j0"], nblk)
+    b1 = nblk if plan["rank"] == last else min(plan["j1"], nblk)
+    if plan["nown"] == 0:
+        b0 = b1 = 0
+    return b0, b1, nout
+
+
+def resynth_local(tid_local, pk_local, plan, plans, max_end, sr, hop, nfft, hop_an, edge=1.0, minframes=3,
+                  out=None, ws=None, block_range=None, reuse_tracks=False):
+    """Render this rank's block range (or the sub-range ``block_range`` of it, global block
+    indices) from its LOCAL tables: float64 device tensor holding global samples
+    [b0*hop, min(b1*hop, nout))."""
+    b0, b1, nout = render_range(plan, plans, max_end, hop, nfft, hop_an, edge)
+    if block_range is not None:
+        b0, b1 = block_range
+    if b1 <= b0:
+        return torch.zeros((0,), dtype=torch.float64, device=tid_local.device)
+    w0 = plan["w0"]
+    nout_local = nout - w0 * hop                       # same signal, local sample origin w0*hop
+    return P.resynth_device(tid_local, pk_local, sr, hop, nfft, hop_an, edge=edge, minframes=minframes,
+                            block0=b0 - w0, nblocks=b1 - b0, nout=nout_local, out=out, ws=ws,
+                            reuse_tracks=reuse_tracks)
+
+
+# --------------------------------------------------------------------------- host API
+class ShardedSinSum(object):
+    """Result of ShardedPV.toSinSum(): the global track table on every rank + this rank's local
+    partials (window rows, local ids) for resynthesis."""
+
+    def __init__(self, spv, local_ss, st, finish_gather):
+        self._spv = spv
+        self.local = local_ss
+        self.ntracks = st["ntracks"]
+        self.max_end = st["max_end"]
+        self.tid_own = st["tid_own"]
+        self._finish = finish_gather
+        self._tid = None
+        self._spans = None
+        self.sr, self.nfft, self.hop = spv.sr, spv.nfft, spv.hop
+
+    @property
+    def device_track_table(self):
+        """int32 CUDA tensor [F, K]: global partial id of every peak slot of every frame."""
+        if self._tid is None:
+            self._tid = self._finish()
+        return self._tid
+
+    @property
+    def track_ids(self):
+        return self.device_track_table.cpu().numpy()
+
+    def device_spans(self):
+        """(tstart, tlen) int32 CUDA tensors [ntracks]: first frame and length of every partial."""
+        if self._spans is None:
+            self._spans = P.spans_device(self.device_track_table, self.ntracks)
+        return self._spans
+
+    @property
+    def st(self):
+        return self.device_spans()[0].cpu().numpy().astype(np.int64).tolist()
+
+    @property
+    def end(self):
+        s, n = self.device_spans()
+        return (s.cpu().numpy().astype(np.int64) + n.cpu().numpy() - 1).tolist()
+
+    def gather_tables(self, group=None):
+        """Second, optional collective: collect the sharded peak tables and return an ordinary
+        SinSum (identical on every rank) with the global numbering, e.g. to read ``partial[i]``."""
+        spv = self._spv
+        d = spv.pv.device_tables
+        o0, n = spv.plan["own0"], spv.plan["nown"]
+        glob = {k: gather_rows(d[k][o0:o0 + n], spv.plans, group) for k in ("f", "mag", "ph", "realph")}
+        ss = P.SinSum(self.sr, nfft=self.nfft, hop=self.hop, device=spv.pv._dev)
+        ss._set_device_tables(glob["f"], glob["mag"], glob["ph"], glob["realph"])
+        ss._set_device_tracks(self.device_track_table, None, self.ntracks)
+        return ss
+
+    def synth_local(self, sr=None, hop=None, edge=1.0, minframes=3, hostbuf=None, chunks=8, to_host=False):
+        """Render this rank's own block range of the resynthesised signal (the last rank also renders
+        the tail): global samples [b0*hop, ...).  Returns (signal, first global sample).  ``hostbuf``:
+        render in ``chunks`` ranges and download each into pinned ``hostbuf['w']`` meanwhile."""
+        spv = self._spv
+        sr = spv.sr if sr is None else sr
+        hop = spv.hop if hop is None else int(hop)
+        if (edge, minframes) != (spv.edge, spv.minframes):
+            raise ValueError("the segment halos were planned for edge=%r, minframes=%r" % (spv.edge, spv.minframes))
+        pk = self.local._ensure_packed()
+        tidl = self.local._trk["tid"]
+        b0, b1, nout = render_range(spv.plan, spv.plans, self.max_end, hop, self.nfft, self.hop, edge)
+        n_local = max(min(b1 * hop, nout) - b0 * hop, 0)
+        dev = tidl.device
+        if hostbuf is None:
+            w = resynth_local(tidl, pk, spv.plan, spv.plans, self.max_end, sr, hop, self.nfft, self.hop, edge, minframes)
+            return (w.cpu().numpy() if to_host else w), b0 * hop
+        cur = torch.cuda.current_stream(dev)
+        _, d2h = P._side_streams(dev)
+        with torch.cuda.device(dev):
+            out = torch.empty((n_local,), dtype=torch.float64, device=dev)
+            hw = P._pinned(hostbuf, "w", (n_local,), torch.float64)
+            d2h.wait_stream(cur)
+            nblk = b1 - b0
+            chunks = max(1, min(chunks, nblk // 64 if nblk >= 64 else 1))
+            F, K = tidl.shape
+            ws = P.resynth_workspace(F, K, int(pk["tstart"].shape[0]), -(-nblk // chunks), dev) if nblk else None
+            for i in range(chunks if nblk else 0):
+                c0, c1 = b0 + (nblk * i) // chunks, b0 + (nblk * (i + 1)) // chunks
+                n0, n1 = (c0 - b0) * hop, min((c1 - b0) * hop, n_local)
+                resynth_local(tidl, pk, spv.plan, spv.plans, self.max_end, sr, hop, self.nfft, self.hop, edge,
+                              minframes, out=out[n0:n1], ws=ws, block_range=(c0, c1), reuse_tracks=i > 0)
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                with torch.cuda.stream(d2h):
+                    d2h.wait_event(ev)
+                    hw[n0:n1].copy_(out[n0:n1], non_blocking=True)
+            d2h.synchronize()
+        self.d2h_bytes = n_local * 8
+        self._last_out = out
+        return hw[:n_local].numpy(), b0 * hop
 
 
 class ShardedPV(object):
@@ -154,18 +400,20 @@ class ShardedPV(object):
 
     Every rank constructs it with ITS window of the signal (``plan['sample0']`` ..
     ``+plan['nsamp']``; see :func:`plan_segments`), host or device.  ``run_pv`` analyses the
-    rank's frames, ``toSinSum`` links them and gathers the global track table (one
-    all_gather), ``synth`` renders the rank's own block range of the output signal.
+    rank's window rows, ``toSinSum`` links them locally, makes the numbering global and gathers
+    the track table (the one all_gather), ``ShardedSinSum.synth_local`` renders the rank's own
+    block range of the output signal from local data.
     """
 
     def __init__(self, x_local, sr, nsamp_total, nfft=1024, hop=None, npks=20, pkthresh=0.005, wind=np.hanning,
-                 rank=None, world=None, device=None):
+                 rank=None, world=None, device=None, edge=1.0, minframes=3, group=None):
         import torch.distributed as dist
         self.rank = dist.get_rank() if rank is None else rank
         self.world = dist.get_world_size() if world is None else world
         hop = int(nfft / 2) if hop is None else int(hop)
-        self.plans = plan_segments(nsamp_total, nfft, hop, self.world)
-        self.plan = dict(self.plans[self.rank], all=self.plans)
+        self.edge, self.minframes, self.group = edge, minframes, group
+        self.plans = plan_segments(nsamp_total, nfft, hop, self.world, edge, minframes)
+        self.plan = self.plans[self.rank]
         self.pv = P.PV(x_local, sr, nfft=nfft, hop=hop, npks=npks, pkthresh=pkthresh, wind=wind, progress=False,
                        device=device)
         if self.pv.nsamp != self.plan["nsamp"]:
@@ -173,33 +421,33 @@ class ShardedPV(object):
                 self.rank, self.plan["nsamp"], self.plan["sample0"], self.pv.nsamp))
         self.sr, self.nfft, self.hop = sr, nfft, hop
 
-    def run_pv(self):
-        """Analyse this rank's frames (rows: overlap row first on ranks > 0, then own frames)."""
+    def run_pv(self, hostbuf=None, chunks=8):
+        """Analyse this rank's window rows [w0, w1) (own rows: ``own_rows``).  ``hostbuf``: stream the
+        tables into pinned host memory as in PV.run_pv."""
         p, pv = self.plan, self.pv
-        pv._devout = P.analyze_device(pv._xd, pv.sr, pv.nfft, pv.hop, pv.npeaks, pv.peakthresh, pv._tb,
-                                      frame0=p["frame0"], nframes=p["nframes"], prev_zero=p["prev_zero"])
+        pv._hostbuf = None
+        pv._d2h_event = None
+        if hostbuf is not None and p["nframes"] > 0:
+            pv._run_pv_streamed(hostbuf, int(chunks), 0, frame_lo=p["frame0"], nframes=p["nframes"],
+                                prev_zero=p["prev_zero"])
+        else:
+            pv._devout = P.analyze_device(pv._xd, pv.sr, pv.nfft, pv.hop, pv.npeaks, pv.peakthresh, pv._tb,
+                                          frame0=p["frame0"], nframes=p["nframes"], prev_zero=p["prev_zero"])
         pv.nframes = p["nframes"]
         pv._host = {}
-        j_first = p["j0"] - (1 if p["has_overlap"] else 0)
-        pv._host["t"] = ((np.arange(pv.nframes) + j_first) * pv.hop + pv.nfft / 2.0) / pv.sr
+        pv._host["t"] = ((np.arange(pv.nframes) + p["w0"]) * pv.hop + pv.nfft / 2.0) / pv.sr
 
-    def toSinSum(self):
-        """Global SinSum (identical on every rank) + this rank's block range."""
-        g = track_segment(self.pv._devout, self.plan, self.world)
+    @property
+    def own_rows(self):
+        """slice of the window rows (pv.f etc.) this rank owns."""
+        return slice(self.plan["own0"], self.plan["own0"] + self.plan["nown"])
+
+    def toSinSum(self, async_gather=True):
+        """Local linking + global numbering + the all_gather of the track table."""
+        d = self.pv.device_tables
         ss = P.SinSum(self.sr, nfft=self.nfft, hop=self.hop, device=self.pv._dev)
-        ss._set_device_tables(g["f"], g["mag"], g["ph"], g["realph"])
-        ss._set_device_tracks(g["tid"], g["link"], g["ntracks"])
-        self.block0, self.nblocks = g["block0"], g["nblocks"]
-        return ss
-
-    def synth_local(self, ss, hop=None, edge=1.0, minframes=3):
-        """Render this rank's own block range [j0, j1) (the last rank also renders the tail)."""
-        hop = self.hop if hop is None else int(hop)
-        pk = ss._ensure_packed()
-        max_end = int((pk["tstart"] + pk["tlen"] - 1).max().item()) if ss._trk["ntracks"] else -1
-        nout, _ = P.synth_geometry(max_end, hop, self.nfft, self.hop, edge)
-        nblk = -(-nout // hop)
-        b0 = self.block0
-        nb = (nblk - b0) if self.rank == self.world - 1 else self.nblocks
-        return P.resynth_device(ss._trk["tid"], pk, self.sr, hop, self.nfft, self.hop, edge=edge, minframes=minframes,
-                                max_end=max_end, block0=b0, nblocks=nb)
+        ss._set_device_tables(d["f"], d["mag"], d["ph"], d["realph"])
+        tr = ss._ensure_tracks()
+        st = stitch(tr["tid"], self.plan, self.plans, self.group)
+        _, finish = gather_track_table(st["tid_own"], self.plans, self.group, async_op=async_gather and self.world > 1)
+        return ShardedSinSum(self, ss, st, finish)

@@ -211,6 +211,19 @@ def pack_device(fd, magd, phd, realphd, tid, link, ntracks):   # link: unused, k
                 pph=packed[2][:npts], prealph=packed[3][:npts], npts=npts)
 
 
+def spans_device(tid, ntracks):
+    """pvk_track_spans: first frame / length of every partial of an id table ``[F, K]`` (device)."""
+    L = _lib.lib()
+    dev = tid.device
+    F, K = tid.shape
+    nt = int(ntracks)
+    tstart = torch.empty((max(nt, 1),), dtype=torch.int32, device=dev)
+    tlen = torch.empty((max(nt, 1),), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.pvk_track_spans(_ptr(tid), F, K, nt, _ptr(tstart), _ptr(tlen), _stream()), "pvk_track_spans")
+    return tstart[:nt], tlen[:nt]
+
+
 def synth_geometry(max_end, hop, nfft, hop_an, edge=1.0):
     """Output length of SinSum.synth (PVAnalysis.py:1055-1059,1070) and the edge length."""
     dfr = nfft / hop_an / 2.
@@ -219,16 +232,17 @@ def synth_geometry(max_end, hop, nfft, hop_an, edge=1.0):
 
 
 def resynth_device(tid, pk, sr, hop, nfft, hop_an, edge=1.0, minframes=3, max_end=None, block0=0,
-                   nblocks=-1, out=None, ws=None, reuse_tracks=False):
+                   nblocks=-1, out=None, ws=None, reuse_tracks=False, nout=None):
     """pvk_resynth for one clip; returns the float64 device signal (asynchronous).  ``ws``: a
     workspace tensor to (re)use; ``reuse_tracks``: ``ws`` already holds the per-partial masks and
     fade parameters of an earlier call with the same tracks and synthesis parameters."""
     L = _lib.lib()
     dev = tid.device
     F, K = tid.shape
-    if max_end is None:
-        max_end = int((pk["tstart"] + pk["tlen"] - 1).max().item()) if len(pk["tstart"]) else -1
-    nout, _ = synth_geometry(max_end, hop, nfft, hop_an, edge)
+    if nout is None:
+        if max_end is None:
+            max_end = int((pk["tstart"] + pk["tlen"] - 1).max().item()) if len(pk["tstart"]) else -1
+        nout, _ = synth_geometry(max_end, hop, nfft, hop_an, edge)
     nblk = -(-nout // hop)
     nb = nblk - block0 if nblocks < 0 else nblocks
     if out is None:
@@ -438,9 +452,11 @@ class PV(object):
         if self.progress:
             self.progress.update(self.nsamp)
 
-    def _run_pv_streamed(self, hostbuf, chunks, run_frames):
+    def _run_pv_streamed(self, hostbuf, chunks, run_frames, frame_lo=0, nframes=None, prev_zero=True):
+        """Rows r = 0 .. F-1 are the frames starting at sample (frame_lo + r)*hop (frame_lo = 1 with
+        prev_zero=False: frame 0 of the buffer is only the warm-up of a sharded window)."""
         dev, K = self._dev, self.npeaks
-        F = n_frames(self.nsamp, self.nfft, self.hop)
+        F = n_frames(self.nsamp, self.nfft, self.hop) - frame_lo if nframes is None else int(nframes)
         cur = torch.cuda.current_stream(dev)
         h2d, d2h = _side_streams(dev)
         names = ("f", "mag", "ph", "realph", "binno")
@@ -463,7 +479,7 @@ class PV(object):
             for i in range(chunks if F else 0):
                 j0, j1 = (F * i) // chunks, (F * (i + 1)) // chunks
                 if upload:
-                    s_end = self.nsamp if i == chunks - 1 else (j1 - 1) * self.hop + self.nfft
+                    s_end = self.nsamp if i == chunks - 1 else (frame_lo + j1 - 1) * self.hop + self.nfft
                     with torch.cuda.stream(h2d):
                         xd[s_done:s_end].copy_(self._xh_pinned[s_done:s_end], non_blocking=True)
                         ev = torch.cuda.Event()
@@ -472,8 +488,8 @@ class PV(object):
                     cur.wait_event(ev)
                     s_done = s_end
                 view = {k: v[:, j0:j1] for k, v in out.items()}
-                analyze_device(xd, self.sr, self.nfft, self.hop, K, self.peakthresh, self._tb, frame0=j0,
-                               nframes=j1 - j0, prev_zero=(j0 == 0), run_frames=run_frames, out=view)
+                analyze_device(xd, self.sr, self.nfft, self.hop, K, self.peakthresh, self._tb, frame0=frame_lo + j0,
+                               nframes=j1 - j0, prev_zero=(prev_zero and j0 == 0), run_frames=run_frames, out=view)
                 ev2 = torch.cuda.Event()
                 ev2.record(cur)
                 _mark("analysis %d" % i, cur)

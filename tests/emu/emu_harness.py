@@ -149,3 +149,29 @@ def resynth(tid, pk, sr, hop, nfft, hop_an, edge=1.0, minframes=3, block0=0, nbl
                         ptr(pk["prealph"]), float(sr), int(hop), int(nfft), int(hop_an), float(edge),
                         int(minframes), ptr(out), nout, block0, nblocks, ptr(ws), wsb, 0, None))
     return out
+
+
+def segment_stitch(tids, plans):
+    """pvk_segment_summary -> (concatenate = all_gather) -> pvk_segment_resolve -> pvk_segment_rename for
+    every segment; tids[r]: local ids int32 [rows, K] of segment r.  Returns (list of global id arrays of
+    the own rows, total partials, last frame with a point)."""
+    L = lib()
+    world = len(plans)
+    K = tids[0].shape[1]
+    summ = np.zeros((world, 2 * K + 4), dtype=np.int32)
+    tids = [np.ascontiguousarray(t, dtype=np.int32) for t in tids]
+    for r, p in enumerate(plans):
+        check(L.pvk_segment_summary(ptr(tids[r]), K, p["own0"], p["nown"], p["j0"], ptr(summ[r]), None))
+    out, ntot, max_end = [], None, None
+    for r, p in enumerate(plans):
+        cap = max(max(q["own0"] for q in plans) * K, 1)      # scratch holds any segment's back-halo ids
+        scratch = np.zeros(cap, dtype=np.int32)
+        gidlow = np.zeros(cap, dtype=np.int32)
+        params = np.zeros(8, dtype=np.int32)
+        check(L.pvk_segment_resolve(ptr(summ), world, K, r, ptr(scratch), cap, ptr(gidlow), ptr(params), None))
+        own = np.ascontiguousarray(tids[r][p["own0"]:p["own0"] + p["nown"]])
+        res = np.empty_like(own)
+        check(L.pvk_segment_rename(ptr(own), own.size, ptr(gidlow), ptr(params), ptr(res), None))
+        out.append(res)
+        ntot, max_end = int(params[3]), int(params[4])
+    return out, ntot, max_end

@@ -1,7 +1,8 @@
-"""CPU, world_size 2 over gloo: the segment planner and the all_gather stitch of track ids
+"""CPU, world_size 2/3 over gloo: the segment planner, the global numbering of locally linked
+partials (tiny all_gather + sequential pass) and the all_gather of the track table
 (pypevoc_b200/dist.py) reproduce the unsharded track numbering bit for bit.  Local linking is
 done here by the oracle (the GPU kernel is checked in the -m gpu tests); what this test pins is
-the host-side sharding logic and the collective."""
+the host-side sharding logic and the collectives."""
 import os
 import sys
 
@@ -15,44 +16,71 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+CASE = dict(cfg3_clip=(512, 128), metric_1s=(2048, 512))
 
-def _worker(rank, world, port, result_dir):
+
+def _worker(rank, world, port, result_dir, name):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from oracle import pv_oracle as orc
     from pypevoc_b200 import dist as D
     from golden_util import case_golden
-    g = case_golden("cfg3_clip")                       # 371 frames x 20 peaks from the real reference
+    g = case_golden(name)                              # peak tables from the real reference
     F, K = g["f"].shape
-    # a frame plan over `world` ranks (sample counts are irrelevant for the stitch)
-    nfft, hop = 512, 128
-    nsamp = (F - 1) * hop + nfft + 1
+    nfft, hop = CASE[name]
+    nsamp = (F - 1) * hop + nfft + 1                   # sample counts are irrelevant for the stitch
     plans = D.plan_segments(nsamp, nfft, hop, world)
     assert plans[0]["frames_total"] == F
     p = plans[rank]
-    lo = p["j0"] - (1 if p["has_overlap"] else 0)
-    tables = {k: torch.from_numpy(np.ascontiguousarray(g[k][lo:p["j1"]])) for k in ("f", "mag", "ph", "realph")}
-    assert tables["f"].shape[0] == p["nframes"]
-    loc = orc.track(tables["f"].numpy(), tables["mag"].numpy())     # local ids, overlap row first
-    glob = D.gather_tables(tables, torch.from_numpy(loc["tid"]), len(loc["st"]), plans)
-    np.savez(os.path.join(result_dir, "r%d.npz" % rank), tid=glob["tid"].numpy(), f=glob["f"].numpy(),
-             ntracks=glob["ntracks"])
+    f = np.ascontiguousarray(g["f"][p["w0"]:p["w1"]])
+    mag = np.ascontiguousarray(g["mag"][p["w0"]:p["w1"]])
+    assert f.shape[0] == p["nframes"]
+    loc = orc.track(f, mag)                            # local ids over the window rows
+    st = D.stitch(torch.from_numpy(loc["tid"]), p, plans)
+    _, finish = D.gather_track_table(st["tid_own"], plans, async_op=False)
+    table = finish()
+    fglob = D.gather_rows(torch.from_numpy(f[p["own0"]:p["own0"] + p["nown"]]), plans)
+    np.savez(os.path.join(result_dir, "r%d.npz" % rank), tid=table.numpy(), f=fglob.numpy(),
+             ntracks=st["ntracks"], max_end=st["max_end"])
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_stitch_matches_unsharded_tracking(tmp_path, world):
+@pytest.mark.parametrize("world,name", [(2, "cfg3_clip"), (3, "cfg3_clip"), (2, "metric_1s")])
+def test_stitch_matches_unsharded_tracking(tmp_path, world, name):
     from golden_util import case_golden
     port = 29600 + world + (os.getpid() % 200)
-    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
-    g = case_golden("cfg3_clip")
+    mp.spawn(_worker, args=(world, port, str(tmp_path), name), nprocs=world, join=True)
+    g = case_golden(name)
     for r in range(world):
         z = np.load(os.path.join(str(tmp_path), "r%d.npz" % r))
         assert np.array_equal(z["f"], g["f"])
         assert np.array_equal(z["tid"], g["tid"]), "rank %d: stitched ids differ from the reference numbering" % r
         assert int(z["ntracks"]) == len(g["st"])
+        assert int(z["max_end"]) == int(np.max(g["end"]))
+
+
+def test_resolve_ids_many_ranks_single_process():
+    """The numbering pass alone, 5 'ranks' in one process (no collective)."""
+    from oracle import pv_oracle as orc
+    from pypevoc_b200 import dist as D
+    from golden_util import case_golden
+    g = case_golden("cfg3_clip")
+    F, K = g["f"].shape
+    world = 5
+    plans = D.plan_segments((F - 1) * 128 + 512 + 1, 512, 128, world)
+    locs, summ = [], []
+    for p in plans:
+        loc = orc.track(g["f"][p["w0"]:p["w1"]], g["mag"][p["w0"]:p["w1"]])
+        locs.append(torch.from_numpy(loc["tid"]))
+        summ.append(D.local_summary(locs[-1], p).numpy())
+    summ = np.stack(summ)
+    bases, gprevs, ntot, max_end = D.resolve_ids(summ, K)
+    rows = [D.global_ids(locs[r], plans[r], bases[r], gprevs[r], int(summ[r, 2 * K]), int(summ[r, 2 * K + 1]))
+            for r in range(world)]
+    assert np.array_equal(torch.cat(rows).numpy(), g["tid"])
+    assert ntot == len(g["st"])
 
 
 def test_plan_covers_all_frames():
@@ -62,12 +90,14 @@ def test_plan_covers_all_frames():
                                     (44100 * 600 * 8, 2048, 256, 8)):
         plans = D.plan_segments(nsamp, nfft, hop, world)
         F = n_frames(nsamp, nfft, hop)
+        Lb, Lf = D.halos(nfft, hop)
         assert plans[0]["j0"] == 0 and plans[-1]["j1"] == F
         for a, b in zip(plans[:-1], plans[1:]):
             assert a["j1"] == b["j0"]
         for p in plans:
             if p["nframes"]:
                 assert p["sample0"] + p["nsamp"] <= nsamp
-                first = p["j0"] - (1 if p["has_overlap"] else 0)
-                assert p["sample0"] + p["frame0"] * hop == first * hop
+                assert p["w0"] == max(0, p["j0"] - Lb) and p["w1"] == min(F, p["j1"] + Lf)
+                assert p["sample0"] + p["frame0"] * hop == p["w0"] * hop
                 assert (p["frame0"] + p["nframes"] - 1) * hop + nfft == p["nsamp"]
+                assert p["own0"] == p["j0"] - p["w0"] and p["nown"] == p["j1"] - p["j0"]

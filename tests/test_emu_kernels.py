@@ -114,3 +114,17 @@ def test_emu_track_stitch_across_tiles():
     tr = eh.track(f, mag)
     assert np.array_equal(tr["tid"][0], o["tid"])
     assert int(tr["ntracks"][0]) == len(o["st"])
+
+
+@pytest.mark.parametrize("world", [2, 5])
+def test_emu_segment_numbering_kernels(world):
+    """pvk_segment_summary / _resolve / _rename (global numbering of per-segment linked partials)
+    against the reference's numbering of the unsharded table."""
+    from pypevoc_b200 import dist as D
+    g = case_golden("cfg3_clip")
+    F, K = g["f"].shape
+    plans = D.plan_segments((F - 1) * 128 + 512 + 1, 512, 128, world)
+    tids = [orc.track(g["f"][p["w0"]:p["w1"]], g["mag"][p["w0"]:p["w1"]])["tid"] for p in plans]
+    rows, ntot, max_end = eh.segment_stitch(tids, plans)
+    assert np.array_equal(np.concatenate(rows), g["tid"])
+    assert ntot == len(g["st"]) and max_end == int(np.max(g["end"]))

@@ -311,3 +311,57 @@ def test_streamed_pipeline_equals_plain_calls(pvmod):
         assert np.array_equal(np.asarray(pv0.totalmag), np.asarray(pv1.totalmag))
         assert w1.shape == w0.shape and np.array_equal(w0, w1)
         assert pv1.d2h_bytes == pv1.nframes * (5 * 50 + 1) * 8 and ss1.d2h_bytes == w1.nbytes
+
+
+@pytest.mark.parametrize("world", [2, 5])
+def test_sharded_pipeline_equals_unsharded(pvmod, world):
+    """Every 'rank' (run one after the other on this GPU, the all_gathers replaced by their
+    definition) analyses its window, links it locally and renders its own blocks from LOCAL
+    tables: own rows, global track ids and the concatenated signal equal the unsharded run bit
+    for bit (pypevoc_b200/dist.py)."""
+    from pypevoc_b200 import signals, dist as D
+    from pypevoc_b200 import pv as P
+    sr, nfft, hop, npks = 44100, 2048, 512, 50
+    x = signals.harm(sr, 4.0, 220, 90, 0.5, 0.02, 9)
+    x[int(2.2 * sr):int(2.6 * sr)] = 0.0                      # a silent gap: partials end and restart
+    pv0 = pvmod.PV(x, sr, nfft=nfft, hop=hop, npks=npks, progress=False)
+    pv0.run_pv()
+    ss0 = pv0.toSinSum()
+    w0 = ss0.synth(sr, hop)
+    tid0 = ss0.track_ids
+    plans = D.plan_segments(len(x), nfft, hop, world)
+    locs, summ, tabs = [], [], []
+    for p in plans:
+        xs = torch.from_numpy(x[p["sample0"]:p["sample0"] + p["nsamp"]]).cuda()
+        a = P.analyze_device(xs, sr, nfft, hop, npks, 0.005, pv0._tb, frame0=p["frame0"], nframes=p["nframes"],
+                             prev_zero=p["prev_zero"])
+        tab = {k: a[k][0] for k in ("f", "mag", "ph", "realph")}
+        own = slice(p["own0"], p["own0"] + p["nown"])
+        for k in ("f", "mag", "ph", "realph"):
+            assert np.array_equal(tab[k][own].cpu().numpy(), getattr(pv0, k)[p["j0"]:p["j1"]]), k
+        tr = P.track_device(tab["f"], tab["mag"])
+        locs.append((tab, tr))
+        summ.append(D.local_summary(tr["tid"], p).cpu().numpy())
+    summ = np.stack(summ)
+    bases, gprevs, ntot, max_end = D.resolve_ids(summ, npks)
+    assert ntot == len(ss0.st) and max_end == max(ss0.end)
+    rows, sig = [], []
+    for r, p in enumerate(plans):
+        tab, tr = locs[r]
+        rows.append(D.global_ids(tr["tid"], p, bases[r], gprevs[r], int(summ[r, 2 * npks]), int(summ[r, 2 * npks + 1])))
+        pk = P.pack_device(tab["f"], tab["mag"], tab["ph"], tab["realph"], tr["tid"], None, int(tr["ntracks"][0].item()))
+        sig.append(D.resynth_local(tr["tid"], pk, p, plans, max_end, sr, hop, nfft, hop).cpu().numpy())
+    table = torch.cat(rows)
+    assert np.array_equal(table.cpu().numpy(), tid0)
+    # the same numbering through the libpvk segment kernels (summary -> [all_gather] -> resolve -> rename)
+    allv = torch.cat([D.segment_summary_device(locs[r][1]["tid"].contiguous(), p) for r, p in enumerate(plans)])
+    for r, p in enumerate(plans):
+        st = D.segment_rename_device(locs[r][1]["tid"].contiguous(), p, world, allv, max(q["own0"] for q in plans))
+        assert st["ntracks"] == ntot and st["max_end"] == max_end
+        assert torch.equal(st["tid_own"], rows[r]), r
+    tstart, tlen = P.spans_device(table.contiguous(), ntot)
+    assert tstart.cpu().numpy().tolist() == ss0.st
+    assert (tstart + tlen - 1).cpu().numpy().tolist() == ss0.end
+    w = np.concatenate(sig)
+    assert w.shape == w0.shape
+    assert np.array_equal(w, w0)
