@@ -320,11 +320,19 @@ __global__ void track_scan_kernel(const int32_t *__restrict__ newcount, int32_t 
   int32_t *out = base + clip * F;
   if (tid == 0) carry_s = 0;
   __syncthreads();
+  int vn[E];                                               // next tile, loaded one tile ahead
+#pragma unroll
+  for (int j = 0; j < E; ++j) { const int64_t i = (int64_t)tid * E + j; vn[j] = i < F ? in[i] : 0; }
   for (int64_t s = 0; s < F; s += (int64_t)blockDim.x * E) {
     const int64_t i0 = s + (int64_t)tid * E;
     int v[E], loc = 0;
 #pragma unroll
-    for (int j = 0; j < E; ++j) { v[j] = (i0 + j < F) ? in[i0 + j] : 0; loc += v[j]; }
+    for (int j = 0; j < E; ++j) { v[j] = vn[j]; loc += v[j]; }
+    {
+      const int64_t n0 = i0 + (int64_t)blockDim.x * E;
+#pragma unroll
+      for (int j = 0; j < E; ++j) vn[j] = (n0 + j < F) ? in[n0 + j] : 0;
+    }
     const int inc = warp_scan_incl(loc);
     if (lane == 31) wsum[warp] = inc;
     __syncthreads();
@@ -342,29 +350,62 @@ __global__ void track_scan_kernel(const int32_t *__restrict__ newcount, int32_t 
 }
 
 // ------------------------------------------------------------------ chain resolution
-// tid values while unresolved: >= 0 final id; -1 not a point; <= -2: descends from column
-// (-2 - v) of the first row of this chunk, whose own id is not known yet.
+// tid values while unresolved: >= 0 final id; -1 not a point; <= -2: "same id as column -2-v of
+// the row before" (inside a tile) or, once a chunk is done, "same id as column -2-v of the first
+// row of this chunk", whose own id is not known yet.
+//
+// Sequential resolve of `n` rows held in shared memory by ONE warp (lane owns columns lane,
+// lane+32, ...): entry <= -2 takes the value of column -2-v of the row before (prev for row 0),
+// which is already resolved.  One __syncwarp per row, no block barrier.
+__device__ __forceinline__ void warp_resolve_rows(int *rows, int n, int K, const int *prev) {
+  const int lane = threadIdx.x & 31;
+  for (int i = 0; i < n; ++i) {
+    int *r = rows + i * K;
+    for (int c = lane; c < K; c += 32) {
+      const int v = r[c];
+      if (v <= -2) r[c] = prev[-2 - v];
+    }
+    __syncwarp();
+    prev = r;
+  }
+}
+
+__host__ __device__ inline int track_tile_rows(int K) {
+  int rt = 4096 / ((K + 31) / 32 * 32);            // <= 16 KB of shared memory per warp
+  return rt > 32 ? 32 : (rt < 1 ? 1 : rt);
+}
+
+// One warp per chunk of TRACK_CHUNK frames, W warps per CTA: link + base -> tid, tile by tile.
 __global__ void track_chunk_kernel(const int32_t *__restrict__ link, const int32_t *__restrict__ base,
-                                   int64_t F, int K, int64_t nchunks, int32_t *__restrict__ tid) {
+                                   int64_t F, int K, int64_t nchunks, int64_t total_chunks, int32_t *__restrict__ tid) {
   PVK_SMEM(smem);
-  int *prevrow = reinterpret_cast<int *>(smem);
-  const int64_t clip = blockIdx.x / nchunks, ch = blockIdx.x % nchunks;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+  const int RT = track_tile_rows(K);
+  int *tile = reinterpret_cast<int *>(smem) + (size_t)warp * (RT + 1) * K;     // [RT][K] + carried row [K]
+  int *carry = tile + RT * K;
+  const int64_t cid = (int64_t)blockIdx.x * W + warp;
+  if (cid >= total_chunks) return;
+  const int64_t clip = cid / nchunks, ch = cid % nchunks;
   const int64_t j0 = ch * TRACK_CHUNK, j1 = (j0 + TRACK_CHUNK < F) ? j0 + TRACK_CHUNK : F;
-  const int c = threadIdx.x;
-  const bool act = c < K;
-  int lk_next = act ? link[(clip * F + j0) * K + c] : LINK_NONE;
-  for (int64_t j = j0; j < j1; ++j) {
-    const int64_t row = clip * F + j;
-    const int lk = lk_next;
-    if (j + 1 < j1 && act) lk_next = link[(row + 1) * K + c];
-    int v;
-    if (lk == LINK_NONE) v = -1;
-    else if (lk <= -2) v = base[row] + (-2 - lk);
-    else if (j == j0) v = -2 - c;
-    else v = prevrow[lk];
-    __syncthreads();
-    if (act) { prevrow[c] = v; tid[row * K + c] = v; }
-    __syncthreads();
+  for (int64_t t0 = j0; t0 < j1; t0 += RT) {
+    const int n = (int)((t0 + RT <= j1) ? RT : j1 - t0);
+    const int64_t row0 = clip * F + t0;
+    for (int e = lane; e < n * K; e += 32) {
+      const int i = e / K, c = e - i * K;
+      const int lk = link[row0 * K + e];
+      int v;
+      if (lk == LINK_NONE) v = -1;
+      else if (lk <= -2) v = base[row0 + i] + (-2 - lk);
+      else if (t0 + i == j0) v = -2 - c;             // continued from the chunk before: unresolved
+      else v = -2 - lk;                              // same id as column lk of the row before
+      tile[e] = v;
+    }
+    __syncwarp();
+    if (t0 == j0) warp_resolve_rows(tile + K, n - 1, K, tile);       // the first row stays as it is
+    else warp_resolve_rows(tile, n, K, carry);
+    for (int e = lane; e < n * K; e += 32) tid[row0 * K + e] = tile[e];
+    for (int c = lane; c < K; c += 32) carry[c] = tile[(n - 1) * K + c];
+    __syncwarp();
   }
 }
 
@@ -386,30 +427,25 @@ __global__ void track_boundary_kernel(const int32_t *__restrict__ link, const in
   }
 }
 
-// sequential over the chunks of one clip; G becomes the final ids of every chunk's first row.
-// The table is streamed through shared memory in tiles of `tile` chunks (coalesced loads and
-// stores by the whole CTA); inside a tile the pass runs out of shared memory, one barrier per
-// chunk: an unresolved entry -2-c takes the (already final) id of column c of the chunk before.
-__global__ void __launch_bounds__(1024) track_stitch_kernel(int32_t *__restrict__ G, int K, int64_t nchunks, int tile) {
+// sequential over the chunks of one clip (one warp per clip); G becomes the final ids of every
+// chunk's first row: an unresolved entry -2-c takes the (already final) id of column c of the
+// chunk before.  The table is streamed through shared memory in tiles.
+__global__ void track_stitch_kernel(int32_t *__restrict__ G, int K, int64_t nchunks, int tile_rows) {
   PVK_SMEM(smem);
-  int *gs = reinterpret_cast<int *>(smem);          // [tile + 1][K]; row 0 = last chunk of the previous tile
+  int *tile = reinterpret_cast<int *>(smem);        // [tile_rows][K] + carried row [K]
+  int *carry = tile + (size_t)tile_rows * K;
   const int64_t clip = blockIdx.x;
   int32_t *g = G + clip * nchunks * K;
-  const int t = threadIdx.x, BD = blockDim.x;
-  for (int64_t c0 = 0; c0 < nchunks; c0 += tile) {
-    const int n = (int)((c0 + tile <= nchunks) ? tile : nchunks - c0);
-    for (int i = t; i < n * K; i += BD) gs[K + i] = g[c0 * K + i];
-    __syncthreads();
-    for (int ch = (c0 == 0 ? 1 : 0); ch < n; ++ch) {   // chunk 0 of the clip has no predecessor
-      if (t < K) {
-        const int v = gs[(ch + 1) * K + t];
-        if (v <= -2) gs[(ch + 1) * K + t] = gs[ch * K + (-2 - v)];
-      }
-      __syncthreads();
-    }
-    for (int i = t; i < n * K; i += BD) g[c0 * K + i] = gs[K + i];
-    if (t < K) gs[t] = gs[n * K + t];
-    __syncthreads();
+  const int lane = threadIdx.x & 31;
+  for (int64_t c0 = 0; c0 < nchunks; c0 += tile_rows) {
+    const int n = (int)((c0 + tile_rows <= nchunks) ? tile_rows : nchunks - c0);
+    for (int e = lane; e < n * K; e += 32) tile[e] = g[c0 * K + e];
+    __syncwarp();
+    if (c0 == 0) warp_resolve_rows(tile + K, n - 1, K, tile);        // chunk 0 has no predecessor
+    else warp_resolve_rows(tile, n, K, carry);
+    for (int e = lane; e < n * K; e += 32) g[c0 * K + e] = tile[e];
+    for (int c = lane; c < K; c += 32) carry[c] = tile[(n - 1) * K + c];
+    __syncwarp();
   }
 }
 
@@ -461,11 +497,19 @@ __global__ void pack_scan_kernel(const int32_t *__restrict__ tlen, int64_t n, in
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NWARP = blockDim.x >> 5;
   if (tid == 0) carry_s = 0;
   __syncthreads();
+  int vn[E];                                               // next tile, loaded one tile ahead
+#pragma unroll
+  for (int j = 0; j < E; ++j) { const int64_t i = (int64_t)tid * E + j; vn[j] = i < n ? tlen[i] : 0; }
   for (int64_t s = 0; s < n; s += (int64_t)blockDim.x * E) {
     const int64_t i0 = s + (int64_t)tid * E;
     long long v[E], loc = 0;
 #pragma unroll
-    for (int j = 0; j < E; ++j) { v[j] = (i0 + j < n) ? tlen[i0 + j] : 0; loc += v[j]; }
+    for (int j = 0; j < E; ++j) { v[j] = vn[j]; loc += v[j]; }
+    {
+      const int64_t n0 = i0 + (int64_t)blockDim.x * E;
+#pragma unroll
+      for (int j = 0; j < E; ++j) vn[j] = (n0 + j < n) ? tlen[n0 + j] : 0;
+    }
     long long inc = loc;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -590,24 +634,35 @@ extern "C" int pvk_track(const double *f, const double *mag, int64_t nclips, int
   }
   PVK_LAUNCH(track_scan_kernel, dim3((unsigned)nclips), dim3(1024), 33 * 4, stream, newcount, base, ntracks, nframes);
   PVK_CHECK_LAUNCH("pvk_track(scan)");
-  const int cb = (K + 31) / 32 * 32;
-  PVK_LAUNCH(track_chunk_kernel, dim3((unsigned)(nclips * nchunks)), dim3(cb), (size_t)K * 4, stream, link, base,
-             nframes, K, nchunks, tid);
-  PVK_CHECK_LAUNCH("pvk_track(chunk)");
+  {
+    const int RT = track_tile_rows(K);
+    const size_t per_warp = (size_t)(RT + 1) * K * 4;
+    int W = (int)((64 * 1024) / per_warp);
+    if (W > 4) W = 4;
+    if (W < 1) W = 1;
+    const size_t csm = per_warp * W;
+    if (csm > 48 * 1024 && PVK_SET_SMEM(track_chunk_kernel, (int)csm) != 0) {
+      set_error("pvk_track: cannot reserve %d bytes of shared memory", (int)csm);
+      return PVK_ERR_CUDA;
+    }
+    const int64_t total_chunks = nclips * nchunks;
+    PVK_LAUNCH(track_chunk_kernel, dim3((unsigned)((total_chunks + W - 1) / W)), dim3(W * 32), csm, stream, link, base,
+               nframes, K, nchunks, total_chunks, tid);
+    PVK_CHECK_LAUNCH("pvk_track(chunk)");
+  }
   if (nchunks > 1) {
     PVK_LAUNCH(track_boundary_kernel, dim3(grid_for(nclips * nchunks * K, 256)), dim3(256), 0, stream, link, tid,
                nframes, K, nchunks, nclips, G);
     PVK_CHECK_LAUNCH("pvk_track(boundary)");
-    int tile = (96 * 1024) / (K * 4) - 1;                       // <= 96 KB of shared memory
+    int tile = (64 * 1024) / (K * 4) - 1;                       // <= 64 KB of shared memory
     if (tile > nchunks) tile = (int)nchunks;
     if (tile < 1) tile = 1;
-    const int sb = cb > 256 ? cb : 256;
     const size_t ssm = (size_t)(tile + 1) * K * 4;
     if (ssm > 48 * 1024 && PVK_SET_SMEM(track_stitch_kernel, (int)ssm) != 0) {
       set_error("pvk_track: cannot reserve %d bytes of shared memory", (int)ssm);
       return PVK_ERR_CUDA;
     }
-    PVK_LAUNCH(track_stitch_kernel, dim3((unsigned)nclips), dim3(sb), ssm, stream, G, K, nchunks, tile);
+    PVK_LAUNCH(track_stitch_kernel, dim3((unsigned)nclips), dim3(32), ssm, stream, G, K, nchunks, tile);
     PVK_CHECK_LAUNCH("pvk_track(stitch)");
     PVK_LAUNCH(track_fix_kernel, dim3(grid_for(rows * K, 256)), dim3(256), 0, stream, tid, G, nframes, K, nchunks,
                nclips);
