@@ -370,41 +370,66 @@ __device__ __forceinline__ void warp_resolve_rows(int *rows, int n, int K, const
   }
 }
 
+// copy n ints global <-> shared by one warp, 16 bytes per lane and step when both are aligned
+__device__ __forceinline__ void warp_copy_ints(int *dst, const int *src, int n) {
+  const int lane = threadIdx.x & 31;
+  if ((((uintptr_t)dst | (uintptr_t)src) & 15) == 0) {
+    const int n4 = n >> 2;
+    const int4 *s4 = reinterpret_cast<const int4 *>(src);
+    int4 *d4 = reinterpret_cast<int4 *>(dst);
+#pragma unroll 4
+    for (int e = lane; e < n4; e += 32) d4[e] = s4[e];
+    for (int e = (n4 << 2) + lane; e < n; e += 32) dst[e] = src[e];
+  } else {
+#pragma unroll 4
+    for (int e = lane; e < n; e += 32) dst[e] = src[e];
+  }
+}
+
 __host__ __device__ inline int track_tile_rows(int K) {
   int rt = 4096 / ((K + 31) / 32 * 32);            // <= 16 KB of shared memory per warp
   return rt > 32 ? 32 : (rt < 1 ? 1 : rt);
 }
 
-// One warp per chunk of TRACK_CHUNK frames, W warps per CTA: link + base -> tid, tile by tile.
+// One warp per chunk of TRACK_CHUNK frames, W warps per CTA: link + base -> tid, tile by tile
+// (<= 32 rows): bulk copy of the link rows into shared memory, sequential pass, bulk copy out.
 __global__ void track_chunk_kernel(const int32_t *__restrict__ link, const int32_t *__restrict__ base,
                                    int64_t F, int K, int64_t nchunks, int64_t total_chunks, int32_t *__restrict__ tid) {
   PVK_SMEM(smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
   const int RT = track_tile_rows(K);
-  int *tile = reinterpret_cast<int *>(smem) + (size_t)warp * (RT + 1) * K;     // [RT][K] + carried row [K]
-  int *carry = tile + RT * K;
+  const int KP = (K + 3) & ~3;                                                  // keeps `rows` 16-byte aligned
+  int *tile = reinterpret_cast<int *>(smem) + (size_t)warp * ((KP + RT * K + 3) & ~3);
   const int64_t cid = (int64_t)blockIdx.x * W + warp;
   if (cid >= total_chunks) return;
   const int64_t clip = cid / nchunks, ch = cid % nchunks;
   const int64_t j0 = ch * TRACK_CHUNK, j1 = (j0 + TRACK_CHUNK < F) ? j0 + TRACK_CHUNK : F;
+  int *rows = tile + KP;                                                        // tile[0..K) = carried row
   for (int64_t t0 = j0; t0 < j1; t0 += RT) {
     const int n = (int)((t0 + RT <= j1) ? RT : j1 - t0);
     const int64_t row0 = clip * F + t0;
-    for (int e = lane; e < n * K; e += 32) {
-      const int i = e / K, c = e - i * K;
-      const int lk = link[row0 * K + e];
-      int v;
-      if (lk == LINK_NONE) v = -1;
-      else if (lk <= -2) v = base[row0 + i] + (-2 - lk);
-      else if (t0 + i == j0) v = -2 - c;             // continued from the chunk before: unresolved
-      else v = -2 - lk;                              // same id as column lk of the row before
-      tile[e] = v;
-    }
+    warp_copy_ints(rows, link + row0 * K, n * K);
+    const int mybase = lane < n ? base[row0 + lane] : 0;
     __syncwarp();
-    if (t0 == j0) warp_resolve_rows(tile + K, n - 1, K, tile);       // the first row stays as it is
-    else warp_resolve_rows(tile, n, K, carry);
-    for (int e = lane; e < n * K; e += 32) tid[row0 * K + e] = tile[e];
-    for (int c = lane; c < K; c += 32) carry[c] = tile[(n - 1) * K + c];
+    const int *prev = tile;
+    for (int i = 0; i < n; ++i) {
+      int *r = rows + i * K;
+      const int bi = __shfl_sync(FULL, mybase, i);
+      const bool first = (t0 + i == j0);
+      for (int c = lane; c < K; c += 32) {
+        const int lk = r[c];
+        int v;
+        if (lk == LINK_NONE) v = -1;
+        else if (lk <= -2) v = bi + (-2 - lk);
+        else if (first) v = -2 - c;                  // continued from the chunk before: unresolved
+        else v = prev[lk];                           // same id as column lk of the row before
+        r[c] = v;
+      }
+      __syncwarp();
+      prev = r;
+    }
+    warp_copy_ints(tid + row0 * K, rows, n * K);
+    for (int c = lane; c < K; c += 32) tile[c] = rows[(n - 1) * K + c];
     __syncwarp();
   }
 }
@@ -432,19 +457,19 @@ __global__ void track_boundary_kernel(const int32_t *__restrict__ link, const in
 // chunk before.  The table is streamed through shared memory in tiles.
 __global__ void track_stitch_kernel(int32_t *__restrict__ G, int K, int64_t nchunks, int tile_rows) {
   PVK_SMEM(smem);
-  int *tile = reinterpret_cast<int *>(smem);        // [tile_rows][K] + carried row [K]
-  int *carry = tile + (size_t)tile_rows * K;
+  int *tile = reinterpret_cast<int *>(smem);        // carried row [K] + [tile_rows][K]
+  int *rows = tile + ((K + 3) & ~3);
   const int64_t clip = blockIdx.x;
   int32_t *g = G + clip * nchunks * K;
   const int lane = threadIdx.x & 31;
   for (int64_t c0 = 0; c0 < nchunks; c0 += tile_rows) {
     const int n = (int)((c0 + tile_rows <= nchunks) ? tile_rows : nchunks - c0);
-    for (int e = lane; e < n * K; e += 32) tile[e] = g[c0 * K + e];
+    warp_copy_ints(rows, g + c0 * K, n * K);
     __syncwarp();
-    if (c0 == 0) warp_resolve_rows(tile + K, n - 1, K, tile);        // chunk 0 has no predecessor
-    else warp_resolve_rows(tile, n, K, carry);
-    for (int e = lane; e < n * K; e += 32) g[c0 * K + e] = tile[e];
-    for (int c = lane; c < K; c += 32) carry[c] = tile[(n - 1) * K + c];
+    if (c0 == 0) warp_resolve_rows(rows + K, n - 1, K, rows);        // chunk 0 has no predecessor
+    else warp_resolve_rows(rows, n, K, tile);
+    warp_copy_ints(g + c0 * K, rows, n * K);
+    for (int c = lane; c < K; c += 32) tile[c] = rows[(n - 1) * K + c];
     __syncwarp();
   }
 }
@@ -636,7 +661,7 @@ extern "C" int pvk_track(const double *f, const double *mag, int64_t nclips, int
   PVK_CHECK_LAUNCH("pvk_track(scan)");
   {
     const int RT = track_tile_rows(K);
-    const size_t per_warp = (size_t)(RT + 1) * K * 4;
+    const size_t per_warp = (size_t)((((K + 3) & ~3) + RT * K + 3) & ~3) * 4;
     int W = (int)((64 * 1024) / per_warp);
     if (W > 4) W = 4;
     if (W < 1) W = 1;
@@ -657,7 +682,7 @@ extern "C" int pvk_track(const double *f, const double *mag, int64_t nclips, int
     int tile = (64 * 1024) / (K * 4) - 1;                       // <= 64 KB of shared memory
     if (tile > nchunks) tile = (int)nchunks;
     if (tile < 1) tile = 1;
-    const size_t ssm = (size_t)(tile + 1) * K * 4;
+    const size_t ssm = (size_t)(tile * K + ((K + 3) & ~3)) * 4;
     if (ssm > 48 * 1024 && PVK_SET_SMEM(track_stitch_kernel, (int)ssm) != 0) {
       set_error("pvk_track: cannot reserve %d bytes of shared memory", (int)ssm);
       return PVK_ERR_CUDA;
