@@ -23,6 +23,9 @@
 namespace pvk {
 
 #define PADC(i) ((i) + ((i) >> 4))
+// |fx| lives in shared memory with 4 pad words per 16 bins: a thread reads its contiguous run of
+// bins with 128-bit loads, conflict free
+#define FA(i) ((i) + (((i) >> 4) << 2))
 
 struct AParams {
   const float *x;
@@ -77,7 +80,6 @@ template <int LOGM> struct Plan {
   }
   static constexpr int TWR_TOTAL = twr_off(NPASS) > 0 ? twr_off(NPASS) : 1;
   static constexpr int MP = M + (M >> 4) + 1;
-  static constexpr int MW = M >= 32 ? M / 32 : 1;
   static constexpr int NW = T / 32;
 };
 
@@ -267,10 +269,10 @@ __device__ __forceinline__ bool peak_epilogue(int k, int M, const float2 *cur, c
     if (m == 0 || a < ba) { bf = fq; bdf = df; ba = a; }     // np.argmin: first minimum, nan sticks
   }
   // mag = sqrt(sum(famp[max(nbin-1,1) : min(nbin+1,len)+1]**2)), left to right :197-199
-  const double a0 = famp[k];
+  const double a0 = famp[FA(k)];
   double s = a0 * a0;
-  if (k - 1 >= 1) { const double am = famp[k - 1]; s = am * am + s; }
-  if (k + 1 <= M - 1) { const double ap = famp[k + 1]; s = s + ap * ap; }
+  if (k - 1 >= 1) { const double am = famp[FA(k - 1)]; s = am * am + s; }
+  if (k + 1 <= M - 1) { const double ap = famp[FA(k + 1)]; s = s + ap * ap; }
   o.f = bf;
   o.mag = sqrt(s);
   o.ph = thisph;
@@ -284,11 +286,8 @@ template <int LOGM> struct Smem {
   static constexpr int OFF_BUF0 = 0;
   static constexpr int OFF_BUF1 = OFF_BUF0 + P::MP * 8;
   static constexpr int OFF_FAMP = OFF_BUF1 + P::MP * 8;
-  static constexpr int OFF_CKEY = OFF_FAMP + P::M * 4;       // candidate keys (compact, bin order)
-  static constexpr int OFF_MC = OFF_CKEY + P::M * 4;         // candidate mask words
-  static constexpr int OFF_WCNT = OFF_MC + P::MW * 4;
-  static constexpr int OFF_WBASE = OFF_WCNT + P::MW * 4;
-  static constexpr int OFF_HIST = OFF_WBASE + (P::MW + 1) * 4;
+  static constexpr int OFF_CKEY = OFF_FAMP + (P::M + P::M / 4 + 4) * 4;   // candidate keys (compact, bin order)
+  static constexpr int OFF_HIST = OFF_CKEY + P::M * 4;
   static constexpr int OFF_RED = (OFF_HIST + 256 * 4 + 7) / 8 * 8;   // doubles: 8 sums
   static constexpr int OFF_REDF = OFF_RED + 8 * 8;                   // floats: 8 min, 8 max
   static constexpr int OFF_REDU = OFF_REDF + 16 * 4;                 // uints: 8 cnt, 8 kmin, 8 kmax
@@ -298,20 +297,6 @@ template <int LOGM> struct Smem {
   static constexpr int OFF_PK = OFF_CBIN + P::M * 2;                 // 2 x npks uint16
   static int bytes(int npks) { return OFF_PK + 2 * ((npks + 7) / 8 * 8) * 2; }
 };
-
-// exclusive scan of cnt[0..n) into base[0..n], total in base[n]; executed by warp 0 only
-__device__ __forceinline__ void warp0_excl_scan(const int *cnt, int *base, int n) {
-  const int lane = lane_id();
-  int carry = 0;
-  for (int s = 0; s < n; s += 32) {
-    const int i = s + lane;
-    const int v = i < n ? cnt[i] : 0;
-    const int inc = warp_scan_incl(v);
-    if (i < n) base[i] = carry + inc - v;
-    carry += __shfl_sync(FULL, inc, 31);
-  }
-  if (lane == 0) base[n] = carry;
-}
 
 // Ordered compaction of a list processed in rounds of blockDim threads: position of this
 // thread's entry among the flagged ones (valid if flag), running total in `base`.
@@ -331,19 +316,16 @@ __device__ __forceinline__ int round_pos(bool flag, int *wsum, int round, int &b
 }
 
 template <int LOGM>
-__global__ void __launch_bounds__(Plan<LOGM>::T) analyze_kernel(AParams prm) {
+__global__ void __launch_bounds__(Plan<LOGM>::T, 512 / Plan<LOGM>::T) analyze_kernel(AParams prm) {
   using P = Plan<LOGM>;
   using S = Smem<LOGM>;
-  constexpr int M = P::M, T = P::T, MW = P::MW, NW = P::NW, N = 2 * M;
-  constexpr int NIT = M / T;
+  constexpr int M = P::M, T = P::T, NW = P::NW, N = 2 * M;
+  constexpr int CB = M / T;                                  // contiguous bins per thread in the candidate scan
   PVK_SMEM(smem);
   float2 *bufs[2] = {reinterpret_cast<float2 *>(smem + S::OFF_BUF0),
                      reinterpret_cast<float2 *>(smem + S::OFF_BUF1)};
   float *famp = reinterpret_cast<float *>(smem + S::OFF_FAMP);
   unsigned *ckey = reinterpret_cast<unsigned *>(smem + S::OFF_CKEY);
-  unsigned *maskC = reinterpret_cast<unsigned *>(smem + S::OFF_MC);
-  int *wcnt = reinterpret_cast<int *>(smem + S::OFF_WCNT);
-  int *wbase = reinterpret_cast<int *>(smem + S::OFF_WBASE);
   int *hist = reinterpret_cast<int *>(smem + S::OFF_HIST);
   double *redd = reinterpret_cast<double *>(smem + S::OFF_RED);
   float *redf = reinterpret_cast<float *>(smem + S::OFF_REDF);
@@ -431,8 +413,8 @@ __global__ void __launch_bounds__(Plan<LOGM>::T) analyze_kernel(AParams prm) {
       // |fx| without FMA contraction: bit-identical to float32 numpy sqrt(re*re + im*im)
       const float aa = sqrtf(__fadd_rn(__fmul_rn(xa.x, xa.x), __fmul_rn(xa.y, xa.y)));
       const float ab = sqrtf(__fadd_rn(__fmul_rn(xb.x, xb.x), __fmul_rn(xb.y, xb.y)));
-      famp[k] = aa;
-      famp[kb] = ab;
+      famp[FA(k)] = aa;
+      famp[FA(kb)] = ab;
       if (so) { so[k] = xa; so[kb] = xb; }
       lmin = fminf(lmin, fminf(aa, ab));
       lmax = fmaxf(lmax, fmaxf(aa, ab));
@@ -459,50 +441,74 @@ __global__ void __launch_bounds__(Plan<LOGM>::T) analyze_kernel(AParams prm) {
     const double th = minamp - miny_d;
 
     // ---- candidates: interior local maxima above threshold (or everything when th < 0),
-    //      compacted in bin order into (cbin, ckey)
-    unsigned keyr[NIT];
-    unsigned mybits = 0;
-    {
-      unsigned wc = 0, kmin = 0xffffffffu, kmax = 0u;
-#pragma unroll
-      for (int n = 0; n < NIT; ++n) {
-        const int k = tid + n * T;
-        const bool interior = (k >= 1) && (k <= M - 2);
-        const float y = famp[k];
-        const float yl = famp[interior ? k - 1 : k], yr = famp[interior ? k + 1 : k];
-        const bool ispk = interior && (yl < y) && (y >= yr);
-        bool c;
-        if (ispk) c = ((double)y - miny_d) > th;
-        else c = interior && (th < 0.0);
-        const unsigned key = ispk ? __float_as_uint(y) : 0u;
-        keyr[n] = key;
-        const unsigned m = __ballot_sync(FULL, c);
-        if (lane == 0) { maskC[k >> 5] = m; wcnt[k >> 5] = __popc(m); }
-        wc += __popc(m);
-        if (c) { mybits |= 1u << n; kmin = key < kmin ? key : kmin; kmax = key > kmax ? key : kmax; }
-      }
-      kmin = warp_umin(kmin);
-      kmax = warp_umax(kmax);
-      if (lane == 0) { redu[warp] = wc; redu[8 + warp] = kmin; redu[16 + warp] = kmax; }
-    }
-    __syncthreads();
+    //      compacted in bin order into (cbin, ckey).  Thread t scans bins [t*CB, (t+1)*CB).
+    //      The strict fp64 test (y - miny) > th is decided in fp32 outside a guard band of
+    //      2^-18 relative around minamp (fp64 rounding moves either side by < 2^-51 relative).
     int C = 0;
     unsigned lo = 0xffffffffu, hi = 0u;
+    {
+      const int kb0 = tid * CB;
+      float y[CB + 2];
+      if constexpr (CB % 4 == 0) {
 #pragma unroll
-    for (int w = 0; w < NW; ++w) {
-      C += (int)redu[w];
-      lo = redu[8 + w] < lo ? redu[8 + w] : lo;
-      hi = redu[16 + w] > hi ? redu[16 + w] : hi;
-    }
-    if (warp == 0) warp0_excl_scan(wcnt, wbase, MW);
-    __syncthreads();
+        for (int j = 0; j < CB / 4; ++j) {
+          const float4 v = *reinterpret_cast<const float4 *>(famp + FA(kb0 + 4 * j));
+          y[4 * j + 1] = v.x; y[4 * j + 2] = v.y; y[4 * j + 3] = v.z; y[4 * j + 4] = v.w;
+        }
+      } else {
 #pragma unroll
-    for (int n = 0; n < NIT; ++n) {
-      if ((mybits >> n) & 1u) {
-        const int k = tid + n * T;
-        const int pos = wbase[k >> 5] + __popc(maskC[k >> 5] & lanemask_lt());
-        cbin[pos] = (unsigned short)k;
-        ckey[pos] = keyr[n];
+        for (int j = 0; j < CB; ++j) y[j + 1] = famp[FA(kb0 + j)];
+      }
+      y[0] = kb0 > 0 ? famp[FA(kb0 - 1)] : 0.f;
+      y[CB + 1] = kb0 + CB < M ? famp[FA(kb0 + CB)] : 0.f;
+      const float mf = (float)minamp;
+      const float thr_hi = mf * (1.f + 3.8146973e-6f), thr_lo = mf * (1.f - 3.8146973e-6f);
+      const bool allc = th < 0.0;
+      unsigned cbits = 0, pbits = 0;
+      unsigned kmin = 0xffffffffu, kmax = 0u;
+#pragma unroll
+      for (int i = 0; i < CB; ++i) {
+        const int k = kb0 + i;
+        const bool interior = (k >= 1) && (k <= M - 2);
+        const float yv = y[i + 1];
+        const bool ispk = interior && (y[i] < yv) && (yv >= y[i + 2]);
+        bool c;
+        if (ispk) {
+          c = yv > thr_hi;
+          if (!c && !(yv < thr_lo)) c = ((double)yv - miny_d) > th;
+        } else {
+          c = interior && allc;
+        }
+        if (ispk) pbits |= 1u << i;
+        if (c) {
+          cbits |= 1u << i;
+          const unsigned key = ispk ? __float_as_uint(yv) : 0u;
+          kmin = key < kmin ? key : kmin; kmax = key > kmax ? key : kmax;
+        }
+      }
+      const int cnt = __popc(cbits);
+      const int incl = warp_scan_incl(cnt);
+      kmin = warp_umin(kmin);
+      kmax = warp_umax(kmax);
+      if (lane == 31) redu[warp] = (unsigned)incl;
+      if (lane == 0) { redu[8 + warp] = kmin; redu[16 + warp] = kmax; }
+      __syncthreads();
+      int pos = incl - cnt;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        const int cw = (int)redu[w];
+        pos += (w < warp) ? cw : 0;
+        C += cw;
+        lo = redu[8 + w] < lo ? redu[8 + w] : lo;
+        hi = redu[16 + w] > hi ? redu[16 + w] : hi;
+      }
+#pragma unroll
+      for (int i = 0; i < CB; ++i) {
+        if ((cbits >> i) & 1u) {
+          cbin[pos] = (unsigned short)(kb0 + i);
+          ckey[pos] = ((pbits >> i) & 1u) ? __float_as_uint(y[i + 1]) : 0u;
+          ++pos;
+        }
       }
     }
     __syncthreads();
@@ -577,10 +583,10 @@ __global__ void __launch_bounds__(Plan<LOGM>::T) analyze_kernel(AParams prm) {
       int k = 0;
       if (e < ns) {
         k = sel[e];
-        const float y = famp[k];
+        const float y = famp[FA(k)];
         const int a = k - 5 > 1 ? k - 5 : 1, b = k + 5 < M - 1 ? k + 5 : M - 1;
         keep = true;
-        for (int m = a; m <= b; ++m) keep = keep && !(famp[m] > y);
+        for (int m = a; m <= b; ++m) keep = keep && !(famp[FA(m)] > y);
       }
       const int pos = round_pos<NW>(keep, wsA, round, nk);
       if (keep) pk2[pos] = (unsigned short)k;

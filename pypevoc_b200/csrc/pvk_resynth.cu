@@ -220,14 +220,133 @@ __global__ void __launch_bounds__(128) resynth_prepare_kernel(RParams p, int64_t
 }
 
 // ------------------------------------------------------------------ kernel 3: render
-// One CTA renders one output block of h samples.  Thread t = g * nchp + ch: chunk ch (RS
-// consecutive samples) of item group g; the groups split the partials of the block among
-// themselves and their partial sums are added through shared memory, so every thread renders
-// for any hop.  Fast path (no knot inside the chunk -- practically always): the phase polynomial
-// is evaluated once in fp64 at the chunk centre, reduced to [-0.5, 0.5] cycles and advanced over
-// the RS samples as an fp32 quadratic in radians (|increment| < RS/2 * pi); one MUFU cosine + 5
-// FMA-pipe instructions per partial-sample.  Slow path (knot inside the chunk, fade-in / fade-out
-// segments): fp64 phase per sample.
+// Inner loops shared by the two render kernels.  A thread owns RS consecutive samples qs..qs+RS
+// of block b and adds the staged partial bodies items[c], c = g, g+G, ... < nbody, to acc[].
+// Fast path (no knot inside the chunk -- practically always): the phase polynomial is evaluated
+// once in fp64 at the chunk centre, reduced to [-0.5, 0.5] cycles and advanced over the RS samples
+// as an fp32 quadratic in radians (|increment| < RS/2 * pi); one MUFU cosine + 5 FMA-pipe
+// instructions per partial-sample.  Slow path (knot inside the chunk): fp64 phase per sample.
+template <int RS>
+__device__ __forceinline__ void render_bodies(const RParams &p, const BodyItem *items, int nbody, int g, int G,
+                                              int qs, bool fast, float *acc) {
+  const float TWO_PI_F = 6.283185307179586f;
+  if (fast) {
+    const int sf = qs >= p.qk ? 1 : 0, sm = qs >= p.qkm ? 1 : 0;
+    const double qcd = (double)(qs + RS / 2);
+    const float qcf = (float)(qs + RS / 2);
+    for (int c = g; c < nbody; c += G) {
+      const PhaseSeg *sp = &items[c].s[sf];
+      const double2 ab = *reinterpret_cast<const double2 *>(&sp->A);
+      const double2 cw = *reinterpret_cast<const double2 *>(&sp->C);        // C | (tB, tC2)
+      const float2 am = *reinterpret_cast<const float2 *>(&items[c].mc0 + 2 * sm);
+      const float tB = __int_as_float((int)(__double_as_longlong(cw.y) & 0xffffffffLL));
+      const float tC2 = __int_as_float((int)(__double_as_longlong(cw.y) >> 32));
+      const double th = fma(fma(cw.x, qcd, ab.y), qcd, ab.x);     // cycles at the chunk centre
+      const double fr = th - ((th + RINT_MAGIC) - RINT_MAGIC);    // exact reduction to [-0.5, 0.5]
+      const float t0 = TWO_PI_F * (float)fr;
+      const float t1 = fmaf(tC2, qcf, tB);
+      const float t2 = 0.5f * tC2;
+      const float a0 = fmaf(am.y, qcf, am.x);
+#pragma unroll
+      for (int m = 0; m < RS; ++m) {
+        const float fm = (float)(m - RS / 2);
+        const float cs = __cosf(fmaf(fmaf(t2, fm, t1), fm, t0));
+        acc[m] = fmaf(fmaf(am.y, fm, a0), cs, acc[m]);
+      }
+    }
+  } else {
+    for (int c = g; c < nbody; c += G) {
+#pragma unroll
+      for (int m = 0; m < RS; ++m) {
+        const int q = qs + m;
+        if (q < p.h) {
+          const PhaseSeg &sp = items[c].s[q >= p.qk ? 1 : 0];
+          const float *sa = &items[c].mc0 + (q >= p.qkm ? 2 : 0);
+          const double qd = (double)q;
+          const double th = fma(fma(sp.C, qd, sp.B), qd, sp.A);
+          const float fr = (float)(th - rint(th));
+          acc[m] = fmaf(fmaf(sa[1], (float)q, sa[0]), __cosf(TWO_PI_F * fr), acc[m]);
+        }
+      }
+    }
+  }
+}
+
+// Fade-in heads of partials starting in rows (b, b+dE] and fade-out tails of partials ending in
+// rows [b-dE, b): the start / end masks name the slots; no staging, no barrier.  The fades found
+// are dealt round-robin to the G item groups (active: this thread renders at all).
+template <int RS>
+__device__ __forceinline__ void render_fades(const RParams &p, int64_t b, int qs, bool active, int g, int G,
+                                             float *acc) {
+  const float TWO_PI_F = 6.283185307179586f;
+  const int K = p.K, h = p.h;
+  int nf = 0;
+  for (int64_t r = b - p.dE; r <= b + p.dE; ++r) {
+    if (r == b || r < 0 || r >= p.F) continue;                  // uniform
+    const bool head = r > b;
+    const uint32_t *mw = p.mask + (r * 2 + (head ? 0 : 1)) * p.mwk;
+    for (int w = 0; w < p.mwk; ++w) {
+      uint32_t bits = mw[w];                                      // uniform
+      while (bits) {
+        const int c = w * 32 + __ffs((int)bits) - 1;
+        bits &= bits - 1;
+        const bool mine = active && (G == 1 || (nf % G) == g);
+        ++nf;
+        if (!mine) continue;
+        const int v = p.tid[r * K + c];
+        const TrackFade tf = p.tfade[v];
+        double A, B;
+        float m0;
+        int qa, qb, eoff;
+        if (head) {
+          // head sample qh = q + off, off = (b - r)*h + E; valid 0 <= qh < E   (:740-745)
+          const int64_t off = (b - r) * h + p.E;
+          B = tf.fch; A = tf.thh - B * (double)((int64_t)p.E - off); m0 = tf.m0h;
+          qa = (int)(off < 0 ? -off : 0); qb = h; eoff = (int)off;
+        } else {
+          // tail sample qt = q + off, off = (b - r - 1)*h; valid 0 <= qt < E   (:748-751)
+          const int64_t off = (b - r - 1) * h;
+          B = tf.fct; A = tf.thl + B * (double)(off + 1); m0 = tf.m0t;
+          const int64_t qe = (int64_t)p.E - off;
+          qa = 0; qb = (int)(qe < h ? qe : h); eoff = (int)off;
+        }
+        if (qb <= qs || qa >= qs + RS) continue;
+        if (qa <= qs && qs + RS <= qb) {
+          // whole chunk inside the fade: linear phase and linear envelope angle in fp32
+          const double qcd = (double)(qs + RS / 2);
+          const double th = fma(B, qcd, A);
+          const float t0 = TWO_PI_F * (float)(th - ((th + RINT_MAGIC) - RINT_MAGIC));
+          const float t1 = TWO_PI_F * (float)B;
+          const float e1 = 3.14159265358979f * p.einv;
+          const float e0 = e1 * (float)(qs + RS / 2 + eoff);
+          const float hm = 0.5f * m0, sg = head ? -hm : hm;      // m0 * (1 -+ cos) / 2
+#pragma unroll
+          for (int m = 0; m < RS; ++m) {
+            const float fm = (float)(m - RS / 2);
+            const float ce = __cosf(fmaf(e1, fm, e0));
+            acc[m] = fmaf(fmaf(sg, ce, hm), __cosf(fmaf(t1, fm, t0)), acc[m]);
+          }
+        } else {
+#pragma unroll
+          for (int m = 0; m < RS; ++m) {
+            const int q = qs + m;
+            if (q >= qa && q < qb) {
+              const double th = fma(B, (double)q, A);
+              const float fr = (float)(th - rint(th));
+              const float ce = __cosf(3.14159265358979f * (float)(q + eoff) * p.einv);
+              const float am = m0 * (head ? 0.5f * (1.f - ce) : 0.5f * (1.f + ce));
+              acc[m] = fmaf(am, __cosf(TWO_PI_F * fr), acc[m]);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// General render kernel (any hop): one CTA renders one output block of h samples.  Thread
+// t = g * nchp + ch: chunk ch (RS consecutive samples) of item group g; the groups split the
+// partials of the block among themselves and their partial sums are added through shared memory.
 template <int RS>
 __global__ void __launch_bounds__(128, 8) resynth_kernel(RParams p) {
   PVK_SMEM(smem);
@@ -238,7 +357,6 @@ __global__ void __launch_bounds__(128, 8) resynth_kernel(RParams p) {
   const int tid = threadIdx.x;
   const int64_t b = p.block0 + blockIdx.x;
   const int64_t nbase = b * (int64_t)h;
-  const float TWO_PI_F = 6.283185307179586f;
 
   // ---- the staged partial bodies of row b: global -> shared, 16 bytes per thread and step
   const int nbody = p.gcount[b - p.chunk0];
@@ -258,113 +376,9 @@ __global__ void __launch_bounds__(128, 8) resynth_kernel(RParams p) {
     float acc[RS];
 #pragma unroll
     for (int m = 0; m < RS; ++m) acc[m] = 0.f;
-    const bool fast = active && (qs + RS <= h) && !(qs < p.qk && p.qk < qs + RS) &&
-                      !(qs < p.qkm && p.qkm < qs + RS);
-    if (fast) {
-      const int sf = qs >= p.qk ? 1 : 0, sm = qs >= p.qkm ? 1 : 0;
-      const double qcd = (double)(qs + RS / 2);
-      const float qcf = (float)(qs + RS / 2);
-      for (int c = g; c < nbody; c += G) {
-        const PhaseSeg *sp = &items[c].s[sf];
-        const double2 ab = *reinterpret_cast<const double2 *>(&sp->A);
-        const double2 cw = *reinterpret_cast<const double2 *>(&sp->C);        // C | (tB, tC2)
-        const float2 am = *reinterpret_cast<const float2 *>(&items[c].mc0 + 2 * sm);
-        const float tB = __int_as_float((int)(__double_as_longlong(cw.y) & 0xffffffffLL));
-        const float tC2 = __int_as_float((int)(__double_as_longlong(cw.y) >> 32));
-        const double th = fma(fma(cw.x, qcd, ab.y), qcd, ab.x);     // cycles at the chunk centre
-        const double fr = th - ((th + RINT_MAGIC) - RINT_MAGIC);    // exact reduction to [-0.5, 0.5]
-        const float t0 = TWO_PI_F * (float)fr;
-        const float t1 = fmaf(tC2, qcf, tB);
-        const float t2 = 0.5f * tC2;
-        const float a0 = fmaf(am.y, qcf, am.x);
-#pragma unroll
-        for (int m = 0; m < RS; ++m) {
-          const float fm = (float)(m - RS / 2);
-          const float cs = __cosf(fmaf(fmaf(t2, fm, t1), fm, t0));
-          acc[m] = fmaf(fmaf(am.y, fm, a0), cs, acc[m]);
-        }
-      }
-    } else if (active) {
-      for (int c = g; c < nbody; c += G) {
-#pragma unroll
-        for (int m = 0; m < RS; ++m) {
-          const int q = qs + m;
-          if (q < h) {
-            const PhaseSeg &sp = items[c].s[q >= p.qk ? 1 : 0];
-            const float *sa = &items[c].mc0 + (q >= p.qkm ? 2 : 0);
-            const double qd = (double)q;
-            const double th = fma(fma(sp.C, qd, sp.B), qd, sp.A);
-            const float fr = (float)(th - rint(th));
-            acc[m] = fmaf(fmaf(sa[1], (float)q, sa[0]), __cosf(TWO_PI_F * fr), acc[m]);
-          }
-        }
-      }
-    }
-
-    // ---- fade-in heads of partials starting in rows (b, b+dE], fade-out tails of partials
-    //      ending in rows [b-dE, b): the start / end masks name the slots; no staging, no barrier
-    int nf = 0;
-    for (int64_t r = b - p.dE; r <= b + p.dE; ++r) {
-      if (r == b || r < 0 || r >= p.F) continue;                  // uniform
-      const bool head = r > b;
-      const uint32_t *mw = p.mask + (r * 2 + (head ? 0 : 1)) * p.mwk;
-      for (int w = 0; w < p.mwk; ++w) {
-        uint32_t bits = mw[w];                                      // uniform
-        while (bits) {
-          const int c = w * 32 + __ffs((int)bits) - 1;
-          bits &= bits - 1;
-          const bool mine = active && (nf % G) == g;
-          ++nf;
-          if (!mine) continue;
-          const int v = p.tid[r * K + c];
-          const TrackFade tf = p.tfade[v];
-          double A, B;
-          float m0;
-          int qa, qb, eoff;
-          if (head) {
-            // head sample qh = q + off, off = (b - r)*h + E; valid 0 <= qh < E   (:740-745)
-            const int64_t off = (b - r) * h + p.E;
-            B = tf.fch; A = tf.thh - B * (double)((int64_t)p.E - off); m0 = tf.m0h;
-            qa = (int)(off < 0 ? -off : 0); qb = h; eoff = (int)off;
-          } else {
-            // tail sample qt = q + off, off = (b - r - 1)*h; valid 0 <= qt < E   (:748-751)
-            const int64_t off = (b - r - 1) * h;
-            B = tf.fct; A = tf.thl + B * (double)(off + 1); m0 = tf.m0t;
-            const int64_t qe = (int64_t)p.E - off;
-            qa = 0; qb = (int)(qe < h ? qe : h); eoff = (int)off;
-          }
-          if (qb <= qs || qa >= qs + RS) continue;
-          if (qa <= qs && qs + RS <= qb) {
-            // whole chunk inside the fade: linear phase and linear envelope angle in fp32
-            const double qcd = (double)(qs + RS / 2);
-            const double th = fma(B, qcd, A);
-            const float t0 = TWO_PI_F * (float)(th - ((th + RINT_MAGIC) - RINT_MAGIC));
-            const float t1 = TWO_PI_F * (float)B;
-            const float e1 = 3.14159265358979f * p.einv;
-            const float e0 = e1 * (float)(qs + RS / 2 + eoff);
-            const float hm = 0.5f * m0, sg = head ? -hm : hm;      // m0 * (1 -+ cos) / 2
-#pragma unroll
-            for (int m = 0; m < RS; ++m) {
-              const float fm = (float)(m - RS / 2);
-              const float ce = __cosf(fmaf(e1, fm, e0));
-              acc[m] = fmaf(fmaf(sg, ce, hm), __cosf(fmaf(t1, fm, t0)), acc[m]);
-            }
-          } else {
-#pragma unroll
-            for (int m = 0; m < RS; ++m) {
-              const int q = qs + m;
-              if (q >= qa && q < qb) {
-                const double th = fma(B, (double)q, A);
-                const float fr = (float)(th - rint(th));
-                const float ce = __cosf(3.14159265358979f * (float)(q + eoff) * p.einv);
-                const float am = m0 * (head ? 0.5f * (1.f - ce) : 0.5f * (1.f + ce));
-                acc[m] = fmaf(am, __cosf(TWO_PI_F * fr), acc[m]);
-              }
-            }
-          }
-        }
-      }
-    }
+    const bool fast = (qs + RS <= h) && !(qs < p.qk && p.qk < qs + RS) && !(qs < p.qkm && p.qkm < qs + RS);
+    if (active) render_bodies<RS>(p, items, nbody, g, G, qs, fast, acc);
+    render_fades<RS>(p, b, qs, active, g, G, acc);
 
     // ---- add the groups' partial sums and write the block (coalesced fp64 stores)
     if (g < G) {
@@ -382,6 +396,76 @@ __global__ void __launch_bounds__(128, 8) resynth_kernel(RParams p) {
       }
     }
     __syncthreads();
+  }
+}
+
+// Tile render kernel (hop a multiple of 32*RS): one WARP renders one tile of 32*RS consecutive
+// samples of a block, lane l the samples [l*RS, (l+1)*RS).  No block barrier, no cross-group
+// reduction, block-level scalar work (row lookup, fade scan) done once per tile.  The staged
+// bodies stream through a per-warp shared-memory buffer in batches of 32, the next batch is in
+// flight (registers) while the current one is rendered.  The finished tile is transposed through
+// the same buffer so that the fp64 stores are coalesced.
+constexpr int TILE_BATCH = 32;
+constexpr int TILE_WARP_BYTES = TILE_BATCH * (int)sizeof(BodyItem);   // 2560 >= RS * 33 * 4 for RS <= 16
+constexpr int TILE_WARPS = 4;
+
+template <int RS>
+__global__ void __launch_bounds__(TILE_WARPS * 32, 8) resynth_tile_kernel(RParams p, int64_t ntiles, int tpb) {
+  PVK_SMEM(smem);
+  constexpr int TILE = 32 * RS;
+  constexpr int V = (int)(sizeof(BodyItem) / 16);                 // int4 per item
+  static_assert(RS * 33 * 4 <= TILE_WARP_BYTES, "transpose buffer");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t tile = (int64_t)blockIdx.x * TILE_WARPS + warp;
+  if (tile >= ntiles) return;                                     // warp uniform; the kernel has no block barrier
+  BodyItem *items = reinterpret_cast<BodyItem *>(smem + warp * TILE_WARP_BYTES);
+  const int h = p.h;
+  const int64_t b = p.block0 + tile / tpb;
+  const int q0 = (int)(tile % tpb) * TILE;
+  const int qs = q0 + lane * RS;
+  const int nbody = p.gcount[b - p.chunk0];
+  const int4 *src = reinterpret_cast<const int4 *>(p.gitems + (b - p.chunk0) * p.K);
+  int4 *dst = reinterpret_cast<int4 *>(items);
+
+  float acc[RS];
+#pragma unroll
+  for (int m = 0; m < RS; ++m) acc[m] = 0.f;
+  const bool fast = !(qs < p.qk && p.qk < qs + RS) && !(qs < p.qkm && p.qkm < qs + RS);
+
+  int4 pre[V];
+  {
+    const int n16 = (nbody < TILE_BATCH ? nbody : TILE_BATCH) * V;
+#pragma unroll
+    for (int v = 0; v < V; ++v) { const int i = lane + 32 * v; if (i < n16) pre[v] = src[i]; }
+  }
+  for (int c0 = 0; c0 < nbody; c0 += TILE_BATCH) {
+    const int n = nbody - c0 < TILE_BATCH ? nbody - c0 : TILE_BATCH;
+#pragma unroll
+    for (int v = 0; v < V; ++v) { const int i = lane + 32 * v; if (i < n * V) dst[i] = pre[v]; }
+    __syncwarp();
+    if (c0 + TILE_BATCH < nbody) {
+      const int rest = nbody - c0 - TILE_BATCH;
+      const int n16 = (rest < TILE_BATCH ? rest : TILE_BATCH) * V;
+      const int4 *s2 = src + (c0 + TILE_BATCH) * V;
+#pragma unroll
+      for (int v = 0; v < V; ++v) { const int i = lane + 32 * v; if (i < n16) pre[v] = s2[i]; }
+    }
+    render_bodies<RS>(p, items, n, 0, 1, qs, fast, acc);
+    __syncwarp();
+  }
+  render_fades<RS>(p, b, qs, true, 0, 1, acc);
+
+  // ---- transpose through shared memory, coalesced fp64 stores
+  float *red = reinterpret_cast<float *>(items);
+#pragma unroll
+  for (int m = 0; m < RS; ++m) red[lane * (RS + 1) + m] = acc[m];
+  __syncwarp();
+  const int64_t n0 = b * (int64_t)h + q0;
+  double *o = p.out + (n0 - p.block0 * (int64_t)h);
+#pragma unroll
+  for (int j = 0; j < RS; ++j) {
+    const int q = j * 32 + lane;
+    if (n0 + q < p.nout) o[q] = (double)red[q + q / RS];
   }
 }
 
@@ -414,6 +498,16 @@ static int launch_resynth(const RParams &p, int64_t nblocks, int bd, void *strea
   }
   PVK_LAUNCH(resynth_kernel<RS>, dim3((unsigned)nblocks), dim3(bd), smem, stream, p);
   PVK_CHECK_LAUNCH("pvk_resynth(render)");
+  return PVK_OK;
+}
+
+template <int RS>
+static int launch_resynth_tile(const RParams &p, int64_t nblocks, void *stream) {
+  const int tpb = p.h / (32 * RS);
+  const int64_t ntiles = nblocks * tpb;
+  PVK_LAUNCH(resynth_tile_kernel<RS>, dim3((unsigned)((ntiles + TILE_WARPS - 1) / TILE_WARPS)), dim3(TILE_WARPS * 32),
+             TILE_WARPS * TILE_WARP_BYTES, stream, p, ntiles, tpb);
+  PVK_CHECK_LAUNCH("pvk_resynth(render tiles)");
   return PVK_OK;
 }
 
@@ -496,7 +590,10 @@ extern "C" int pvk_resynth(const int32_t *tid, int64_t nframes, int npks, int64_
     p.out = out + (c0 - block0) * (int64_t)hop;
     PVK_LAUNCH(resynth_prepare_kernel, dim3((unsigned)((n + 3) / 4)), dim3(128), 0, stream, p, n, gitems, gcount);
     PVK_CHECK_LAUNCH("pvk_resynth(prepare)");
-    const int rc = RS == 16 ? launch_resynth<16>(p, n, bd, stream) : launch_resynth<8>(p, n, bd, stream);
+    int rc;
+    if (hop % 512 == 0) rc = launch_resynth_tile<16>(p, n, stream);          // one warp per 512-sample tile
+    else if (hop % 256 == 0) rc = launch_resynth_tile<8>(p, n, stream);
+    else rc = RS == 16 ? launch_resynth<16>(p, n, bd, stream) : launch_resynth<8>(p, n, bd, stream);
     if (rc != PVK_OK) return rc;
   }
   return PVK_OK;
