@@ -196,15 +196,15 @@ def gpu_main(args):
         if e: e[1].record()
         tab = {k: a[k][0] for k in ("f", "mag", "ph", "realph")}
         tr = P.track_device(tab["f"], tab["mag"])        # local link + ids
-        ntl = int(tr["ntracks"][0].item())
+        ntl, npts, last = P.track_counts(tr)             # the step's one host read-back (24 bytes)
         if world > 1:
             # global numbering (2K+4-int all_gather) and THE all_gather of the track table (async)
             st = D.stitch(tr["tid"], plan, plans)
             _, finish = D.gather_track_table(st["tid_own"], plans, async_op=True)
         if e: e[2].record()
-        pk = P.pack_device(tab["f"], tab["mag"], tab["ph"], tab["realph"], tr["tid"], None, ntl)
+        pk = P.pack_device(tab["f"], tab["mag"], tab["ph"], tab["realph"], tr["tid"], None, ntl, npts=npts)
         if world == 1:
-            st = dict(ntracks=ntl, max_end=int((pk["tstart"] + pk["tlen"] - 1).max().item()) if ntl else -1)
+            st = dict(ntracks=ntl, max_end=last)
         if e: e[3].record()
         w = D.resynth_local(tr["tid"], pk, plan, plans, st["max_end"], sr, hop, nfft, hop)
         if world > 1:

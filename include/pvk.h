@@ -112,15 +112,25 @@ int pvk_track(const double *f, const double *mag, int64_t nclips, int64_t nframe
 int pvk_track_spans(const int32_t *tid, int64_t nframes, int npks, int64_t ntracks,
                     int32_t *tstart, int32_t *tlen, void *stream);
 
+/* Sizes of a track-id table in one small read-back: stats int64 [3][nclips] = number of points
+ * (= sum of len(partial.f), the length of the packed arrays of pvk_track_pack) | last frame
+ * holding a point (= max(ss.end), :1059; -1 = none) | number of partials (copy of ntracks). */
+int pvk_track_stats(const int32_t *tid, const int32_t *ntracks, int64_t nclips, int64_t nframes,
+                    int npks, int64_t *stats, void *stream);
+
 /* Pack per-track value runs (= RegPartial.f/mag/ph/realph lists, :616-626, with
  * start_idx = tstart, :598) from the frame tables of ONE clip.  ntracks must be the value
  * pvk_track reported.  Outputs: tstart / tlen int32 [ntracks] (= ss.st and
  * ss.end - ss.st + 1, :827-828,950), toff int64 [ntracks+1] exclusive offsets, packed
- * float64 arrays of length sum(tlen) (pph may be NULL). */
+ * float64 arrays of length sum(tlen) (pph may be NULL).  workspace: scratch of
+ * pvk_track_pack_workspace_bytes(ntracks) bytes. */
+int64_t pvk_track_pack_workspace_bytes(int64_t ntracks);
+
 int pvk_track_pack(const double *f, const double *mag, const double *ph, const double *realph,
                    const int32_t *tid, int64_t nframes, int npks,
                    int64_t ntracks, int32_t *tstart, int32_t *tlen, int64_t *toff, double *pf,
-                   double *pmag, double *pph, double *prealph, void *stream);
+                   double *pmag, double *pph, double *prealph, void *workspace,
+                   int64_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------ segment sharding
  * A long signal split into per-GPU frame ranges is linked per segment (pvk_track on the

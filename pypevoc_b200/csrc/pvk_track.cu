@@ -82,6 +82,75 @@ __device__ __forceinline__ int link_prepare(const double *__restrict__ f, const 
   return nc;
 }
 
+// link_prepare for K <= 32*S: same result, but a lane ranks its S slots in ONE pass over the row
+// (one shared-memory read per compared magnitude instead of S).
+template <int S>
+__device__ __forceinline__ int link_prepare_s(const double *__restrict__ f, const double *__restrict__ mag,
+                                              int64_t row, bool has_prev, int K, int32_t *__restrict__ link,
+                                              double *cf, double *cm, double *pf, double *pm, short *ord,
+                                              short *prank, int &chi_out, int &phi_out) {
+  const int lane = threadIdx.x & 31;
+  int chi = 0, phi = 0;
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const int i = lane + 32 * s;
+    if (i < K) {
+      const double a = f[row * K + i], b = mag[row * K + i];
+      const bool v = a > 0.0 && b > 0.0;                        // :876
+      cf[i] = a; cm[i] = v ? b : -1.0;
+      if (v) chi = i + 1; else link[row * K + i] = LINK_NONE;
+      if (has_prev) {
+        const double c = f[(row - 1) * K + i], d = mag[(row - 1) * K + i];
+        const bool vp = c > 0.0 && d > 0.0;
+        pf[i] = c; pm[i] = vp ? d : -1.0;
+        if (vp) phi = i + 1;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    chi = max(chi, __shfl_xor_sync(FULL, chi, o));
+    phi = max(phi, __shfl_xor_sync(FULL, phi, o));
+  }
+  __syncwarp();
+  // order of the current peaks: magnitude descending (:874-875)
+  int nc = 0;
+  {
+    double mi[S];
+    int r[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) { const int i = lane + 32 * s; mi[s] = i < chi ? cm[i] : -1.0; r[s] = 0; }
+    for (int i2 = 0; i2 < chi; ++i2) {
+      const double m2 = cm[i2];
+#pragma unroll
+      for (int s = 0; s < S; ++s) r[s] += (m2 > mi[s] || (m2 == mi[s] && i2 > lane + 32 * s)) ? 1 : 0;
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const bool vi = mi[s] > 0.0;
+      if (vi) ord[r[s]] = (short)(lane + 32 * s);
+      nc += __popc(__ballot_sync(FULL, vi));
+    }
+  }
+  // rank of the previous peaks in descending magnitude (:891-900)
+  {
+    double mi[S];
+    int r[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) { const int i = lane + 32 * s; mi[s] = i < phi ? pm[i] : -1.0; r[s] = 0; }
+    for (int i2 = 0; i2 < phi; ++i2) {
+      const double m2 = pm[i2];
+#pragma unroll
+      for (int s = 0; s < S; ++s) r[s] += (m2 > mi[s] || (m2 == mi[s] && i2 < lane + 32 * s)) ? 1 : 0;
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s) { const int i = lane + 32 * s; if (i < phi) prank[i] = (short)(mi[s] > 0.0 ? r[s] : 0); }
+  }
+  __syncwarp();
+  chi_out = chi; phi_out = phi;
+  return nc;
+}
+
 // abs(17.312*(fc/pf - 1.0)): dpitch2st :62-68 as called at :914
 __device__ __forceinline__ double stonediff(double fc, double pfv) {
   return fabs(__dmul_rn(17.312, __dsub_rn(__ddiv_rn(fc, pfv), 1.0)));
@@ -190,9 +259,18 @@ __global__ void track_link_fast_kernel(const double *__restrict__ f, const doubl
 
   for (int64_t row = (int64_t)blockIdx.x * W + warp; row < nrows; row += (int64_t)gridDim.x * W) {
     int chi, phi;
-    const int nc = link_prepare(f, mag, row, (row % F) > 0, K, link, cf, cm, pf, pm, ord, prank, chi, phi);
+    const int nc = link_prepare_s<S>(f, mag, row, (row % F) > 0, K, link, cf, cm, pf, pm, ord, prank, chi, phi);
     int32_t *lrow = link + row * K;
-    for (int p = lane; p < phi; p += 32) pf32[p] = pm[p] > 0.0 ? (float)pf[p] : -1.f;
+    // previous frequencies in fp32; `asc`: every slot below phi is a point and they ascend (rows
+    // come out of the analysis in bin order) -> the candidate window is found by binary search
+    bool okasc = true;
+    for (int p = lane; p < phi; p += 32) {
+      const bool vp = pm[p] > 0.0;
+      const float a = vp ? (float)pf[p] : -1.f;
+      pf32[p] = a;
+      okasc = okasc && vp && (p + 1 >= phi || (pm[p + 1] > 0.0 && a <= (float)pf[p + 1]));
+    }
+    const bool asc = __all_sync(FULL, okasc);
     __syncwarp();
     // ---- candidate lists: cheap window scan over the previous row, then exact distances
     int ncand[S], cidx[S];
@@ -206,8 +284,21 @@ __global__ void track_link_fast_kernel(const double *__restrict__ f, const doubl
         cidx[s] = c;
         const float fc32 = (float)cf[c];
         int n = 0;
-        for (int p = 0; p < phi; ++p) {
+        int p0 = 0, p1 = phi;
+        float fhi = 3.0e38f;
+        if (asc) {
+          // every p passing the window test below has pf32[p] in [flo, fhi]
+          const float flo = fc32 * (1.f - eps32);
+          fhi = fc32 * (1.f + eps32 + 2.f * eps32 * eps32);
+#pragma unroll
+          for (int step = KM / 2; step >= 1; step >>= 1) {
+            const int mid = p0 + step;
+            if (mid <= phi && pf32[mid - 1] < flo) p0 = mid;
+          }
+        }
+        for (int p = p0; p < p1; ++p) {
           const float pv = pf32[p];
+          if (pv > fhi) break;
           if (fabsf(fc32 - pv) < eps32 * pv) {
             if (n < LINK_NC) cand_p[(n * S + s) * 32 + lane] = (short)p;
             ++n;
@@ -307,47 +398,106 @@ __global__ void track_link_fast_kernel(const double *__restrict__ f, const doubl
   }
 }
 
-// ------------------------------------------------------------------ per-clip exclusive scan
-__global__ void track_scan_kernel(const int32_t *__restrict__ newcount, int32_t *__restrict__ base,
-                                  int32_t *__restrict__ ntracks, int64_t F) {
-  PVK_SMEM(smem);
-  int *wsum = reinterpret_cast<int *>(smem);
-  int &carry_s = wsum[32];
-  constexpr int E = 8;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NWARP = blockDim.x >> 5;
-  const int64_t clip = blockIdx.x;
-  const int32_t *in = newcount + clip * F;
-  int32_t *out = base + clip * F;
-  if (tid == 0) carry_s = 0;
-  __syncthreads();
-  int vn[E];                                               // next tile, loaded one tile ahead
-#pragma unroll
-  for (int j = 0; j < E; ++j) { const int64_t i = (int64_t)tid * E + j; vn[j] = i < F ? in[i] : 0; }
-  for (int64_t s = 0; s < F; s += (int64_t)blockDim.x * E) {
-    const int64_t i0 = s + (int64_t)tid * E;
-    int v[E], loc = 0;
-#pragma unroll
-    for (int j = 0; j < E; ++j) { v[j] = vn[j]; loc += v[j]; }
-    {
-      const int64_t n0 = i0 + (int64_t)blockDim.x * E;
-#pragma unroll
-      for (int j = 0; j < E; ++j) vn[j] = (n0 + j < F) ? in[n0 + j] : 0;
-    }
-    const int inc = warp_scan_incl(loc);
-    if (lane == 31) wsum[warp] = inc;
-    __syncthreads();
-    int woff = 0, tot = 0;
-    for (int w = 0; w < NWARP; ++w) { const int x = wsum[w]; woff += (w < warp) ? x : 0; tot += x; }
-    const int carry = carry_s;
-    int run = carry + woff + inc - loc;
-#pragma unroll
-    for (int j = 0; j < E; ++j) { if (i0 + j < F) out[i0 + j] = run; run += v[j]; }
-    __syncthreads();
-    if (tid == 0) carry_s = carry + tot;
-    __syncthreads();
-  }
-  if (tid == 0) ntracks[clip] = carry_s;
+// ------------------------------------------------------------------ exclusive scans
+// Tiled exclusive scan of int32 counts in two launches, every CTA independent: (1) per-tile sums,
+// (2) each tile adds up the sums of the tiles before it (a few hundred values even for an 8 hour
+// signal), scans its own SCAN_TILE elements and writes them.  grid = (tiles, rows of `in`); the
+// element count of a row is n, or min(n, *n_dev) when the count lives on the device.
+constexpr int SCAN_BD = 256, SCAN_E = 16, SCAN_TILE = SCAN_BD * SCAN_E, SCAN_SMEM = 2 * (SCAN_BD / 32) * 8;
+
+__device__ __forceinline__ int64_t scan_count(int64_t n, const int32_t *n_dev) {
+  if (n_dev) { const int64_t m = *n_dev; return m < n ? m : n; }
+  return n;
 }
+
+__device__ __forceinline__ void scan_load_tile(const int32_t *__restrict__ in, int64_t i0, int64_t n, int *v) {
+  if (i0 + SCAN_E <= n && ((reinterpret_cast<uintptr_t>(in + i0) & 15) == 0)) {
+#pragma unroll
+    for (int j = 0; j < SCAN_E / 4; ++j) {
+      const int4 q = *reinterpret_cast<const int4 *>(in + i0 + 4 * j);
+      v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < SCAN_E; ++j) v[j] = (i0 + j < n) ? in[i0 + j] : 0;
+  }
+}
+
+// block-wide sum of one long long per thread (SCAN_BD threads), result in every thread
+__device__ __forceinline__ long long scan_block_sum(long long v, long long *sh) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  long long t = 0;
+#pragma unroll
+  for (int w = 0; w < SCAN_BD / 32; ++w) t += sh[w];
+  __syncthreads();
+  return t;
+}
+
+__global__ void __launch_bounds__(SCAN_BD) scan_tile_sums_kernel(const int32_t *__restrict__ in, int64_t stride, int64_t n,
+                                                                 const int32_t *__restrict__ n_dev, int64_t ntiles,
+                                                                 long long *__restrict__ tsum) {
+  PVK_SMEM(smem);
+  long long *sh = reinterpret_cast<long long *>(smem);
+  n = scan_count(n, n_dev);
+  const int64_t t = blockIdx.x, row = blockIdx.y;
+  int v[SCAN_E];
+  scan_load_tile(in + row * stride, t * SCAN_TILE + (int64_t)threadIdx.x * SCAN_E, n, v);
+  long long loc = 0;
+#pragma unroll
+  for (int j = 0; j < SCAN_E; ++j) loc += v[j];
+  const long long tot = scan_block_sum(loc, sh);
+  if (threadIdx.x == 0) tsum[row * ntiles + t] = tot;
+}
+
+// out[i] = sum of in[0..i) (TO = int32 or int64); the grand total goes to total[row] (int32,
+// optional) and, when out_total is set, to out[n] (the one-past-the-end offset).
+template <class TO>
+__global__ void __launch_bounds__(SCAN_BD) scan_tile_apply_kernel(const int32_t *__restrict__ in, int64_t stride, int64_t n,
+                                                                  const int32_t *__restrict__ n_dev, int64_t ntiles,
+                                                                  const long long *__restrict__ tsum, TO *__restrict__ out,
+                                                                  int64_t out_stride, int32_t *__restrict__ total,
+                                                                  int out_total) {
+  PVK_SMEM(smem);
+  long long *sh = reinterpret_cast<long long *>(smem);
+  long long *wsum = sh + SCAN_BD / 32;
+  n = scan_count(n, n_dev);
+  const int64_t t = blockIdx.x, row = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long *ts = tsum + row * ntiles;
+  long long before = 0;
+  for (int64_t i = tid; i < t; i += SCAN_BD) before += ts[i];
+  before = scan_block_sum(before, sh);
+  const int64_t i0 = t * SCAN_TILE + (int64_t)tid * SCAN_E;
+  int v[SCAN_E];
+  scan_load_tile(in + row * stride, i0, n, v);
+  long long loc = 0;
+#pragma unroll
+  for (int j = 0; j < SCAN_E; ++j) loc += v[j];
+  long long inc = loc;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long u = __shfl_up_sync(FULL, inc, o);
+    if (lane >= o) inc += u;
+  }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  long long woff = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < SCAN_BD / 32; ++w) { const long long x = wsum[w]; woff += (w < warp) ? x : 0; tot += x; }
+  long long run = before + woff + inc - loc;
+  TO *o = out + row * out_stride;
+#pragma unroll
+  for (int j = 0; j < SCAN_E; ++j) { if (i0 + j < n) o[i0 + j] = (TO)run; run += v[j]; }
+  if (t == ntiles - 1 && tid == 0) {
+    // the last tile of the grid may lie beyond a device-side count: its `before` is still the total
+    if (total) total[row] = (int32_t)(before + tot);
+    if (out_total) o[n] = (TO)(before + tot);
+  }
+}
+
+static inline int64_t scan_tiles(int64_t n) { return n < 1 ? 1 : (n + SCAN_TILE - 1) / SCAN_TILE; }
 
 // ------------------------------------------------------------------ chain resolution
 // tid values while unresolved: >= 0 final id; -1 not a point; <= -2: "same id as column -2-v of
@@ -452,25 +602,45 @@ __global__ void track_boundary_kernel(const int32_t *__restrict__ link, const in
   }
 }
 
-// sequential over the chunks of one clip (one warp per clip); G becomes the final ids of every
-// chunk's first row: an unresolved entry -2-c takes the (already final) id of column c of the
-// chunk before.  The table is streamed through shared memory in tiles.
-__global__ void track_stitch_kernel(int32_t *__restrict__ G, int K, int64_t nchunks, int tile_rows) {
+// G becomes the final ids of every chunk's first row: an unresolved entry -2-c takes the (final)
+// id of column c of the chunk before.  One CTA per clip streams the table through shared memory in
+// tiles of R rows and resolves a tile by pointer jumping: in round r an unresolved entry of row i
+// names a column of row i - 2^r and takes what it finds there -- a final id, or that entry's own
+// reference, which then sits 2^(r+1) rows back.  Rows i < 2^(r+1) - 1 are final after round r (row
+// -1 = last row of the tile before, kept in `carry`), so ceil(log2(R + 1)) rounds do instead of R
+// sequential row steps.
+__global__ void __launch_bounds__(1024) track_stitch_kernel(int32_t *__restrict__ G, int K, int64_t nchunks, int R) {
   PVK_SMEM(smem);
-  int *tile = reinterpret_cast<int *>(smem);        // carried row [K] + [tile_rows][K]
-  int *rows = tile + ((K + 3) & ~3);
-  const int64_t clip = blockIdx.x;
-  int32_t *g = G + clip * nchunks * K;
-  const int lane = threadIdx.x & 31;
-  for (int64_t c0 = 0; c0 < nchunks; c0 += tile_rows) {
-    const int n = (int)((c0 + tile_rows <= nchunks) ? tile_rows : nchunks - c0);
-    warp_copy_ints(rows, g + c0 * K, n * K);
-    __syncwarp();
-    if (c0 == 0) warp_resolve_rows(rows + K, n - 1, K, rows);        // chunk 0 has no predecessor
-    else warp_resolve_rows(rows, n, K, tile);
-    warp_copy_ints(g + c0 * K, rows, n * K);
-    for (int c = lane; c < K; c += 32) tile[c] = rows[(n - 1) * K + c];
-    __syncwarp();
+  const int KP = (K + 3) & ~3;
+  int *carry = reinterpret_cast<int *>(smem);
+  int *A = carry + KP;
+  int *B = A + (size_t)R * K + ((4 - ((R * K) & 3)) & 3);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NWARP = blockDim.x >> 5, BD = blockDim.x;
+  int32_t *g = G + (int64_t)blockIdx.x * nchunks * K;
+  for (int c = tid; c < K; c += BD) carry[c] = -1;                 // chunk 0 has no references
+  for (int64_t c0 = 0; c0 < nchunks; c0 += R) {
+    const int n = (int)((c0 + R <= nchunks) ? R : nchunks - c0);
+    const int ne = n * K;
+    for (int e = tid; e < ne; e += BD) A[e] = g[c0 * K + e];
+    __syncthreads();
+    for (int d = 1;; d <<= 1) {
+      int pending = 0;
+      for (int i = warp; i < n; i += NWARP) {
+        const int j = i - d;
+        const int *srow = j < 0 ? carry : A + j * K;
+        for (int c = lane; c < K; c += 32) {
+          int v = A[i * K + c];
+          if (v <= -2) { v = srow[-2 - v]; pending |= (v <= -2) ? 1 : 0; }
+          B[i * K + c] = v;
+        }
+      }
+      int *t = A; A = B; B = t;
+      if (__syncthreads_count(pending) == 0) break;
+    }
+    for (int e = tid; e < ne; e += BD) g[c0 * K + e] = A[e];
+    __syncthreads();
+    for (int c = tid; c < K; c += BD) carry[c] = A[(n - 1) * K + c];
+    __syncthreads();
   }
 }
 
@@ -513,49 +683,6 @@ __global__ void pack_count_kernel(const int32_t *__restrict__ tid, int64_t F, in
   }
 }
 
-// single-CTA exclusive scan int32 -> int64 (ntracks + 1 outputs), 8 elements per thread per tile
-__global__ void pack_scan_kernel(const int32_t *__restrict__ tlen, int64_t n, int64_t *__restrict__ toff) {
-  PVK_SMEM(smem);
-  long long *wsum = reinterpret_cast<long long *>(smem);
-  long long &carry_s = wsum[32];
-  constexpr int E = 8;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NWARP = blockDim.x >> 5;
-  if (tid == 0) carry_s = 0;
-  __syncthreads();
-  int vn[E];                                               // next tile, loaded one tile ahead
-#pragma unroll
-  for (int j = 0; j < E; ++j) { const int64_t i = (int64_t)tid * E + j; vn[j] = i < n ? tlen[i] : 0; }
-  for (int64_t s = 0; s < n; s += (int64_t)blockDim.x * E) {
-    const int64_t i0 = s + (int64_t)tid * E;
-    long long v[E], loc = 0;
-#pragma unroll
-    for (int j = 0; j < E; ++j) { v[j] = vn[j]; loc += v[j]; }
-    {
-      const int64_t n0 = i0 + (int64_t)blockDim.x * E;
-#pragma unroll
-      for (int j = 0; j < E; ++j) vn[j] = (n0 + j < n) ? tlen[n0 + j] : 0;
-    }
-    long long inc = loc;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const long long t = __shfl_up_sync(FULL, inc, o);
-      if (lane >= o) inc += t;
-    }
-    if (lane == 31) wsum[warp] = inc;
-    __syncthreads();
-    long long woff = 0, tot = 0;
-    for (int w = 0; w < NWARP; ++w) { const long long x = wsum[w]; woff += (w < warp) ? x : 0; tot += x; }
-    const long long carry = carry_s;
-    long long run = carry + woff + inc - loc;
-#pragma unroll
-    for (int j = 0; j < E; ++j) { if (i0 + j < n) toff[i0 + j] = run; run += v[j]; }
-    __syncthreads();
-    if (tid == 0) carry_s = carry + tot;
-    __syncthreads();
-  }
-  if (tid == 0) toff[n] = carry_s;
-}
-
 __global__ void pack_scatter_kernel(const double *__restrict__ f, const double *__restrict__ mag,
                                     const double *__restrict__ ph, const double *__restrict__ realph,
                                     const int32_t *__restrict__ tid, int64_t F, int K,
@@ -574,6 +701,29 @@ __global__ void pack_scatter_kernel(const double *__restrict__ f, const double *
   }
 }
 
+// stats[0][clip] = number of points, stats[1][clip] = last frame holding a point (-1: none),
+// stats[2][clip] = number of partials: everything the host needs to size the packed tracks and
+// the resynthesis, in one read-back
+__global__ void track_stats_kernel(const int32_t *__restrict__ tid, const int32_t *__restrict__ ntracks, int64_t F, int K,
+                                   long long *__restrict__ stats) {
+  const int64_t clip = blockIdx.y, n = F * K;
+  const int32_t *t = tid + clip * n;
+  long long cnt = 0;
+  long long last = -1;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    if (t[e] >= 0) { ++cnt; last = e; }                      // e ascends: the last hit is the largest
+  }
+  if (last >= 0) last /= K;
+  cnt = warp_sum(cnt);
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) { const long long u = __shfl_xor_sync(FULL, last, o); last = u > last ? u : last; }
+  if ((threadIdx.x & 31) == 0) {
+    if (cnt) atomicAdd(reinterpret_cast<unsigned long long *>(stats + clip), (unsigned long long)cnt);
+    if (last >= 0) atomicMax(stats + gridDim.y + clip, last);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) stats[2 * gridDim.y + clip] = ntracks[clip];
+}
+
 static inline int grid_for(int64_t n, int block) {
   int64_t g = (n + block - 1) / block;
   const int64_t cap = 148 * 16;
@@ -588,7 +738,8 @@ extern "C" int64_t pvk_track_workspace_bytes(int64_t nclips, int64_t nframes, in
   if (nclips < 0 || nframes < 0 || npks < 1) return -1;
   const int64_t rows = nclips * nframes;
   const int64_t nchunks = (nframes + TRACK_CHUNK - 1) / TRACK_CHUNK;
-  return align_up(rows * 4, 256) * 2 + align_up(nclips * nchunks * npks * 4, 256) + 256;
+  return align_up(rows * 4, 256) * 2 + align_up(nclips * nchunks * npks * 4, 256) +
+         align_up(nclips * scan_tiles(nframes) * 8, 256) + 256;
 }
 
 extern "C" int pvk_track(const double *f, const double *mag, int64_t nclips, int64_t nframes, int npks,
@@ -615,6 +766,7 @@ extern "C" int pvk_track(const double *f, const double *mag, int64_t nclips, int
   int32_t *newcount = reinterpret_cast<int32_t *>(ws);
   int32_t *base = reinterpret_cast<int32_t *>(ws + align_up(rows * 4, 256));
   int32_t *G = reinterpret_cast<int32_t *>(ws + 2 * align_up(rows * 4, 256));
+  long long *tsum = reinterpret_cast<long long *>(ws + 2 * align_up(rows * 4, 256) + align_up(nclips * nchunks * npks * 4, 256));
 
   {  // link: one warp per frame pair
     int64_t g;
@@ -657,8 +809,15 @@ extern "C" int pvk_track(const double *f, const double *mag, int64_t nclips, int
     }
     PVK_CHECK_LAUNCH("pvk_track(link)");
   }
-  PVK_LAUNCH(track_scan_kernel, dim3((unsigned)nclips), dim3(1024), 33 * 4, stream, newcount, base, ntracks, nframes);
-  PVK_CHECK_LAUNCH("pvk_track(scan)");
+  {
+    const int64_t nt = scan_tiles(nframes);
+    PVK_REQUIRE(nclips <= 65535, "pvk_track: at most 65535 clips per call (got %lld)", (long long)nclips);
+    PVK_LAUNCH(scan_tile_sums_kernel, dim3((unsigned)nt, (unsigned)nclips), dim3(SCAN_BD), SCAN_SMEM, stream, newcount, nframes,
+               nframes, (const int32_t *)nullptr, nt, tsum);
+    PVK_LAUNCH(scan_tile_apply_kernel<int32_t>, dim3((unsigned)nt, (unsigned)nclips), dim3(SCAN_BD), SCAN_SMEM, stream, newcount,
+               nframes, nframes, (const int32_t *)nullptr, nt, tsum, base, nframes, ntracks, 0);
+    PVK_CHECK_LAUNCH("pvk_track(scan)");
+  }
   {
     const int RT = track_tile_rows(K);
     const size_t per_warp = (size_t)((((K + 3) & ~3) + RT * K + 3) & ~3) * 4;
@@ -679,15 +838,18 @@ extern "C" int pvk_track(const double *f, const double *mag, int64_t nclips, int
     PVK_LAUNCH(track_boundary_kernel, dim3(grid_for(nclips * nchunks * K, 256)), dim3(256), 0, stream, link, tid,
                nframes, K, nchunks, nclips, G);
     PVK_CHECK_LAUNCH("pvk_track(boundary)");
-    int tile = (64 * 1024) / (K * 4) - 1;                       // <= 64 KB of shared memory
+    int tile = (48 * 1024) / (K * 4);                           // two tile buffers, <= 96 KB of shared memory
+    if (tile > 256) tile = 256;
     if (tile > nchunks) tile = (int)nchunks;
     if (tile < 1) tile = 1;
-    const size_t ssm = (size_t)(tile * K + ((K + 3) & ~3)) * 4;
+    const size_t ssm = (size_t)(2 * (tile * K + 4) + ((K + 3) & ~3)) * 4;
     if (ssm > 48 * 1024 && PVK_SET_SMEM(track_stitch_kernel, (int)ssm) != 0) {
       set_error("pvk_track: cannot reserve %d bytes of shared memory", (int)ssm);
       return PVK_ERR_CUDA;
     }
-    PVK_LAUNCH(track_stitch_kernel, dim3((unsigned)nclips), dim3(32), ssm, stream, G, K, nchunks, tile);
+    int sbd = (tile * K + 31) / 32 * 32;                        // one thread per entry of a tile, <= 1024
+    if (sbd > 1024) sbd = 1024;
+    PVK_LAUNCH(track_stitch_kernel, dim3((unsigned)nclips), dim3(sbd), ssm, stream, G, K, nchunks, tile);
     PVK_CHECK_LAUNCH("pvk_track(stitch)");
     PVK_LAUNCH(track_fix_kernel, dim3(grid_for(rows * K, 256)), dim3(256), 0, stream, tid, G, nframes, K, nchunks,
                nclips);
@@ -711,10 +873,31 @@ extern "C" int pvk_track_spans(const int32_t *tid, int64_t nframes, int npks, in
   return PVK_OK;
 }
 
+extern "C" int pvk_track_stats(const int32_t *tid, const int32_t *ntracks, int64_t nclips, int64_t nframes, int npks,
+                               int64_t *stats, void *stream) {
+  PVK_REQUIRE(npks >= 1 && nframes >= 0 && nclips >= 0 && nclips <= 65535, "pvk_track_stats: bad sizes");
+  if (nclips == 0) return PVK_OK;
+  PVK_REQUIRE(stats && ntracks && (tid || nframes == 0), "pvk_track_stats: NULL pointer argument");
+  cudaMemsetAsync(stats, 0, (size_t)nclips * 8, (cudaStream_t)stream);
+  cudaMemsetAsync(stats + nclips, 0xff, (size_t)nclips * 8, (cudaStream_t)stream);        // -1
+  int g = grid_for(nframes * npks, 256);
+  if (g > 148 * 4) g = 148 * 4;
+  PVK_LAUNCH(track_stats_kernel, dim3((unsigned)g, (unsigned)nclips), dim3(256), 0, stream, tid, ntracks, nframes, npks,
+             reinterpret_cast<long long *>(stats));
+  PVK_CHECK_LAUNCH("pvk_track_stats");
+  return PVK_OK;
+}
+
+extern "C" int64_t pvk_track_pack_workspace_bytes(int64_t ntracks) {
+  if (ntracks < 0) return -1;
+  return align_up(scan_tiles(ntracks) * 8, 256);
+}
+
 extern "C" int pvk_track_pack(const double *f, const double *mag, const double *ph, const double *realph,
                               const int32_t *tid, int64_t nframes, int npks,
                               int64_t ntracks, int32_t *tstart, int32_t *tlen, int64_t *toff, double *pf,
-                              double *pmag, double *pph, double *prealph, void *stream) {
+                              double *pmag, double *pph, double *prealph, void *workspace,
+                              int64_t workspace_bytes, void *stream) {
   PVK_REQUIRE(npks >= 1 && nframes >= 0 && ntracks >= 0, "pvk_track_pack: bad sizes");
   PVK_REQUIRE(toff != nullptr, "pvk_track_pack: toff is NULL");
   if (ntracks == 0 || nframes == 0) {
@@ -723,14 +906,24 @@ extern "C" int pvk_track_pack(const double *f, const double *mag, const double *
   }
   PVK_REQUIRE(f && mag && realph && tid && tstart && tlen && pf && pmag && prealph,
               "pvk_track_pack: NULL pointer argument");
+  PVK_REQUIRE(workspace != nullptr && workspace_bytes >= pvk_track_pack_workspace_bytes(ntracks),
+              "pvk_track_pack: workspace too small (%lld bytes; pvk_track_pack_workspace_bytes gives the size)",
+              (long long)workspace_bytes);
   const int64_t n = nframes * npks;
   cudaMemsetAsync(tlen, 0, 4 * (size_t)ntracks, (cudaStream_t)stream);
   cudaMemsetAsync(tstart, 0x7f, 4 * (size_t)ntracks, (cudaStream_t)stream);   // 0x7f7f7f7f: "no frame yet"
   PVK_LAUNCH(pack_count_kernel, dim3(grid_for((nframes + PACK_STRIP - 1) / PACK_STRIP * npks, 128)), dim3(128), 0,
              stream, tid, nframes, npks, tstart, tlen);
   PVK_CHECK_LAUNCH("pvk_track_pack(count)");
-  PVK_LAUNCH(pack_scan_kernel, dim3(1), dim3(1024), 33 * 8, stream, tlen, ntracks, toff);
-  PVK_CHECK_LAUNCH("pvk_track_pack(scan)");
+  {
+    const int64_t nt = scan_tiles(ntracks);
+    long long *tsum = reinterpret_cast<long long *>(workspace);
+    PVK_LAUNCH(scan_tile_sums_kernel, dim3((unsigned)nt), dim3(SCAN_BD), SCAN_SMEM, stream, tlen, ntracks, ntracks,
+               (const int32_t *)nullptr, nt, tsum);
+    PVK_LAUNCH(scan_tile_apply_kernel<int64_t>, dim3((unsigned)nt), dim3(SCAN_BD), SCAN_SMEM, stream, tlen, ntracks, ntracks,
+               (const int32_t *)nullptr, nt, tsum, toff, ntracks + 1, (int32_t *)nullptr, 1);
+    PVK_CHECK_LAUNCH("pvk_track_pack(scan)");
+  }
   PVK_LAUNCH(pack_scatter_kernel, dim3(grid_for(n, 256)), dim3(256), 0, stream, f, mag, ph, realph, tid, nframes,
              npks, tstart, toff, pf, pmag, pph, prealph);
   PVK_CHECK_LAUNCH("pvk_track_pack(scatter)");

@@ -184,29 +184,43 @@ def track_device(fd, magd, maxpitchjmp=0.5):
     ntracks = torch.empty((nclips,), dtype=torch.int32, device=dev)
     wsb = L.pvk_track_workspace_bytes(nclips, F, K)
     ws = torch.empty(max(int(wsb), 8), dtype=torch.uint8, device=dev)
+    stats = torch.empty((3, nclips), dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
         _lib.check(L.pvk_track(_ptr(fd), _ptr(magd), nclips, F, K, float(maxpitchjmp), _ptr(tid), _ptr(link),
                                _ptr(ntracks), _ptr(ws), int(wsb), _stream()), "pvk_track")
+        _lib.check(L.pvk_track_stats(_ptr(tid), _ptr(ntracks), nclips, F, K, _ptr(stats), _stream()),
+                   "pvk_track_stats")
     if squeeze:
         tid, link = tid[0], link[0]
-    return dict(tid=tid, link=link, ntracks=ntracks)
+    return dict(tid=tid, link=link, ntracks=ntracks, stats=stats)
 
 
-def pack_device(fd, magd, phd, realphd, tid, link, ntracks):   # link: unused, kept for call sites
-    """pvk_track_pack for one clip (``[F, K]`` device tables, ``ntracks`` python int)."""
+def track_counts(tr, clip=0):
+    """(number of partials, number of points, last frame holding a point) of one clip of a
+    track_device() result: ONE 24-byte device->host read-back (synchronises the stream)."""
+    s = tr["stats"][:, clip].cpu()
+    return int(s[2]), int(s[0]), int(s[1])
+
+
+def pack_device(fd, magd, phd, realphd, tid, link, ntracks, npts=None):   # link: unused, kept for call sites
+    """pvk_track_pack for one clip (``[F, K]`` device tables, ``ntracks`` python int; ``npts`` =
+    number of points from track_counts(), counted here when not given)."""
     L = _lib.lib()
     dev = fd.device
     F, K = fd.shape
-    npts = int((tid >= 0).sum().item()) if F * K else 0
+    if npts is None:
+        npts = int((tid >= 0).sum().item()) if F * K else 0
     nt = int(ntracks)
     tstart = torch.empty((max(nt, 1),), dtype=torch.int32, device=dev)
     tlen = torch.empty((max(nt, 1),), dtype=torch.int32, device=dev)
     toff = torch.empty((nt + 1,), dtype=torch.int64, device=dev)
     packed = [torch.empty((max(npts, 1),), dtype=torch.float64, device=dev) for _ in range(4)]
+    wsb = int(L.pvk_track_pack_workspace_bytes(nt))
+    ws = torch.empty(max(wsb, 8), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         _lib.check(L.pvk_track_pack(_ptr(fd), _ptr(magd), _ptr(phd), _ptr(realphd), _ptr(tid), F, K, nt,
                                     _ptr(tstart), _ptr(tlen), _ptr(toff), _ptr(packed[0]), _ptr(packed[1]),
-                                    _ptr(packed[2]), _ptr(packed[3]), _stream()), "pvk_track_pack")
+                                    _ptr(packed[2]), _ptr(packed[3]), _ptr(ws), wsb, _stream()), "pvk_track_pack")
     return dict(tstart=tstart[:nt], tlen=tlen[:nt], toff=toff, pf=packed[0][:npts], pmag=packed[1][:npts],
                 pph=packed[2][:npts], prealph=packed[3][:npts], npts=npts)
 
@@ -782,7 +796,7 @@ class SinSum(object):
                 self._trk = dict(tid=torch.zeros((0, 1), dtype=torch.int32, device=self._dev), link=None, ntracks=0)
             else:
                 tr = track_device(t["f"], t["mag"], self._maxpitchjmp)
-                tr["ntracks"] = int(tr["ntracks"][0].item())
+                tr["ntracks"], tr["npts"], tr["max_end"] = track_counts(tr)
                 self._trk = tr
         return self._trk
 
@@ -797,7 +811,8 @@ class SinSum(object):
                                 toff=torch.zeros((1,), dtype=torch.int64, device=self._dev),
                                 pf=e, pmag=e, pph=e, prealph=e, npts=0)
             else:
-                self._pk = pack_device(t["f"], t["mag"], t["ph"], t["realph"], tr["tid"], tr["link"], tr["ntracks"])
+                self._pk = pack_device(t["f"], t["mag"], t["ph"], t["realph"], tr["tid"], tr["link"], tr["ntracks"],
+                                       npts=tr.get("npts"))
         return self._pk
 
     def _ntracks(self):
@@ -854,13 +869,16 @@ class SinSum(object):
             raise ValueError("max() arg is an empty sequence")     # what the reference raises (:1059)
         if hostbuf is not None:
             return self._synth_streamed(pk, tr, sr, int(hop), edge, minframes, hostbuf, int(chunks))
-        out = resynth_device(tr["tid"], pk, sr, int(hop), self.nfft, self.hop, edge=edge, minframes=minframes)
+        out = resynth_device(tr["tid"], pk, sr, int(hop), self.nfft, self.hop, edge=edge, minframes=minframes,
+                             max_end=tr.get("max_end"))
         return out.cpu().numpy() if to_host else out
 
     def _synth_streamed(self, pk, tr, sr, hop, edge, minframes, hostbuf, chunks):
         dev = self._dev
         F, K = tr["tid"].shape
-        max_end = int((pk["tstart"] + pk["tlen"] - 1).max().item())
+        max_end = tr.get("max_end")
+        if max_end is None:
+            max_end = int((pk["tstart"] + pk["tlen"] - 1).max().item())
         nout, _ = synth_geometry(max_end, hop, self.nfft, self.hop, edge)
         nblk = -(-nout // hop)
         cur = torch.cuda.current_stream(dev)

@@ -102,8 +102,10 @@ def track(f, mag, maxpitchjmp=0.5):
     wsb = L.pvk_track_workspace_bytes(nclips, F, K)
     ws = np.zeros(max(wsb, 8), dtype=np.uint8)
     check(L.pvk_track(ptr(f), ptr(mag), nclips, F, K, maxpitchjmp, ptr(tid), ptr(link), ptr(ntracks),
-                      ptr(ws), wsb, 0, None))
-    return dict(tid=tid, link=link, ntracks=ntracks)
+                      ptr(ws), wsb, None))
+    stats = np.full((3, nclips), -77, dtype=np.int64)
+    check(L.pvk_track_stats(ptr(tid), ptr(ntracks), nclips, F, K, ptr(stats), None))
+    return dict(tid=tid, link=link, ntracks=ntracks, stats=stats)
 
 
 def track_pack(f, mag, ph, realph, tid, link, ntracks):   # link unused (kept for call sites)
@@ -117,9 +119,11 @@ def track_pack(f, mag, ph, realph, tid, link, ntracks):   # link unused (kept fo
     tlen = np.full(max(ntracks, 1), -1, dtype=np.int32)
     toff = np.full(ntracks + 1, -1, dtype=np.int64)
     packed = [np.full(max(npts, 1), np.nan) for _ in range(4)]
+    wsb = L.pvk_track_pack_workspace_bytes(ntracks)
+    ws = np.zeros(max(wsb, 8), dtype=np.uint8)
     check(L.pvk_track_pack(ptr(arrs[0]), ptr(arrs[1]), ptr(arrs[2]), ptr(arrs[3]), ptr(tid), F, K,
                            ntracks, ptr(tstart), ptr(tlen), ptr(toff), ptr(packed[0]), ptr(packed[1]),
-                           ptr(packed[2]), ptr(packed[3]), None))
+                           ptr(packed[2]), ptr(packed[3]), ptr(ws), int(wsb), None))
     return dict(tstart=tstart[:ntracks], tlen=tlen[:ntracks], toff=toff, pf=packed[0][:npts],
                 pmag=packed[1][:npts], pph=packed[2][:npts], prealph=packed[3][:npts])
 

@@ -116,6 +116,31 @@ def test_emu_track_stitch_across_tiles():
     assert int(tr["ntracks"][0]) == len(o["st"])
 
 
+def test_emu_track_long_table_scans_stitch_rounds_and_stats():
+    """38 400 frames x 8 slots: ten scan tiles, 300 chunk boundary rows = two pointer-jumping tiles of
+    256 rows with 9 rounds; partials of every length (short ones die inside a chunk, one lives for
+    the whole table, one is reborn every 1000 frames); pvk_track_stats against the oracle."""
+    rng = np.random.RandomState(5)
+    F, K = 128 * 300, 8
+    f = np.zeros((F, K)); mag = np.zeros((F, K))
+    for j in range(F):
+        cols = rng.permutation(K)
+        f[j, cols[0]] = 440.0 * (1 + 0.002 * np.sin(j / 40.0)); mag[j, cols[0]] = 0.5
+        if j % 1000 != 999:
+            f[j, cols[1]] = 1500.0 + 0.01 * (j % 1000); mag[j, cols[1]] = 0.3
+        if rng.rand() < 0.3:
+            f[j, cols[2]] = 3000.0 + 900.0 * rng.rand(); mag[j, cols[2]] = 0.1 * rng.rand() + 0.01
+    f[-3:] = 0.0; mag[-3:] = 0.0                              # the table ends with empty frames
+    o = orc.track(f, mag)
+    tr = eh.track(f, mag)
+    assert np.array_equal(tr["tid"][0], o["tid"])
+    assert int(tr["ntracks"][0]) == len(o["st"])
+    assert tr["stats"][:, 0].tolist() == [int((o["tid"] >= 0).sum()), int(np.max(o["end"])), len(o["st"])]
+    pk = eh.track_pack(f, mag, f, f, tr["tid"][0], None, len(o["st"]))
+    assert np.array_equal(pk["tstart"], o["st"]) and np.array_equal(pk["tstart"] + pk["tlen"] - 1, o["end"])
+    assert pk["toff"][-1] == tr["stats"][0, 0] and np.array_equal(np.diff(pk["toff"]), pk["tlen"])
+
+
 @pytest.mark.parametrize("world", [2, 5])
 def test_emu_segment_numbering_kernels(world):
     """pvk_segment_summary / _resolve / _rename (global numbering of per-segment linked partials)
