@@ -137,8 +137,9 @@ def analyze(x, sr, nfft=1024, hop=None, npks=20, pkthresh=0.005, wind=np.hanning
     (``calc_fft_frame(pos)[:nfft/2]``, :150-158,169).
 
     ``fx_given`` (complex64 ``[nframes, nfft/2]``): skip the FFT and run everything after
-    PVAnalysis.py:169 on these spectra, with ``famp`` formed in float32 as
-    ``sqrt(re*re + im*im)`` exactly like the CUDA kernel -- used to check the kernel's
+    PVAnalysis.py:169 on these spectra, with ``famp = sqrt(float64(re*re + im*im))`` on the
+    float32 power exactly as the CUDA kernel forms it (the kernel compares powers, which is
+    order-isomorphic to comparing this famp) -- used to check the kernel's
     integer / per-peak logic bit-for-bit on the kernel's own spectrum.  ``old0`` replaces
     the all-zero spectrum before frame 0 (segment warm-up).
     """
@@ -163,7 +164,8 @@ def analyze(x, sr, nfft=1024, hop=None, npks=20, pkthresh=0.005, wind=np.hanning
             if fx_given is not None:
                 g = np.asarray(fx_given[j], dtype=np.complex64)
                 fx = g.astype(np.complex128)
-                famp = np.sqrt(g.real * g.real + g.imag * g.imag).astype(np.float64)   # float32 ops
+                pw = g.real * g.real + g.imag * g.imag     # float32 ops, as the kernel forms |fx|^2
+                famp = np.sqrt(pw.astype(np.float64))
             else:
                 xw = x[pos:pos + nfft] * win               # :155-156
                 if fft_dtype == np.float32:

@@ -55,5 +55,5 @@ def _build(verbose, defines, OUT):
 
 if __name__ == "__main__":
     defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
-    outs = [a[4:] for a in sys.argv[1:] if a.startswith("-o=")]
+    outs = [a[3:] for a in sys.argv[1:] if a.startswith("-o=")]
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=outs[0] if outs else None))

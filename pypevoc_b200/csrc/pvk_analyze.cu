@@ -269,10 +269,9 @@ __device__ __forceinline__ bool peak_epilogue(int k, int M, const float2 *cur, c
     if (m == 0 || a < ba) { bf = fq; bdf = df; ba = a; }     // np.argmin: first minimum, nan sticks
   }
   // mag = sqrt(sum(famp[max(nbin-1,1) : min(nbin+1,len)+1]**2)), left to right :197-199
-  const double a0 = famp[FA(k)];
-  double s = a0 * a0;
-  if (k - 1 >= 1) { const double am = famp[FA(k - 1)]; s = am * am + s; }
-  if (k + 1 <= M - 1) { const double ap = famp[FA(k + 1)]; s = s + ap * ap; }
+  double s = famp[FA(k)];                                      // famp holds |fx|^2
+  if (k - 1 >= 1) s = (double)famp[FA(k - 1)] + s;
+  if (k + 1 <= M - 1) s = s + (double)famp[FA(k + 1)];
   o.f = bf;
   o.mag = sqrt(s);
   o.ph = thisph;
@@ -393,9 +392,13 @@ __global__ void __launch_bounds__(Plan<LOGM>::T, 512 / Plan<LOGM>::T) analyze_ke
     // ---- untangle -> fx[0..M), |fx|, min / max / sum of squares
     float lmin = 3.402823466e+38f, lmax = 0.f, lsum = 0.f;
     float2 *so = prm.spec_out ? prm.spec_out + row * M : nullptr;
-    for (int k = tid; k < M / 2; k += T) {
+    constexpr int UI = (M / 2) / T;                            // pairs per thread (0: fewer pairs than threads)
+#pragma unroll
+    for (int it = 0; it < (UI > 0 ? UI : 1); ++it) {
+      const int k = tid + it * T;
+      if (UI == 0 && k >= M / 2) break;
       float2 xa, xb;
-      if (k == 0) {
+      if (it == 0 && k == 0) {
         const float2 z0 = cur[PADC(0)], zh = cur[PADC(M / 2)];
         xa = make_float2(z0.x + z0.y, 0.f);
         xb = make_float2(zh.x, -zh.y);
@@ -410,18 +413,23 @@ __global__ void __launch_bounds__(Plan<LOGM>::T, 512 / Plan<LOGM>::T) analyze_ke
       const int kb = (k == 0) ? M / 2 : M - k;
       cur[PADC(k)] = xa;
       cur[PADC(kb)] = xb;
-      // |fx| without FMA contraction: bit-identical to float32 numpy sqrt(re*re + im*im)
-      const float aa = sqrtf(__fadd_rn(__fmul_rn(xa.x, xa.x), __fmul_rn(xa.y, xa.y)));
-      const float ab = sqrtf(__fadd_rn(__fmul_rn(xb.x, xb.x), __fmul_rn(xb.y, xb.y)));
-      famp[FA(k)] = aa;
-      famp[FA(kb)] = ab;
+      // |fx|^2 in fp32 without FMA contraction (bit-identical to numpy float32 re*re + im*im).
+      // Every comparison PeakFinder makes on |fx| is made on this power instead: fp64
+      // sqrt is strictly increasing on distinct fp32 values, so the decisions are exactly
+      // those on famp = sqrt(float64(power)) -- and no square root per bin is needed.
+      const float pa = __fadd_rn(__fmul_rn(xa.x, xa.x), __fmul_rn(xa.y, xa.y));
+      const float pb = __fadd_rn(__fmul_rn(xb.x, xb.x), __fmul_rn(xb.y, xb.y));
+      famp[FA(k)] = pa;
+      famp[FA(kb)] = pb;
       if (so) { so[k] = xa; so[kb] = xb; }
-      lmin = fminf(lmin, fminf(aa, ab));
-      lmax = fmaxf(lmax, fmaxf(aa, ab));
-      lsum += aa * aa + ab * ab;
+      lmin = fminf(lmin, fminf(pa, pb));
+      lmax = fmaxf(lmax, fmaxf(pa, pb));
+      lsum += pa + pb;
     }
     {
-      const float wmin = warp_min(lmin), wmax = warp_max(lmax);
+      // powers are >= 0: their bit patterns order like the values, so one REDUX each
+      const float wmin = __uint_as_float(warp_umin(__float_as_uint(lmin)));
+      const float wmax = __uint_as_float(warp_umax(__float_as_uint(lmax)));
       const double wsum = warp_sum((double)lsum);
       if (lane == 0) { redf[warp] = wmin; redf[8 + warp] = wmax; redd[warp] = wsum; }
     }
@@ -434,16 +442,16 @@ __global__ void __launch_bounds__(Plan<LOGM>::T, 512 / Plan<LOGM>::T) analyze_ke
       ymax = fmaxf(ymax, redf[8 + w]);
       sumsq += redd[w];
     }
-    // PeakFinder.__init__ :57-70 and findpos :164,174
-    const double miny_d = (double)miny;
-    double minamp = (double)ymax * prm.pkthresh;
+    // PeakFinder.__init__ :57-70 and findpos :164,174 (miny / ymax are powers here)
+    const double miny_d = sqrt((double)miny);
+    double minamp = sqrt((double)ymax) * prm.pkthresh;
     if (minamp == 0.0) minamp = miny_d;
     const double th = minamp - miny_d;
 
     // ---- candidates: interior local maxima above threshold (or everything when th < 0),
     //      compacted in bin order into (cbin, ckey).  Thread t scans bins [t*CB, (t+1)*CB).
-    //      The strict fp64 test (y - miny) > th is decided in fp32 outside a guard band of
-    //      2^-18 relative around minamp (fp64 rounding moves either side by < 2^-51 relative).
+    //      The strict fp64 test (y - miny) > th is decided on the fp32 power outside a guard
+    //      band of 2^-17 relative around minamp^2 (fp64 rounding moves either side by < 2^-50).
     int C = 0;
     unsigned lo = 0xffffffffu, hi = 0u;
     {
@@ -461,30 +469,40 @@ __global__ void __launch_bounds__(Plan<LOGM>::T, 512 / Plan<LOGM>::T) analyze_ke
       }
       y[0] = kb0 > 0 ? famp[FA(kb0 - 1)] : 0.f;
       y[CB + 1] = kb0 + CB < M ? famp[FA(kb0 + CB)] : 0.f;
-      const float mf = (float)minamp;
-      const float thr_hi = mf * (1.f + 3.8146973e-6f), thr_lo = mf * (1.f - 3.8146973e-6f);
       const bool allc = th < 0.0;
-      unsigned cbits = 0, pbits = 0;
-      unsigned kmin = 0xffffffffu, kmax = 0u;
+      float thr_hi = -1.f, thr_lo = -1.f;                      // th < 0: every local maximum passes
+      if (!allc) {
+        const float mf = (float)(minamp * minamp);
+        thr_hi = mf * (1.f + 7.6293945e-6f); thr_lo = mf * (1.f - 7.6293945e-6f);
+      }
+      unsigned interior = (1u << CB) - 1u;                     // bins 1 .. M-2
+      if (tid == 0) interior &= ~1u;
+      if (tid == T - 1) interior &= ~(1u << (CB - 1));
+      unsigned pbits = 0;                                      // local maxima not below the band
 #pragma unroll
       for (int i = 0; i < CB; ++i) {
-        const int k = kb0 + i;
-        const bool interior = (k >= 1) && (k <= M - 2);
         const float yv = y[i + 1];
-        const bool ispk = interior && (y[i] < yv) && (yv >= y[i + 2]);
-        bool c;
-        if (ispk) {
-          c = yv > thr_hi;
-          if (!c && !(yv < thr_lo)) c = ((double)yv - miny_d) > th;
-        } else {
-          c = interior && allc;
-        }
-        if (ispk) pbits |= 1u << i;
+        if ((y[i] < yv) && (yv >= y[i + 2]) && !(yv < thr_lo)) pbits |= 1u << i;
+      }
+      pbits &= interior;
+      unsigned kmin = 0xffffffffu, kmax = 0u;
+      for (unsigned rem = pbits; rem;) {                       // few per thread: settle the band, key range
+        const int i = __ffs((int)rem) - 1;
+        rem &= rem - 1u;
+        const float yv = famp[FA(kb0 + i)];
+        bool c = yv > thr_hi;
+        if (!c) c = (sqrt((double)yv) - miny_d) > th;
         if (c) {
-          cbits |= 1u << i;
-          const unsigned key = ispk ? __float_as_uint(yv) : 0u;
+          const unsigned key = __float_as_uint(yv);
           kmin = key < kmin ? key : kmin; kmax = key > kmax ? key : kmax;
+        } else {
+          pbits &= ~(1u << i);
         }
+      }
+      unsigned cbits = pbits;
+      if (allc) {                                              // non-maxima are candidates too, key 0
+        cbits = interior;
+        if (interior & ~pbits) kmin = 0u;
       }
       const int cnt = __popc(cbits);
       const int incl = warp_scan_incl(cnt);
@@ -502,13 +520,12 @@ __global__ void __launch_bounds__(Plan<LOGM>::T, 512 / Plan<LOGM>::T) analyze_ke
         lo = redu[8 + w] < lo ? redu[8 + w] : lo;
         hi = redu[16 + w] > hi ? redu[16 + w] : hi;
       }
-#pragma unroll
-      for (int i = 0; i < CB; ++i) {
-        if ((cbits >> i) & 1u) {
-          cbin[pos] = (unsigned short)(kb0 + i);
-          ckey[pos] = ((pbits >> i) & 1u) ? __float_as_uint(y[i + 1]) : 0u;
-          ++pos;
-        }
+      for (unsigned rem = cbits; rem;) {
+        const int i = __ffs((int)rem) - 1;
+        rem &= rem - 1u;
+        cbin[pos] = (unsigned short)(kb0 + i);
+        ckey[pos] = ((pbits >> i) & 1u) ? __float_as_uint(famp[FA(kb0 + i)]) : 0u;
+        ++pos;
       }
     }
     __syncthreads();

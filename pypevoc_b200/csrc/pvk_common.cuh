@@ -76,16 +76,8 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o >= 1; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
   return v;
 }
-__device__ __forceinline__ unsigned warp_umin(unsigned v) {
-#pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) { unsigned w = __shfl_xor_sync(FULL, v, o); v = w < v ? w : v; }
-  return v;
-}
-__device__ __forceinline__ unsigned warp_umax(unsigned v) {
-#pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) { unsigned w = __shfl_xor_sync(FULL, v, o); v = w > v ? w : v; }
-  return v;
-}
+__device__ __forceinline__ unsigned warp_umin(unsigned v) { return __reduce_min_sync(FULL, v); }   // REDUX
+__device__ __forceinline__ unsigned warp_umax(unsigned v) { return __reduce_max_sync(FULL, v); }
 // inclusive warp scan (sum)
 __device__ __forceinline__ int warp_scan_incl(int v) {
 #pragma unroll

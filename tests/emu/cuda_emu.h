@@ -112,6 +112,24 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
   emu_warp_barrier();
   return m;
 }
+static inline unsigned __reduce_min_sync(unsigned, unsigned v) {
+  emu::Warp &w = emu::g_blk->warps[threadIdx.x >> 5];
+  w.scratch[threadIdx.x & 31] = v;
+  emu_warp_barrier();
+  unsigned m = 0xffffffffu;
+  for (int i = 0; i < 32; ++i) if ((unsigned)w.scratch[i] < m) m = (unsigned)w.scratch[i];
+  emu_warp_barrier();
+  return m;
+}
+static inline unsigned __reduce_max_sync(unsigned, unsigned v) {
+  emu::Warp &w = emu::g_blk->warps[threadIdx.x >> 5];
+  w.scratch[threadIdx.x & 31] = v;
+  emu_warp_barrier();
+  unsigned m = 0u;
+  for (int i = 0; i < 32; ++i) if ((unsigned)w.scratch[i] > m) m = (unsigned)w.scratch[i];
+  emu_warp_barrier();
+  return m;
+}
 static inline int __any_sync(unsigned m, int p) { return __ballot_sync(m, p) != 0; }
 static inline int __all_sync(unsigned m, int p) { return __ballot_sync(m, p) == 0xffffffffu; }
 static inline int __syncthreads_count(int p) {

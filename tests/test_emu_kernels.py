@@ -73,6 +73,8 @@ def test_emu_degenerate_and_select_paths():
     imp = np.zeros(1024 * 4, dtype=np.float32); imp[1500] = 1.0; cases.append((imp, 1024, 256, 20, 0.005))
     flat = np.zeros(256 * 4, dtype=np.float32); flat[300] = 1.0; flat[301] = 1e-4; cases.append((flat, 256, 64, 5, 0.5))
     tr_ = np.zeros(512 * 6, dtype=np.float32); tr_[::32] = 1.0; cases.append((tr_, 512, 128, 30, 0.005))
+    cases.append((rng.randn(256 * 5).astype(np.float32), 256, 64, 200, -0.1))         # th < 0: every bin a candidate
+    cases.append((rng.randn(256 * 5).astype(np.float32), 256, 64, 40, -0.1))          # ... with C > K
     for x, nfft, hop, npks, th in cases:
         o = eh.analyze(x, sr, nfft, hop, npks, pkthresh=th, spectra=True)
         got = {k: o[k][0] for k in ("f", "mag", "ph", "realph", "binno", "totalmag", "npk")}
