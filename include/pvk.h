@@ -86,6 +86,55 @@ int pvk_analyze(const float *x, int64_t nclips, int64_t clip_stride, int64_t nsa
                 double *binno, int32_t *npk, double *totalmag, float *spec_out,
                 void *stream);
 
+/*
+ * pvk_analyze with two more optional outputs (both NULL or both set): float64
+ * [nclips, nframes, npks] fine_pos / fine_val = PeakFinder.refine (PeakFinder.py:331-372,
+ * fun=None, default x) of every emitted peak on famp = |fx|: the vertex of the parabola through
+ * the three bins around the peak (position in bins, value).  PV itself never calls refine
+ * (PVAnalysis.py:175-178 keeps integer positions): this is the opt-in "quadratic bin
+ * interpolation" of the peak kernel, columns aligned with f / mag / binno.
+ */
+int pvk_analyze_ex(const float *x, int64_t nclips, int64_t clip_stride, int64_t nsamp,
+                   const float *win_scaled, const double *fbin, const double *wfbin,
+                   const void *tables, int nfft, int hop, int npks, double pkthresh,
+                   double dt, double fstep, int64_t frame0, int64_t nframes, int prev_zero,
+                   int run_frames, double *f, double *mag, double *ph, double *realph,
+                   double *binno, int32_t *npk, double *totalmag, float *spec_out,
+                   double *fine_pos, double *fine_val, void *stream);
+
+/* ------------------------------------------------------------------ f0-guided analysis
+ * Replaces PVHarmonic.run_pv / PVHarmonic.calc_pv_frame (PVAnalysis.py:419-538) for one
+ * signal: frame r (starting at sample r*hop) is processed when f0[r] > 0 and not NaN (:509);
+ * its bins are round(arange(f0bin, nfft/2-1, f0bin)), f0bin = f0[r]/sr*nfft (:461-462), the
+ * harmonics above the first re-centred on the measured first harmonic when that exceeds
+ * `fmin` (:464-468); per harmonic dphase2freq, the 3-bin magnitude and the phase (:471-488).
+ * The phase difference is taken against the last PROCESSED frame (:491), all-zero before the
+ * first one (:121).
+ *
+ *   f0        float64 [nframes]  (what set_f0 leaves in PVHarmonic.f0, :424-441)
+ *   f mag ph  float64 [nframes, npks], cut / zero padded to npks (:512-516); skipped frames
+ *             are zero rows
+ *   residual  float64 [nframes]: sqrt(sum(famp^2) - sum over ALL harmonics of their 3-bin
+ *             powers) (:490), NaN for skipped frames (:507)
+ *   nharm     int32 [nframes]: number of harmonics evaluated (len(bins)), 0 for skipped frames
+ */
+int pvk_harmonic(const float *x, int64_t nsamp, const float *win_scaled, const double *fbin,
+                 const double *wfbin, const void *tables, int nfft, int hop, int npks, double dt,
+                 double sr, double fmin, const double *f0, int64_t nframes, int run_frames,
+                 double *f, double *mag, double *ph, double *residual, int32_t *nharm, void *stream);
+
+/* ------------------------------------------------------------------ per-frame consumers
+ * PV.calc_f0 (PVAnalysis.py:371-391) and PV.partial_sum_magnitude (:411-413) over peak tables
+ * f, mag float64 [nrows, npks]:
+ *   fm              float64 [nrows]: lowest frequency with fmin < f < fmax and
+ *                   mag > max(mag)*thr (first column on ties), 0 when there is none
+ *   fundamental_idx int32 [nrows]: its column (0 when there is none)
+ *   partial_sum_mag float64 [nrows]: sqrt(sum(mag^2))
+ */
+int pvk_frame_stats(const double *f, const double *mag, int64_t nrows, int npks, double fmin, double fmax,
+                    double thr, double *fm, int32_t *fundamental_idx, double *partial_sum_mag,
+                    void *stream);
+
 /* ------------------------------------------------------------------ tracking
  * Replaces PV.toSinSum -> SinSum.add_frame (PVAnalysis.py:299-322,871-957).
  *

@@ -117,8 +117,112 @@ def peakfinder_cases():
         sel=np.array(sels, dtype=object), keep=np.array(keeps, dtype=object))
 
 
+# name -> (generator, gen kwargs, PVHarmonic kwargs, nominal f0)
+HARM_CASES = {
+    "h_readme": ("readme_vibrato", {}, dict(nfft=2048, hop=512, npks=8), 500.0),
+    "h_metric": ("harm", dict(sr=44100, dur=0.5, f0=220, nharm=90, p=0.5, sigma=0.01, seed=1),
+                 dict(nfft=2048, hop=512, npks=50), 220.0),
+    "h_odd_hop": ("harm", dict(sr=22050, dur=0.4, f0=300, nharm=20, p=1.0, sigma=0.2, seed=7),
+                  dict(nfft=1024, hop=300, npks=5), 300.0),
+    "h_speech": ("speech_like_clip", dict(seed=1000, sr=16000, dur=3.0), dict(nfft=512, hop=128, npks=20), 150.0),
+    "h_tiny_f0": ("harm", dict(sr=44100, dur=0.3, f0=110, nharm=150, p=0.5, sigma=0.01, seed=2),
+                  dict(nfft=4096, hop=512, npks=30), 7.0),
+    "h_high_f0": ("harm", dict(sr=8000, dur=0.5, f0=100, nharm=10, p=0.5, sigma=0.01, seed=2),
+                  dict(nfft=256, hop=64, npks=4), 3900.0),
+}
+
+
+def harmonic_f0(name, nframes):
+    """The f0 track of a harmonic case: nominal f0 with 2 % jitter, ~15 % unvoiced (0) and ~5 % NaN
+    frames (both are skipped by PVHarmonic.run_pv, PVAnalysis.py:509)."""
+    base = HARM_CASES[name][3]
+    rng = np.random.RandomState(sum(map(ord, name)))
+    f0 = base * (1 + 0.02 * rng.randn(nframes))
+    f0[rng.rand(nframes) < 0.15] = 0.0
+    f0[rng.rand(nframes) < 0.05] = np.nan
+    if name == "h_high_f0":
+        f0[3] = 4100.0          # f0bin beyond nfft/2 - 1: no harmonics at all
+    return f0
+
+
+def harmonic_cases():
+    """PVHarmonic.set_f0 + run_pv of the unmodified reference (progress=True: its run_pv calls
+    self.progress unconditionally, :528-530; the bar's output is swallowed)."""
+    import contextlib
+    import io
+    mod = ref_loader.load()
+    out = {}
+    for name, (gen, gkw, pkw, _) in HARM_CASES.items():
+        x, sr = make_signal(gen, gkw)
+        nfr = -(-(len(x) - pkw["nfft"]) // pkw["hop"])
+        f0 = harmonic_f0(name, nfr)
+        with contextlib.redirect_stdout(io.StringIO()), np.errstate(all="ignore"):
+            pv = mod.PVHarmonic(x.astype(np.float64), sr, progress=True, **pkw)
+            pv.set_f0(f0)
+            pv.run_pv()
+        assert pv.nframes == nfr
+        for k in ("f", "mag", "ph", "residuals", "t"):
+            out["%s.%s" % (name, k)] = getattr(pv, k)
+        out["%s.f0" % name] = f0
+        print(name, nfr, int(np.isnan(pv.residuals).sum()))
+    np.savez_compressed(os.path.join(GOLD, "harmonic.npz"), **out)
+    with open(os.path.join(GOLD, "harmonic_cases.json"), "w") as fh:
+        json.dump({k: dict(generator=v[0], gen_kwargs=v[1], pv_kwargs=v[2]) for k, v in HARM_CASES.items()},
+                  fh, indent=1, sort_keys=True)
+
+
+def consumer_cases():
+    """PV.calc_f0 / fundamental_idx / partial_sum_magnitude / partial_magnitude_ratio
+    (PVAnalysis.py:371-417) of the reference on its own tables, for every analysis case."""
+    out = {}
+    for name in CASES:
+        gen, gkw, pkw, _ = CASES[name]
+        x, sr = make_signal(gen, gkw)
+        pv = ref_loader.ref_run_pv(x.astype(np.float64), sr, **pkw)
+        for args in ((50, 10000, 0.1), (200, 3000, 0.5)):
+            fm = pv.calc_f0(*args)
+            tag = "%s.%d_%d_%g" % ((name,) + args)
+            out[tag + ".fm"] = fm
+            out[tag + ".idx"] = np.array(pv.fundamental_idx)
+        out[name + ".psm"] = pv.partial_sum_magnitude
+        out[name + ".pmr"] = pv.partial_magnitude_ratio
+    np.savez_compressed(os.path.join(GOLD, "consumers.npz"), **out)
+
+
+def refine_cases():
+    """PeakFinder.refine_all (PeakFinder.py:331-406) of the reference: the known answers of its
+    tests/test_peak_finder.py:22-48 and random spectra."""
+    pfm = ref_loader.load_peakfinder()
+
+    def parabolic_peak(max_pos=1.0, max_val=1.0, n=3, a=-1.):      # tests/test_peak_finder.py:7-11
+        x = np.arange(n)
+        b = -max_pos * 2 * a
+        c = max_val - a * max_pos * (b + max_pos)
+        return a * x * x + b * x + c
+    ys, idxs, fps, fvs = [], [], [], []
+    known = [(1.0, 3), (1.2, 4), (1.5, 4), (1.499, 4)]
+    rng = np.random.RandomState(99)
+    for trial in range(60):
+        if trial < len(known):
+            y = parabolic_peak(max_pos=known[trial][0], n=known[trial][1])
+        elif trial % 2:
+            y = rng.rayleigh(1.0, int(rng.choice([32, 256, 1024])))
+        else:
+            y = np.abs(np.sinc(np.linspace(-8, 8, 512) + rng.rand())) + 0.001 * rng.rand(512)
+        pk = pfm.PeakFinder(y, npeaks=50)
+        pk.refine_all()
+        ys.append(y), idxs.append(np.array(pk._idx, dtype=np.int64))
+        fps.append(np.array(pk._fine_pos)), fvs.append(np.array(pk._fine_val))
+    assert [float(v[0]) for v in fps[:3]] == [1.0, 1.2, 1.5] and abs(fps[3][0] - 1.499) < 1e-7
+    np.savez_compressed(os.path.join(GOLD, "refine.npz"), y=np.array(ys, dtype=object), idx=np.array(idxs, dtype=object),
+                        fine_pos=np.array(fps, dtype=object), fine_val=np.array(fvs, dtype=object))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    if "--extras-only" in sys.argv:
+        harmonic_cases(), consumer_cases(), refine_cases()
+        return
     meta = {}
     for name in CASES:
         F, P = run_case(name)
@@ -127,6 +231,7 @@ def main():
                           nframes=int(F), npartials=int(P))
         print(name, F, P)
     peakfinder_cases()
+    harmonic_cases(), consumer_cases(), refine_cases()
     with open(os.path.join(GOLD, "cases.json"), "w") as fh:
         json.dump(meta, fh, indent=1, sort_keys=True)
 

@@ -213,6 +213,136 @@ def analyze(x, sr, nfft=1024, hop=None, npks=20, pkthresh=0.005, wind=np.hanning
     return out
 
 
+# --------------------------------------------------------------------------- f0-guided analysis
+def harmonic_bins(f0bin, nfft2):
+    """``np.round(np.arange(f0bin, nfft2 - 1, f0bin)).astype('int')`` (PVAnalysis.py:462)."""
+    return np.round(np.arange(f0bin, nfft2 - 1, f0bin)).astype('int')
+
+
+def analyze_harmonic(x, sr, f0, nfft=1024, hop=None, npks=20, wind=np.hanning, fmin=30.0,
+                     fx_given=None):
+    """``PVHarmonic(...).run_pv()`` (PVAnalysis.py:419-538) after ``set_f0(f0)`` (:424-441,
+    ``t=None``: one f0 value per frame).
+
+    Per frame with ``f0[j] > 0`` and not NaN (:509): bins at multiples of ``f0bin =
+    f0/sr*nfft`` (:461-462), harmonics 2.. re-centred on the measured first harmonic when it
+    exceeds ``fmin`` (:464-468), ``dphase2freq`` (:474), 3-bin magnitude (:479-483), phase;
+    ``residual = sqrt(sum(famp**2) - sum of all harmonics' 3-bin powers)`` (:490).  The
+    previous spectrum ``oldfft`` is only replaced by processed frames (:491), rows are cut /
+    zero padded to ``npks`` (:512-516), skipped frames give zero rows and a NaN residual.
+    ``fx_given``: as in :func:`analyze` (spectra of ALL frames; skipped ones are ignored).
+    Returns ``f mag ph`` ``[nframes, npks]``, ``residuals``, ``t``, ``nframes``, ``nharm`` and
+    (not a reference attribute, used to scale tolerances) ``totalmag = sqrt(sum(famp**2))``.
+    """
+    x = np.array(x, dtype=np.float64)
+    nfft2 = int(nfft / 2)
+    if hop is None:
+        hop = int(nfft / 2)
+    tb = pv_tables(sr, nfft, hop, wind)
+    win, wfact = tb["win"], tb["wfact"]
+    old = np.zeros(nfft2)
+    nfr = n_frames(len(x), nfft, hop) if fx_given is None else len(fx_given)
+    K = npks
+    out = {k: np.zeros((nfr, K)) for k in ("f", "mag", "ph")}
+    res = np.full(nfr, np.nan)
+    tot = np.full(nfr, np.nan)
+    nharm = np.zeros(nfr, dtype=np.int64)
+    t = []
+    with np.errstate(all="ignore"):
+        for j in range(nfr):
+            pos = j * hop
+            thisf = f0[int(pos / hop)]                                    # :506
+            t.append((pos + nfft / 2.0) / sr)                             # :523
+            if not (thisf > 0 and not np.isnan(thisf)):                   # :509
+                continue
+            if fx_given is not None:
+                g = np.asarray(fx_given[j], dtype=np.complex64)
+                fx = g.astype(np.complex128)
+                famp = np.sqrt((g.real * g.real + g.imag * g.imag).astype(np.float64))
+            else:
+                fx = (np.fft.fft(x[pos:pos + nfft] * win) / wfact)[:nfft2]    # :150-158,452
+                famp = abs(fx)                                            # :456
+            frat = fx / old                                               # :454
+            f0bin = thisf / sr * nfft                                     # :461
+            bins = harmonic_bins(f0bin, nfft2)
+            ff, mm, pp = [], [], []
+            cummagsq = 0
+            for ipk, nbin in enumerate(bins):
+                if ipk > 0:
+                    if ff[0] > fmin:                                      # :465
+                        corrbin = ff[0] / sr * nfft * (ipk + 1)           # :466
+                        if corrbin < nfft2 - 1:
+                            nbin = int(round(corrbin))                    # :468
+                thisph = np.angle(fx[nbin])                               # :471
+                dph = np.angle(frat[nbin])                                # :473
+                fr_, _ = dphase2freq(np.array([dph]), np.array([nbin]), tb)   # :474
+                ff.append(fr_[0])
+                imin = max(nbin - 1, 1)                                   # :479
+                imax = min(nbin + 1, len(famp))                           # :480
+                thismagsq = sum(famp[imin:imax + 1] ** 2)                 # :481
+                cummagsq += thismagsq
+                mm.append(np.sqrt(thismagsq))
+                pp.append(thisph)
+            res[j] = np.sqrt(np.sum(famp ** 2) - cummagsq)                # :490
+            tot[j] = np.sqrt(np.sum(famp ** 2))
+            old = fx                                                      # :491
+            nh = min(len(ff), K)                                          # :512
+            out["f"][j, :nh] = ff[:nh]
+            out["mag"][j, :nh] = mm[:nh]
+            out["ph"][j, :nh] = pp[:nh]
+            nharm[j] = len(ff)
+    out.update(residuals=res, t=np.array(t), nframes=nfr, nharm=nharm, nfft=nfft, hop=hop, sr=sr,
+               totalmag=tot)
+    return out
+
+
+# --------------------------------------------------------------------------- consumers
+def calc_f0(f, mag, fmin=50, fmax=10000, thr=0.1):
+    """``PV.calc_f0`` (PVAnalysis.py:371-391): per frame the lowest-frequency peak with
+    ``fmin < f < fmax`` and ``mag > max(mag)*thr``.  Returns ``(fm, fundamental_idx)``."""
+    f = np.asarray(f, dtype=np.float64)
+    mag = np.asarray(mag, dtype=np.float64)
+    fm = np.zeros(f.shape[0])
+    im = np.zeros(f.shape[0], dtype='i')
+    for ii in range(len(fm)):
+        ff, mm = f[ii, :], mag[ii, :]
+        maxmag = np.max(mm)
+        in0 = np.flatnonzero(np.all((ff > fmin, ff < fmax, mm > maxmag * thr), axis=0))
+        if len(in0) > 0:
+            isel = np.argmin(ff[in0])                                     # :385
+            fm[ii] = ff[in0][isel]
+            im[ii] = in0[isel]
+    return fm, im
+
+
+def partial_sum_magnitude(mag):
+    """``PV.partial_sum_magnitude`` (PVAnalysis.py:411-413)."""
+    return np.sqrt(np.sum(np.asarray(mag, dtype=np.float64) ** 2, axis=1))
+
+
+def refine_peaks(y, bins):
+    """``PeakFinder.refine`` (PeakFinder.py:331-372, ``fun=None``, default ``x = arange``) for
+    the peaks at integer ``bins`` of ``y``: parabola through the three samples around a
+    peak -> (fine position, fine value); a non-peak returns (pos, y[pos])."""
+    y = np.asarray(y, dtype=np.float64)
+    fpos = np.zeros(len(bins))
+    fval = np.zeros(len(bins))
+    with np.errstate(all="ignore"):
+        for q, pos in enumerate(bins):
+            sur = y[pos - 1:pos + 2]
+            if sur[1] > sur[0] and sur[1] >= sur[2]:                      # :354
+                c = sur[1]
+                b = (sur[2] - sur[0]) / 2
+                a = (sur[2] + sur[0]) / 2 - c
+                lpos = - b / 2 / a
+                fpos[q] = float(pos) + lpos
+                fval[q] = a * lpos * lpos + b * lpos + c                  # :365
+            else:
+                fpos[q] = pos
+                fval[q] = sur[1]
+    return fpos, fval
+
+
 # --------------------------------------------------------------------------- tracking
 def track(f, mag, maxpitchjmp=0.5):
     """``PV.toSinSum`` -> ``SinSum.add_frame`` (PVAnalysis.py:299-322,871-957), restated as

@@ -43,6 +43,7 @@ struct AParams {
   int32_t *npk;
   double *totalmag;
   float2 *spec_out;
+  double *fine_pos, *fine_val;   // optional PeakFinder.refine outputs (PeakFinder.py:331-372)
 };
 
 // tuning knobs (compile time): PVK_TSHIFT = log2 of extra threads per frame for nfft >= 1024,
@@ -232,15 +233,16 @@ __device__ __forceinline__ void fft_frame(const float *__restrict__ xf, bool al8
 // ------------------------------------------------------------------ per-peak epilogue
 struct PeakVals { double f, mag, ph, realph; };
 
-// PVAnalysis.py:188-207 + dphase2freq :133-147, in fp64 and in the reference's operation
-// order (explicit _rn intrinsics: no FMA contraction where rounding decides ties).
-__device__ __forceinline__ bool peak_epilogue(int k, int M, const float2 *cur, const float2 *prev,
-                                              const float *famp, const double *__restrict__ fbin,
-                                              const double *__restrict__ wfbin, double dt,
-                                              double fstep, PeakVals &o) {
+// np.angle(fx[k]) and dphase2freq(np.angle((fx/oldfft)[k]), k): PVAnalysis.py:188-191 +
+// :133-147, in fp64 and in the reference's operation order (explicit _rn intrinsics: no FMA
+// contraction where rounding decides ties).  bf = freq, bdf = fbin[k] - freq.
+__device__ __forceinline__ void peak_phase_freq(int k, const float2 *cur, const float2 *prev,
+                                                const double *__restrict__ fbin,
+                                                const double *__restrict__ wfbin, double dt,
+                                                double &thisph, double &bf, double &bdf) {
   const float2 c = cur[PADC(k)], p = prev[PADC(k)];
   const double re = c.x, im = c.y, ore = p.x, oim = p.y;
-  const double thisph = atan2(im, re);                       // np.angle(fx[nbin]) :188
+  thisph = atan2(im, re);                                    // np.angle(fx[nbin]) :188
   // frat = fx / oldfft (:171): numpy's complex128 division (Smith), incl. the x/0 case
   double qr, qi;
   const double ar = fabs(ore), ai = fabs(oim);
@@ -259,7 +261,8 @@ __device__ __forceinline__ bool peak_epilogue(int k, int M, const float2 *cur, c
   const double PI2 = 6.283185307179586;
   const double fb = __ldg(fbin + k);
   const double base = __dadd_rn(dph, __ldg(wfbin + k));      // :140
-  double bf = 0.0, bdf = 0.0, ba = 0.0;
+  double ba = 0.0;
+  bf = 0.0; bdf = 0.0;
 #pragma unroll
   for (int m = 0; m < 3; ++m) {
     const double dphw = __dadd_rn(base, m == 0 ? -PI2 : (m == 1 ? 0.0 : PI2));
@@ -268,6 +271,15 @@ __device__ __forceinline__ bool peak_epilogue(int k, int M, const float2 *cur, c
     const double a = fabs(df);
     if (m == 0 || a < ba) { bf = fq; bdf = df; ba = a; }     // np.argmin: first minimum, nan sticks
   }
+}
+
+// PVAnalysis.py:188-207 for the peak at bin k (1 <= k <= M-2)
+__device__ __forceinline__ bool peak_epilogue(int k, int M, const float2 *cur, const float2 *prev,
+                                              const float *famp, const double *__restrict__ fbin,
+                                              const double *__restrict__ wfbin, double dt,
+                                              double fstep, PeakVals &o) {
+  double thisph, bf, bdf;
+  peak_phase_freq(k, cur, prev, fbin, wfbin, dt, thisph, bf, bdf);
   // mag = sqrt(sum(famp[max(nbin-1,1) : min(nbin+1,len)+1]**2)), left to right :197-199
   double s = famp[FA(k)];                                      // famp holds |fx|^2
   if (k - 1 >= 1) s = (double)famp[FA(k - 1)] + s;
@@ -277,6 +289,24 @@ __device__ __forceinline__ bool peak_epilogue(int k, int M, const float2 *cur, c
   o.ph = thisph;
   o.realph = __dadd_rn(thisph, __ddiv_rn(__dmul_rn(3.141592653589793, bdf), fstep));   // :207
   return bf > 0.0;                                           // :193 (drops nan too)
+}
+
+// PeakFinder.refine (PeakFinder.py:331-372, fun=None, x = arange): parabola through
+// famp[k-1], famp[k], famp[k+1] (famp = sqrt of the stored power) -> fine position and value;
+// a bin that is not a local maximum keeps (k, famp[k]).  1 <= k <= M-2.
+__device__ __forceinline__ void refine_peak(int k, const float *famp, double &fpos, double &fval) {
+  const double s0 = sqrt((double)famp[FA(k - 1)]), s1 = sqrt((double)famp[FA(k)]), s2 = sqrt((double)famp[FA(k + 1)]);
+  if (s1 > s0 && s1 >= s2) {                                 // :354
+    const double c = s1;
+    const double b = __ddiv_rn(__dsub_rn(s2, s0), 2.0);
+    const double a = __dsub_rn(__ddiv_rn(__dadd_rn(s2, s0), 2.0), c);
+    const double lpos = __ddiv_rn(__ddiv_rn(-b, 2.0), a);    // - b/2/a
+    fpos = __dadd_rn((double)k, lpos);
+    fval = __dadd_rn(__dadd_rn(__dmul_rn(__dmul_rn(a, lpos), lpos), __dmul_rn(b, lpos)), c);   // :365
+  } else {
+    fpos = (double)k;
+    fval = s1;
+  }
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -627,11 +657,17 @@ __global__ void __launch_bounds__(Plan<LOGM>::T, 512 / Plan<LOGM>::T) analyze_ke
       if (valid) {
         prm.f[pos] = v.f; prm.mag[pos] = v.mag; prm.ph[pos] = v.ph;
         prm.realph[pos] = v.realph; prm.binno[pos] = (double)k;
+        if (prm.fine_pos) {
+          double fp, fv;
+          refine_peak(k, famp, fp, fv);
+          prm.fine_pos[pos] = fp; prm.fine_val[pos] = fv;
+        }
       }
     }
     for (int p = outbase + tid; p < K; p += T) {
       prm.f[ob + p] = 0.0; prm.mag[ob + p] = 0.0; prm.ph[ob + p] = 0.0;
       prm.realph[ob + p] = 0.0; prm.binno[ob + p] = 0.0;
+      if (prm.fine_pos) { prm.fine_pos[ob + p] = 0.0; prm.fine_val[ob + p] = 0.0; }
     }
     if (tid == 0) {
       prm.npk[row] = outbase;
@@ -640,6 +676,236 @@ __global__ void __launch_bounds__(Plan<LOGM>::T, 512 / Plan<LOGM>::T) analyze_ke
     __syncthreads();   // prev buffer is overwritten by the next frame's FFT
   }
   (void)N;
+}
+
+// ------------------------------------------------------------------ f0-guided analysis
+// PVHarmonic.run_pv / calc_pv_frame (PVAnalysis.py:419-538): same framing / FFT / phase
+// difference as analyze_kernel, but the bins are read at multiples of a given f0 instead of
+// being peak-picked.  One CTA walks a run of frames; the "previous spectrum" is that of the
+// last PROCESSED frame (f0 > 0 and not NaN, :509), as the reference only replaces oldfft there
+// (:491) -- a run starts by searching backwards for it.
+struct HParams {
+  const float *x;
+  const float *win;
+  const float2 *tables;
+  const double *fbin;
+  const double *wfbin;
+  const double *f0;
+  int hop, npks;
+  double dt, sr, fmin;
+  int64_t nframes;
+  int run;
+  double *f, *mag, *ph, *residual;
+  int32_t *nharm;
+};
+
+__device__ __forceinline__ bool f0_valid(double v) { return v > 0.0; }   // false for NaN too (:509)
+
+template <int LOGM>
+__device__ __forceinline__ void untangle_power(float2 *cur, float *famp, const float2 *__restrict__ twr, bool power,
+                                               double &lsum) {
+  using P = Plan<LOGM>;
+  constexpr int M = P::M, T = P::T;
+  const int tid = threadIdx.x;
+  for (int k = tid; k < M / 2; k += T) {
+    float2 xa, xb;
+    if (k == 0) {
+      const float2 z0 = cur[PADC(0)], zh = cur[PADC(M / 2)];
+      xa = make_float2(z0.x + z0.y, 0.f);
+      xb = make_float2(zh.x, -zh.y);
+    } else {
+      const float2 a = cur[PADC(k)], bq = cur[PADC(M - k)];
+      const float2 e = make_float2(0.5f * (a.x + bq.x), 0.5f * (a.y - bq.y));
+      const float2 o = make_float2(0.5f * (a.y + bq.y), -0.5f * (a.x - bq.x));
+      const float2 wo = cmul(o, __ldg(twr + k));
+      xa = make_float2(e.x + wo.x, e.y + wo.y);
+      xb = make_float2(e.x - wo.x, -(e.y - wo.y));
+    }
+    const int kb = (k == 0) ? M / 2 : M - k;
+    cur[PADC(k)] = xa;
+    cur[PADC(kb)] = xb;
+    if (power) {
+      const float pa = __fadd_rn(__fmul_rn(xa.x, xa.x), __fmul_rn(xa.y, xa.y));
+      const float pb = __fadd_rn(__fmul_rn(xb.x, xb.x), __fmul_rn(xb.y, xb.y));
+      famp[FA(k)] = pa;
+      famp[FA(kb)] = pb;
+      lsum += (double)pa + (double)pb;
+    }
+  }
+}
+
+// bin of harmonic i (0-based): np.round(np.arange(f0bin, M-1, f0bin))[i] = rint(f0bin + i*f0bin)
+// (numpy's arange fill: start + i*delta, delta = (start+step) - start = f0bin exactly), re-centred
+// on the measured first harmonic f1 when f1 > fmin and the corrected bin is below M-1 (:464-468)
+__device__ __forceinline__ int harmonic_bin(int64_t i, double f0bin, double f1, bool corr, double sr, int M) {
+  int nbin = (int)rint(__dadd_rn(f0bin, __dmul_rn((double)i, f0bin)));
+  if (i > 0 && corr) {
+    const double corrbin = __dmul_rn(__dmul_rn(__ddiv_rn(f1, sr), (double)(2 * M)), (double)(i + 1));
+    if (corrbin < (double)(M - 1)) nbin = (int)rint(corrbin);
+  }
+  return nbin;
+}
+
+template <int LOGM>
+__global__ void __launch_bounds__(Plan<LOGM>::T) harmonic_kernel(HParams prm) {
+  using P = Plan<LOGM>;
+  using S = Smem<LOGM>;
+  constexpr int M = P::M, T = P::T, NW = P::NW;
+  PVK_SMEM(smem);
+  float2 *bufs[2] = {reinterpret_cast<float2 *>(smem + S::OFF_BUF0),
+                     reinterpret_cast<float2 *>(smem + S::OFF_BUF1)};
+  float *famp = reinterpret_cast<float *>(smem + S::OFF_FAMP);
+  double *redd = reinterpret_cast<double *>(smem + S::OFF_RED);      // 8 doubles
+  double *redc = reinterpret_cast<double *>(smem + S::OFF_CKEY);     // 8 doubles (candidate area is free here)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t r0 = (int64_t)blockIdx.x * prm.run;
+  const int64_t r1 = (r0 + prm.run < prm.nframes) ? r0 + prm.run : prm.nframes;
+  const float2 *twp = prm.tables;
+  const float2 *twr = prm.tables + P::TW_TOTAL;
+  const int K = prm.npks;
+  float2 treg[P::TWR_TOTAL];
+#if PVK_TWREG
+  if constexpr (P::NPASS > 1) Pass<LOGM, 1>::load_tw(twp, treg);
+#endif
+  int cb = 0;                                                 // bufs[cb] = spectrum of the last processed frame
+  {
+    int64_t p = r0 - 1;
+    while (p >= 0 && !f0_valid(__ldg(prm.f0 + p))) --p;       // uniform across the CTA
+    float2 *pb = bufs[cb];
+    if (p < 0) {
+      for (int i = tid; i < P::MP; i += T) pb[i] = make_float2(0.f, 0.f);   // oldfft = zeros (:121)
+    } else {
+      const float *xf = prm.x + p * (int64_t)prm.hop;
+      const bool al8 = ((reinterpret_cast<uintptr_t>(xf) & 7) == 0);
+      fft_frame<LOGM>(xf, al8, prm.win, twp, treg, pb);
+      double dummy = 0.0;
+      untangle_power<LOGM>(pb, famp, twr, false, dummy);
+    }
+    __syncthreads();
+  }
+  for (int64_t r = r0; r < r1; ++r) {
+    const int64_t ob = r * K;
+    const double thisf = __ldg(prm.f0 + r);
+    if (!f0_valid(thisf)) {                                   // skipped frame: zero row, NaN residual (:501-507)
+      for (int p = tid; p < K; p += T) { prm.f[ob + p] = 0.0; prm.mag[ob + p] = 0.0; prm.ph[ob + p] = 0.0; }
+      if (tid == 0) { prm.residual[r] = __longlong_as_double(0x7ff8000000000000LL); prm.nharm[r] = 0; }
+      continue;
+    }
+    float2 *cur = bufs[cb ^ 1];
+    const float2 *prev = bufs[cb];
+    const float *xf = prm.x + r * (int64_t)prm.hop;
+    const bool al8 = ((reinterpret_cast<uintptr_t>(xf) & 7) == 0);
+    fft_frame<LOGM>(xf, al8, prm.win, twp, treg, cur);
+    double lsum = 0.0;
+    untangle_power<LOGM>(cur, famp, twr, true, lsum);
+    {
+      const double wsum = warp_sum(lsum);
+      if (lane == 0) redd[warp] = wsum;
+    }
+    __syncthreads();
+    double sumsq = redd[0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) sumsq += redd[w];
+    // harmonics: H = len(np.arange(f0bin, M-1, f0bin)) = ceil((M-1 - f0bin)/f0bin)
+    const double f0bin = __dmul_rn(__ddiv_rn(thisf, prm.sr), (double)(2 * M));     // :461
+    const double hq = ceil(__ddiv_rn(__dsub_rn((double)(M - 1), f0bin), f0bin));
+    const int64_t H = (hq > 0.0 && hq < 4.0e9) ? (int64_t)hq : 0;                   // non-finite f0bin: no harmonics
+    double f1 = 0.0;
+    bool corr = false;
+    if (H > 0) {
+      // every thread evaluates the first harmonic itself (identical result, no broadcast)
+      double ph0, df0;
+      peak_phase_freq(harmonic_bin(0, f0bin, 0.0, false, prm.sr, M), cur, prev, prm.fbin, prm.wfbin, prm.dt, ph0, f1, df0);
+      corr = f1 > prm.fmin;                                   // :465 (false for NaN)
+    }
+    double csum = 0.0;
+    for (int64_t i = tid; i < H; i += T) {
+      const int k = harmonic_bin(i, f0bin, f1, corr, prm.sr, M);
+      double thisph, bf, bdf;
+      peak_phase_freq(k, cur, prev, prm.fbin, prm.wfbin, prm.dt, thisph, bf, bdf);
+      // thismagsq = sum(famp[max(k-1,1) : min(k+1,len)+1]**2), left to right (:479-481)
+      const int lo = k - 1 > 1 ? k - 1 : 1, hi = k + 1 < M - 1 ? k + 1 : M - 1;
+      double s = 0.0;
+      for (int m = lo; m <= hi; ++m) s = s + (double)famp[FA(m)];
+      csum += s;
+      if (i < K) { prm.f[ob + i] = bf; prm.mag[ob + i] = sqrt(s); prm.ph[ob + i] = thisph; }
+    }
+    for (int64_t p = (H < K ? H : K) + tid; p < K; p += T) { prm.f[ob + p] = 0.0; prm.mag[ob + p] = 0.0; prm.ph[ob + p] = 0.0; }
+    {
+      const double wc = warp_sum(csum);
+      if (lane == 0) redc[warp] = wc;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double cum = redc[0];
+      for (int w = 1; w < NW; ++w) cum += redc[w];
+      prm.residual[r] = sqrt(sumsq - cum);                    // :490 (NaN when the windows overlap enough)
+      prm.nharm[r] = (int32_t)(H < 2147483647 ? H : 2147483647);
+    }
+    cb ^= 1;                                                  // :491
+    __syncthreads();
+  }
+}
+
+template <int LOGM> static int launch_harmonic(HParams prm, int run_frames, void *stream) {
+  using P = Plan<LOGM>;
+  const int smem = Smem<LOGM>::bytes(8);
+  if (smem > 48 * 1024) {
+    if (PVK_SET_SMEM(harmonic_kernel<LOGM>, smem) != 0) {
+      set_error("pvk_harmonic: cannot reserve %d bytes of shared memory", smem);
+      return PVK_ERR_CUDA;
+    }
+  }
+  int64_t run = run_frames;
+  if (run <= 0) {
+    run = (prm.nframes + 148 * 7 - 1) / (148 * 7);
+    if (run < 8) run = 8;
+    if (run > 256) run = 256;
+  }
+  if (run > prm.nframes) run = prm.nframes;
+  prm.run = (int)run;
+  const int64_t nblk = (prm.nframes + run - 1) / run;
+  PVK_REQUIRE(nblk < (int64_t)2147483647, "pvk_harmonic: grid too large (%lld CTAs)", (long long)nblk);
+  PVK_LAUNCH(harmonic_kernel<LOGM>, dim3((unsigned)nblk), dim3(P::T), smem, stream, prm);
+  PVK_CHECK_LAUNCH("pvk_harmonic");
+  return PVK_OK;
+}
+
+// ------------------------------------------------------------------ per-frame consumers
+// PV.calc_f0 (PVAnalysis.py:371-391) and PV.partial_sum_magnitude (:411-413) over the peak
+// table: one warp per frame.
+__global__ void frame_stats_kernel(const double *__restrict__ f, const double *__restrict__ mag, int64_t nrows, int K,
+                                   double flo, double fhi, double thr, double *__restrict__ fm,
+                                   int32_t *__restrict__ fidx, double *__restrict__ psum) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = w0; row < nrows; row += nw) {
+    const double *fr = f + row * K, *mr = mag + row * K;
+    double mx = __longlong_as_double(0xfff0000000000000LL), sq = 0.0;   // -inf
+    for (int c = lane; c < K; c += 32) { const double m = mr[c]; mx = fmax(mx, m); sq += m * m; }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) { mx = fmax(mx, __shfl_xor_sync(FULL, mx, o)); sq += __shfl_xor_sync(FULL, sq, o); }
+    const double lim = __dmul_rn(mx, thr);
+    // lowest frequency among (f > fmin, f < fmax, mag > max*thr); first column on ties (np.argmin)
+    double bf = __longlong_as_double(0x7ff0000000000000LL);   // +inf
+    int bc = 0x7fffffff;
+    for (int c = lane; c < K; c += 32) {
+      const double fv = fr[c];
+      if (fv > flo && fv < fhi && mr[c] > lim && (fv < bf || (fv == bf && c < bc))) { bf = fv; bc = c; }
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      const double of = __shfl_xor_sync(FULL, bf, o);
+      const int oc = __shfl_xor_sync(FULL, bc, o);
+      if (oc != 0x7fffffff && (bc == 0x7fffffff || of < bf || (of == bf && oc < bc))) { bf = of; bc = oc; }
+    }
+    if (lane == 0) {
+      const bool has = bc != 0x7fffffff;
+      fm[row] = has ? bf : 0.0;
+      fidx[row] = has ? bc : 0;
+      psum[row] = sqrt(sq);
+    }
+  }
 }
 
 // ------------------------------------------------------------------ twiddle tables
@@ -763,13 +1029,13 @@ extern "C" int pvk_analyze_init(int nfft, void *tables, void *stream) {
   return PVK_ERR_ARG;
 }
 
-extern "C" int pvk_analyze(const float *x, int64_t nclips, int64_t clip_stride, int64_t nsamp,
-                           const float *win_scaled, const double *fbin, const double *wfbin,
-                           const void *tables, int nfft, int hop, int npks, double pkthresh,
-                           double dt, double fstep, int64_t frame0, int64_t nframes, int prev_zero,
-                           int run_frames, double *f, double *mag, double *ph, double *realph,
-                           double *binno, int32_t *npk, double *totalmag, float *spec_out,
-                           void *stream) {
+extern "C" int pvk_analyze_ex(const float *x, int64_t nclips, int64_t clip_stride, int64_t nsamp,
+                              const float *win_scaled, const double *fbin, const double *wfbin,
+                              const void *tables, int nfft, int hop, int npks, double pkthresh,
+                              double dt, double fstep, int64_t frame0, int64_t nframes, int prev_zero,
+                              int run_frames, double *f, double *mag, double *ph, double *realph,
+                              double *binno, int32_t *npk, double *totalmag, float *spec_out,
+                              double *fine_pos, double *fine_val, void *stream) {
   const int l = log2_exact(nfft);
   PVK_REQUIRE(l >= 0 && nfft >= PVK_MIN_NFFT && nfft <= PVK_MAX_NFFT,
               "pvk_analyze: nfft=%d must be a power of two in [%d, %d]", nfft, PVK_MIN_NFFT, PVK_MAX_NFFT);
@@ -795,8 +1061,63 @@ extern "C" int pvk_analyze(const float *x, int64_t nclips, int64_t clip_stride, 
   prm.f = f; prm.mag = mag; prm.ph = ph; prm.realph = realph; prm.binno = binno;
   prm.npk = npk; prm.totalmag = totalmag;
   prm.spec_out = reinterpret_cast<float2 *>(spec_out);
+  PVK_REQUIRE((fine_pos == nullptr) == (fine_val == nullptr), "pvk_analyze: fine_pos and fine_val go together");
+  prm.fine_pos = fine_pos; prm.fine_val = fine_val;
 #define CALL(L) launch_analyze<L>(prm, nclips, run_frames, stream)
   PVK_DISPATCH_LOGM(l - 1, CALL)
 #undef CALL
   return PVK_ERR_ARG;
+}
+
+extern "C" int pvk_analyze(const float *x, int64_t nclips, int64_t clip_stride, int64_t nsamp,
+                           const float *win_scaled, const double *fbin, const double *wfbin,
+                           const void *tables, int nfft, int hop, int npks, double pkthresh,
+                           double dt, double fstep, int64_t frame0, int64_t nframes, int prev_zero,
+                           int run_frames, double *f, double *mag, double *ph, double *realph,
+                           double *binno, int32_t *npk, double *totalmag, float *spec_out,
+                           void *stream) {
+  return pvk_analyze_ex(x, nclips, clip_stride, nsamp, win_scaled, fbin, wfbin, tables, nfft, hop, npks, pkthresh,
+                        dt, fstep, frame0, nframes, prev_zero, run_frames, f, mag, ph, realph, binno, npk, totalmag,
+                        spec_out, nullptr, nullptr, stream);
+}
+
+extern "C" int pvk_harmonic(const float *x, int64_t nsamp, const float *win_scaled, const double *fbin,
+                            const double *wfbin, const void *tables, int nfft, int hop, int npks, double dt,
+                            double sr, double fmin, const double *f0, int64_t nframes, int run_frames,
+                            double *f, double *mag, double *ph, double *residual, int32_t *nharm, void *stream) {
+  const int l = log2_exact(nfft);
+  PVK_REQUIRE(l >= 0 && nfft >= PVK_MIN_NFFT && nfft <= PVK_MAX_NFFT,
+              "pvk_harmonic: nfft=%d must be a power of two in [%d, %d]", nfft, PVK_MIN_NFFT, PVK_MAX_NFFT);
+  PVK_REQUIRE(hop >= 1, "pvk_harmonic: hop=%d must be >= 1", hop);
+  PVK_REQUIRE(npks >= 1 && npks <= PVK_MAX_NPKS, "pvk_harmonic: npks=%d must be in [1, %d]", npks, PVK_MAX_NPKS);
+  PVK_REQUIRE(nframes >= 0, "pvk_harmonic: negative sizes");
+  if (nframes == 0) return PVK_OK;
+  PVK_REQUIRE((nframes - 1) * (int64_t)hop + nfft <= nsamp, "pvk_harmonic: last frame ends at sample %lld > nsamp=%lld",
+              (long long)((nframes - 1) * (int64_t)hop + nfft), (long long)nsamp);
+  PVK_REQUIRE(x && win_scaled && fbin && wfbin && tables && f0 && f && mag && ph && residual && nharm,
+              "pvk_harmonic: NULL pointer argument");
+  PVK_REQUIRE((reinterpret_cast<uintptr_t>(win_scaled) & 7) == 0, "pvk_harmonic: win_scaled must be 8-byte aligned");
+  HParams prm;
+  prm.x = x; prm.win = win_scaled; prm.tables = reinterpret_cast<const float2 *>(tables);
+  prm.fbin = fbin; prm.wfbin = wfbin; prm.f0 = f0; prm.hop = hop; prm.npks = npks;
+  prm.dt = dt; prm.sr = sr; prm.fmin = fmin; prm.nframes = nframes; prm.run = 0;
+  prm.f = f; prm.mag = mag; prm.ph = ph; prm.residual = residual; prm.nharm = nharm;
+#define CALL(L) launch_harmonic<L>(prm, run_frames, stream)
+  PVK_DISPATCH_LOGM(l - 1, CALL)
+#undef CALL
+  return PVK_ERR_ARG;
+}
+
+extern "C" int pvk_frame_stats(const double *f, const double *mag, int64_t nrows, int npks, double fmin, double fmax,
+                               double thr, double *fm, int32_t *fundamental_idx, double *partial_sum_mag,
+                               void *stream) {
+  PVK_REQUIRE(nrows >= 0 && npks >= 1, "pvk_frame_stats: bad sizes");
+  if (nrows == 0) return PVK_OK;
+  PVK_REQUIRE(f && mag && fm && fundamental_idx && partial_sum_mag, "pvk_frame_stats: NULL pointer argument");
+  int64_t g = (nrows + 7) / 8;
+  if (g > 148 * 32) g = 148 * 32;
+  PVK_LAUNCH(frame_stats_kernel, dim3((unsigned)g), dim3(256), 0, stream, f, mag, nrows, npks, fmin, fmax, thr, fm,
+             fundamental_idx, partial_sum_mag);
+  PVK_CHECK_LAUNCH("pvk_frame_stats");
+  return PVK_OK;
 }

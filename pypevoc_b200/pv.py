@@ -126,13 +126,14 @@ def host_tables(sr, nfft, hop, wind=np.hanning):
 
 
 def analyze_device(xd, sr, nfft, hop, npks, pkthresh, tb, frame0=0, nframes=None, prev_zero=True,
-                   run_frames=0, spectra=False, out=None):
+                   run_frames=0, spectra=False, out=None, refine=False):
     """Launch pvk_analyze on a device signal.
 
     ``xd``: float32 CUDA tensor, ``[nsamp]`` or ``[nclips, nsamp]``.  Returns a dict of device
     tensors ``f mag ph realph binno`` (float64 ``[nclips, nframes, npks]``), ``npk`` (int32),
-    ``totalmag`` (float64) and optionally ``fx`` (complex64 ``[nclips, nframes, nfft/2]``).
-    Asynchronous on the current stream.
+    ``totalmag`` (float64) and optionally ``fx`` (complex64 ``[nclips, nframes, nfft/2]``);
+    ``refine=True`` adds ``fine_pos`` / ``fine_val`` (PeakFinder.refine of every emitted peak,
+    PeakFinder.py:331-372).  Asynchronous on the current stream.
     """
     L = _lib.lib()
     if xd.dim() == 1:
@@ -157,16 +158,72 @@ def analyze_device(xd, sr, nfft, hop, npks, pkthresh, tb, frame0=0, nframes=None
         out["npk"] = torch.empty((nclips, nframes), dtype=torch.int32, device=dev)
         out["totalmag"] = torch.empty((nclips, nframes), dtype=torch.float64, device=dev)
     spec = torch.empty((nclips, nframes, nfft // 2), dtype=torch.complex64, device=dev) if spectra else None
+    if refine and "fine_pos" not in out:
+        out["fine_pos"] = torch.empty((nclips, nframes, npks), dtype=torch.float64, device=dev)
+        out["fine_val"] = torch.empty((nclips, nframes, npks), dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(L.pvk_analyze(
+        _lib.check(L.pvk_analyze_ex(
             _ptr(xd), nclips, xd.stride(0), nsamp, _ptr(dtb["win"]), _ptr(dtb["fbin"]), _ptr(dtb["wfbin"]),
             _ptr(tables), int(nfft), int(hop), int(npks), float(pkthresh), float(tb["dt"]), float(tb["fstep"]),
             int(frame0), int(nframes), 1 if prev_zero else 0, int(run_frames),
             _ptr(out["f"]), _ptr(out["mag"]), _ptr(out["ph"]), _ptr(out["realph"]), _ptr(out["binno"]),
-            _ptr(out["npk"]), _ptr(out["totalmag"]), _ptr(spec), _stream()), "pvk_analyze")
+            _ptr(out["npk"]), _ptr(out["totalmag"]), _ptr(spec),
+            _ptr(out["fine_pos"]) if refine else None, _ptr(out["fine_val"]) if refine else None,
+            _stream()), "pvk_analyze")
     if spectra:
         out["fx"] = spec
     return out
+
+
+def _device_tables(tb, dev):
+    key = ("dev", dev.index)
+    if key not in tb:
+        tb[key] = dict(
+            win=torch.from_numpy(np.ascontiguousarray((tb["win"] / tb["wfact"]).astype(np.float32))).to(dev),
+            fbin=torch.from_numpy(np.ascontiguousarray(tb["fbin"], dtype=np.float64)).to(dev),
+            wfbin=torch.from_numpy(np.ascontiguousarray(tb["wfbin"], dtype=np.float64)).to(dev))
+    return tb[key]
+
+
+def harmonic_device(xd, sr, nfft, hop, npks, f0d, tb, fmin=30.0, nframes=None, run_frames=0):
+    """Launch pvk_harmonic (PVHarmonic.run_pv, PVAnalysis.py:419-538) on a 1-D float32 device
+    signal with one float64 device f0 value per frame.  Returns device ``f mag ph``
+    (float64 ``[nframes, npks]``), ``residuals`` (float64), ``nharm`` (int32).  Asynchronous."""
+    L = _lib.lib()
+    assert xd.dtype == torch.float32 and xd.is_cuda and xd.dim() == 1 and xd.is_contiguous()
+    dev = xd.device
+    nsamp = xd.shape[0]
+    if nframes is None:
+        nframes = n_frames(nsamp, nfft, hop)
+    assert f0d.dtype == torch.float64 and f0d.is_cuda and f0d.is_contiguous() and f0d.numel() >= nframes
+    dtb = _device_tables(tb, dev)
+    tables = _analysis_tables(nfft, dev)
+    out = {k: torch.empty((nframes, npks), dtype=torch.float64, device=dev) for k in ("f", "mag", "ph")}
+    out["residuals"] = torch.empty((nframes,), dtype=torch.float64, device=dev)
+    out["nharm"] = torch.empty((nframes,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.pvk_harmonic(
+            _ptr(xd), nsamp, _ptr(dtb["win"]), _ptr(dtb["fbin"]), _ptr(dtb["wfbin"]), _ptr(tables), int(nfft),
+            int(hop), int(npks), float(tb["dt"]), float(sr), float(fmin), _ptr(f0d), int(nframes), int(run_frames),
+            _ptr(out["f"]), _ptr(out["mag"]), _ptr(out["ph"]), _ptr(out["residuals"]), _ptr(out["nharm"]),
+            _stream()), "pvk_harmonic")
+    return out
+
+
+def frame_stats_device(fd, magd, fmin=50, fmax=10000, thr=0.1):
+    """pvk_frame_stats on device tables ``[F, K]``: (fm, fundamental_idx, partial_sum_magnitude)
+    = PV.calc_f0 (PVAnalysis.py:371-391) and PV.partial_sum_magnitude (:411-413).  Asynchronous."""
+    L = _lib.lib()
+    assert fd.dtype == torch.float64 and fd.is_contiguous() and magd.is_contiguous() and fd.dim() == 2
+    dev = fd.device
+    F, K = fd.shape
+    fm = torch.empty((F,), dtype=torch.float64, device=dev)
+    idx = torch.empty((F,), dtype=torch.int32, device=dev)
+    ps = torch.empty((F,), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.pvk_frame_stats(_ptr(fd), _ptr(magd), F, K, float(fmin), float(fmax), float(thr), _ptr(fm),
+                                     _ptr(idx), _ptr(ps), _stream()), "pvk_frame_stats")
+    return fm, idx, ps
 
 
 def track_device(fd, magd, maxpitchjmp=0.5):
@@ -351,6 +408,7 @@ class PV(object):
         self._devout = None
         self._hostbuf = None
         self._d2h_event = None
+        self._stats = None
         if progress:
             self.progress = Progress(end=self.nsamp)
         else:
@@ -384,6 +442,8 @@ class PV(object):
             return hb if self.nframes else np.array([])
         if name == "totalmag":
             return [v for v in d["totalmag"][0].cpu().numpy()]
+        if name not in d:
+            raise AttributeError("%s was not computed by the last run_pv" % name)
         if self.nframes == 0:
             return np.array([])
         return d[name][0].cpu().numpy()
@@ -403,6 +463,8 @@ class PV(object):
     binno = _prop("binno")
     totalmag = _prop("totalmag")
     t = _prop("t")
+    fine_pos = _prop("fine_pos")
+    fine_val = _prop("fine_val")
     del _prop
 
     @property
@@ -443,7 +505,7 @@ class PV(object):
         return nbytes
 
     # -- analysis ----------------------------------------------------------------------
-    def run_pv(self, run_frames=0, hostbuf=None, chunks=8):
+    def run_pv(self, run_frames=0, hostbuf=None, chunks=8, refine=False):
         """STFT + peak picking + instantaneous frequency for every frame (PVAnalysis.py:213-264)
         in one kernel launch.  Results appear as the reference's attributes ``f mag ph realph
         binno`` (float64 ``[nframes, npks]``), ``t``, ``nframes``, ``totalmag`` (list).
@@ -452,21 +514,27 @@ class PV(object):
         while the analysis is still running -- the frames are analysed in ``chunks`` launches, the
         upload of a pinned host signal, the kernels and the download of finished rows overlap on
         three streams; the attributes are numpy views of the pinned buffers (valid until the next
-        call with the same ``hostbuf``) and synchronise on first access."""
+        call with the same ``hostbuf``) and synchronise on first access.
+
+        ``refine=True`` additionally evaluates ``PeakFinder.refine`` (PeakFinder.py:331-372) for
+        every peak: attributes ``fine_pos`` (fractional bin) and ``fine_val`` (interpolated
+        |fx|), float64 ``[nframes, npks]``, columns aligned with ``binno``.  The reference's PV
+        never refines (PVAnalysis.py:175-178), so this is an opt-in extra."""
         self._hostbuf = None
         self._d2h_event = None
+        self._stats = None
         if hostbuf is not None:
-            self._run_pv_streamed(hostbuf, int(chunks), run_frames)
+            self._run_pv_streamed(hostbuf, int(chunks), run_frames, refine=refine)
         else:
             self._devout = analyze_device(self._xd, self.sr, self.nfft, self.hop, self.npeaks, self.peakthresh,
-                                          self._tb, run_frames=run_frames)
+                                          self._tb, run_frames=run_frames, refine=refine)
         self.nframes = int(self._devout["f"].shape[1])
         self._host = {}
         self._host["t"] = (np.arange(self.nframes) * self.hop + self.nfft / 2.0) / self.sr   # :247
         if self.progress:
             self.progress.update(self.nsamp)
 
-    def _run_pv_streamed(self, hostbuf, chunks, run_frames, frame_lo=0, nframes=None, prev_zero=True):
+    def _run_pv_streamed(self, hostbuf, chunks, run_frames, frame_lo=0, nframes=None, prev_zero=True, refine=False):
         """Rows r = 0 .. F-1 are the frames starting at sample (frame_lo + r)*hop (frame_lo = 1 with
         prev_zero=False: frame 0 of the buffer is only the warm-up of a sharded window)."""
         dev, K = self._dev, self.npeaks
@@ -478,6 +546,9 @@ class PV(object):
             out = {k: torch.empty((1, F, K), dtype=torch.float64, device=dev) for k in names}
             out["npk"] = torch.empty((1, F), dtype=torch.int32, device=dev)
             out["totalmag"] = torch.empty((1, F), dtype=torch.float64, device=dev)
+            if refine:      # stays on the device, fetched on first access
+                out["fine_pos"] = torch.empty((1, F, K), dtype=torch.float64, device=dev)
+                out["fine_val"] = torch.empty((1, F, K), dtype=torch.float64, device=dev)
             hb = {k: _pinned(hostbuf, k, (F, K), torch.float64) for k in names}
             hb["totalmag"] = _pinned(hostbuf, "totalmag", (F,), torch.float64)
             upload = self._xd_t is None
@@ -503,7 +574,8 @@ class PV(object):
                     s_done = s_end
                 view = {k: v[:, j0:j1] for k, v in out.items()}
                 analyze_device(xd, self.sr, self.nfft, self.hop, K, self.peakthresh, self._tb, frame0=frame_lo + j0,
-                               nframes=j1 - j0, prev_zero=(prev_zero and j0 == 0), run_frames=run_frames, out=view)
+                               nframes=j1 - j0, prev_zero=(prev_zero and j0 == 0), run_frames=run_frames, out=view,
+                               refine=refine)
                 ev2 = torch.cuda.Event()
                 ev2.record(cur)
                 _mark("analysis %d" % i, cur)
@@ -602,8 +674,28 @@ class PV(object):
     def get_sample_vector(self):
         return (self.t * self.sr).astype('int')
 
+    def _on_device(self):
+        """True while f / mag are the untouched device tables of the last run_pv."""
+        return self._devout is not None and "f" not in self._host and "mag" not in self._host and self.nframes > 0
+
+    def _frame_stats(self, fmin=50, fmax=10000, thr=0.1):
+        key = (float(fmin), float(fmax), float(thr))
+        st = getattr(self, "_stats", None)
+        if st is None or st[0] != key:
+            d = self._devout
+            fm, idx, ps = frame_stats_device(d["f"][0], d["mag"][0], fmin, fmax, thr)
+            st = (key, fm.cpu().numpy(), idx.cpu().numpy().astype('i'), ps.cpu().numpy())
+            self._stats = st
+        return st
+
     def calc_f0(self, fmin=50, fmax=10000, thr=0.1):
-        """Lowest-frequency strong peak of every frame (PVAnalysis.py:371-391), vectorised."""
+        """Lowest-frequency strong peak of every frame (PVAnalysis.py:371-391).  While the peak
+        tables live on the device this is one pvk_frame_stats launch and a read-back of one value
+        per frame (the tables are not downloaded); on host tables it is vectorised numpy."""
+        if self._on_device():
+            _, fm, im, _ = self._frame_stats(fmin, fmax, thr)
+            self.fundamental_idx = im
+            return fm.copy()
         f, mag = self.f, self.mag
         if f.ndim != 2:
             self.fundamental_idx = np.zeros(0, dtype='i')
@@ -635,11 +727,105 @@ class PV(object):
 
     @property
     def partial_sum_magnitude(self):
+        if self._on_device():
+            st = getattr(self, "_stats", None)
+            return (st if st is not None else self._frame_stats())[3].copy()
         return np.sqrt(np.sum(self.mag ** 2, axis=1))
 
     @property
     def partial_magnitude_ratio(self):
         return self.partial_sum_magnitude / self.totalmag
+
+
+class PVHarmonic(PV):
+    """f0-guided phase vocoder (PVAnalysis.py:419-538): instead of picking peaks, every frame
+    reads the bins at the multiples of a given fundamental.  Same constructor as PV;
+    ``set_f0`` then ``run_pv`` leave ``f mag ph`` (float64 ``[nframes, npks]``), ``residuals``,
+    ``t`` and ``nframes``.  One pvk_harmonic launch; no CPU fallback."""
+
+    def __init__(self, *args, **kwargs):
+        self.fmin = 30.0                                       # :421
+        PV.__init__(self, *args, **kwargs)
+
+    def set_f0(self, f0, t=None):
+        '''
+        Assign a f0 vector to the search (PVAnalysis.py:424-441)
+        Argument:
+            * f0: f0 vector over time
+            * t: if present, values of time corresponding to f0
+                 otherwise, the time values correspond to the hop size
+        '''
+        tint = np.arange(round(self.hop + self.nfft / 2), self.nsamp, self.hop) / float(self.sr)
+        if t is None:
+            self.f0 = f0
+        else:
+            self.f0 = np.interp(tint, t, f0)
+
+    def _f0_device(self, nframes):
+        f0 = self.f0
+        if torch.is_tensor(f0):
+            f0d = f0.detach().to(device=self._dev, dtype=torch.float64).contiguous()
+        else:
+            f0d = torch.from_numpy(np.ascontiguousarray(np.asarray(f0, dtype=np.float64))).to(self._dev)
+        if f0d.dim() != 1 or f0d.numel() < nframes:
+            # the reference fails with IndexError at f0[int(curpos/hop)] (:506)
+            raise IndexError("f0 has %d values, run_pv needs one per frame (%d)" % (f0d.numel(), nframes))
+        return f0d
+
+    def run_pv(self, run_frames=0):
+        if not hasattr(self, "f0"):
+            raise AttributeError("PVHarmonic.run_pv: call set_f0() first")
+        F = n_frames(self.nsamp, self.nfft, self.hop)
+        f0d = self._f0_device(F)
+        o = harmonic_device(self._xd, self.sr, self.nfft, self.hop, self.npeaks, f0d, self._tb, fmin=self.fmin,
+                            nframes=F, run_frames=run_frames)
+        self._hdev = o
+        self._devout = None
+        self._stats = None
+        self.nframes = F
+        self._host = {}
+        empty = F == 0
+        self._host["f"] = np.array([]) if empty else o["f"].cpu().numpy()
+        self._host["mag"] = np.array([]) if empty else o["mag"].cpu().numpy()
+        self._host["ph"] = np.array([]) if empty else o["ph"].cpu().numpy()
+        self.residuals = o["residuals"].cpu().numpy()
+        self.nharmonics = o["nharm"].cpu().numpy()
+        self._host["t"] = (np.arange(F) * self.hop + self.nfft / 2.0) / self.sr   # :523
+        if self.progress:
+            self.progress.update(self.nsamp)
+
+    @property
+    def device_tables(self):
+        """Device tensors of the last run_pv: f mag ph [nframes, npks], residuals, nharm."""
+        if getattr(self, "_hdev", None) is None:
+            raise RuntimeError("run_pv() has not been called")
+        return self._hdev
+
+    def calc_pv_frame(self, pos, f0):
+        '''Harmonics of the frame at sample ``pos`` for fundamental ``f0`` with the frame at
+        ``pos - hop`` as previous frame (all-zero spectrum if pos < hop), like the reference
+        when called in run order (PVAnalysis.py:443-492).  Returns f, mag, ph (lists with one
+        entry per harmonic, at most npks of them) and the residual.'''
+        if pos + self.nfft > self.nsamp:
+            raise ValueError("frame exceeds the signal")
+        if pos >= self.hop:
+            seg = self._xd[pos - self.hop:pos + self.nfft].contiguous()
+            f0d = torch.tensor([1.0, float(f0)], dtype=torch.float64, device=self._dev)
+            row = 1
+        else:
+            seg = self._xd[pos:pos + self.nfft].contiguous()
+            f0d = torch.tensor([float(f0)], dtype=torch.float64, device=self._dev)
+            row = 0
+        o = harmonic_device(seg, self.sr, self.nfft, self.hop, self.npeaks, f0d, self._tb, fmin=self.fmin,
+                            nframes=row + 1)
+        n = min(int(o["nharm"][row].item()), self.npeaks)
+        vals = [o[k][row, :n].cpu().numpy().tolist() for k in ("f", "mag", "ph")]
+        return vals[0], vals[1], vals[2], float(o["residuals"][row].item())
+
+    def toSinSum(self, maxpitchjmp=0.5):
+        # the reference inherits PV.toSinSum, which needs realph (PVAnalysis.py:320) that
+        # PVHarmonic.run_pv never sets (:532-538): AttributeError there, stated here
+        raise AttributeError("PVHarmonic has no realph table: toSinSum is not available (as in the reference)")
 
 
 # =========================================================================== partials

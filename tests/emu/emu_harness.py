@@ -57,7 +57,7 @@ def host_tables(sr, nfft, hop, wind=np.hanning):
 
 
 def analyze(x, sr, nfft, hop, npks, pkthresh=0.005, nclips=1, frame0=0, nframes=None,
-            prev_zero=1, run_frames=0, spectra=False, wind=np.hanning):
+            prev_zero=1, run_frames=0, spectra=False, wind=np.hanning, refine=False):
     L = lib()
     x = np.ascontiguousarray(x, dtype=np.float32)
     if x.ndim == 1:
@@ -77,15 +77,58 @@ def analyze(x, sr, nfft, hop, npks, pkthresh=0.005, nclips=1, frame0=0, nframes=
     npk = np.full((nclips, nframes), -7, dtype=np.int32)
     totalmag = np.full((nclips, nframes), np.nan)
     spec = np.zeros((nclips, nframes, nfft // 2, 2), dtype=np.float32) if spectra else None
-    check(L.pvk_analyze(ptr(x), nclips, x.strides[0] // 4, nsamp, ptr(tb["win_scaled"]), ptr(tb["fbin"]),
-                        ptr(tb["wfbin"]), ptr(tables), nfft, hop, npks, pkthresh, tb["dt"], tb["fstep"],
-                        frame0, nframes, prev_zero, run_frames, ptr(out["f"]), ptr(out["mag"]),
-                        ptr(out["ph"]), ptr(out["realph"]), ptr(out["binno"]), ptr(npk), ptr(totalmag),
-                        ptr(spec), None))
+    if refine:
+        out["fine_pos"], out["fine_val"] = np.full(shp, np.nan), np.full(shp, np.nan)
+        check(L.pvk_analyze_ex(ptr(x), nclips, x.strides[0] // 4, nsamp, ptr(tb["win_scaled"]), ptr(tb["fbin"]),
+                               ptr(tb["wfbin"]), ptr(tables), nfft, hop, npks, pkthresh, tb["dt"], tb["fstep"],
+                               frame0, nframes, prev_zero, run_frames, ptr(out["f"]), ptr(out["mag"]),
+                               ptr(out["ph"]), ptr(out["realph"]), ptr(out["binno"]), ptr(npk), ptr(totalmag),
+                               ptr(spec), ptr(out["fine_pos"]), ptr(out["fine_val"]), None))
+    else:
+        check(L.pvk_analyze(ptr(x), nclips, x.strides[0] // 4, nsamp, ptr(tb["win_scaled"]), ptr(tb["fbin"]),
+                            ptr(tb["wfbin"]), ptr(tables), nfft, hop, npks, pkthresh, tb["dt"], tb["fstep"],
+                            frame0, nframes, prev_zero, run_frames, ptr(out["f"]), ptr(out["mag"]),
+                            ptr(out["ph"]), ptr(out["realph"]), ptr(out["binno"]), ptr(npk), ptr(totalmag),
+                            ptr(spec), None))
     out.update(npk=npk, totalmag=totalmag, nframes=nframes)
     if spectra:
         out["fx"] = spec[..., 0] + 1j * spec[..., 1]
     return out
+
+
+def harmonic(x, sr, f0, nfft, hop, npks, fmin=30.0, run_frames=0, wind=np.hanning):
+    """pvk_harmonic on host arrays (PVHarmonic.run_pv)."""
+    L = lib()
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    nsamp = len(x)
+    tb = host_tables(sr, nfft, hop, wind)
+    span = nsamp - nfft
+    nframes = 0 if span <= 0 else -(-span // hop)
+    f0 = np.ascontiguousarray(f0, dtype=np.float64)
+    assert len(f0) >= nframes
+    tables = np.zeros(L.pvk_analyze_tables_bytes(nfft), dtype=np.uint8)
+    check(L.pvk_analyze_init(nfft, ptr(tables), None))
+    out = {k: np.full((nframes, npks), np.nan) for k in ("f", "mag", "ph")}
+    res = np.full(nframes, -5.0)
+    nharm = np.full(nframes, -7, dtype=np.int32)
+    check(L.pvk_harmonic(ptr(x), nsamp, ptr(tb["win_scaled"]), ptr(tb["fbin"]), ptr(tb["wfbin"]), ptr(tables),
+                         nfft, hop, npks, tb["dt"], float(sr), float(fmin), ptr(f0), nframes, run_frames,
+                         ptr(out["f"]), ptr(out["mag"]), ptr(out["ph"]), ptr(res), ptr(nharm), None))
+    out.update(residuals=res, nharm=nharm, nframes=nframes)
+    return out
+
+
+def frame_stats(f, mag, fmin=50, fmax=10000, thr=0.1):
+    """pvk_frame_stats on host arrays [F, K]."""
+    L = lib()
+    f = np.ascontiguousarray(f, dtype=np.float64)
+    mag = np.ascontiguousarray(mag, dtype=np.float64)
+    F, K = f.shape
+    fm = np.full(F, np.nan)
+    idx = np.full(F, -9, dtype=np.int32)
+    ps = np.full(F, np.nan)
+    check(L.pvk_frame_stats(ptr(f), ptr(mag), F, K, float(fmin), float(fmax), float(thr), ptr(fm), ptr(idx), ptr(ps), None))
+    return fm, idx, ps
 
 
 def track(f, mag, maxpitchjmp=0.5):

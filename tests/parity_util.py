@@ -70,3 +70,53 @@ def snr_db(x, ref):
     num = float(np.sum(np.asarray(ref, dtype=float) ** 2))
     den = float(np.sum((np.asarray(x, dtype=float) - np.asarray(ref, dtype=float)) ** 2))
     return 10 * np.log10(num / max(den, 1e-300))
+
+
+def compare_harmonic(got, ref, f0, sr, nfft, totalmag, exact=False):
+    """PVHarmonic tables: got/ref dicts with f mag ph [F, K] and residuals [F].
+
+    Skipped frames (f0 <= 0 or NaN) must be zero rows with a NaN residual, bit for bit.
+    ``exact``: ref was computed from the kernel's own spectrum -> every entry to fp64 rounding.
+    Otherwise ref is the fp64 reference: north-star tolerances on the harmonics that carry
+    energy (mag > 1e-2 of the frame's ``totalmag`` >= max|fx|; the fp32 FFT's relative error on
+    a bin grows as max/|bin|), and the residual through its square (power), which is what is subtracted:
+    |residual^2 - ref^2| <= 2e-5 (1e-12 when exact) of the frame's total power ``totalmag^2``."""
+    f0 = np.asarray(f0, dtype=float)[:len(ref["f"])]
+    skip = ~(f0 > 0)
+    for k in ("f", "mag", "ph"):
+        assert got[k].shape == ref[k].shape, (k, got[k].shape, ref[k].shape)
+        assert not np.any(got[k][skip]), k
+    assert np.all(np.isnan(got["residuals"][skip]))
+    run = ~skip
+    rep = dict(frames=int(len(f0)), processed=int(run.sum()))
+    if not run.any():
+        return rep
+    gf, rf = got["f"][run], ref["f"][run]
+    gm, rm = got["mag"][run], ref["mag"][run]
+    gp, rp = got["ph"][run], ref["ph"][run]
+    assert np.array_equal(np.isnan(gf), np.isnan(rf))
+    fstep = sr / float(nfft)
+    if exact:
+        for k, a, b in (("f", gf, rf), ("mag", gm, rm), ("ph", gp, rp)):
+            d = np.abs(a - b) / (np.abs(b) + 1.0)
+            m = float(np.nanmax(d)) if d.size else 0.0
+            assert m <= 1e-11, (k, m)
+        strong = np.ones_like(rm, dtype=bool)
+    else:
+        strong = rm > 1e-2 * np.asarray(totalmag, dtype=float)[:len(f0)][run][:, None]
+        strong &= ~np.isnan(rf)
+        rep["df"] = float(np.abs(gf - rf)[strong].max() / fstep) if strong.any() else 0.0
+        rep["dmag"] = float((np.abs(gm - rm)[strong] / rm[strong]).max()) if strong.any() else 0.0
+        rep["dph"] = float(angdiff(gp, rp)[strong].max()) if strong.any() else 0.0
+        assert rep["df"] < TOL_F and rep["dmag"] < TOL_MAG and rep["dph"] < TOL_PH, rep
+    # residual^2 = total power - harmonic power
+    g2, r2 = got["residuals"][run], ref["residuals"][run]
+    power = np.asarray(totalmag, dtype=float)[:len(f0)][run] ** 2
+    tol = (1e-12 if exact else 2e-5) * np.maximum(power, 1e-300)
+    both = ~np.isnan(g2) & ~np.isnan(r2)
+    assert np.all(np.abs(g2[both] ** 2 - r2[both] ** 2) <= tol[both]), "residual power differs"
+    one = np.isnan(g2) != np.isnan(r2)          # the difference changed sign within rounding
+    fin = np.where(np.isnan(g2), r2, g2)
+    assert np.all(fin[one] ** 2 <= tol[one]), "residual NaN pattern differs"
+    rep["strong"] = int(strong.sum())
+    return rep
