@@ -196,22 +196,27 @@ def gpu_main(args):
         if e: e[1].record()
         tab = {k: a[k][0] for k in ("f", "mag", "ph", "realph")}
         tr = P.track_device(tab["f"], tab["mag"])        # local link + ids
-        ntl, npts, last = P.track_counts(tr)             # the step's one host read-back (24 bytes)
+        ntl, npts, last = P.track_counts(tr)             # the step's one hot-path host read-back (24 bytes)
         if world > 1:
-            # global numbering (2K+4-int all_gather) and THE all_gather of the track table (async)
-            st = D.stitch(tr["tid"], plan, plans)
-            _, finish = D.gather_track_table(st["tid_own"], plans, async_op=True)
+            # global numbering (2K+4-int all_gather) and THE all_gather of the track table run on a
+            # side stream; packing and resynthesis below use LOCAL ids and overlap them
+            sh = D.StitchHandle(tr["tid"], plan, plans)
         if e: e[2].record()
         pk = P.pack_device(tab["f"], tab["mag"], tab["ph"], tab["realph"], tr["tid"], None, ntl, npts=npts)
+        if e: e[3].record()
         if world == 1:
             st = dict(ntracks=ntl, max_end=last)
-        if e: e[3].record()
-        w = D.resynth_local(tr["tid"], pk, plan, plans, st["max_end"], sr, hop, nfft, hop)
-        if world > 1:
-            table = finish()                             # the gather overlapped pack + resynthesis
-            spans = P.spans_device(table, st["ntracks"]) # first frame / length of every partial
-        else:
+            w = D.resynth_local(tr["tid"], pk, plan, plans, last, sr, hop, nfft, hop)
             table, spans = tr["tid"], (pk["tstart"], pk["tlen"])
+        else:
+            ll = last + plan["w0"] if last >= 0 else -1
+            w = D.resynth_local(tr["tid"], pk, plan, plans, None, sr, hop, nfft, hop, local_last=ll)
+            b0 = D.render_range_local(plan, plans, ll, hop, nfft, hop)[0]
+            ntg, max_end = sh.counts()                   # 8 ints; the numbering finished long ago
+            st = dict(ntracks=ntg, max_end=max_end)
+            w = w[:D.trim_local(w.numel(), b0, plan, plans, max_end, hop, nfft, hop)[0]]
+            table = sh.table()                           # the gather overlapped pack + resynthesis
+            spans = P.spans_device(table, ntg)           # first frame / length of every partial
         if e: e[4].record()
         state.update(a=a, tr=tr, pk=pk, w=w, st=st, table=table, spans=spans)
         if timed is not None:

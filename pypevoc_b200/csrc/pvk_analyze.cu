@@ -54,6 +54,12 @@ struct AParams {
 #ifndef PVK_TWREG
 #define PVK_TWREG 0
 #endif
+// PVK_CKEY = 1 keeps a compact copy of the candidate keys in shared memory; 0 (default) looks
+// the key up in |fx|^2 through the candidate's bin (4 KB less shared memory at nfft 2048: one
+// more resident CTA per SM)
+#ifndef PVK_CKEY
+#define PVK_CKEY 0
+#endif
 
 template <int LOGM> struct Plan {
   static constexpr int M = 1 << LOGM;
@@ -316,7 +322,7 @@ template <int LOGM> struct Smem {
   static constexpr int OFF_BUF1 = OFF_BUF0 + P::MP * 8;
   static constexpr int OFF_FAMP = OFF_BUF1 + P::MP * 8;
   static constexpr int OFF_CKEY = OFF_FAMP + (P::M + P::M / 4 + 4) * 4;   // candidate keys (compact, bin order)
-  static constexpr int OFF_HIST = OFF_CKEY + P::M * 4;
+  static constexpr int OFF_HIST = OFF_CKEY + (PVK_CKEY ? P::M * 4 : 0);
   static constexpr int OFF_RED = (OFF_HIST + 256 * 4 + 7) / 8 * 8;   // doubles: 8 sums
   static constexpr int OFF_REDF = OFF_RED + 8 * 8;                   // floats: 8 min, 8 max
   static constexpr int OFF_REDU = OFF_REDF + 16 * 4;                 // uints: 8 cnt, 8 kmin, 8 kmax
@@ -354,7 +360,15 @@ __global__ void __launch_bounds__(Plan<LOGM>::T, 512 / Plan<LOGM>::T) analyze_ke
   float2 *bufs[2] = {reinterpret_cast<float2 *>(smem + S::OFF_BUF0),
                      reinterpret_cast<float2 *>(smem + S::OFF_BUF1)};
   float *famp = reinterpret_cast<float *>(smem + S::OFF_FAMP);
+#if PVK_CKEY
   unsigned *ckey = reinterpret_cast<unsigned *>(smem + S::OFF_CKEY);
+#define PVK_KEY(e) ckey[e]
+#define PVK_BIN(v) (v)
+#else
+  // candidate list entry = bin | 0x8000 for a candidate that is not a local maximum (key 0)
+#define PVK_KEY(e) ((cbin[e] & 0x8000) ? 0u : __float_as_uint(famp[FA(cbin[e])]))
+#define PVK_BIN(v) ((v) & 0x7fff)
+#endif
   int *hist = reinterpret_cast<int *>(smem + S::OFF_HIST);
   double *redd = reinterpret_cast<double *>(smem + S::OFF_RED);
   float *redf = reinterpret_cast<float *>(smem + S::OFF_REDF);
@@ -553,8 +567,12 @@ __global__ void __launch_bounds__(Plan<LOGM>::T, 512 / Plan<LOGM>::T) analyze_ke
       for (unsigned rem = cbits; rem;) {
         const int i = __ffs((int)rem) - 1;
         rem &= rem - 1u;
+#if PVK_CKEY
         cbin[pos] = (unsigned short)(kb0 + i);
         ckey[pos] = ((pbits >> i) & 1u) ? __float_as_uint(famp[FA(kb0 + i)]) : 0u;
+#else
+        cbin[pos] = (unsigned short)((kb0 + i) | (((pbits >> i) & 1u) ? 0 : 0x8000));
+#endif
         ++pos;
       }
     }
@@ -573,7 +591,7 @@ __global__ void __launch_bounds__(Plan<LOGM>::T, 512 / Plan<LOGM>::T) analyze_ke
         for (int h = tid; h < 256; h += T) hist[h] = 0;
         __syncthreads();
         for (int e = tid; e < C; e += T) {
-          const unsigned key = ckey[e];
+          const unsigned key = PVK_KEY(e);
           if (key >= lo && key <= hi) atomicAdd(&hist[(key - lo) >> sh], 1);
         }
         __syncthreads();
@@ -605,7 +623,7 @@ __global__ void __launch_bounds__(Plan<LOGM>::T, 512 / Plan<LOGM>::T) analyze_ke
       int base = 0, tbase = 0;
       for (int e0 = 0, round = 0; e0 < C; e0 += T, ++round) {
         const int e = e0 + tid;
-        const unsigned key = e < C ? ckey[e] : 0u;
+        const unsigned key = e < C ? PVK_KEY(e) : 0u;
         const bool inA = e < C && key > hi;
         const bool inB = e < C && key >= lo && key <= hi;
         bool s = inA || inB;
@@ -614,7 +632,7 @@ __global__ void __launch_bounds__(Plan<LOGM>::T, 512 / Plan<LOGM>::T) analyze_ke
           s = inA || (inB && tpos < rr);
         }
         const int pos = round_pos<NW>(s, wsB, round, base);
-        if (s) pk1[pos] = cbin[e];
+        if (s) pk1[pos] = PVK_BIN(cbin[e]);
       }
       sel = pk1;
       ns = K;
@@ -629,7 +647,7 @@ __global__ void __launch_bounds__(Plan<LOGM>::T, 512 / Plan<LOGM>::T) analyze_ke
       bool keep = false;
       int k = 0;
       if (e < ns) {
-        k = sel[e];
+        k = PVK_BIN(sel[e]);
         const float y = famp[FA(k)];
         const int a = k - 5 > 1 ? k - 5 : 1, b = k + 5 < M - 1 ? k + 5 : M - 1;
         keep = true;

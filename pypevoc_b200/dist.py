@@ -164,9 +164,11 @@ def segment_summary_device(tid_local, plan):
     return mine
 
 
-def segment_rename_device(tid_local, plan, world, allv, max_own0=None):
+def segment_rename_device(tid_local, plan, world, allv, max_own0=None, sync=True):
     """pvk_segment_resolve + pvk_segment_rename: global ids of the own rows from the gathered
-    summaries ``allv`` (CUDA int32 [world * (2K + 4)]).  One host read-back (8 ints) at the end."""
+    summaries ``allv`` (CUDA int32 [world * (2K + 4)]).  One host read-back (8 ints) at the end;
+    ``sync=False`` leaves it to the caller (``params`` int32 [8] on the device: slot 3 = total
+    number of partials, slot 4 = global index of the last frame holding a point)."""
     import ctypes as C
     from . import _lib
     L = _lib.lib()
@@ -186,6 +188,8 @@ def segment_rename_device(tid_local, plan, world, allv, max_own0=None):
         tid_own = torch.empty_like(own)
         _lib.check(L.pvk_segment_rename(ptr(own), own.numel(), ptr(scratch[1]), ptr(params), ptr(tid_own), stream),
                    "pvk_segment_rename")
+        if not sync:
+            return dict(tid_own=tid_own, params=params)
         ph = params.cpu().numpy()
     return dict(tid_own=tid_own, ntracks=int(ph[3]), max_end=int(ph[4]))
 
@@ -226,6 +230,108 @@ def stitch(tid_local, plan, plans, group=None):
     g = plan["rank"]
     tid_own = global_ids(tid_local, plan, bases[g], gprevs[g], int(summ[g, 2 * K]), int(summ[g, 2 * K + 1]))
     return dict(tid_own=tid_own, ntracks=ntot, max_end=max_end)
+
+
+_STITCH_STREAMS = {}
+
+
+def _stitch_stream(dev):
+    """The side stream the numbering + gather run on (one per device; not the copy streams of
+    pv._side_streams: the collectives must not queue behind table downloads)."""
+    key = (dev.type, dev.index)
+    if key not in _STITCH_STREAMS:
+        _STITCH_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _STITCH_STREAMS[key]
+
+
+class StitchHandle(object):
+    """Global numbering and THE all_gather of the track table, launched on a side stream so that
+    neither the collectives nor their host-side launch cost sit on the hot path: packing and
+    resynthesis of the rank's own blocks use LOCAL ids and run meanwhile on the main stream.
+    ``counts()`` is the one host read-back (8 ints); ``table()`` joins the streams."""
+
+    def __init__(self, tid_local, plan, plans, group=None):
+        import torch.distributed as dist
+        self.plans, self.plan = plans, plan
+        world = len(plans)
+        dev = tid_local.device
+        self.dev = dev
+        cur = torch.cuda.current_stream(dev)
+        self.side = _stitch_stream(dev)
+        self.side.wait_stream(cur)
+        tid_local = tid_local.contiguous()
+        tid_local.record_stream(self.side)
+        self._counts = None
+        self._joined = False
+        with torch.cuda.stream(self.side):
+            mine = segment_summary_device(tid_local, plan)
+            if world > 1:
+                allv = torch.empty((world * mine.numel(),), dtype=torch.int32, device=dev)
+                dist.all_gather_into_tensor(allv, mine, group=group)
+            else:
+                allv = mine
+            r = segment_rename_device(tid_local, plan, world, allv, max(p["own0"] for p in plans), sync=False)
+            self._tid_own, self._params = r["tid_own"], r["params"]
+            _, finish = gather_track_table(self._tid_own, plans, group, async_op=False)
+            self._table = finish()                        # queued behind the gather on the side stream
+
+    def counts(self):
+        """(total number of partials, global index of the last frame holding a point)."""
+        if self._counts is None:
+            with torch.cuda.stream(self.side):
+                ph = self._params.cpu().numpy()          # synchronises the side stream only
+            self._counts = (int(ph[3]), int(ph[4]))
+        return self._counts
+
+    def _join(self):
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_stream(self.side)
+        return cur
+
+    @property
+    def tid_own(self):
+        cur = self._join()
+        self._tid_own.record_stream(cur)
+        return self._tid_own
+
+    def table(self):
+        """int32 [F, K] global ids of every frame (the main stream waits for the gather)."""
+        if not self._joined:
+            cur = self._join()
+            self._table.record_stream(cur)
+            self._joined = True
+        return self._table
+
+
+def render_range_local(plan, plans, local_last, hop, nfft, hop_an, edge=1.0):
+    """render_range() without knowing the GLOBAL last frame: ``local_last`` is the global index of
+    the last frame holding a point inside this rank's window (-1 = none).  The rank owning the
+    last frames sees the signal's last point in its window whenever its range is not empty (the
+    back halo is longer than the fade-out), so its range equals render_range(); every other rank
+    renders its whole own range [j0, j1) -- samples at or beyond the true output length are
+    simply dropped afterwards (trim_local), rendering them is harmless.  Returns (b0, b1, bound)
+    with ``bound`` = the sample count stores are clipped at."""
+    if plan["nown"] == 0:
+        return 0, 0, 0
+    last = max(p["rank"] for p in plans if p["nown"] > 0)
+    if plan["rank"] != last:
+        return plan["j0"], plan["j1"], plan["j1"] * hop
+    if local_last < 0:
+        return 0, 0, 0
+    nout, _ = P.synth_geometry(local_last, hop, nfft, hop_an, edge)
+    nblk = -(-nout // hop)
+    return min(plan["j0"], nblk), nblk, nout
+
+
+def trim_local(n_rendered, b0, plan, plans, max_end, hop, nfft, hop_an, edge=1.0):
+    """Samples of a render_range_local() rendering that belong to the output signal, once the
+    global ``max_end`` is known: (count, first global sample) exactly as render_range() has them."""
+    g0, g1, nout = render_range(plan, plans, max_end, hop, nfft, hop_an, edge)
+    n = max(min(g1 * hop, nout) - g0 * hop, 0)
+    if n == 0:
+        return 0, g0 * hop
+    assert g0 == b0 and n <= n_rendered, (g0, b0, n, n_rendered)
+    return n, g0 * hop
 
 
 def gather_track_table(tid_own, plans, group=None, async_op=False):
@@ -282,11 +388,15 @@ def render_range(plan, plans, max_end, hop, nfft, hop_an, edge=1.0):
 
 
 def resynth_local(tid_local, pk_local, plan, plans, max_end, sr, hop, nfft, hop_an, edge=1.0, minframes=3,
-                  out=None, ws=None, block_range=None, reuse_tracks=False):
+                  out=None, ws=None, block_range=None, reuse_tracks=False, local_last=None):
     """Render this rank's block range (or the sub-range ``block_range`` of it, global block
     indices) from its LOCAL tables: float64 device tensor holding global samples
-    [b0*hop, min(b1*hop, nout))."""
-    b0, b1, nout = render_range(plan, plans, max_end, hop, nfft, hop_an, edge)
+    [b0*hop, min(b1*hop, nout)).  ``local_last`` (instead of the global ``max_end``): the range
+    of render_range_local(), to be cut with trim_local() once ``max_end`` is known."""
+    if local_last is not None:
+        b0, b1, nout = render_range_local(plan, plans, local_last, hop, nfft, hop_an, edge)
+    else:
+        b0, b1, nout = render_range(plan, plans, max_end, hop, nfft, hop_an, edge)
     if block_range is not None:
         b0, b1 = block_range
     if b1 <= b0:
@@ -303,23 +413,32 @@ class ShardedSinSum(object):
     """Result of ShardedPV.toSinSum(): the global track table on every rank + this rank's local
     partials (window rows, local ids) for resynthesis."""
 
-    def __init__(self, spv, local_ss, st, finish_gather):
+    def __init__(self, spv, local_ss, handle):
         self._spv = spv
         self.local = local_ss
-        self.ntracks = st["ntracks"]
-        self.max_end = st["max_end"]
-        self.tid_own = st["tid_own"]
-        self._finish = finish_gather
-        self._tid = None
+        self._h = handle                     # StitchHandle: numbering + gather in flight on a side stream
         self._spans = None
         self.sr, self.nfft, self.hop = spv.sr, spv.nfft, spv.hop
 
     @property
+    def ntracks(self):
+        """Total number of partials of the whole signal (host read-back of the numbering pass)."""
+        return self._h.counts()[0]
+
+    @property
+    def max_end(self):
+        """Global index of the last frame holding a point."""
+        return self._h.counts()[1]
+
+    @property
+    def tid_own(self):
+        """int32 CUDA tensor [nown, K]: global ids of this rank's own rows."""
+        return self._h.tid_own
+
+    @property
     def device_track_table(self):
         """int32 CUDA tensor [F, K]: global partial id of every peak slot of every frame."""
-        if self._tid is None:
-            self._tid = self._finish()
-        return self._tid
+        return self._h.table()
 
     @property
     def track_ids(self):
@@ -363,12 +482,19 @@ class ShardedSinSum(object):
             raise ValueError("the segment halos were planned for edge=%r, minframes=%r" % (spv.edge, spv.minframes))
         pk = self.local._ensure_packed()
         tidl = self.local._trk["tid"]
-        b0, b1, nout = render_range(spv.plan, spv.plans, self.max_end, hop, self.nfft, self.hop, edge)
-        n_local = max(min(b1 * hop, nout) - b0 * hop, 0)
+        # block range from LOCAL knowledge (the numbering / gather may still be in flight); the
+        # few samples beyond the true output length are cut below, once max_end is known
+        ll = self.local._trk.get("max_end", -1)
+        ll = ll + spv.plan["w0"] if ll is not None and ll >= 0 else -1
+        args = (spv.plan, spv.plans)
+        b0, b1, bound = render_range_local(spv.plan, spv.plans, ll, hop, self.nfft, self.hop, edge)
+        n_local = max(min(b1 * hop, bound) - b0 * hop, 0)
         dev = tidl.device
         if hostbuf is None:
-            w = resynth_local(tidl, pk, spv.plan, spv.plans, self.max_end, sr, hop, self.nfft, self.hop, edge, minframes)
-            return (w.cpu().numpy() if to_host else w), b0 * hop
+            w = resynth_local(tidl, pk, *args, None, sr, hop, self.nfft, self.hop, edge, minframes, local_last=ll)
+            n, s0 = trim_local(w.numel(), b0, *args, self.max_end, hop, self.nfft, self.hop, edge)
+            w = w[:n]
+            return (w.cpu().numpy() if to_host else w), s0
         cur = torch.cuda.current_stream(dev)
         _, d2h = P._side_streams(dev)
         with torch.cuda.device(dev):
@@ -382,17 +508,18 @@ class ShardedSinSum(object):
             for i in range(chunks if nblk else 0):
                 c0, c1 = b0 + (nblk * i) // chunks, b0 + (nblk * (i + 1)) // chunks
                 n0, n1 = (c0 - b0) * hop, min((c1 - b0) * hop, n_local)
-                resynth_local(tidl, pk, spv.plan, spv.plans, self.max_end, sr, hop, self.nfft, self.hop, edge,
-                              minframes, out=out[n0:n1], ws=ws, block_range=(c0, c1), reuse_tracks=i > 0)
+                resynth_local(tidl, pk, *args, None, sr, hop, self.nfft, self.hop, edge, minframes, out=out[n0:n1],
+                              ws=ws, block_range=(c0, c1), reuse_tracks=i > 0, local_last=ll)
                 ev = torch.cuda.Event()
                 ev.record(cur)
                 with torch.cuda.stream(d2h):
                     d2h.wait_event(ev)
                     hw[n0:n1].copy_(out[n0:n1], non_blocking=True)
             d2h.synchronize()
+        n, s0 = trim_local(n_local, b0, *args, self.max_end, hop, self.nfft, self.hop, edge)
         self.d2h_bytes = n_local * 8
         self._last_out = out
-        return hw[:n_local].numpy(), b0 * hop
+        return hw[:n].numpy(), s0
 
 
 class ShardedPV(object):
@@ -448,6 +575,4 @@ class ShardedPV(object):
         ss = P.SinSum(self.sr, nfft=self.nfft, hop=self.hop, device=self.pv._dev)
         ss._set_device_tables(d["f"], d["mag"], d["ph"], d["realph"])
         tr = ss._ensure_tracks()
-        st = stitch(tr["tid"], self.plan, self.plans, self.group)
-        _, finish = gather_track_table(st["tid_own"], self.plans, self.group, async_op=async_gather and self.world > 1)
-        return ShardedSinSum(self, ss, st, finish)
+        return ShardedSinSum(self, ss, StitchHandle(tr["tid"], self.plan, self.plans, self.group))

@@ -101,3 +101,34 @@ def test_plan_covers_all_frames():
                 assert p["sample0"] + p["frame0"] * hop == p["w0"] * hop
                 assert (p["frame0"] + p["nframes"] - 1) * hop + nfft == p["nsamp"]
                 assert p["own0"] == p["j0"] - p["w0"] and p["nown"] == p["j1"] - p["j0"]
+
+
+def test_local_render_range_matches_global():
+    """render_range_local() + trim_local() (block range from LOCAL knowledge, cut once the global
+    last frame is known) give exactly render_range()'s sample range on every rank, whatever the
+    position of the signal's last point."""
+    from pypevoc_b200 import dist as D
+    for nfft, hop in ((2048, 512), (512, 128), (1024, 300), (8192, 1024)):
+        for world in (1, 2, 3, 8):
+            F = 40 * world + 7
+            nsamp = (F - 1) * hop + nfft + 1
+            plans = D.plan_segments(nsamp, nfft, hop, world)
+            assert plans[0]["frames_total"] == F
+            for max_end in [-1, 0, 1, 5] + [p["j0"] + d for p in plans for d in (-3, -1, 0, 1, 2)] + [F - 2, F - 1]:
+                if max_end < -1 or max_end >= F:
+                    continue
+                covered = 0
+                for p in plans:
+                    # what the rank sees: the last point inside its window, if any
+                    ll = max_end if (p["nown"] and p["w0"] <= max_end < p["w1"]) else -1
+                    if p["nown"] and max_end >= p["w1"]:
+                        ll = p["w1"] - 1                      # some later point exists; only ranks before the last
+                    b0, b1, bound = D.render_range_local(p, plans, ll, hop, nfft, hop)
+                    n_r = max(min(b1 * hop, bound) - b0 * hop, 0)
+                    g0, g1, nout = D.render_range(p, plans, max_end, hop, nfft, hop)
+                    n_g = max(min(g1 * hop, nout) - g0 * hop, 0)
+                    n, s0 = D.trim_local(n_r, b0, p, plans, max_end, hop, nfft, hop)
+                    assert (n, s0) == (n_g, g0 * hop), (nfft, hop, world, max_end, p["rank"])
+                    covered += n
+                nout = D.P.synth_geometry(max_end, hop, nfft, hop)[0] if max_end >= 0 else 0
+                assert covered == nout, (nfft, hop, world, max_end, covered, nout)

@@ -351,6 +351,13 @@ def test_sharded_pipeline_equals_unsharded(pvmod, world):
         rows.append(D.global_ids(tr["tid"], p, bases[r], gprevs[r], int(summ[r, 2 * npks]), int(summ[r, 2 * npks + 1])))
         pk = P.pack_device(tab["f"], tab["mag"], tab["ph"], tab["realph"], tr["tid"], None, int(tr["ntracks"][0].item()))
         sig.append(D.resynth_local(tr["tid"], pk, p, plans, max_end, sr, hop, nfft, hop).cpu().numpy())
+        # the overlapped variant: block range from LOCAL knowledge, cut once max_end is known
+        last = P.track_counts(tr)[2]
+        ll = last + p["w0"] if last >= 0 else -1
+        wl = D.resynth_local(tr["tid"], pk, p, plans, None, sr, hop, nfft, hop, local_last=ll)
+        b0 = D.render_range_local(p, plans, ll, hop, nfft, hop)[0]
+        n, s0 = D.trim_local(wl.numel(), b0, p, plans, max_end, hop, nfft, hop)
+        assert np.array_equal(wl[:n].cpu().numpy(), sig[-1]), r
     table = torch.cat(rows)
     assert np.array_equal(table.cpu().numpy(), tid0)
     # the same numbering through the libpvk segment kernels (summary -> [all_gather] -> resolve -> rename)

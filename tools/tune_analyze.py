@@ -22,7 +22,10 @@ def child():
     dev = torch.device("cuda")
     res = {}
     runs = [int(r) for r in os.environ.get("PVK_RUNS", "0").split(",")]
+    only = [c for c in os.environ.get("PVK_CASES", "").split(",") if c]
     for name, sr, sec, nfft, hop, npks, f0, nh, p, sg, seed in CASES:
+        if only and name not in only:
+            continue
         x = signals.harm_torch(sr, sr * sec, f0, nh, p, sg, seed, dev, scale=0.25)
         tb = P.host_tables(sr, nfft, hop)
         for run in runs:
