@@ -196,11 +196,13 @@ def gpu_main(args):
         if e: e[1].record()
         tab = {k: a[k][0] for k in ("f", "mag", "ph", "realph")}
         tr = P.track_device(tab["f"], tab["mag"])        # local link + ids
-        ntl, npts, last = P.track_counts(tr)             # the step's one hot-path host read-back (24 bytes)
         if world > 1:
-            # global numbering (2K+4-int all_gather) and THE all_gather of the track table run on a
-            # side stream; packing and resynthesis below use LOCAL ids and overlap them
+            # global numbering (2K+4-int all_gather) and THE all_gather of the track table go to a
+            # side stream, queued behind the link kernels while those still run (their host-side
+            # launch cost hides behind analysis + linking); packing and resynthesis below use LOCAL
+            # ids and overlap them
             sh = D.StitchHandle(tr["tid"], plan, plans)
+        ntl, npts, last = P.track_counts(tr)             # the step's one hot-path host read-back (24 bytes)
         if e: e[2].record()
         pk = P.pack_device(tab["f"], tab["mag"], tab["ph"], tab["realph"], tr["tid"], None, ntl, npts=npts)
         if e: e[3].record()

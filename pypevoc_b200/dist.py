@@ -574,5 +574,13 @@ class ShardedPV(object):
         d = self.pv.device_tables
         ss = P.SinSum(self.sr, nfft=self.nfft, hop=self.hop, device=self.pv._dev)
         ss._set_device_tables(d["f"], d["mag"], d["ph"], d["realph"])
-        tr = ss._ensure_tracks()
-        return ShardedSinSum(self, ss, StitchHandle(tr["tid"], self.plan, self.plans, self.group))
+        if d["f"].shape[0] == 0:
+            tr = ss._ensure_tracks()
+            return ShardedSinSum(self, ss, StitchHandle(tr["tid"], self.plan, self.plans, self.group))
+        # queue the numbering + gather behind the link kernels BEFORE the host waits for their
+        # counts: the launch cost of the collectives hides behind analysis + linking
+        tr = P.track_device(ss._tables["f"], ss._tables["mag"], ss._maxpitchjmp)
+        h = StitchHandle(tr["tid"], self.plan, self.plans, self.group)
+        tr["ntracks"], tr["npts"], tr["max_end"] = P.track_counts(tr)
+        ss._trk = tr
+        return ShardedSinSum(self, ss, h)
