@@ -185,27 +185,34 @@ def gpu_main(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    trace = bool(os.environ.get("PVK_BENCH_TRACE"))
     state = {}
 
     def step(timed=None):
         """One pass of the hot path over this rank's segment (device resident)."""
         e = [ev() for _ in range(5)] if timed is not None else None
+        ht = [time.perf_counter()] if trace else None     # PVK_BENCH_TRACE=1: host-side launch timeline
         if e: e[0].record()
         a = P.analyze_device(xd, sr, nfft, hop, npks, c["pkthresh"], tb, frame0=plan["frame0"],
                              nframes=plan["nframes"], prev_zero=plan["prev_zero"])
         if e: e[1].record()
+        if ht: ht.append(time.perf_counter())
         tab = {k: a[k][0] for k in ("f", "mag", "ph", "realph")}
         tr = P.track_device(tab["f"], tab["mag"])        # local link + ids
+        if ht: ht.append(time.perf_counter())
         if world > 1:
             # global numbering (2K+4-int all_gather) and THE all_gather of the track table go to a
             # side stream, queued behind the link kernels while those still run (their host-side
             # launch cost hides behind analysis + linking); packing and resynthesis below use LOCAL
             # ids and overlap them
             sh = D.StitchHandle(tr["tid"], plan, plans)
+        if ht: ht.append(time.perf_counter())
         ntl, npts, last = P.track_counts(tr)             # the step's one hot-path host read-back (24 bytes)
+        if ht: ht.append(time.perf_counter())
         if e: e[2].record()
         pk = P.pack_device(tab["f"], tab["mag"], tab["ph"], tab["realph"], tr["tid"], None, ntl, npts=npts)
         if e: e[3].record()
+        if ht: ht.append(time.perf_counter())
         if world == 1:
             st = dict(ntracks=ntl, max_end=last)
             w = D.resynth_local(tr["tid"], pk, plan, plans, last, sr, hop, nfft, hop)
@@ -214,12 +221,21 @@ def gpu_main(args):
             ll = last + plan["w0"] if last >= 0 else -1
             w = D.resynth_local(tr["tid"], pk, plan, plans, None, sr, hop, nfft, hop, local_last=ll)
             b0 = D.render_range_local(plan, plans, ll, hop, nfft, hop)[0]
+            if ht: ht.append(time.perf_counter())
             ntg, max_end = sh.counts()                   # 8 ints; the numbering finished long ago
+            if ht: ht.append(time.perf_counter())
             st = dict(ntracks=ntg, max_end=max_end)
             w = w[:D.trim_local(w.numel(), b0, plan, plans, max_end, hop, nfft, hop)[0]]
             table = sh.table()                           # the gather overlapped pack + resynthesis
             spans = P.spans_device(table, ntg)           # first frame / length of every partial
         if e: e[4].record()
+        if ht:
+            ht.append(time.perf_counter())
+            torch.cuda.synchronize()
+            ht.append(time.perf_counter())
+            sys.stderr.write("trace rank %d: host ms since step start [analysis launched, track launched, stitch "
+                             "launched, counts read, pack launched, resynth launched, global counts read, all "
+                             "launched, gpu idle] = %s\n" % (rank, ["%.3f" % (1e3 * (v - ht[0])) for v in ht[1:]]))
         state.update(a=a, tr=tr, pk=pk, w=w, st=st, table=table, spans=spans)
         if timed is not None:
             timed.append(e)
@@ -238,6 +254,7 @@ def gpu_main(args):
     launches0 = int(_lib.lib().pvk_launch_count())
     timed = []
     for _ in range(args.steps):
+        torch.cuda.synchronize()                         # every timed step starts from an idle device
         flush.fill_(1)                                   # L2 flush between timed iterations
         step(timed)
     barrier()

@@ -123,6 +123,26 @@ int pvk_harmonic(const float *x, int64_t nsamp, const float *win_scaled, const d
                  double sr, double fmin, const double *f0, int64_t nframes, int run_frames,
                  double *f, double *mag, double *ph, double *residual, int32_t *nharm, void *stream);
 
+/* ------------------------------------------------------------------ frame-wise spectral consumers
+ * The framing + window + FFT front end of pvk_analyze for the reference's other frame loops:
+ * FFTFilters.FilterBank.specout (pypevoc/FFTFilters.py:274-292; mel / MFCC banks :300-374),
+ * SoundUtils.RMSWind (pypevoc/SoundUtils.py:74-103) and SoundUtils.SpecFlux (:196-231).
+ * Frame r covers samples [r*hop, r*hop + nfft); `win` float32 [nfft] is the raw window.
+ * Any of the three outputs may be NULL (at least one is required):
+ *   bank  float64 [nframes, nfilt]: sum over ALL nfft bins of |FFT|^2 * fb[i, :] (:285-288), with
+ *         the filter folded onto bins 0..nfft/2 by the caller: fb_folded float64
+ *         [nfilt, nfft/2 + 1], fb_folded[i, h] = fb[i, h] + fb[i, nfft - h] (0 < h < nfft/2),
+ *         and the support of every row as fb_lo / fb_hi int32 [nfilt] (zero weights outside
+ *         [lo, hi) are skipped)
+ *   flux  float64 [nframes - 1]: flux[j] = sqrt(sum_{k in [minbin, maxbin)} (|X_j[k]| -
+ *         |X_{j+1}[k]|)^2) over bins of the full nfft-point spectrum (SoundUtils.py:222-225)
+ *   rms   float64 [nframes]: sqrt(sum((x*win)^2) * inv_wsum2) (SoundUtils.py:96,103)
+ */
+int pvk_stft_bank(const float *x, int64_t nsamp, const float *win, const void *tables, int nfft, int hop,
+                  int64_t nframes, int run_frames, const double *fb_folded, const int32_t *fb_lo,
+                  const int32_t *fb_hi, int nfilt, double *bank, int flux_minbin, int flux_maxbin,
+                  double *flux, double inv_wsum2, double *rms, void *stream);
+
 /* ------------------------------------------------------------------ per-frame consumers
  * PV.calc_f0 (PVAnalysis.py:371-391) and PV.partial_sum_magnitude (:411-413) over peak tables
  * f, mag float64 [nrows, npks]:

@@ -889,6 +889,158 @@ template <int LOGM> static int launch_harmonic(HParams prm, int run_frames, void
   return PVK_OK;
 }
 
+// ------------------------------------------------------------------ frame-wise spectral consumers
+// FFTFilters.FilterBank.specout (FFTFilters.py:274-292), SoundUtils.RMSWind (SoundUtils.py:74-103)
+// and SoundUtils.SpecFlux (:196-231) on the same framing + window + FFT front end as
+// analyze_kernel.  One CTA walks a run of frames; the power spectrum |X|^2 of bins 0..M (M =
+// nfft/2, Nyquist included) lives in shared memory and every requested output is reduced from it:
+//   bank[r, i] = sum_h |X_h|^2 * fbw[i, h]   fbw = the filter folded onto the half spectrum
+//                (|X_{N-h}| = |X_h| for a real frame), summed over its support [lo_i, hi_i)
+//   rms[r]     = sqrt(sum_n (x_n w_n)^2 / wsum2) through Parseval
+//   flux[r-1]  = sqrt(sum_h mult_h (|X_h(r)| - |X_h(r-1)|)^2), mult_h = how many of the bins
+//                h, N-h fall in [minbin, maxbin)
+struct BParams {
+  const float *x;
+  const float *win;
+  const float2 *tables;
+  int hop;
+  int64_t nframes;
+  int run;
+  const double *fbw;
+  const int32_t *fb_lo, *fb_hi;
+  int nfilt;
+  double *bank;
+  int minbin, maxbin;
+  double *flux;
+  double inv_wsum2;
+  double *rms;
+};
+
+// untangle the packed FFT in `buf` into the power spectrum pw[0..M] (fp32, no FMA contraction:
+// bit-identical to numpy float32 re*re + im*im)
+template <int LOGM> __device__ __forceinline__ void untangle_to_power(const float2 *buf, float *pw, const float2 *__restrict__ twr) {
+  using P = Plan<LOGM>;
+  constexpr int M = P::M, T = P::T;
+  for (int k = threadIdx.x; k <= M / 2; k += T) {
+    if (k == 0) {
+      const float2 z0 = buf[PADC(0)];
+      const float dc = z0.x + z0.y, ny = z0.x - z0.y;
+      pw[0] = __fmul_rn(dc, dc);
+      pw[M] = __fmul_rn(ny, ny);
+    } else if (k == M / 2) {
+      const float2 zh = buf[PADC(M / 2)];
+      pw[M / 2] = __fadd_rn(__fmul_rn(zh.x, zh.x), __fmul_rn(zh.y, zh.y));
+    } else {
+      const float2 a = buf[PADC(k)], bq = buf[PADC(M - k)];
+      const float2 e = make_float2(0.5f * (a.x + bq.x), 0.5f * (a.y - bq.y));
+      const float2 o = make_float2(0.5f * (a.y + bq.y), -0.5f * (a.x - bq.x));
+      const float2 wo = cmul(o, __ldg(twr + k));
+      const float2 xa = make_float2(e.x + wo.x, e.y + wo.y);
+      const float2 xb = make_float2(e.x - wo.x, -(e.y - wo.y));
+      pw[k] = __fadd_rn(__fmul_rn(xa.x, xa.x), __fmul_rn(xa.y, xa.y));
+      pw[M - k] = __fadd_rn(__fmul_rn(xb.x, xb.x), __fmul_rn(xb.y, xb.y));
+    }
+  }
+}
+
+template <int LOGM>
+__global__ void __launch_bounds__(Plan<LOGM>::T) bank_kernel(BParams prm) {
+  using P = Plan<LOGM>;
+  using S = Smem<LOGM>;
+  constexpr int M = P::M, T = P::T, NW = P::NW, N = 2 * M;
+  PVK_SMEM(smem);
+  float2 *buf = reinterpret_cast<float2 *>(smem + S::OFF_BUF0);
+  float *pws[2] = {reinterpret_cast<float *>(smem + S::OFF_BUF1), reinterpret_cast<float *>(smem + S::OFF_BUF1) + (M + 2)};
+  double *redd = reinterpret_cast<double *>(smem + S::OFF_RED);       // 8 doubles
+  double *redf = reinterpret_cast<double *>(smem + S::OFF_CKEY);      // 8 doubles
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t r0 = (int64_t)blockIdx.x * prm.run;
+  const int64_t r1 = (r0 + prm.run < prm.nframes) ? r0 + prm.run : prm.nframes;
+  const float2 *twp = prm.tables;
+  const float2 *twr = prm.tables + P::TW_TOTAL;
+  float2 treg[P::TWR_TOTAL];
+#if PVK_TWREG
+  if constexpr (P::NPASS > 1) Pass<LOGM, 1>::load_tw(twp, treg);
+#endif
+  const bool want_flux = prm.flux != nullptr;
+  int cb = 0;
+  if (want_flux && r0 > 0) {                                  // spectrum of the frame before the run
+    const float *xf = prm.x + (r0 - 1) * (int64_t)prm.hop;
+    fft_frame<LOGM>(xf, (reinterpret_cast<uintptr_t>(xf) & 7) == 0, prm.win, twp, treg, buf);
+    untangle_to_power<LOGM>(buf, pws[cb ^ 1], twr);
+    __syncthreads();
+  }
+  for (int64_t r = r0; r < r1; ++r) {
+    float *pw = pws[cb];
+    const float *pprev = pws[cb ^ 1];
+    const float *xf = prm.x + r * (int64_t)prm.hop;
+    fft_frame<LOGM>(xf, (reinterpret_cast<uintptr_t>(xf) & 7) == 0, prm.win, twp, treg, buf);
+    untangle_to_power<LOGM>(buf, pw, twr);
+    __syncthreads();
+    if (prm.bank) {                                           // one warp per filter
+      for (int i = warp; i < prm.nfilt; i += NW) {
+        const int lo = __ldg(prm.fb_lo + i), hi = __ldg(prm.fb_hi + i);
+        const double *w = prm.fbw + (int64_t)i * (M + 1);
+        double acc = 0.0;
+        for (int h = lo + lane; h < hi; h += 32) acc = fma((double)pw[h], __ldg(w + h), acc);
+        acc = warp_sum(acc);
+        if (lane == 0) prm.bank[r * prm.nfilt + i] = acc;
+      }
+    }
+    if (prm.rms || (want_flux && r > 0)) {
+      double e = 0.0, d = 0.0;
+      for (int h = tid; h <= M; h += T) {
+        const float p = pw[h];
+        e += (h == 0 || h == M) ? (double)p : 2.0 * (double)p;
+        if (want_flux && r > 0) {
+          const int mult = ((h >= prm.minbin && h < prm.maxbin) ? 1 : 0) +
+                           ((h != 0 && h != M && N - h >= prm.minbin && N - h < prm.maxbin) ? 1 : 0);
+          if (mult) {
+            const double df = sqrt((double)p) - sqrt((double)pprev[h]);
+            d = fma((double)mult * df, df, d);
+          }
+        }
+      }
+      e = warp_sum(e);
+      d = warp_sum(d);
+      if (lane == 0) { redd[warp] = e; redf[warp] = d; }
+      __syncthreads();
+      if (tid == 0) {
+        double es = redd[0], ds = redf[0];
+        for (int w = 1; w < NW; ++w) { es += redd[w]; ds += redf[w]; }
+        if (prm.rms) prm.rms[r] = sqrt(es / (double)N * prm.inv_wsum2);
+        if (want_flux && r > 0) prm.flux[r - 1] = sqrt(ds);
+      }
+    }
+    if (want_flux) cb ^= 1;
+    __syncthreads();
+  }
+}
+
+template <int LOGM> static int launch_bank(BParams prm, int run_frames, void *stream) {
+  using P = Plan<LOGM>;
+  const int smem = Smem<LOGM>::bytes(8);
+  if (smem > 48 * 1024) {
+    if (PVK_SET_SMEM(bank_kernel<LOGM>, smem) != 0) {
+      set_error("pvk_stft_bank: cannot reserve %d bytes of shared memory", smem);
+      return PVK_ERR_CUDA;
+    }
+  }
+  int64_t run = run_frames;
+  if (run <= 0) {
+    run = (prm.nframes + 148 * 7 - 1) / (148 * 7);
+    if (run < 8) run = 8;
+    if (run > 256) run = 256;
+  }
+  if (run > prm.nframes) run = prm.nframes;
+  prm.run = (int)run;
+  const int64_t nblk = (prm.nframes + run - 1) / run;
+  PVK_REQUIRE(nblk < (int64_t)2147483647, "pvk_stft_bank: grid too large (%lld CTAs)", (long long)nblk);
+  PVK_LAUNCH(bank_kernel<LOGM>, dim3((unsigned)nblk), dim3(P::T), smem, stream, prm);
+  PVK_CHECK_LAUNCH("pvk_stft_bank");
+  return PVK_OK;
+}
+
 // ------------------------------------------------------------------ per-frame consumers
 // PV.calc_f0 (PVAnalysis.py:371-391) and PV.partial_sum_magnitude (:411-413) over the peak
 // table: one warp per frame.
@@ -1121,6 +1273,37 @@ extern "C" int pvk_harmonic(const float *x, int64_t nsamp, const float *win_scal
   prm.dt = dt; prm.sr = sr; prm.fmin = fmin; prm.nframes = nframes; prm.run = 0;
   prm.f = f; prm.mag = mag; prm.ph = ph; prm.residual = residual; prm.nharm = nharm;
 #define CALL(L) launch_harmonic<L>(prm, run_frames, stream)
+  PVK_DISPATCH_LOGM(l - 1, CALL)
+#undef CALL
+  return PVK_ERR_ARG;
+}
+
+extern "C" int pvk_stft_bank(const float *x, int64_t nsamp, const float *win, const void *tables, int nfft, int hop,
+                             int64_t nframes, int run_frames, const double *fb_folded, const int32_t *fb_lo,
+                             const int32_t *fb_hi, int nfilt, double *bank, int flux_minbin, int flux_maxbin,
+                             double *flux, double inv_wsum2, double *rms, void *stream) {
+  const int l = log2_exact(nfft);
+  PVK_REQUIRE(l >= 0 && nfft >= PVK_MIN_NFFT && nfft <= PVK_MAX_NFFT,
+              "pvk_stft_bank: nfft=%d must be a power of two in [%d, %d]", nfft, PVK_MIN_NFFT, PVK_MAX_NFFT);
+  PVK_REQUIRE(hop >= 1, "pvk_stft_bank: hop=%d must be >= 1", hop);
+  PVK_REQUIRE(nframes >= 0 && nfilt >= 0, "pvk_stft_bank: negative sizes");
+  if (nframes == 0) return PVK_OK;
+  PVK_REQUIRE((nframes - 1) * (int64_t)hop + nfft <= nsamp, "pvk_stft_bank: last frame ends at sample %lld > nsamp=%lld",
+              (long long)((nframes - 1) * (int64_t)hop + nfft), (long long)nsamp);
+  PVK_REQUIRE(x && win && tables, "pvk_stft_bank: NULL pointer argument");
+  PVK_REQUIRE((reinterpret_cast<uintptr_t>(win) & 7) == 0, "pvk_stft_bank: win must be 8-byte aligned");
+  PVK_REQUIRE(bank == nullptr || (nfilt >= 1 && fb_folded && fb_lo && fb_hi),
+              "pvk_stft_bank: bank output needs nfilt >= 1 and the folded filter matrix with its supports");
+  PVK_REQUIRE(flux == nullptr || (flux_minbin >= 0 && flux_maxbin <= nfft),
+              "pvk_stft_bank: flux bins [%d, %d) must lie in [0, nfft]", flux_minbin, flux_maxbin);
+  PVK_REQUIRE(bank || flux || rms, "pvk_stft_bank: no output requested");
+  BParams prm;
+  prm.x = x; prm.win = win; prm.tables = reinterpret_cast<const float2 *>(tables);
+  prm.hop = hop; prm.nframes = nframes; prm.run = 0;
+  prm.fbw = fb_folded; prm.fb_lo = fb_lo; prm.fb_hi = fb_hi; prm.nfilt = bank ? nfilt : 0; prm.bank = bank;
+  prm.minbin = flux_minbin; prm.maxbin = flux_maxbin; prm.flux = flux;
+  prm.inv_wsum2 = inv_wsum2; prm.rms = rms;
+#define CALL(L) launch_bank<L>(prm, run_frames, stream)
   PVK_DISPATCH_LOGM(l - 1, CALL)
 #undef CALL
   return PVK_ERR_ARG;

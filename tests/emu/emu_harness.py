@@ -222,3 +222,30 @@ def segment_stitch(tids, plans):
         out.append(res)
         ntot, max_end = int(params[3]), int(params[4])
     return out, ntot, max_end
+
+
+def stft_bank(x, win, nfft, hop, nframes, fb_folded=None, fb_lo=None, fb_hi=None, flux_bins=None, inv_wsum2=None,
+              run_frames=0):
+    """pvk_stft_bank through the emulator; returns dict(bank, flux, rms) of the requested outputs."""
+    L = lib()
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    win = np.ascontiguousarray(win, dtype=np.float32)
+    tables = np.zeros(L.pvk_analyze_tables_bytes(nfft), dtype=np.uint8)
+    check(L.pvk_analyze_init(nfft, ptr(tables), None))
+    out = {}
+    nfilt = 0
+    if fb_folded is not None:
+        fb_folded = np.ascontiguousarray(fb_folded, dtype=np.float64)
+        fb_lo = np.ascontiguousarray(fb_lo, dtype=np.int32)
+        fb_hi = np.ascontiguousarray(fb_hi, dtype=np.int32)
+        nfilt = fb_folded.shape[0]
+        out["bank"] = np.full((nframes, nfilt), np.nan)
+    if flux_bins is not None:
+        out["flux"] = np.full((max(nframes - 1, 0),), np.nan)
+    if inv_wsum2 is not None:
+        out["rms"] = np.full((nframes,), np.nan)
+    lo, hi = flux_bins if flux_bins is not None else (0, 0)
+    check(L.pvk_stft_bank(ptr(x), x.size, ptr(win), ptr(tables), nfft, hop, nframes, run_frames, ptr(fb_folded),
+                          ptr(fb_lo), ptr(fb_hi), nfilt, ptr(out.get("bank")), int(lo), int(hi), ptr(out.get("flux")),
+                          float(inv_wsum2 or 0.0), ptr(out.get("rms")), None))
+    return out
