@@ -198,21 +198,25 @@ def gpu_main(args):
         if e: e[1].record()
         if ht: ht.append(time.perf_counter())
         tab = {k: a[k][0] for k in ("f", "mag", "ph", "realph")}
-        tr = P.track_device(tab["f"], tab["mag"])        # local link + ids
-        if ht: ht.append(time.perf_counter())
-        if world > 1:
+        box = []
+
+        def after_link(tr):
             # global numbering (2K+4-int all_gather) and THE all_gather of the track table go to a
             # side stream, queued behind the link kernels while those still run (their host-side
             # launch cost hides behind analysis + linking); packing and resynthesis below use LOCAL
             # ids and overlap them
-            sh = D.StitchHandle(tr["tid"], plan, plans)
-        if ht: ht.append(time.perf_counter())
-        ntl, npts, last = P.track_counts(tr)             # the step's one hot-path host read-back (24 bytes)
-        if ht: ht.append(time.perf_counter())
-        if e: e[2].record()
-        pk = P.pack_device(tab["f"], tab["mag"], tab["ph"], tab["realph"], tr["tid"], None, ntl, npts=npts)
+            if ht: ht.append(time.perf_counter())
+            if world > 1:
+                box.append(D.StitchHandle(tr["tid"], plan, plans))
+            if ht: ht.append(time.perf_counter())
+            if e: e[2].record()
+        # local link + ids, then the pack sized by upper bounds, then the step's one hot-path host
+        # read-back (24 bytes: partials, points, last frame)
+        tr, pk = P.track_pack_device(tab["f"], tab["mag"], tab["ph"], tab["realph"], after_link=after_link)
+        ntl, npts, last = tr["ntracks"], tr["npts"], tr["max_end"]
+        sh = box[0] if box else None
         if e: e[3].record()
-        if ht: ht.append(time.perf_counter())
+        if ht: ht.append(time.perf_counter()); ht.append(ht[-1])
         if world == 1:
             st = dict(ntracks=ntl, max_end=last)
             w = D.resynth_local(tr["tid"], pk, plan, plans, last, sr, hop, nfft, hop)

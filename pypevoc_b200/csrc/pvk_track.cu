@@ -195,23 +195,169 @@ __device__ __forceinline__ int link_greedy_generic(const double *cf, const doubl
   return nnew;
 }
 
+// ---- large rows (K > 128): ranks by a warp bitonic sort, nearest-unused search inside a window
+// Sort (magnitude, column) pairs of one row held in shared memory: descending magnitude, ties by
+// column (hi_first: higher column first -- the current row's rule; else lower column first --
+// the previous row's).  KP = power of two >= the row length; invalid slots carry magnitude -1
+// and end up last.  O(KP log^2 KP / 32) per lane instead of the O(K^2 / 32) counting rank.
+__device__ __forceinline__ void warp_sort_desc(double *key, short *idx, int KP, bool hi_first) {
+  const int lane = threadIdx.x & 31;
+  for (int k = 2; k <= KP; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < KP; i += 32) {
+        const int x = i ^ j;
+        if (x > i) {
+          const double a = key[i], b = key[x];
+          const short ia = idx[i], ib = idx[x];
+          // "a sorts before b"
+          const bool a_first = a > b || (a == b && (hi_first ? ia > ib : ia < ib));
+          const bool up = (i & k) == 0;
+          if (up ? !a_first : a_first) { key[i] = b; key[x] = a; idx[i] = ib; idx[x] = ia; }
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// The reference's loop (:903-950) for one row, one current peak at a time; when the previous
+// row is a gap-free ascending run of frequencies (rows come out of the analysis in bin order)
+// only the window of previous peaks that can lie within maxpitchjmp is scanned: it is found by a
+// binary search on the fp32 frequencies with the fast kernel's guard band, every peak outside it
+// has a distance >= maxjump and can never be taken (:923).  Returns the number of new partials.
+__device__ __forceinline__ int link_greedy_window(const double *cf, const double *pf, const float *pf32,
+                                                  const short *ord, const short *prank, unsigned *usedw,
+                                                  int nc, int phi, int KP, double maxjump, float eps32,
+                                                  int32_t *__restrict__ link_row) {
+  const int lane = threadIdx.x & 31;
+  for (int w = lane; w < (phi + 31) / 32; w += 32) usedw[w] = 0u;
+  __syncwarp();
+  int nnew = 0;
+  for (int t = 0; t < nc; ++t) {
+    const int c = ord[t];
+    const double fc = cf[c];
+    const float fc32 = (float)fc;
+    const float flo = fc32 * (1.f - eps32), fhi = fc32 * (1.f + eps32 + 2.f * eps32 * eps32);
+    int p0 = 0;
+    for (int step = KP >> 1; step >= 1; step >>= 1) {
+      const int mid = p0 + step;
+      if (mid <= phi && pf32[mid - 1] < flo) p0 = mid;
+    }
+    double bd = 1e300;
+    int br = 0x7fffffff, bp = -1;
+    for (int pb = p0; pb < phi; pb += 32) {
+      if (pf32[pb] > fhi) break;                                  // warp uniform
+      const int p = pb + lane;
+      if (p < phi) {
+        const float pv = pf32[p];
+        if (fabsf(fc32 - pv) < eps32 * pv && !((usedw[p >> 5] >> (p & 31)) & 1u)) {
+          const double d = stonediff(fc, pf[p]);
+          const int r = prank[p];
+          if (d < bd || (d == bd && r < br)) { bd = d; br = r; bp = p; }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      const double od = __shfl_xor_sync(FULL, bd, o);
+      const int orr = __shfl_xor_sync(FULL, br, o), op = __shfl_xor_sync(FULL, bp, o);
+      if (od < bd || (od == bd && orr < br)) { bd = od; br = orr; bp = op; }
+    }
+    int lk;
+    if (bp >= 0 && bd < maxjump) {                              // :923
+      lk = bp;
+      if (lane == 0) usedw[bp >> 5] |= 1u << (bp & 31);
+    } else {
+      lk = -2 - nnew;                                           // add_empty_partial :941
+      ++nnew;
+    }
+    if (lane == 0) link_row[c] = lk;
+    __syncwarp();
+  }
+  return nnew;
+}
+
+__host__ __device__ constexpr int link_pow2(int K) {
+  int p = 32;
+  while (p < K) p <<= 1;
+  return p;
+}
+// per warp: cf cm pf pm (double, K) | sort keys (double, KP) | pf32 (float, K) | usedw (32 words)
+//           | ord prank (short, K) | sort columns (short, KP)
+__host__ __device__ constexpr int link_generic_smem_per_warp(int K) {
+  return (K * (4 * 8 + 4 + 2 * 2) + link_pow2(K) * (8 + 2) + 32 * 4 + 15) / 16 * 16;
+}
+
 __global__ void track_link_kernel(const double *__restrict__ f, const double *__restrict__ mag,
                                   int64_t nrows, int64_t F, int K, double maxjump,
                                   int32_t *__restrict__ link, int32_t *__restrict__ newcount) {
   PVK_SMEM(smem);
   const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int per_warp = K * (4 * 8 + 2 * 2);
-  unsigned char *base = smem + (size_t)warp * ((per_warp + 15) / 16 * 16);
+  const int KP = link_pow2(K);
+  unsigned char *base = smem + (size_t)warp * link_generic_smem_per_warp(K);
   double *cf = reinterpret_cast<double *>(base);
   double *cm = cf + K;
   double *pf = cm + K;
   double *pm = pf + K;
-  short *ord = reinterpret_cast<short *>(pm + K);
+  double *skey = pm + K;
+  float *pf32 = reinterpret_cast<float *>(skey + KP);
+  unsigned *usedw = reinterpret_cast<unsigned *>(pf32 + K);
+  short *ord = reinterpret_cast<short *>(usedw + 32);
   short *prank = ord + K;
+  short *sidx = prank + K;
+  const float eps32 = (float)(maxjump / 17.312 * (1.0 + 1e-4) + 1e-6);   // guard band as in the fast kernel
   for (int64_t row = (int64_t)blockIdx.x * W + warp; row < nrows; row += (int64_t)gridDim.x * W) {
-    int chi, phi;
-    const int nc = link_prepare(f, mag, row, (row % F) > 0, K, link, cf, cm, pf, pm, ord, prank, chi, phi);
-    const int nnew = link_greedy_generic(cf, pf, pm, ord, prank, nc, phi, maxjump, link + row * K);
+    const bool has_prev = (row % F) > 0;
+    // ---- load both rows (invalid slots: magnitude -1)
+    int nc = 0, phi = 0;
+    bool okasc = true;
+    for (int i0 = 0; i0 < K; i0 += 32) {
+      const int i = i0 + lane;
+      bool v = false;
+      if (i < K) {
+        const double a = f[row * K + i], b = mag[row * K + i];
+        v = a > 0.0 && b > 0.0;                                   // :876
+        cf[i] = a; cm[i] = v ? b : -1.0;
+        if (!v) link[row * K + i] = LINK_NONE;
+        if (has_prev) {
+          const double c = f[(row - 1) * K + i], d = mag[(row - 1) * K + i];
+          const bool vp = c > 0.0 && d > 0.0;
+          pf[i] = c; pm[i] = vp ? d : -1.0;
+          pf32[i] = vp ? (float)c : -1.f;
+          if (vp) phi = i + 1;
+        }
+      }
+      nc += __popc(__ballot_sync(FULL, v));
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) phi = max(phi, __shfl_xor_sync(FULL, phi, o));
+    __syncwarp();
+    // ---- order of the current peaks: magnitude descending (:874-875), ties higher column first
+    for (int i = lane; i < KP; i += 32) { skey[i] = i < K ? cm[i] : -1.0; sidx[i] = (short)i; }
+    __syncwarp();
+    warp_sort_desc(skey, sidx, KP, true);
+    for (int t = lane; t < nc; t += 32) ord[t] = sidx[t];
+    __syncwarp();
+    int nnew;
+    if (!has_prev || phi == 0) {
+      for (int t = lane; t < nc; t += 32) link[row * K + ord[t]] = -2 - t;   // everything is new (:941)
+      nnew = nc;
+    } else {
+      // ---- rank of the previous peaks in descending magnitude (:891-900), ties lower column first
+      for (int i = lane; i < KP; i += 32) { skey[i] = i < phi ? pm[i] : -1.0; sidx[i] = (short)i; }
+      __syncwarp();
+      warp_sort_desc(skey, sidx, KP, false);
+      for (int t = lane; t < KP; t += 32) {
+        const int i = sidx[t];
+        if (i < phi) prank[i] = (short)(skey[t] > 0.0 ? t : 0);
+      }
+      for (int p = lane; p < phi; p += 32)
+        okasc = okasc && pm[p] > 0.0 && (p + 1 >= phi || (pm[p + 1] > 0.0 && pf32[p] <= pf32[p + 1]));
+      const bool asc = __all_sync(FULL, okasc);
+      __syncwarp();
+      nnew = asc ? link_greedy_window(cf, pf, pf32, ord, prank, usedw, nc, phi, KP, maxjump, eps32, link + row * K)
+                 : link_greedy_generic(cf, pf, pm, ord, prank, nc, phi, maxjump, link + row * K);
+    }
     if (lane == 0) newcount[row] = nnew;
     __syncwarp();
   }
@@ -791,8 +937,8 @@ extern "C" int pvk_track(const double *f, const double *mag, int64_t nclips, int
       else PVK_LINK_FAST(4);
 #undef PVK_LINK_FAST
     } else {
-      const int per_warp = (K * (4 * 8 + 2 * 2) + 15) / 16 * 16;
-      int W = 160 * 1024 / per_warp;
+      const int per_warp = link_generic_smem_per_warp(K);
+      int W = 96 * 1024 / per_warp;                               // two CTAs per SM
       if (W > 8) W = 8;
       if (W < 1) W = 1;
       const int smem = W * per_warp;

@@ -579,8 +579,8 @@ class ShardedPV(object):
             return ShardedSinSum(self, ss, StitchHandle(tr["tid"], self.plan, self.plans, self.group))
         # queue the numbering + gather behind the link kernels BEFORE the host waits for their
         # counts: the launch cost of the collectives hides behind analysis + linking
-        tr = P.track_device(ss._tables["f"], ss._tables["mag"], ss._maxpitchjmp)
-        h = StitchHandle(tr["tid"], self.plan, self.plans, self.group)
-        tr["ntracks"], tr["npts"], tr["max_end"] = P.track_counts(tr)
-        ss._trk = tr
-        return ShardedSinSum(self, ss, h)
+        box = []
+        ss._after_link = lambda tr: box.append(StitchHandle(tr["tid"], self.plan, self.plans, self.group))
+        ss._ensure_tracks()                                  # link -> [numbering + gather] -> pack -> counts
+        ss._after_link = None
+        return ShardedSinSum(self, ss, box[0])

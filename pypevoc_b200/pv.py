@@ -282,6 +282,49 @@ def pack_device(fd, magd, phd, realphd, tid, link, ntracks, npts=None):   # link
                 pph=packed[2][:npts], prealph=packed[3][:npts], npts=npts)
 
 
+PACK_SPEC_CAP = 4 << 20      # most partials a speculative pack is sized for (larger tables are re-packed)
+
+
+def track_pack_device(fd, magd, phd, realphd, maxpitchjmp=0.5, after_link=None):
+    """pvk_track + pvk_track_pack of one clip with ONE host read-back: the pack is launched with
+    upper bounds for the number of partials / points (the exact counts still sit on the device)
+    before the host waits for them, so the device does not idle while the host sizes and
+    launches it; the few KB of over-allocated index arrays are sliced afterwards.  ``after_link``
+    (optional) is called with the track dict right after the link kernels are launched.
+    Returns (tr, pk) as track_device() + track_counts() and pack_device() give them."""
+    L = _lib.lib()
+    tr = track_device(fd, magd, maxpitchjmp)
+    if after_link is not None:
+        after_link(tr)
+    dev = fd.device
+    F, K = fd.shape
+    raw = None
+    if F * K > 0:
+        nt_ub = min(F * K, PACK_SPEC_CAP)
+        tstart = torch.empty((nt_ub,), dtype=torch.int32, device=dev)
+        tlen = torch.empty((nt_ub,), dtype=torch.int32, device=dev)
+        toff = torch.empty((nt_ub + 1,), dtype=torch.int64, device=dev)
+        packed = [torch.empty((F * K,), dtype=torch.float64, device=dev) for _ in range(4)]
+        wsb = int(L.pvk_track_pack_workspace_bytes(nt_ub))
+        ws = torch.empty(max(wsb, 8), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.pvk_track_pack(_ptr(fd), _ptr(magd), _ptr(phd), _ptr(realphd), _ptr(tr["tid"]), F, K, nt_ub,
+                                        _ptr(tstart), _ptr(tlen), _ptr(toff), _ptr(packed[0]), _ptr(packed[1]),
+                                        _ptr(packed[2]), _ptr(packed[3]), _ptr(ws), wsb, _stream()), "pvk_track_pack")
+        raw = (nt_ub, tstart, tlen, toff, packed)
+    nt, npts, last = track_counts(tr)
+    tr["ntracks"], tr["npts"], tr["max_end"] = nt, npts, last
+    if raw is not None and 0 < nt <= raw[0]:
+        _, tstart, tlen, toff, packed = raw
+        pk = dict(tstart=tstart[:nt], tlen=tlen[:nt], toff=toff[:nt + 1], pf=packed[0][:npts], pmag=packed[1][:npts],
+                  pph=packed[2][:npts], prealph=packed[3][:npts], npts=npts)
+    elif nt == 0:
+        pk = None
+    else:                                                       # more partials than the speculative cap
+        pk = pack_device(fd, magd, phd, realphd, tr["tid"], None, nt, npts=npts)
+    return tr, pk
+
+
 def spans_device(tid, ntracks):
     """pvk_track_spans: first frame / length of every partial of an id table ``[F, K]`` (device)."""
     L = _lib.lib()
@@ -933,6 +976,7 @@ class SinSum(object):
         self._pk = None          # device packed tracks
         self._hosttrk = None
         self._maxpitchjmp = 0.5
+        self._after_link = None  # hook of sharded runs: called once the link kernels are launched
 
     # -- construction ------------------------------------------------------------------
     def _set_device_tables(self, f, mag, ph, realph):
@@ -981,9 +1025,11 @@ class SinSum(object):
             if t["f"].shape[0] == 0:
                 self._trk = dict(tid=torch.zeros((0, 1), dtype=torch.int32, device=self._dev), link=None, ntracks=0)
             else:
-                tr = track_device(t["f"], t["mag"], self._maxpitchjmp)
-                tr["ntracks"], tr["npts"], tr["max_end"] = track_counts(tr)
+                tr, pk = track_pack_device(t["f"], t["mag"], t["ph"], t["realph"], self._maxpitchjmp,
+                                           after_link=self._after_link)
                 self._trk = tr
+                if pk is not None:
+                    self._pk = pk
         return self._trk
 
     def _ensure_packed(self):

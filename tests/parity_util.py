@@ -120,3 +120,29 @@ def compare_harmonic(got, ref, f0, sr, nfft, totalmag, exact=False):
     assert np.all(fin[one] ** 2 <= tol[one]), "residual NaN pattern differs"
     rep["strong"] = int(strong.sum())
     return rep
+
+
+def wide_rows(K, mode, F=9):
+    """Random peak tables [F, K] for the link kernels: ascending gap-free rows ("asc", "asc_dense"),
+    rows with holes and one empty frame ("gaps"), out-of-order columns ("shuffled"), many equal
+    magnitudes ("ties")."""
+    rng = np.random.RandomState(K)
+    f = np.zeros((F, K))
+    mag = np.zeros((F, K))
+    base = np.sort(rng.uniform(200., 18000., K)) if mode != "asc_dense" else 200. + 30. * np.arange(K)
+    for j in range(F):
+        n = K if mode in ("asc", "asc_dense", "ties") else rng.randint(K // 2, K + 1)
+        fr = np.sort(base[:n] * (1.0 + 0.004 * rng.randn(n)))
+        mg = rng.uniform(0.01, 1.0, n)
+        if mode == "ties":
+            mg = np.round(mg, 1) + 0.1                       # many equal magnitudes
+        if mode == "shuffled":
+            perm = rng.permutation(n)
+            fr, mg = fr[perm], mg[perm]
+        cols = np.arange(n)
+        if mode == "gaps":
+            cols = np.sort(rng.choice(K, n, replace=False))
+        f[j, cols], mag[j, cols] = fr, mg
+    if mode == "gaps":
+        f[4] = 0.0; mag[4] = 0.0                            # an empty frame: everything restarts
+    return f, mag

@@ -155,3 +155,15 @@ def test_emu_segment_numbering_kernels(world):
     rows, ntot, max_end = eh.segment_stitch(tids, plans)
     assert np.array_equal(np.concatenate(rows), g["tid"])
     assert ntot == len(g["st"]) and max_end == int(np.max(g["end"]))
+
+
+@pytest.mark.parametrize("K,mode", [(150, "asc"), (300, "asc_dense"), (200, "gaps"), (160, "shuffled"), (130, "ties")])
+def test_emu_large_row_link_kernel(K, mode):
+    """Rows wider than 128 peaks take the sorted-rank / windowed link kernel: ascending gap-free
+    rows (binary-searched window), rows with holes or out of order (full scan fallback),
+    magnitude ties -- all against the oracle's sequential greedy loop, bit for bit."""
+    f, mag = pu.wide_rows(K, mode)
+    tr = eh.track(f, mag)
+    ref = orc.track(f, mag)
+    assert np.array_equal(tr["tid"][0], ref["tid"])
+    assert int(tr["ntracks"][0]) == int(ref["tid"].max()) + 1

@@ -182,3 +182,20 @@ def test_refine_output_exact_on_own_spectrum(pvmod, name):
     pvs = pvmod.PV(torch.from_numpy(x).pin_memory(), sr, progress=False, **kw)
     pvs.run_pv(hostbuf=hb, refine=True)
     assert np.array_equal(pvs.fine_pos, fp) and np.array_equal(pvs.fine_val, fv) and np.array_equal(pvs.f, pv.f)
+
+
+@pytest.mark.parametrize("K,mode", [(150, "asc"), (300, "asc_dense"), (200, "gaps"), (160, "shuffled"), (130, "ties"),
+                                    (1024, "asc"), (100, "ties"), (50, "gaps")])
+def test_link_kernels_on_random_wide_rows(K, mode):
+    """pvk_track on random tables, bit for bit against the oracle's sequential greedy loop: rows
+    wider than 128 peaks (sorted ranks + binary-searched window, full-scan fallback for rows with
+    holes or out of order) and the propose/commit kernel below that."""
+    import torch
+    import parity_util as pu
+    from oracle import pv_oracle as orc
+    from pypevoc_b200 import pv as P
+    f, mag = pu.wide_rows(K, mode, F=40)
+    tr = P.track_device(torch.from_numpy(f).cuda(), torch.from_numpy(mag).cuda())
+    ref = orc.track(f, mag)
+    assert np.array_equal(tr["tid"].cpu().numpy(), ref["tid"])
+    assert P.track_counts(tr)[0] == int(ref["tid"].max()) + 1
