@@ -363,6 +363,188 @@ __global__ void track_link_kernel(const double *__restrict__ f, const double *__
   }
 }
 
+// ---- wide rows, 128 < K <= 512: the propose / commit schedule of the fast kernel below (every
+// current peak proposes its nearest unused previous peak at once, the longest conflict-free
+// prefix of the magnitude order is committed per round) without stored candidate lists: a
+// proposal is found by scanning the peak's binary-searched window of the previous row and is
+// kept across rounds until its target gets taken.  Ranks come from warp bitonic sorts.  Rows
+// whose previous row has holes or is out of order take the sequential loop.
+__host__ __device__ constexpr int link_wide_smem_per_warp(int S) {
+  // cf cm pf pm skey (double) | pf32 | winner | usedw (32 words) | ord prank sidx (short)
+  return 32 * S * (5 * 8 + 4 + 4 + 3 * 2) + 32 * 4;
+}
+
+template <int S>
+__global__ void track_link_wide_kernel(const double *__restrict__ f, const double *__restrict__ mag,
+                                       int64_t nrows, int64_t F, int K, double maxjump,
+                                       int32_t *__restrict__ link, int32_t *__restrict__ newcount) {
+  PVK_SMEM(smem);
+  constexpr int KM = 32 * S;
+  const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char *base = smem + (size_t)warp * link_wide_smem_per_warp(S);
+  double *cf = reinterpret_cast<double *>(base);
+  double *cm = cf + KM;
+  double *pf = cm + KM;
+  double *pm = pf + KM;
+  double *skey = pm + KM;
+  float *pf32 = reinterpret_cast<float *>(skey + KM);
+  int *winner = reinterpret_cast<int *>(pf32 + KM);
+  unsigned *usedw = reinterpret_cast<unsigned *>(winner + KM);
+  short *ord = reinterpret_cast<short *>(usedw + 32);
+  short *prank = ord + KM;
+  short *sidx = prank + KM;
+  const float eps32 = (float)(maxjump / 17.312 * (1.0 + 1e-4) + 1e-6);   // guard band as in the fast kernel
+
+  for (int64_t row = (int64_t)blockIdx.x * W + warp; row < nrows; row += (int64_t)gridDim.x * W) {
+    const bool has_prev = (row % F) > 0;
+    int32_t *lrow = link + row * K;
+    int nc = 0, phi = 0;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const int i = lane + 32 * s;
+      bool v = false;
+      double cmv = -1.0, pmv = -1.0;
+      if (i < K) {
+        const double a = f[row * K + i], b = mag[row * K + i];
+        v = a > 0.0 && b > 0.0;                                   // :876
+        cf[i] = a; cmv = v ? b : -1.0;
+        if (!v) lrow[i] = LINK_NONE;
+        if (has_prev) {
+          const double c = f[(row - 1) * K + i], d = mag[(row - 1) * K + i];
+          const bool vp = c > 0.0 && d > 0.0;
+          pf[i] = c; pmv = vp ? d : -1.0;
+          pf32[i] = vp ? (float)c : -1.f;
+          if (vp) phi = i + 1;
+        }
+      }
+      cm[i] = cmv; pm[i] = pmv;
+      nc += __popc(__ballot_sync(FULL, v));
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) phi = max(phi, __shfl_xor_sync(FULL, phi, o));
+    __syncwarp();
+    // ---- order of the current peaks (:874-875), ties higher column first
+    for (int i = lane; i < KM; i += 32) { skey[i] = cm[i]; sidx[i] = (short)i; }
+    __syncwarp();
+    warp_sort_desc(skey, sidx, KM, true);
+    for (int t = lane; t < nc; t += 32) ord[t] = sidx[t];
+    __syncwarp();
+    if (!has_prev || phi == 0) {
+      for (int t = lane; t < nc; t += 32) lrow[ord[t]] = -2 - t;  // everything is new (:941)
+      if (lane == 0) newcount[row] = nc;
+      __syncwarp();
+      continue;
+    }
+    // ---- rank of the previous peaks (:891-900), ties lower column first
+    for (int i = lane; i < KM; i += 32) { skey[i] = i < phi ? pm[i] : -1.0; sidx[i] = (short)i; }
+    __syncwarp();
+    warp_sort_desc(skey, sidx, KM, false);
+    bool okasc = true;
+    for (int t = lane; t < KM; t += 32) {
+      const int i = sidx[t];
+      if (i < phi) prank[i] = (short)(skey[t] > 0.0 ? t : 0);
+    }
+    for (int p = lane; p < phi; p += 32)
+      okasc = okasc && pm[p] > 0.0 && (p + 1 >= phi || (pm[p + 1] > 0.0 && pf32[p] <= pf32[p + 1]));
+    const bool asc = __all_sync(FULL, okasc);
+    __syncwarp();
+    if (!asc) {                                                   // holes / out of order: sequential loop
+      const int nnew = link_greedy_generic(cf, pf, pm, ord, prank, nc, phi, maxjump, lrow);
+      if (lane == 0) newcount[row] = nnew;
+      __syncwarp();
+      continue;
+    }
+    // ---- per current peak t = lane + 32 s: column, start of its window in the previous row
+    int cidx[S], p0[S], res[S], prop[S];                          // res: -3 unresolved, -2 new, >= 0 matched column
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const int t = lane + 32 * s;
+      cidx[s] = 0; p0[s] = 0; prop[s] = -1;
+      res[s] = t < nc ? -3 : -4;
+      if (t < nc) {
+        cidx[s] = ord[t];
+        const float fc32 = (float)cf[cidx[s]];
+        const float flo = fc32 * (1.f - eps32);
+        int q = 0;
+#pragma unroll
+        for (int step = KM / 2; step >= 1; step >>= 1) {
+          const int mid = q + step;
+          if (mid <= phi && pf32[mid - 1] < flo) q = mid;
+        }
+        p0[s] = q;
+      }
+    }
+    if (lane < 32) usedw[lane] = 0u;
+    __syncwarp();
+    bool first = true;
+    for (;;) {
+      for (int p = lane; p < phi; p += 32) winner[p] = 0x7fffffff;
+      __syncwarp();
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        if (res[s] == -3) {
+          // a kept proposal stays the arg-min while its target is unused (the unused set only shrinks)
+          const bool rescan = first || (prop[s] >= 0 && ((usedw[prop[s] >> 5] >> (prop[s] & 31)) & 1u));
+          if (rescan) {
+            const double fc = cf[cidx[s]];
+            const float fc32 = (float)fc;
+            const float fhi = fc32 * (1.f + eps32 + 2.f * eps32 * eps32);
+            double bd = 1e300;
+            int br = 0x7fffffff, bp = -1;
+            for (int p = p0[s]; p < phi; ++p) {
+              const float pv = pf32[p];
+              if (pv > fhi) break;
+              if (fabsf(fc32 - pv) < eps32 * pv && !((usedw[p >> 5] >> (p & 31)) & 1u)) {
+                const double d = stonediff(fc, pf[p]);
+                if (d < maxjump) {                                // :923: only these can ever match
+                  const int r = prank[p];
+                  if (d < bd || (d == bd && r < br)) { bd = d; br = r; bp = p; }
+                }
+              }
+            }
+            prop[s] = bp;
+          }
+          if (prop[s] >= 0) atomicMin(&winner[prop[s]], lane + 32 * s);
+        }
+      }
+      first = false;
+      __syncwarp();
+      int L = nc;                                                 // first loser in the order
+#pragma unroll
+      for (int s = S - 1; s >= 0; --s) {
+        const bool lose = res[s] == -3 && prop[s] >= 0 && winner[prop[s]] != lane + 32 * s;
+        const unsigned m = __ballot_sync(FULL, lose);
+        if (m) L = 32 * s + __ffs((int)m) - 1;
+      }
+      bool pending = false;
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        if (res[s] == -3) {
+          if (lane + 32 * s < L) {
+            res[s] = prop[s] >= 0 ? prop[s] : -2;
+            if (prop[s] >= 0) atomicOr(&usedw[prop[s] >> 5], 1u << (prop[s] & 31));
+          } else {
+            pending = true;
+          }
+        }
+      }
+      __syncwarp();
+      if (!__any_sync(FULL, pending)) break;
+    }
+    int nnew = 0;                                                 // new partials in processing order (:941)
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const bool isnew = res[s] == -2;
+      const unsigned m = __ballot_sync(FULL, isnew);
+      if (res[s] >= 0) lrow[cidx[s]] = res[s];
+      else if (isnew) lrow[cidx[s]] = -2 - (nnew + __popc(m & lanemask_lt()));
+      nnew += __popc(m);
+    }
+    if (lane == 0) newcount[row] = nnew;
+    __syncwarp();
+  }
+}
+
 // Fast link for K <= 32*S (S = slots per lane).  Same result as the generic loop, different
 // schedule: every lane owns the current peaks t = lane + 32*s (t = position in the descending
 // magnitude order), collects the few previous peaks within maxpitchjmp of it (cheap fp64
@@ -936,6 +1118,25 @@ extern "C" int pvk_track(const double *f, const double *mag, int64_t nclips, int
       else if (S == 2) PVK_LINK_FAST(2);
       else PVK_LINK_FAST(4);
 #undef PVK_LINK_FAST
+    } else if (K <= 512) {
+      const int S = K <= 256 ? 8 : 16;
+      const int per_warp = link_wide_smem_per_warp(S);
+      const int W = S == 8 ? 4 : 2;
+      const int smem = W * per_warp;
+      g = (rows + W - 1) / W;
+      if (g > 148 * 64) g = 148 * 64;
+#define PVK_LINK_WIDE(SS)                                                                          \
+      do {                                                                                           \
+        if (smem > 48 * 1024 && PVK_SET_SMEM(track_link_wide_kernel<SS>, smem) != 0) {              \
+          set_error("pvk_track: cannot reserve %d bytes of shared memory", smem);                    \
+          return PVK_ERR_CUDA;                                                                       \
+        }                                                                                            \
+        PVK_LAUNCH(track_link_wide_kernel<SS>, dim3((unsigned)g), dim3(W * 32), smem, stream, f, mag, rows, \
+                   nframes, K, maxpitchjmp, link, newcount);                                         \
+      } while (0)
+      if (S == 8) PVK_LINK_WIDE(8);
+      else PVK_LINK_WIDE(16);
+#undef PVK_LINK_WIDE
     } else {
       const int per_warp = link_generic_smem_per_warp(K);
       int W = 96 * 1024 / per_warp;                               // two CTAs per SM

@@ -157,11 +157,13 @@ def test_emu_segment_numbering_kernels(world):
     assert ntot == len(g["st"]) and max_end == int(np.max(g["end"]))
 
 
-@pytest.mark.parametrize("K,mode", [(150, "asc"), (300, "asc_dense"), (200, "gaps"), (160, "shuffled"), (130, "ties")])
+@pytest.mark.parametrize("K,mode", [(150, "asc"), (300, "asc_dense"), (200, "gaps"), (160, "shuffled"), (130, "ties"),
+                                    (400, "ties"), (600, "asc_dense"), (520, "gaps")])
 def test_emu_large_row_link_kernel(K, mode):
-    """Rows wider than 128 peaks take the sorted-rank / windowed link kernel: ascending gap-free
-    rows (binary-searched window), rows with holes or out of order (full scan fallback),
-    magnitude ties -- all against the oracle's sequential greedy loop, bit for bit."""
+    """Rows wider than 128 peaks: the propose/commit kernel with window re-scans (K <= 512) and the
+    sequential sorted-rank / windowed kernel above that -- ascending gap-free rows
+    (binary-searched window), rows with holes or out of order (full scan fallback), magnitude
+    ties, all against the oracle's sequential greedy loop, bit for bit."""
     f, mag = pu.wide_rows(K, mode)
     tr = eh.track(f, mag)
     ref = orc.track(f, mag)

@@ -185,7 +185,7 @@ def test_refine_output_exact_on_own_spectrum(pvmod, name):
 
 
 @pytest.mark.parametrize("K,mode", [(150, "asc"), (300, "asc_dense"), (200, "gaps"), (160, "shuffled"), (130, "ties"),
-                                    (1024, "asc"), (100, "ties"), (50, "gaps")])
+                                    (1024, "asc"), (100, "ties"), (50, "gaps"), (400, "asc_dense"), (512, "ties"), (257, "gaps")])
 def test_link_kernels_on_random_wide_rows(K, mode):
     """pvk_track on random tables, bit for bit against the oracle's sequential greedy loop: rows
     wider than 128 peaks (sorted ranks + binary-searched window, full-scan fallback for rows with
