@@ -244,48 +244,69 @@ struct PeakVals { double f, mag, ph, realph; };
 // contraction where rounding decides ties).  bf = freq, bdf = fbin[k] - freq.
 __device__ __forceinline__ void peak_phase_freq(int k, const float2 *cur, const float2 *prev,
                                                 const double *__restrict__ fbin,
-                                                const double *__restrict__ wfbin, double dt,
-                                                double &thisph, double &bf, double &bdf) {
+                                                const double *__restrict__ wfbin, double dt, double inv,
+                                                double step, double &thisph, double &bf, double &bdf) {
   const float2 c = cur[PADC(k)], p = prev[PADC(k)];
   const double re = c.x, im = c.y, ore = p.x, oim = p.y;
   thisph = atan2(im, re);                                    // np.angle(fx[nbin]) :188
-  // frat = fx / oldfft (:171): numpy's complex128 division (Smith), incl. the x/0 case
+  // frat = fx / oldfft (:171): numpy's complex128 division (Smith), incl. the x/0 case.  Only the
+  // ANGLE of the quotient is used (:190), so the common positive factor 1/|denominator| of Smith's
+  // formula is dropped (its sign is kept): one fp64 division less, angle equal to ~1 ulp.
   double qr, qi;
   const double ar = fabs(ore), ai = fabs(oim);
   if (ar >= ai) {
     if (ar == 0.0 && ai == 0.0) {
       qr = re / ar; qi = im / ar;                            // (+-inf | nan, +-inf | nan)
     } else {
-      const double rat = oim / ore, scl = 1.0 / (ore + oim * rat);
-      qr = (re + im * rat) * scl; qi = (im - re * rat) * scl;
+      const double rat = oim / ore, den = ore + oim * rat;
+      qr = re + im * rat; qi = im - re * rat;
+      if (den < 0.0) { qr = -qr; qi = -qi; }
     }
   } else {
-    const double rat = ore / oim, scl = 1.0 / (oim + ore * rat);
-    qr = (re * rat + im) * scl; qi = (im * rat - re) * scl;
+    const double rat = ore / oim, den = oim + ore * rat;
+    qr = re * rat + im; qi = im * rat - re;
+    if (den < 0.0) { qr = -qr; qi = -qi; }
   }
   const double dph = atan2(qi, qr);                          // np.angle(frat[nbin]) :190
   const double PI2 = 6.283185307179586;
   const double fb = __ldg(fbin + k);
   const double base = __dadd_rn(dph, __ldg(wfbin + k));      // :140
-  double ba = 0.0;
-  bf = 0.0; bdf = 0.0;
+  // :141-147: freq_m = (base + 2 pi {-1,0,1}) / dt / 2 pi, pick the first minimum of |fbin - freq_m|.
+  // The candidates are one frame rate (1/dt) apart, so the winner is decided on a
+  // multiply-by-reciprocal estimate unless two of them are within 1e-9 (relative) of a tie; the
+  // reference's two correctly rounded divisions are then made for the winner only.
+  // (inv = 1 / (2 pi dt), step = 1 / dt: computed once per kernel)
+  const double e1 = fb - base * inv;                         // df estimate of m = 1; m = 0 / 2 are +- step away
+  const double a0 = fabs(e1 + step), a1 = fabs(e1), a2 = fabs(e1 - step);
+  int best = a0 <= a1 ? (a0 <= a2 ? 0 : 2) : (a1 <= a2 ? 1 : 2);
+  const double lo = fmin(a0, fmin(a1, a2));
+  const double second = best == 0 ? fmin(a1, a2) : (best == 1 ? fmin(a0, a2) : fmin(a0, a1));
+  const bool clear = (second - lo) > 1e-9 * step;            // false for NaN as well
+  if (clear) {
+    const double dphw = __dadd_rn(base, best == 0 ? -PI2 : (best == 1 ? 0.0 : PI2));
+    bf = __ddiv_rn(__ddiv_rn(dphw, dt), PI2);                // :142
+    bdf = __dsub_rn(fb, bf);                                 // :144
+  } else {
+    double ba = 0.0;
+    bf = 0.0; bdf = 0.0;
 #pragma unroll
-  for (int m = 0; m < 3; ++m) {
-    const double dphw = __dadd_rn(base, m == 0 ? -PI2 : (m == 1 ? 0.0 : PI2));
-    const double fq = __ddiv_rn(__ddiv_rn(dphw, dt), PI2);   // :142
-    const double df = __dsub_rn(fb, fq);                     // :144
-    const double a = fabs(df);
-    if (m == 0 || a < ba) { bf = fq; bdf = df; ba = a; }     // np.argmin: first minimum, nan sticks
+    for (int m = 0; m < 3; ++m) {
+      const double dphw = __dadd_rn(base, m == 0 ? -PI2 : (m == 1 ? 0.0 : PI2));
+      const double fq = __ddiv_rn(__ddiv_rn(dphw, dt), PI2); // :142
+      const double df = __dsub_rn(fb, fq);                   // :144
+      const double a = fabs(df);
+      if (m == 0 || a < ba) { bf = fq; bdf = df; ba = a; }   // np.argmin: first minimum, nan sticks
+    }
   }
 }
 
 // PVAnalysis.py:188-207 for the peak at bin k (1 <= k <= M-2)
 __device__ __forceinline__ bool peak_epilogue(int k, int M, const float2 *cur, const float2 *prev,
                                               const float *famp, const double *__restrict__ fbin,
-                                              const double *__restrict__ wfbin, double dt,
-                                              double fstep, PeakVals &o) {
+                                              const double *__restrict__ wfbin, double dt, double inv,
+                                              double step, double fstep, PeakVals &o) {
   double thisph, bf, bdf;
-  peak_phase_freq(k, cur, prev, fbin, wfbin, dt, thisph, bf, bdf);
+  peak_phase_freq(k, cur, prev, fbin, wfbin, dt, inv, step, thisph, bf, bdf);
   // mag = sqrt(sum(famp[max(nbin-1,1) : min(nbin+1,len)+1]**2)), left to right :197-199
   double s = famp[FA(k)];                                      // famp holds |fx|^2
   if (k - 1 >= 1) s = (double)famp[FA(k - 1)] + s;
@@ -389,6 +410,7 @@ __global__ void __launch_bounds__(Plan<LOGM>::T, 512 / Plan<LOGM>::T) analyze_ke
   const float2 *twp = prm.tables;
   const float2 *twr = prm.tables + P::TW_TOTAL;
   const int K = prm.npks;
+  const double inv_2pidt = 1.0 / (prm.dt * 6.283185307179586), inv_dt = 1.0 / prm.dt;
 
   float2 treg[P::TWR_TOTAL];
 #if PVK_TWREG
@@ -669,7 +691,7 @@ __global__ void __launch_bounds__(Plan<LOGM>::T, 512 / Plan<LOGM>::T) analyze_ke
       int k = 0;
       if (p < nk) {
         k = pk[p];
-        valid = peak_epilogue(k, M, cur, prev, famp, prm.fbin, prm.wfbin, prm.dt, prm.fstep, v);
+        valid = peak_epilogue(k, M, cur, prev, famp, prm.fbin, prm.wfbin, prm.dt, inv_2pidt, inv_dt, prm.fstep, v);
       }
       const int64_t pos = ob + round_pos<NW>(valid, wsB, round, outbase);
       if (valid) {
@@ -781,6 +803,7 @@ __global__ void __launch_bounds__(Plan<LOGM>::T) harmonic_kernel(HParams prm) {
   const float2 *twp = prm.tables;
   const float2 *twr = prm.tables + P::TW_TOTAL;
   const int K = prm.npks;
+  const double inv_2pidt = 1.0 / (prm.dt * 6.283185307179586), inv_dt = 1.0 / prm.dt;
   float2 treg[P::TWR_TOTAL];
 #if PVK_TWREG
   if constexpr (P::NPASS > 1) Pass<LOGM, 1>::load_tw(twp, treg);
@@ -833,14 +856,15 @@ __global__ void __launch_bounds__(Plan<LOGM>::T) harmonic_kernel(HParams prm) {
     if (H > 0) {
       // every thread evaluates the first harmonic itself (identical result, no broadcast)
       double ph0, df0;
-      peak_phase_freq(harmonic_bin(0, f0bin, 0.0, false, prm.sr, M), cur, prev, prm.fbin, prm.wfbin, prm.dt, ph0, f1, df0);
+      peak_phase_freq(harmonic_bin(0, f0bin, 0.0, false, prm.sr, M), cur, prev, prm.fbin, prm.wfbin, prm.dt, inv_2pidt,
+                      inv_dt, ph0, f1, df0);
       corr = f1 > prm.fmin;                                   // :465 (false for NaN)
     }
     double csum = 0.0;
     for (int64_t i = tid; i < H; i += T) {
       const int k = harmonic_bin(i, f0bin, f1, corr, prm.sr, M);
       double thisph, bf, bdf;
-      peak_phase_freq(k, cur, prev, prm.fbin, prm.wfbin, prm.dt, thisph, bf, bdf);
+      peak_phase_freq(k, cur, prev, prm.fbin, prm.wfbin, prm.dt, inv_2pidt, inv_dt, thisph, bf, bdf);
       // thismagsq = sum(famp[max(k-1,1) : min(k+1,len)+1]**2), left to right (:479-481)
       const int lo = k - 1 > 1 ? k - 1 : 1, hi = k + 1 < M - 1 ? k + 1 : M - 1;
       double s = 0.0;
