@@ -65,6 +65,12 @@ def plan_segments(nsamp_total, nfft, hop, world, edge=1.0, minframes=3):
     return plans
 
 
+def clip_range(nclips, rank, world):
+    """Clips [c0, c1) of a batch that rank ``rank`` analyses (clip batches): independent
+    units split evenly, no halo, no collective -- every rank runs a ``PVBatch`` on its slice."""
+    return (nclips * rank) // world, (nclips * (rank + 1)) // world
+
+
 # --------------------------------------------------------------------------- global numbering
 def local_summary(tid_local, plan):
     """int32 [2K + 4]: local ids of the row before the first own row (-1 = none), local ids of the

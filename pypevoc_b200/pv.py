@@ -780,6 +780,91 @@ class PV(object):
         return self.partial_sum_magnitude / self.totalmag
 
 
+class PVBatch(object):
+    """Clip batch (BASELINE configs[2]): ``nclips`` independent signals of equal length
+    analysed by ONE pvk_analyze launch and linked by ONE pvk_track launch (every clip starts from
+    the all-zero previous spectrum and its own partial numbering, exactly as a ``PV`` per clip).
+
+        pb = PVBatch(x, sr, nfft=512, hop=128, npks=20)      # x: [nclips, nsamp] numpy / torch
+        pb.run_pv()
+        pb.f, pb.mag, pb.ph, pb.realph, pb.binno               # float64 [nclips, nframes, npks]
+        pb.track()["tid"]                                      # int32 CUDA [nclips, nframes, npks]
+        pv3 = pb[3]                                            # a PV over clip 3 sharing the device tables
+
+    Across GPUs a batch shards by clip with no halo and no collective
+    (``dist.clip_range(nclips, rank, world)``)."""
+
+    def __init__(self, x, sr, nfft=1024, hop=None, npks=20, pkthresh=0.005, wind=np.hanning, device=None):
+        self._dev = _device(device)
+        if isinstance(x, torch.Tensor):
+            xd = x.detach()
+        else:
+            xd = torch.from_numpy(np.ascontiguousarray(np.asarray(x), dtype=np.float32))
+        if xd.dim() != 2:
+            raise ValueError("PVBatch expects a [nclips, nsamp] array")
+        self._xd = xd.to(device=self._dev, dtype=torch.float32).contiguous()
+        self.nclips, self.nsamp = (int(v) for v in self._xd.shape)
+        self._kw = dict(nfft=nfft, hop=hop, npks=npks, pkthresh=pkthresh, wind=wind)
+        # argument checks and host tables are PV's own
+        proto = PV(self._xd[0] if self.nclips else torch.zeros(1), sr, progress=False, device=self._dev, **self._kw)
+        self.sr, self.nfft, self.hop, self.npeaks, self.peakthresh = sr, proto.nfft, proto.hop, proto.npeaks, pkthresh
+        self._tb = proto._tb
+        self._devout = None
+        self._trk = None
+        self._host = {}
+        self.nframes = 0
+
+    def run_pv(self, run_frames=0):
+        self._devout = analyze_device(self._xd, self.sr, self.nfft, self.hop, self.npeaks, self.peakthresh, self._tb,
+                                      run_frames=run_frames)
+        self.nframes = int(self._devout["f"].shape[1])
+        self._host = {"t": (np.arange(self.nframes) * self.hop + self.nfft / 2.0) / self.sr}
+        self._trk = None
+
+    @property
+    def device_tables(self):
+        """Device tensors of the last run_pv: f mag ph realph binno float64 [nclips, nframes, npks],
+        npk int32 and totalmag float64 [nclips, nframes]."""
+        if self._devout is None:
+            raise RuntimeError("run_pv() has not been called")
+        return dict(self._devout)
+
+    def __getattr__(self, name):
+        if name in ("f", "mag", "ph", "realph", "binno", "totalmag", "t"):
+            host = self.__dict__.get("_host", {})
+            if name not in host:
+                dev = self.__dict__.get("_devout")
+                if dev is None:
+                    raise AttributeError(name)
+                host[name] = dev[name].cpu().numpy()
+            return host[name]
+        raise AttributeError(name)
+
+    def track(self, maxpitchjmp=0.5):
+        """pvk_track over all clips: dict(tid, link int32 [nclips, nframes, npks], ntracks int32 [nclips])."""
+        if self._trk is None:
+            d = self.device_tables
+            self._trk = track_device(d["f"], d["mag"], maxpitchjmp)
+        return self._trk
+
+    def __len__(self):
+        return self.nclips
+
+    def __getitem__(self, i):
+        """``PV`` over clip ``i``; its tables are views of the batch's device tables."""
+        i = int(i)
+        if i < 0:
+            i += self.nclips
+        if not 0 <= i < self.nclips:
+            raise IndexError(i)
+        pv = PV(self._xd[i], self.sr, progress=False, device=self._dev, **self._kw)
+        if self._devout is not None:
+            pv._devout = {k: v[i:i + 1] for k, v in self._devout.items()}
+            pv.nframes = self.nframes
+            pv._host = {"t": self._host["t"]}
+        return pv
+
+
 class PVHarmonic(PV):
     """f0-guided phase vocoder (PVAnalysis.py:419-538): instead of picking peaks, every frame
     reads the bins at the multiples of a given fundamental.  Same constructor as PV;

@@ -132,3 +132,12 @@ def test_local_render_range_matches_global():
                     covered += n
                 nout = D.P.synth_geometry(max_end, hop, nfft, hop)[0] if max_end >= 0 else 0
                 assert covered == nout, (nfft, hop, world, max_end, covered, nout)
+
+
+def test_clip_range_partitions_the_batch():
+    from pypevoc_b200 import dist as D
+    for nclips, world in ((4096, 8), (5, 3), (2, 4), (0, 2)):
+        r = [D.clip_range(nclips, g, world) for g in range(world)]
+        assert r[0][0] == 0 and r[-1][1] == nclips
+        assert all(a[1] == b[0] for a, b in zip(r[:-1], r[1:]))
+        assert max(c1 - c0 for c0, c1 in r) - min(c1 - c0 for c0, c1 in r) <= 1

@@ -199,3 +199,35 @@ def test_link_kernels_on_random_wide_rows(K, mode):
     ref = orc.track(f, mag)
     assert np.array_equal(tr["tid"].cpu().numpy(), ref["tid"])
     assert P.track_counts(tr)[0] == int(ref["tid"].max()) + 1
+
+
+def test_pvbatch_equals_single_clips():
+    """PVBatch (one launch over [nclips, nsamp]) == a PV per clip, bit for bit, incl. tracking and
+    the per-clip PV views; clips shard across ranks by dist.clip_range without overlap."""
+    import pypevoc_b200 as pb200
+    from pypevoc_b200 import dist as D
+    clips = np.stack([signals.speech_like_clip(seed=1000 + i, sr=16000, dur=0.8) for i in range(5)]).astype(np.float32)
+    pb = pb200.PVBatch(clips, 16000, nfft=512, hop=128, npks=20)
+    pb.run_pv()
+    assert len(pb) == 5 and pb.f.shape == (5, pb.nframes, 20)
+    tr = pb.track()
+    for i in range(5):
+        pv = pb200.PV(clips[i], 16000, nfft=512, hop=128, npks=20, progress=False)
+        pv.run_pv()
+        for k in ("f", "mag", "ph", "realph", "binno"):
+            assert np.array_equal(getattr(pb, k)[i], getattr(pv, k)), (i, k)
+        assert np.array_equal(pb.totalmag[i], np.asarray(pv.totalmag))
+        ss = pv.toSinSum()
+        assert np.array_equal(tr["tid"][i].cpu().numpy(), ss.track_ids)
+        view = pb[i]
+        assert np.array_equal(view.f, pv.f) and np.array_equal(view.t, pv.t)
+        assert np.array_equal(view.toSinSum().synth(16000, 128), ss.synth(16000, 128))
+    got = []
+    for r in range(3):
+        c0, c1 = D.clip_range(5, r, 3)
+        part = pb200.PVBatch(clips[c0:c1], 16000, nfft=512, hop=128, npks=20)
+        part.run_pv()
+        got.append(part.f)
+    assert np.array_equal(np.concatenate(got), pb.f)
+    with pytest.raises(ValueError):
+        pb200.PVBatch(clips[0], 16000)
