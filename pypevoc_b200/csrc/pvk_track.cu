@@ -14,6 +14,7 @@
 // (current frame: higher column first, previous frame: lower column first); the reference's
 // order there comes from numpy's unstable argsort and python's tuple sort on track index.
 #include "pvk_common.cuh"
+#include <stdlib.h>
 
 namespace pvk {
 
@@ -1131,7 +1132,9 @@ extern "C" int pvk_track(const double *f, const double *mag, int64_t nclips, int
 
   {  // link: one warp per frame pair
     int64_t g;
-    if (K <= 128) {
+    // rows of more than `wide_from - 1` peaks take the wide kernel (PVK_LINK_WIDE_FROM: tuning override)
+    static const int wide_from = []() { const char *e = getenv("PVK_LINK_WIDE_FROM"); return e ? atoi(e) : 129; }();
+    if (K <= 128 && K < wide_from) {
       const int S = K <= 32 ? 1 : (K <= 64 ? 2 : 4);
       const int per_warp = link_fast_smem_per_warp(S);
       const int W = S == 4 ? 4 : 8;
@@ -1152,9 +1155,9 @@ extern "C" int pvk_track(const double *f, const double *mag, int64_t nclips, int
       else PVK_LINK_FAST(4);
 #undef PVK_LINK_FAST
     } else if (K <= 512) {
-      const int S = K <= 256 ? 8 : 16;
+      const int S = K <= 128 ? 4 : (K <= 256 ? 8 : 16);
       const int per_warp = link_wide_smem_per_warp(S);
-      const int W = S == 8 ? 4 : 2;
+      const int W = S == 4 ? 8 : (S == 8 ? 4 : 2);
       const int smem = W * per_warp;
       g = (rows + W - 1) / W;
       if (g > 148 * 64) g = 148 * 64;
@@ -1167,7 +1170,8 @@ extern "C" int pvk_track(const double *f, const double *mag, int64_t nclips, int
         PVK_LAUNCH(track_link_wide_kernel<SS>, dim3((unsigned)g), dim3(W * 32), smem, stream, f, mag, rows, \
                    nframes, K, maxpitchjmp, link, newcount);                                         \
       } while (0)
-      if (S == 8) PVK_LINK_WIDE(8);
+      if (S == 4) PVK_LINK_WIDE(4);
+      else if (S == 8) PVK_LINK_WIDE(8);
       else PVK_LINK_WIDE(16);
 #undef PVK_LINK_WIDE
     } else {
