@@ -20,7 +20,10 @@ namespace pvk {
 
 constexpr int LINK_NONE = -1;    // slot is not a point
 // link <= -2: new partial, rank among the frame's new partials = -2 - link
-constexpr int TRACK_CHUNK = 128; // frames per chain-resolution chunk
+#ifndef PVK_TRACK_CHUNK
+#define PVK_TRACK_CHUNK 128
+#endif
+constexpr int TRACK_CHUNK = PVK_TRACK_CHUNK; // frames per chain-resolution chunk
 
 // ------------------------------------------------------------------ link
 // Shared by both link kernels: load the two peak rows of one frame pair into the warp's shared
