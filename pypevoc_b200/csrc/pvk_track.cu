@@ -992,7 +992,10 @@ __global__ void track_fix_kernel(int32_t *__restrict__ tid, const int32_t *__res
 // Every thread walks one column over a strip of PACK_STRIP consecutive frames and merges runs of
 // equal ids (a partial usually stays in its column for a while) before touching the per-track
 // counters: ~PACK_STRIP x fewer atomics than one per point.
-constexpr int PACK_STRIP = 64;
+#ifndef PVK_PACK_STRIP
+#define PVK_PACK_STRIP 64
+#endif
+constexpr int PACK_STRIP = PVK_PACK_STRIP;
 __global__ void pack_count_kernel(const int32_t *__restrict__ tid, int64_t F, int K,
                                   int32_t *__restrict__ tstart, int32_t *__restrict__ tlen) {
   const int64_t nstrips = (F + PACK_STRIP - 1) / PACK_STRIP;
@@ -1003,13 +1006,21 @@ __global__ void pack_count_kernel(const int32_t *__restrict__ tid, int64_t F, in
     const int64_t j1 = j0 + PACK_STRIP < F ? j0 + PACK_STRIP : F;
     int cur = -1, cnt = 0;
     int64_t first = 0;
-    for (int64_t j = j0; j < j1; ++j) {
-      const int v = tid[j * K + c];
-      if (v != cur) {
-        if (cur >= 0) { atomicAdd(&tlen[cur], cnt); atomicMin(&tstart[cur], (int32_t)first); }
-        cur = v; cnt = 0; first = j;
+    for (int64_t jb = j0; jb < j1; jb += 8) {                   // 8 independent loads in flight per thread
+      int v8[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v8[u] = jb + u < j1 ? tid[(jb + u) * K + c] : -1;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (jb + u < j1) {
+          const int v = v8[u];
+          if (v != cur) {
+            if (cur >= 0) { atomicAdd(&tlen[cur], cnt); atomicMin(&tstart[cur], (int32_t)first); }
+            cur = v; cnt = 0; first = jb + u;
+          }
+          ++cnt;
+        }
       }
-      ++cnt;
     }
     if (cur >= 0) { atomicAdd(&tlen[cur], cnt); atomicMin(&tstart[cur], (int32_t)first); }
   }

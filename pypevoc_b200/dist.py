@@ -47,9 +47,10 @@ def plan_segments(nsamp_total, nfft, hop, world, edge=1.0, minframes=3):
     Lb, Lf = halos(nfft, hop, edge, minframes)
     plans = []
     shard = F >= 4 * world          # too short to shard: rank 0 takes everything
-    for g in range(world):
-        j0 = (F * g) // world if shard else (0 if g == 0 else F)
-        j1 = (F * (g + 1)) // world if shard else F
+    per = -(-F // world)            # equal shares; only the last non-empty rank can be short, so the
+    for g in range(world):          # all_gather of the track table lands in frame order without a copy
+        j0 = min(g * per, F) if shard else (0 if g == 0 else F)
+        j1 = min((g + 1) * per, F) if shard else F
         if j1 <= j0:
             plans.append(dict(rank=g, j0=j0, j1=j1, w0=j0, w1=j0, own0=0, nown=0, sample0=0, nsamp=0, frame0=0,
                               nframes=0, prev_zero=True, frames_total=F))
@@ -347,17 +348,26 @@ def gather_track_table(tid_own, plans, group=None, async_op=False):
     world = len(plans)
     K = tid_own.shape[1]
     rows_max = max(p["nown"] for p in plans)
-    mine = torch.full((rows_max, K), -1, dtype=torch.int32, device=tid_own.device)
-    mine[:tid_own.shape[0]] = tid_own
     if world == 1:
         return None, (lambda: tid_own)
+    if tid_own.shape[0] == rows_max and tid_own.is_contiguous():
+        mine = tid_own
+    else:
+        mine = torch.full((rows_max, K), -1, dtype=torch.int32, device=tid_own.device)
+        mine[:tid_own.shape[0]] = tid_own
     flat1 = torch.empty((world * rows_max * K,), dtype=torch.int32, device=tid_own.device)
     work = dist.all_gather_into_tensor(flat1, mine.view(-1), group=group, async_op=async_op)
     flat = flat1.view(world, rows_max, K)
+    F = sum(p["nown"] for p in plans)
+    # plan_segments gives every rank but the last non-empty one rows_max rows: the gathered buffer
+    # is then the table itself (plus padding at the end)
+    in_order = all(p["nown"] == rows_max or all(q["nown"] == 0 for q in plans[i + 1:]) for i, p in enumerate(plans))
 
     def finish():
         if work is not None:
             work.wait()
+        if in_order:
+            return flat1.view(world * rows_max, K)[:F]
         return torch.cat([flat[g, :plans[g]["nown"]] for g in range(world)]).contiguous()
     return work, finish
 
