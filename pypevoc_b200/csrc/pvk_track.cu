@@ -26,68 +26,10 @@ constexpr int LINK_NONE = -1;    // slot is not a point
 constexpr int TRACK_CHUNK = PVK_TRACK_CHUNK; // frames per chain-resolution chunk
 
 // ------------------------------------------------------------------ link
-// Shared by both link kernels: load the two peak rows of one frame pair into the warp's shared
-// memory (invalid slots get magnitude -1), order the current peaks by descending magnitude
-// (ord) and rank the previous ones (prank).  Returns nc; chi / phi = 1 + highest valid column.
-__device__ __forceinline__ int link_prepare(const double *__restrict__ f, const double *__restrict__ mag,
-                                            int64_t row, bool has_prev, int K, int32_t *__restrict__ link,
-                                            double *cf, double *cm, double *pf, double *pm, short *ord,
-                                            short *prank, int &chi_out, int &phi_out) {
-  const int lane = threadIdx.x & 31;
-  int chi = 0, phi = 0;
-  for (int i = lane; i < K; i += 32) {
-    const double a = f[row * K + i], b = mag[row * K + i];
-    const bool v = a > 0.0 && b > 0.0;                        // :876
-    cf[i] = a; cm[i] = v ? b : -1.0;
-    if (v) chi = i + 1; else link[row * K + i] = LINK_NONE;
-    if (has_prev) {
-      const double c = f[(row - 1) * K + i], d = mag[(row - 1) * K + i];
-      const bool vp = c > 0.0 && d > 0.0;
-      pf[i] = c; pm[i] = vp ? d : -1.0;
-      if (vp) phi = i + 1;
-    }
-  }
-#pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) {
-    chi = max(chi, __shfl_xor_sync(FULL, chi, o));
-    phi = max(phi, __shfl_xor_sync(FULL, phi, o));
-  }
-  __syncwarp();
-  // order of the current peaks: magnitude descending (:874-875)
-  int nc = 0;
-  for (int i0 = 0; i0 < chi; i0 += 32) {
-    const int i = i0 + lane;
-    const double mi = i < chi ? cm[i] : -1.0;
-    const bool vi = mi > 0.0;
-    if (vi) {
-      int r = 0;
-      for (int i2 = 0; i2 < chi; ++i2) {
-        const double m2 = cm[i2];
-        r += (m2 > mi || (m2 == mi && i2 > i)) ? 1 : 0;
-      }
-      ord[r] = (short)i;
-    }
-    nc += __popc(__ballot_sync(FULL, vi));
-  }
-  // rank of the previous peaks in descending magnitude (:891-900)
-  for (int i = lane; i < phi; i += 32) {
-    const double mi = pm[i];
-    int r = 0;
-    if (mi > 0.0) {
-      for (int i2 = 0; i2 < phi; ++i2) {
-        const double m2 = pm[i2];
-        r += (m2 > mi || (m2 == mi && i2 < i)) ? 1 : 0;
-      }
-    }
-    prank[i] = (short)r;
-  }
-  __syncwarp();
-  chi_out = chi; phi_out = phi;
-  return nc;
-}
-
-// link_prepare for K <= 32*S: same result, but a lane ranks its S slots in ONE pass over the row
-// (one shared-memory read per compared magnitude instead of S).
+// Load the two peak rows of one frame pair into the warp's shared memory (invalid slots get
+// magnitude -1), order the current peaks by descending magnitude (ord) and rank the previous ones
+// (prank), for K <= 32*S: a lane ranks its S slots in ONE pass over the row (one shared-memory
+// read per compared magnitude).  Returns nc; chi / phi = 1 + highest valid column.
 template <int S>
 __device__ __forceinline__ int link_prepare_s(const double *__restrict__ f, const double *__restrict__ mag,
                                               int64_t row, bool has_prev, int K, int32_t *__restrict__ link,
