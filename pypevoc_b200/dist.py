@@ -47,10 +47,18 @@ def plan_segments(nsamp_total, nfft, hop, world, edge=1.0, minframes=3):
     Lb, Lf = halos(nfft, hop, edge, minframes)
     plans = []
     shard = F >= 4 * world          # too short to shard: rank 0 takes everything
-    per = -(-F // world)            # equal shares; only the last non-empty rank can be short, so the
-    for g in range(world):          # all_gather of the track table lands in frame order without a copy
-        j0 = min(g * per, F) if shard else (0 if g == 0 else F)
-        j1 = min((g + 1) * per, F) if shard else F
+    # equal shares of ceil(F / world) rows with a short LAST rank: the all_gather of the track table
+    # then lands in frame order without a copy.  If that would leave a rank empty (F barely above
+    # 4 * world) the rows are spread evenly instead (gather_track_table concatenates in that case).
+    per = -(-F // world)
+    equal = per * (world - 1) < F
+    for g in range(world):
+        if not shard:
+            j0, j1 = (0, F) if g == 0 else (F, F)
+        elif equal:
+            j0, j1 = g * per, min((g + 1) * per, F)
+        else:
+            j0, j1 = (F * g) // world, (F * (g + 1)) // world
         if j1 <= j0:
             plans.append(dict(rank=g, j0=j0, j1=j1, w0=j0, w1=j0, own0=0, nown=0, sample0=0, nsamp=0, frame0=0,
                               nframes=0, prev_zero=True, frames_total=F))

@@ -141,3 +141,28 @@ def test_clip_range_partitions_the_batch():
         assert r[0][0] == 0 and r[-1][1] == nclips
         assert all(a[1] == b[0] for a, b in zip(r[:-1], r[1:]))
         assert max(c1 - c0 for c0, c1 in r) - min(c1 - c0 for c0, c1 in r) <= 1
+
+
+def test_plan_random_sizes_keep_every_rank_busy():
+    """Random (length, nfft, hop, world): contiguous cover, no empty rank once the signal is long
+    enough to shard, all ranks but the last equal whenever that is possible (copy-free gather)."""
+    from pypevoc_b200 import dist as D
+    from pypevoc_b200.pv import n_frames
+    rng = np.random.RandomState(5)
+    for _ in range(400):
+        nfft = int(2 ** rng.randint(6, 14))
+        hop = int(rng.randint(1, nfft + 1))
+        world = int(rng.randint(1, 9))
+        nsamp = int(nfft + rng.randint(0, 600) * hop + rng.randint(0, hop + 1))
+        F = n_frames(nsamp, nfft, hop)
+        plans = D.plan_segments(nsamp, nfft, hop, world)
+        assert plans[0]["j0"] == 0 and plans[-1]["j1"] == F
+        assert all(a["j1"] == b["j0"] for a, b in zip(plans[:-1], plans[1:]))
+        assert sum(p["nown"] for p in plans) == F
+        if F >= 4 * world:
+            assert all(p["nown"] > 0 for p in plans), (F, world)
+            per = -(-F // world)
+            if per * (world - 1) < F:
+                assert all(p["nown"] == per for p in plans[:-1])
+        else:
+            assert plans[0]["nown"] == F and all(p["nown"] == 0 for p in plans[1:])
