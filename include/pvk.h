@@ -227,6 +227,17 @@ int pvk_segment_resolve(const int32_t *summaries, int world, int npks, int rank,
 int pvk_segment_rename(const int32_t *tid_own, int64_t n, const int32_t *gidlow,
                        const int32_t *params, int32_t *tid_global, void *stream);
 
+/*
+ * pvk_segment_rename fused with the gather of the track table (no reference counterpart; replaces
+ * pvk_segment_rename + an all_gather): the n renamed ids are stored at element offset `dst_offset`
+ * (= first own row * npks) of EVERY table in dst_tables[0..ndst) -- a DEVICE array of device
+ * pointers to the int32 [frames_total, npks] tables of all ranks, the remote ones being peer memory
+ * mapped over NVLink (CUDA IPC / symmetric memory).  P2P stores from the kernel that computes the
+ * ids; the caller provides the cross-rank barriers before (tables free) and after (stores visible).
+ */
+int pvk_segment_rename_push(const int32_t *tid_own, int64_t n, const int32_t *gidlow, const int32_t *params,
+                            int32_t *const *dst_tables, int ndst, int64_t dst_offset, void *stream);
+
 /* ------------------------------------------------------------------ resynthesis
  * Replaces SinSum.synth -> RegPartial.synth (PVAnalysis.py:1053-1070,684-756),
  * phase_preserve=True path, for ONE clip.

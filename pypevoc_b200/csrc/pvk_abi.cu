@@ -17,7 +17,7 @@ void set_error(const char *fmt, ...) {
 }
 }  // namespace pvk
 
-extern "C" int pvk_version(void) { return 4; }
+extern "C" int pvk_version(void) { return 5; }
 
 extern "C" const char *pvk_last_error(void) { return pvk::g_err; }
 

@@ -1362,6 +1362,38 @@ __global__ void segment_rename_kernel(const int32_t *__restrict__ tid_own, int64
   }
 }
 
+// segment_rename fused with the gather of the track table: every renamed id is stored into the
+// table of EVERY rank at the segment's row offset.  dst[d] are int32 tables of all ranks -- the local
+// one and peer memory mapped over NVLink (CUDA IPC / symmetric memory) -- so the exchange is plain
+// P2P stores issued by the kernel that computes the ids, 128 bits at a time where alignment allows;
+// no collective call.  The caller brackets the launch with its cross-rank barriers.
+__global__ void segment_rename_push_kernel(const int32_t *__restrict__ tid_own, int64_t n,
+                                           const int32_t *__restrict__ gidlow, const int32_t *__restrict__ params,
+                                           int32_t *const *__restrict__ dst, int ndst, int64_t offset) {
+  const int base = params[0], nb = params[1];
+  const bool vec = (offset & 3) == 0 && (reinterpret_cast<uintptr_t>(tid_own) & 15) == 0;
+  const int64_t n4 = vec ? n >> 2 : 0;
+  const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, ts = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t q = t0; q < n4; q += ts) {
+    const int4 v = reinterpret_cast<const int4 *>(tid_own)[q];
+    int4 o;
+    o.x = v.x < 0 ? -1 : (v.x >= nb ? base + (v.x - nb) : gidlow[v.x]);
+    o.y = v.y < 0 ? -1 : (v.y >= nb ? base + (v.y - nb) : gidlow[v.y]);
+    o.z = v.z < 0 ? -1 : (v.z >= nb ? base + (v.z - nb) : gidlow[v.z]);
+    o.w = v.w < 0 ? -1 : (v.w >= nb ? base + (v.w - nb) : gidlow[v.w]);
+    for (int d = 0; d < ndst; ++d) {
+      int32_t *t = dst[d] + offset;
+      if ((reinterpret_cast<uintptr_t>(t) & 15) == 0) reinterpret_cast<int4 *>(t)[q] = o;
+      else { t[4 * q] = o.x; t[4 * q + 1] = o.y; t[4 * q + 2] = o.z; t[4 * q + 3] = o.w; }
+    }
+  }
+  for (int64_t e = 4 * n4 + t0; e < n; e += ts) {
+    const int v = tid_own[e];
+    const int o = v < 0 ? -1 : (v >= nb ? base + (v - nb) : gidlow[v]);
+    for (int d = 0; d < ndst; ++d) dst[d][offset + e] = o;
+  }
+}
+
 }  // namespace pvk
 
 extern "C" int pvk_segment_summary(const int32_t *tid, int npks, int64_t own0, int64_t nown, int64_t j0,
@@ -1398,5 +1430,16 @@ extern "C" int pvk_segment_rename(const int32_t *tid_own, int64_t n, const int32
   PVK_REQUIRE(tid_own && gidlow && params && tid_global, "pvk_segment_rename: NULL pointer argument");
   PVK_LAUNCH(segment_rename_kernel, dim3(grid_for(n, 256)), dim3(256), 0, stream, tid_own, n, gidlow, params, tid_global);
   PVK_CHECK_LAUNCH("pvk_segment_rename");
+  return PVK_OK;
+}
+
+extern "C" int pvk_segment_rename_push(const int32_t *tid_own, int64_t n, const int32_t *gidlow, const int32_t *params,
+                                       int32_t *const *dst_tables, int ndst, int64_t dst_offset, void *stream) {
+  PVK_REQUIRE(n >= 0 && ndst >= 1 && dst_offset >= 0, "pvk_segment_rename_push: bad sizes");
+  if (n == 0) return PVK_OK;
+  PVK_REQUIRE(tid_own && gidlow && params && dst_tables, "pvk_segment_rename_push: NULL pointer argument");
+  PVK_LAUNCH(segment_rename_push_kernel, dim3(grid_for(n / 4 + 1, 256)), dim3(256), 0, stream, tid_own, n, gidlow, params,
+             dst_tables, ndst, dst_offset);
+  PVK_CHECK_LAUNCH("pvk_segment_rename_push");
   return PVK_OK;
 }

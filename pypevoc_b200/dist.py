@@ -209,6 +209,36 @@ def segment_rename_device(tid_local, plan, world, allv, max_own0=None, sync=True
     return dict(tid_own=tid_own, ntracks=int(ph[3]), max_end=int(ph[4]))
 
 
+def segment_rename_push_device(tid_local, plan, world, allv, tables, max_own0=None):
+    """pvk_segment_resolve + pvk_segment_rename_push: the renamed own rows are stored straight into
+    every table of ``tables`` (int32 CUDA tensors [frames_total, K]: the local one and, in a
+    multi-GPU run, the peers' tables mapped over NVLink) at this segment's row offset -- the gather
+    of the track table as P2P stores of the kernel that computes the ids, no collective call.
+    The caller owns the cross-rank barriers around it.  Returns ``params`` (device int32 [8], as
+    segment_rename_device(sync=False))."""
+    import ctypes as C
+    from . import _lib
+    L = _lib.lib()
+    K = tid_local.shape[1]
+    dev = tid_local.device
+    own0, nown, g = plan["own0"], plan["nown"], plan["rank"]
+    ptr = lambda t: C.c_void_p(t.data_ptr())                                   # noqa: E731
+    with torch.cuda.device(dev):
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        cap = max((own0 if max_own0 is None else max_own0) * K, 1)
+        scratch = torch.empty((2, cap), dtype=torch.int32, device=dev)
+        params = torch.zeros((8,), dtype=torch.int32, device=dev)
+        _lib.check(L.pvk_segment_resolve(ptr(allv), world, K, g, ptr(scratch[0]), cap, ptr(scratch[1]), ptr(params),
+                                         stream), "pvk_segment_resolve")
+        own = tid_local[own0:own0 + nown].contiguous()
+        dst = torch.tensor([int(t.data_ptr()) for t in tables], dtype=torch.int64, device=dev)
+        _lib.check(L.pvk_segment_rename_push(ptr(own), own.numel(), ptr(scratch[1]), ptr(params), ptr(dst), len(tables),
+                                             plan["j0"] * K, stream), "pvk_segment_rename_push")
+        # keep the operands alive until the stream has consumed them
+        params._pvk_keep = (own, dst, scratch)
+    return params
+
+
 def _stitch_device(tid_local, plan, plans, group):
     """stitch() for CUDA tables: summary / resolve / rename run as three small libpvk kernels."""
     import torch.distributed as dist

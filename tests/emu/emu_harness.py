@@ -224,6 +224,32 @@ def segment_stitch(tids, plans):
     return out, ntot, max_end
 
 
+def segment_stitch_push(tids, plans):
+    """The fused variant: every segment's pvk_segment_rename_push stores its renamed own rows into the
+    tables of ALL ranks (here: `world` numpy arrays standing in for local + peer memory).  Returns the
+    list of tables (each must be the complete global table)."""
+    L = lib()
+    world = len(plans)
+    K = tids[0].shape[1]
+    F = sum(p["nown"] for p in plans)
+    summ = np.zeros((world, 2 * K + 4), dtype=np.int32)
+    tids = [np.ascontiguousarray(t, dtype=np.int32) for t in tids]
+    for r, p in enumerate(plans):
+        check(L.pvk_segment_summary(ptr(tids[r]), K, p["own0"], p["nown"], p["j0"], ptr(summ[r]), None))
+    tables = [np.full((F, K), -7, dtype=np.int32) for _ in range(world)]
+    dst = np.array([t.ctypes.data for t in tables], dtype=np.uint64)
+    for r, p in enumerate(plans):
+        cap = max(max(q["own0"] for q in plans) * K, 1)
+        scratch = np.zeros(cap, dtype=np.int32)
+        gidlow = np.zeros(cap, dtype=np.int32)
+        params = np.zeros(8, dtype=np.int32)
+        check(L.pvk_segment_resolve(ptr(summ), world, K, r, ptr(scratch), cap, ptr(gidlow), ptr(params), None))
+        own = np.ascontiguousarray(tids[r][p["own0"]:p["own0"] + p["nown"]])
+        check(L.pvk_segment_rename_push(ptr(own), own.size, ptr(gidlow), ptr(params), ptr(dst), world,
+                                        p["j0"] * K, None))
+    return tables
+
+
 def stft_bank(x, win, nfft, hop, nframes, fb_folded=None, fb_lo=None, fb_hi=None, flux_bins=None, inv_wsum2=None,
               run_frames=0):
     """pvk_stft_bank through the emulator; returns dict(bank, flux, rms) of the requested outputs."""

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol(libpath):
     for s in syms:
         assert hasattr(lib, s), s
     _lib.declare(lib)
-    assert lib.pvk_version() == 4
+    assert lib.pvk_version() == 5
     assert lib.pvk_last_error() == b""
 
 

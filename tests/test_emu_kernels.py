@@ -155,6 +155,9 @@ def test_emu_segment_numbering_kernels(world):
     rows, ntot, max_end = eh.segment_stitch(tids, plans)
     assert np.array_equal(np.concatenate(rows), g["tid"])
     assert ntot == len(g["st"]) and max_end == int(np.max(g["end"]))
+    # the fused variant: every segment stores its renamed rows into the tables of all ranks
+    for table in eh.segment_stitch_push(tids, plans):
+        assert np.array_equal(table, g["tid"])
 
 
 @pytest.mark.parametrize("K,mode", [(150, "asc"), (300, "asc_dense"), (200, "gaps"), (160, "shuffled"), (130, "ties"),

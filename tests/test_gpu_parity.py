@@ -366,6 +366,15 @@ def test_sharded_pipeline_equals_unsharded(pvmod, world):
         st = D.segment_rename_device(locs[r][1]["tid"].contiguous(), p, world, allv, max(q["own0"] for q in plans))
         assert st["ntracks"] == ntot and st["max_end"] == max_end
         assert torch.equal(st["tid_own"], rows[r]), r
+    # ... and through the fused rename + gather kernel: every segment stores its renamed rows into
+    # the tables of all ranks (here `world` local tensors stand in for local + peer memory)
+    tables = [torch.full((tid0.shape[0], npks), -7, dtype=torch.int32, device="cuda") for _ in range(world)]
+    for r, p in enumerate(plans):
+        prm = D.segment_rename_push_device(locs[r][1]["tid"].contiguous(), p, world, allv, tables,
+                                           max(q["own0"] for q in plans))
+        assert prm.cpu().numpy()[3] == ntot
+    for t in tables:
+        assert np.array_equal(t.cpu().numpy(), tid0)
     tstart, tlen = P.spans_device(table.contiguous(), ntot)
     assert tstart.cpu().numpy().tolist() == ss0.st
     assert (tstart + tlen - 1).cpu().numpy().tolist() == ss0.end
