@@ -24,6 +24,8 @@ then collects the track table (global ids of every frame, int32 [F, K]); first f
 of every partial follow from it (pvk_track_spans).  The peak tables stay sharded;
 `ShardedSinSum.gather_tables()` collects them on request (second, optional collective).
 """
+import os
+
 import numpy as np
 import torch
 
@@ -278,6 +280,7 @@ def stitch(tid_local, plan, plans, group=None):
 
 
 _STITCH_STREAMS = {}
+_PEER_TABLES = {}            # (device, world, rows, K) -> symmetric-memory track tables (PVK_PEER_GATHER=1)
 
 
 def _stitch_stream(dev):
@@ -315,10 +318,72 @@ class StitchHandle(object):
                 dist.all_gather_into_tensor(allv, mine, group=group)
             else:
                 allv = mine
+            self.peer_used = False
+            if world > 1 and os.environ.get("PVK_PEER_GATHER") == "1" and self._peer_gather(tid_local, allv, group):
+                return
             r = segment_rename_device(tid_local, plan, world, allv, max(p["own0"] for p in plans), sync=False)
             self._tid_own, self._params = r["tid_own"], r["params"]
             _, finish = gather_track_table(self._tid_own, plans, group, async_op=False)
             self._table = finish()                        # queued behind the gather on the side stream
+
+    def _peer_gather(self, tid_local, allv, group):
+        """EXPERIMENTAL (PVK_PEER_GATHER=1; not yet measured): rename fused with the gather --
+        pvk_segment_rename_push stores the renamed rows straight into the track tables of all ranks,
+        which are symmetric-memory buffers mapped over NVLink; two signal-pad barriers replace the
+        NCCL all_gather.  Two buffers alternate, so a returned table stays valid until the second
+        next call.  Returns False (and the NCCL path runs) if symmetric memory cannot be set up or the
+        plan is not the equal-share one."""
+        import sys
+        import torch.distributed as dist
+        plans, plan = self.plans, self.plan
+        world = len(plans)
+        K = tid_local.shape[1]
+        rows_max = max(p["nown"] for p in plans)
+        F = sum(p["nown"] for p in plans)
+        if any(p["nown"] and p["j0"] != p["rank"] * rows_max for p in plans):
+            return False
+        try:
+            key = (self.dev.index, world, rows_max, K)
+            ent = _PEER_TABLES.get(key)
+            if ent is None:
+                import torch.distributed._symmetric_memory as sm
+                grp = group if group is not None else dist.group.WORLD
+                bufs = [sm.empty(world * rows_max * K, dtype=torch.int32, device=self.dev) for _ in range(2)]
+                ent = dict(bufs=bufs, hdls=[sm.rendezvous(b, grp) for b in bufs], turn=0)
+                _PEER_TABLES[key] = ent
+            i = ent["turn"]
+            ent["turn"] = 1 - i
+            buf, hdl = ent["bufs"][i], ent["hdls"][i]
+            hdl.barrier()                                 # every rank is done with this buffer's previous content
+            import ctypes as C
+            from . import _lib
+            L = _lib.lib()
+            own0, nown, g = plan["own0"], plan["nown"], plan["rank"]
+            cap = max(max(p["own0"] for p in plans) * K, 1)
+            scratch = torch.empty((2, cap), dtype=torch.int32, device=self.dev)
+            params = torch.zeros((8,), dtype=torch.int32, device=self.dev)
+            ptr = lambda t: C.c_void_p(t.data_ptr())                           # noqa: E731
+            stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(L.pvk_segment_resolve(ptr(allv), world, K, g, ptr(scratch[0]), cap, ptr(scratch[1]), ptr(params),
+                                             stream), "pvk_segment_resolve")
+            own = tid_local[own0:own0 + nown].contiguous()
+            _lib.check(L.pvk_segment_rename_push(ptr(own), own.numel(), ptr(scratch[1]), ptr(params),
+                                                 C.c_void_p(int(hdl.buffer_ptrs_dev)), world, plan["j0"] * K, stream),
+                       "pvk_segment_rename_push")
+            hdl.barrier()                                 # all ranks' stores have landed
+            table = buf.view(world * rows_max, K)[:F]
+            self._keep = (own, scratch)
+            self._params = params
+            self._table = table
+            self._tid_own = table[plan["j0"]:plan["j0"] + nown]
+            self.peer_used = True
+            return True
+        except Exception as e:                            # no symmetric memory here: the NCCL path runs
+            if not _PEER_TABLES.get("warned"):
+                _PEER_TABLES["warned"] = True
+                sys.stderr.write("pypevoc_b200: PVK_PEER_GATHER=1 but the peer path is unavailable (%r); "
+                                 "using the NCCL all_gather\n" % (e,))
+            return False
 
     def counts(self):
         """(total number of partials, global index of the last frame holding a point)."""
@@ -336,14 +401,16 @@ class StitchHandle(object):
     @property
     def tid_own(self):
         cur = self._join()
-        self._tid_own.record_stream(cur)
+        if not self.peer_used:                            # (symmetric-memory buffers are not the caching allocator's)
+            self._tid_own.record_stream(cur)
         return self._tid_own
 
     def table(self):
         """int32 [F, K] global ids of every frame (the main stream waits for the gather)."""
         if not self._joined:
             cur = self._join()
-            self._table.record_stream(cur)
+            if not self.peer_used:
+                self._table.record_stream(cur)
             self._joined = True
         return self._table
 

@@ -13,9 +13,11 @@ sys.path.insert(0, ROOT)
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, result_dir, streamed):
+def _worker(rank, world, port, result_dir, streamed, peer=False):
     import torch
     import torch.distributed as dist
+    if peer:
+        os.environ["PVK_PEER_GATHER"] = "1"               # experimental fused rename + gather over peer memory
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -40,13 +42,13 @@ def _worker(rank, world, port, result_dir, streamed):
         st, end = ss.st, ss.end
         f_own = np.array(spv.pv.f[spv.own_rows])
     np.savez(os.path.join(result_dir, "r%d.npz" % rank), w=w, s0=s0, table=table, st=st, end=end, f=f_own,
-             ntracks=ss.ntracks, max_end=ss.max_end, j0=p["j0"], j1=p["j1"])
+             ntracks=ss.ntracks, max_end=ss.max_end, j0=p["j0"], j1=p["j1"], peer_used=bool(ss._h.peer_used))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("streamed", [False, True])
-def test_sharded_pv_over_nccl(tmp_path, streamed):
+@pytest.mark.parametrize("streamed,peer", [(False, False), (True, False), (False, True)])
+def test_sharded_pv_over_nccl(tmp_path, streamed, peer):
     import torch
     import torch.multiprocessing as mp
     world = min(torch.cuda.device_count(), 4)
@@ -61,8 +63,8 @@ def test_sharded_pv_over_nccl(tmp_path, streamed):
     pv0.run_pv()
     ss0 = pv0.toSinSum()
     w0 = ss0.synth(sr, hop)
-    port = 29700 + (os.getpid() % 200) + (50 if streamed else 0)
-    mp.spawn(_worker, args=(world, port, str(tmp_path), streamed), nprocs=world, join=True)
+    port = 29700 + (os.getpid() % 200) + (50 if streamed else 0) + (25 if peer else 0)
+    mp.spawn(_worker, args=(world, port, str(tmp_path), streamed, peer), nprocs=world, join=True)
     sig = np.zeros_like(w0)
     covered = 0
     for r in range(world):
@@ -76,3 +78,5 @@ def test_sharded_pv_over_nccl(tmp_path, streamed):
         covered += len(w)
     assert covered == len(w0)
     assert np.array_equal(sig, w0)
+    if peer:                                               # falls back to NCCL (with a warning) where unavailable
+        print("peer-memory gather used:", bool(z["peer_used"]))
