@@ -2,6 +2,7 @@
 
     python tests/fuzz_emu.py track <seed> <cases>       link / scan / resolve kernels vs orc.track
     python tests/fuzz_emu.py analyze <seed> <cases>     analysis kernel vs the oracle run on the kernel's own spectrum
+    python tests/fuzz_emu.py synth <seed> <cases>       pack + resynthesis kernels vs orc.synth (random hop, edge, minframes)
 
 tests/test_fuzz_cpu.py runs a short, fixed-seed slice of both.  Known, documented non-bugs are left
 out of the generators: simultaneous exact ties of magnitude AND distance in one frame (the reference
@@ -75,6 +76,41 @@ def analyze_case(rng, lognfft=(6, 12)):
     return x, int(rng.choice([8000, 22050, 44100])), nfft, hop, npks, th, int(rng.choice([0, 1, 2, 3]))
 
 
+def synth_case(rng):
+    f, mag, _ = track_case(rng)
+    reps = int(rng.randint(1, 5))                           # longer tables so that partials reach minframes
+    f = np.concatenate([f * (1 + 0.001 * r) for r in range(reps)])
+    mag = np.concatenate([mag] * reps)
+    F, K = f.shape
+    ph = rng.uniform(-np.pi, np.pi, (F, K))
+    realph = ph + rng.uniform(-0.5, 0.5, (F, K))
+    nfft = int(rng.choice([256, 512, 1024, 2048]))
+    hop_an = nfft // int(rng.choice([1, 2, 4, 8]))
+    hop = int(rng.choice([hop_an, hop_an, max(hop_an // 2, 8), hop_an + 37, 64, 200]))
+    sr = int(rng.choice([8000, 22050, 44100]))
+    f = f * min(1.0, 0.45 * sr / max(f.max(), 1.0))
+    return dict(f=f, mag=mag, ph=ph, realph=realph, nfft=nfft, hop_an=hop_an, hop=hop, sr=sr,
+                edge=float(rng.choice([1.0, 1.0, 0.5, 0.25, 2.0])), minframes=int(rng.choice([3, 3, 1, 2, 5])))
+
+
+def check_synth(eh, orc, pu, c):
+    tr = eh.track(c["f"], c["mag"])
+    ref = orc.track(c["f"], c["mag"])
+    assert np.array_equal(tr["tid"][0], ref["tid"])
+    nt = int(tr["ntracks"][0])
+    if nt == 0:
+        return
+    pk = eh.track_pack(c["f"], c["mag"], c["ph"], c["realph"], tr["tid"][0], tr["link"][0], nt)
+    parts = orc.partials_from_tracks(ref, c["f"], c["mag"], c["ph"], c["realph"])
+    w = eh.resynth(tr["tid"][0], pk, c["sr"], c["hop"], c["nfft"], c["hop_an"], edge=c["edge"], minframes=c["minframes"])
+    r = orc.synth(parts, c["sr"], c["hop"], c["nfft"], c["hop_an"], edge=c["edge"], minframes=c["minframes"])
+    assert w.shape == r.shape, (w.shape, r.shape)
+    if np.any(r):
+        assert pu.snr_db(w, r) > 100.0
+    else:
+        assert not np.any(w)
+
+
 def check_track(eh, orc, case):
     f, mag, mj = case
     return np.array_equal(eh.track(f, mag, maxpitchjmp=mj)["tid"][0], orc.track(f, mag, maxpitchjmp=mj)["tid"])
@@ -105,6 +141,13 @@ if __name__ == "__main__":
             if not check_track(eh, orc, c):
                 bad += 1
                 print("MISMATCH case", it, "K", c[0].shape[1], "maxpitchjmp", c[2])
+        elif what == "synth":
+            c = synth_case(rng)
+            try:
+                check_synth(eh, orc, pu, c)
+            except AssertionError as e:
+                bad += 1
+                print("MISMATCH case", it, {k: v for k, v in c.items() if np.isscalar(v)}, str(e)[:160])
         else:
             c = analyze_case(rng)
             try:

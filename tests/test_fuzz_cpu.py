@@ -1,6 +1,7 @@
 """CPU: a fixed-seed slice of the randomized kernel-vs-oracle comparisons of tests/fuzz_emu.py
 (emulator build of the CUDA sources): every link kernel + id resolution against the oracle's
-sequential greedy loop, the analysis kernel against the oracle on its own spectrum."""
+sequential greedy loop, the analysis kernel against the oracle on its own spectrum, pack +
+resynthesis against orc.synth over random hop / edge / minframes."""
 import os
 import sys
 
@@ -31,3 +32,10 @@ def test_fuzz_analysis_kernel():
     for it in range(40):
         case = fz.analyze_case(rng, lognfft=(6, 11))
         fz.check_analyze(eh, orc, pu, case)
+
+
+def test_fuzz_pack_and_resynthesis_kernels():
+    eh.build()
+    rng = np.random.RandomState(2026)
+    for it in range(30):
+        fz.check_synth(eh, orc, pu, fz.synth_case(rng))
