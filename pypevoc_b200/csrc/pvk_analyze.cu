@@ -60,9 +60,14 @@ struct AParams {
 #ifndef PVK_CKEY
 #define PVK_CKEY 0
 #endif
+// PVK_MINB(T): minimum resident CTAs per SM the analysis kernel is compiled for (register budget)
+#ifndef PVK_MINB
+#define PVK_MINB(T) (512 / (T))
+#endif
 
 template <int LOGM> struct Plan {
   static constexpr int M = 1 << LOGM;
+  // (at most 512 threads = 16 warps per CTA: the per-warp reduction slots of Smem are sized for that)
   static constexpr int LOGT = LOGM <= 8 ? 5 : (LOGM <= 9 ? 6 : (LOGM <= 10 ? 6 : LOGM - 4) + PVK_TSHIFT);
   static constexpr int T = 1 << LOGT;
   static constexpr int LP0 = LOGM - LOGT;
@@ -203,37 +208,77 @@ template <int LOGM, int Q> struct Pass {
   }
 };
 
-// complex FFT of the windowed frame, packed z[m] = (x[2m], x[2m+1]); natural order in buf
+// Two consecutive signal samples.  Build knobs, both OFF by default because they measured neutral
+// to slightly negative on B200 (gpurun_out/tune_r2b.txt: 0.482 ms plain vs 0.495-0.500 ms):
+// PVK_STREAM loads past L1 (ld.global.nc.L1::no_allocate, keeps the window / twiddle tables in the
+// small L1 left beside 8 x 26 KB of shared memory); PVK_PREFETCH requests the samples of row r + 1
+// right after the FFT of row r (32 more live registers during the peak picking).
+__device__ __forceinline__ float2 ldg_stream2(const float *p, bool al8) {
+#if defined(PVK_EMU) || !defined(PVK_STREAM)
+  if (al8) return __ldg(reinterpret_cast<const float2 *>(p));
+  return make_float2(__ldg(p), __ldg(p + 1));
+#else
+  float2 v;
+  if (al8) {
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  } else {
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v.x) : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v.y) : "l"(p + 1));
+  }
+  return v;
+#endif
+}
+
+// samples of one frame -> registers: thread `tid` gets the packed points z[m] = (x[2m], x[2m+1]),
+// m = tid + r * NBF, that its first butterfly needs (raw samples, the window is applied by
+// fft_frame_regs).  Issued one phase ahead of the FFT that consumes them (analyze_kernel).
+template <int LOGM>
+__device__ __forceinline__ void frame_load(const float *__restrict__ xf, float2 *u) {
+  using P = Plan<LOGM>;
+  constexpr int M = P::M, T = P::T;
+  constexpr int LR = P::lr(0), R = 1 << LR;
+  constexpr int NBF = M >> LR;
+  static_assert(NBF <= T, "one first-pass butterfly per thread");
+  const int i = threadIdx.x;
+  const bool al8 = ((reinterpret_cast<uintptr_t>(xf) & 7) == 0);
+  if (NBF >= T || i < NBF) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) u[r] = ldg_stream2(xf + 2 * (i + r * NBF), al8);
+  }
+}
+
+// complex FFT of the windowed frame held in u[] (frame_load), packed z[m] = (x[2m], x[2m+1]);
+// natural order in buf
+template <int LOGM>
+__device__ __forceinline__ void fft_frame_regs(float2 *u, const float *__restrict__ win,
+                                               const float2 *__restrict__ twp, const float2 *treg, float2 *buf) {
+  using P = Plan<LOGM>;
+  constexpr int M = P::M, T = P::T;
+  constexpr int LR = P::lr(0), R = 1 << LR;
+  constexpr int NBF = M >> LR;
+  const int i = threadIdx.x;
+  if (NBF >= T || i < NBF) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float2 wv = __ldg(reinterpret_cast<const float2 *>(win) + i + r * NBF);
+      u[r] = make_float2(u[r].x * wv.x, u[r].y * wv.y);
+    }
+    dft_dif<LR>(u);
+#pragma unroll
+    for (int s = 0; s < R; ++s) buf[PADC(i * R + s)] = u[brev<LR>(s)];
+  }
+  __syncthreads();
+  if constexpr (P::NPASS > 1) Pass<LOGM, 1>::run(twp, treg, buf);
+}
+
 template <int LOGM>
 __device__ __forceinline__ void fft_frame(const float *__restrict__ xf, bool al8,
                                           const float *__restrict__ win,
                                           const float2 *__restrict__ twp, const float2 *treg, float2 *buf) {
-  using P = Plan<LOGM>;
-  constexpr int M = P::M, T = P::T;
-  constexpr int LR = P::lr(0), R = 1 << LR;
-  constexpr int NBF = M >> LR, NB = (NBF + T - 1) / T;
-  const int tid = threadIdx.x;
-#pragma unroll
-  for (int b = 0; b < NB; ++b) {
-    const int i = tid + b * T;
-    if (NBF >= T || i < NBF) {
-      float2 u[R];
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const int m = i + r * NBF;
-        float2 xv;
-        if (al8) xv = __ldg(reinterpret_cast<const float2 *>(xf) + m);
-        else { xv.x = __ldg(xf + 2 * m); xv.y = __ldg(xf + 2 * m + 1); }
-        const float2 wv = __ldg(reinterpret_cast<const float2 *>(win) + m);
-        u[r] = make_float2(xv.x * wv.x, xv.y * wv.y);
-      }
-      dft_dif<LR>(u);
-#pragma unroll
-      for (int s = 0; s < R; ++s) buf[PADC(i * R + s)] = u[brev<LR>(s)];
-    }
-  }
-  __syncthreads();
-  if constexpr (P::NPASS > 1) Pass<LOGM, 1>::run(twp, treg, buf);
+  (void)al8;
+  float2 u[1 << Plan<LOGM>::lr(0)];
+  frame_load<LOGM>(xf, u);
+  fft_frame_regs<LOGM>(u, win, twp, treg, buf);
 }
 
 // ------------------------------------------------------------------ per-peak epilogue
@@ -242,11 +287,10 @@ struct PeakVals { double f, mag, ph, realph; };
 // np.angle(fx[k]) and dphase2freq(np.angle((fx/oldfft)[k]), k): PVAnalysis.py:188-191 +
 // :133-147, in fp64 and in the reference's operation order (explicit _rn intrinsics: no FMA
 // contraction where rounding decides ties).  bf = freq, bdf = fbin[k] - freq.
-__device__ __forceinline__ void peak_phase_freq(int k, const float2 *cur, const float2 *prev,
-                                                const double *__restrict__ fbin,
-                                                const double *__restrict__ wfbin, double dt, double inv,
-                                                double step, double &thisph, double &bf, double &bdf) {
-  const float2 c = cur[PADC(k)], p = prev[PADC(k)];
+__device__ __forceinline__ void peak_phase_freq_exact(float2 c, float2 p, int k,
+                                                      const double *__restrict__ fbin,
+                                                      const double *__restrict__ wfbin, double dt, double inv,
+                                                      double step, double &thisph, double &bf, double &bdf) {
   const double re = c.x, im = c.y, ore = p.x, oim = p.y;
   thisph = atan2(im, re);                                    // np.angle(fx[nbin]) :188
   // frat = fx / oldfft (:171): numpy's complex128 division (Smith), incl. the x/0 case.  Only the
@@ -300,21 +344,77 @@ __device__ __forceinline__ void peak_phase_freq(int k, const float2 *cur, const 
   }
 }
 
+__device__ __forceinline__ void peak_phase_freq(int k, const float2 *cur, const float2 *prev,
+                                                const double *__restrict__ fbin,
+                                                const double *__restrict__ wfbin, double dt, double inv,
+                                                double step, double &thisph, double &bf, double &bdf) {
+  peak_phase_freq_exact(cur[PADC(k)], prev[PADC(k)], k, fbin, wfbin, dt, inv, step, thisph, bf, bdf);
+}
+
+// out-of-line copy of the exact path for analyze_kernel's rare cases (keeps its registers off the hot path)
+__device__ __noinline__ void peak_phase_freq_slow(float2 c, float2 p, int k, const double *__restrict__ fbin,
+                                                  const double *__restrict__ wfbin, double dt, double inv,
+                                                  double step, double *out3) {
+  double thisph, bf, bdf;
+  peak_phase_freq_exact(c, p, k, fbin, wfbin, dt, inv, step, thisph, bf, bdf);
+  out3[0] = thisph; out3[1] = bf; out3[2] = bdf;
+}
+
+// The same three results on the fp32 pipes: the spectrum is an fp32 FFT (relative error ~1e-7), so
+// the two angles are taken with atan2f (<= 2 ulp, ~3e-7 rad; north-star tolerance 1e-4 rad) -- the
+// angle of the quotient fx/oldfft as the angle of fx * conj(oldfft).  Everything that DECIDES
+// something still follows the reference exactly: whenever the unwrap candidates are within
+// 1e-5 of a tie (fp32 moves a candidate by ~5e-8 of their spacing), the frequency is within 1e-4
+// frame rates of zero (the freq > 0 filter, :193), or the previous bin is zero / the product under-
+// or overflows (numpy's x/0 semantics), the exact fp64 path above is taken instead.
+__device__ __forceinline__ void peak_phase_freq_fast(int k, const float2 *cur, const float2 *prev,
+                                                     const double *__restrict__ fbin,
+                                                     const double *__restrict__ wfbin, double dt, double inv,
+                                                     double step, double &thisph, double &bf, double &bdf) {
+  const float2 c = cur[PADC(k)], p = prev[PADC(k)];
+  const float qr = fmaf(c.x, p.x, c.y * p.y), qi = fmaf(c.y, p.x, -(c.x * p.y));
+  const float qn = fabsf(qr) + fabsf(qi);
+  bool ok = qn > 1e-30f && qn < 1e30f;                        // false for NaN / inf / 0 as well
+#ifdef PVK_EPI_EXACT
+  ok = false;
+#endif
+  const double PI2 = 6.283185307179586;
+  const double fb = __ldg(fbin + k);
+  if (ok) {
+    const double base = (double)atan2f(qi, qr) + __ldg(wfbin + k);   // :140
+    const double e1 = fb - base * inv;                        // df of m = 1; m = 0 / 2 are +- step away
+    const double a0 = fabs(e1 + step), a1 = fabs(e1), a2 = fabs(e1 - step);
+    const int best = a0 <= a1 ? (a0 <= a2 ? 0 : 2) : (a1 <= a2 ? 1 : 2);
+    const double lo = fmin(a0, fmin(a1, a2));
+    const double second = best == 0 ? fmin(a1, a2) : (best == 1 ? fmin(a0, a2) : fmin(a0, a1));
+    bf = (base + (best == 0 ? -PI2 : (best == 1 ? 0.0 : PI2))) * inv;   // :142
+    bdf = fb - bf;                                            // :144
+    ok = (second - lo) > 1e-5 * step && fabs(bf) > 1e-4 * step;
+    thisph = (double)atan2f(c.y, c.x);                        // :188
+  }
+  if (!ok) {
+    double o3[3];
+    peak_phase_freq_slow(c, p, k, fbin, wfbin, dt, inv, step, o3);
+    thisph = o3[0]; bf = o3[1]; bdf = o3[2];
+  }
+}
+
 // PVAnalysis.py:188-207 for the peak at bin k (1 <= k <= M-2)
 __device__ __forceinline__ bool peak_epilogue(int k, int M, const float2 *cur, const float2 *prev,
                                               const float *famp, const double *__restrict__ fbin,
                                               const double *__restrict__ wfbin, double dt, double inv,
-                                              double step, double fstep, PeakVals &o) {
+                                              double step, double pi_fstep, PeakVals &o) {
   double thisph, bf, bdf;
-  peak_phase_freq(k, cur, prev, fbin, wfbin, dt, inv, step, thisph, bf, bdf);
-  // mag = sqrt(sum(famp[max(nbin-1,1) : min(nbin+1,len)+1]**2)), left to right :197-199
-  double s = famp[FA(k)];                                      // famp holds |fx|^2
-  if (k - 1 >= 1) s = (double)famp[FA(k - 1)] + s;
-  if (k + 1 <= M - 1) s = s + (double)famp[FA(k + 1)];
+  peak_phase_freq_fast(k, cur, prev, fbin, wfbin, dt, inv, step, thisph, bf, bdf);
+  // mag = sqrt(sum(famp[max(nbin-1,1) : min(nbin+1,len)+1]**2)), left to right :197-199; famp holds
+  // the fp32 powers |fx|^2, summed and rooted in fp32 (relative error ~2e-7, tolerance 1e-4)
+  float s = famp[FA(k)];
+  if (k - 1 >= 1) s = famp[FA(k - 1)] + s;
+  if (k + 1 <= M - 1) s = s + famp[FA(k + 1)];
   o.f = bf;
-  o.mag = sqrt(s);
+  o.mag = (double)sqrtf(s);
   o.ph = thisph;
-  o.realph = __dadd_rn(thisph, __ddiv_rn(__dmul_rn(3.141592653589793, bdf), fstep));   // :207
+  o.realph = fma(bdf, pi_fstep, thisph);                     // :207 ph + pi*df/fstep
   return bf > 0.0;                                           // :193 (drops nan too)
 }
 
@@ -344,12 +444,12 @@ template <int LOGM> struct Smem {
   static constexpr int OFF_FAMP = OFF_BUF1 + P::MP * 8;
   static constexpr int OFF_CKEY = OFF_FAMP + (P::M + P::M / 4 + 4) * 4;   // candidate keys (compact, bin order)
   static constexpr int OFF_HIST = OFF_CKEY + (PVK_CKEY ? P::M * 4 : 0);
-  static constexpr int OFF_RED = (OFF_HIST + 256 * 4 + 7) / 8 * 8;   // doubles: 8 sums
-  static constexpr int OFF_REDF = OFF_RED + 8 * 8;                   // floats: 8 min, 8 max
-  static constexpr int OFF_REDU = OFF_REDF + 16 * 4;                 // uints: 8 cnt, 8 kmin, 8 kmax
-  static constexpr int OFF_BC = OFF_REDU + 24 * 4;                   // 8 broadcast ints
-  static constexpr int OFF_WS = OFF_BC + 8 * 4;                      // 2 x (2 x 8) warp sums
-  static constexpr int OFF_CBIN = OFF_WS + 32 * 4;                   // candidate bins (uint16, compact)
+  static constexpr int OFF_RED = (OFF_HIST + 256 * 4 + 7) / 8 * 8;   // doubles: one sum per warp (<= 16 warps)
+  static constexpr int OFF_REDF = OFF_RED + 16 * 8;                  // floats: 16 min, 16 max
+  static constexpr int OFF_REDU = OFF_REDF + 32 * 4;                 // uints: 16 cnt, 16 kmin, 16 kmax
+  static constexpr int OFF_BC = OFF_REDU + 48 * 4;                   // 8 broadcast ints
+  static constexpr int OFF_WS = OFF_BC + 8 * 4;                      // 2 x (2 x 16) warp sums
+  static constexpr int OFF_CBIN = OFF_WS + 64 * 4;                   // candidate bins (uint16, compact)
   static constexpr int OFF_PK = OFF_CBIN + P::M * 2;                 // 2 x npks uint16
   static int bytes(int npks) { return OFF_PK + 2 * ((npks + 7) / 8 * 8) * 2; }
 };
@@ -372,14 +472,17 @@ __device__ __forceinline__ int round_pos(bool flag, int *wsum, int round, int &b
 }
 
 template <int LOGM>
-__global__ void __launch_bounds__(Plan<LOGM>::T, 512 / Plan<LOGM>::T) analyze_kernel(AParams prm) {
+__global__ void __launch_bounds__(Plan<LOGM>::T, PVK_MINB(Plan<LOGM>::T)) analyze_kernel(AParams prm) {
   using P = Plan<LOGM>;
   using S = Smem<LOGM>;
   constexpr int M = P::M, T = P::T, NW = P::NW, N = 2 * M;
   constexpr int CB = M / T;                                  // contiguous bins per thread in the candidate scan
   PVK_SMEM(smem);
-  float2 *bufs[2] = {reinterpret_cast<float2 *>(smem + S::OFF_BUF0),
-                     reinterpret_cast<float2 *>(smem + S::OFF_BUF1)};
+  // the two spectrum buffers are addressed as smem + parity * stride (not through an array of
+  // pointers): the compiler then keeps the accesses in the shared state space (LDS / STS instead of
+  // generic LD / ST, and no pointer table on the local stack)
+  constexpr int BUF_STRIDE = S::OFF_BUF1 - S::OFF_BUF0;
+#define PVK_BUF(par) reinterpret_cast<float2 *>(smem + S::OFF_BUF0 + (int)(par) * BUF_STRIDE)
   float *famp = reinterpret_cast<float *>(smem + S::OFF_FAMP);
 #if PVK_CKEY
   unsigned *ckey = reinterpret_cast<unsigned *>(smem + S::OFF_CKEY);
@@ -396,7 +499,7 @@ __global__ void __launch_bounds__(Plan<LOGM>::T, 512 / Plan<LOGM>::T) analyze_ke
   unsigned *redu = reinterpret_cast<unsigned *>(smem + S::OFF_REDU);
   int *bc = reinterpret_cast<int *>(smem + S::OFF_BC);
   int *wsA = reinterpret_cast<int *>(smem + S::OFF_WS);
-  int *wsB = wsA + 16;
+  int *wsB = wsA + 32;
   unsigned short *cbin = reinterpret_cast<unsigned short *>(smem + S::OFF_CBIN);
   unsigned short *pk1 = reinterpret_cast<unsigned short *>(smem + S::OFF_PK);
   unsigned short *pk2 = pk1 + (prm.npks + 7) / 8 * 8;
@@ -411,6 +514,7 @@ __global__ void __launch_bounds__(Plan<LOGM>::T, 512 / Plan<LOGM>::T) analyze_ke
   const float2 *twr = prm.tables + P::TW_TOTAL;
   const int K = prm.npks;
   const double inv_2pidt = 1.0 / (prm.dt * 6.283185307179586), inv_dt = 1.0 / prm.dt;
+  const double pi_fstep = 3.141592653589793 / prm.fstep;
 
   float2 treg[P::TWR_TOTAL];
 #if PVK_TWREG
@@ -419,7 +523,7 @@ __global__ void __launch_bounds__(Plan<LOGM>::T, 512 / Plan<LOGM>::T) analyze_ke
 
   // ---- previous spectrum of the first row of this run
   {
-    float2 *pb = bufs[(r0 & 1) ^ 1];
+    float2 *pb = PVK_BUF((r0 & 1) ^ 1);
     if (r0 == 0 && prm.prev_zero) {
       for (int i = tid; i < P::MP; i += T) pb[i] = make_float2(0.f, 0.f);
       __syncthreads();
@@ -447,13 +551,21 @@ __global__ void __launch_bounds__(Plan<LOGM>::T, 512 / Plan<LOGM>::T) analyze_ke
     }
   }
 
+  float2 ux[1 << P::lr(0)];
+#ifdef PVK_PREFETCH
+  if (r0 < r1) frame_load<LOGM>(xc + (prm.frame0 + r0) * (int64_t)prm.hop, ux);
+#endif
   for (int64_t r = r0; r < r1; ++r) {
-    float2 *cur = bufs[r & 1];
-    const float2 *prev = bufs[(r & 1) ^ 1];
+    float2 *cur = PVK_BUF(r & 1);
+    const float2 *prev = PVK_BUF((r & 1) ^ 1);
     const int64_t row = clip * prm.nframes + r;
-    const float *xf = xc + (prm.frame0 + r) * (int64_t)prm.hop;
-    const bool al8 = ((reinterpret_cast<uintptr_t>(xf) & 7) == 0);
-    fft_frame<LOGM>(xf, al8, prm.win, twp, treg, cur);
+#ifndef PVK_PREFETCH
+    frame_load<LOGM>(xc + (prm.frame0 + r) * (int64_t)prm.hop, ux);
+    fft_frame_regs<LOGM>(ux, prm.win, twp, treg, cur);
+#else
+    fft_frame_regs<LOGM>(ux, prm.win, twp, treg, cur);
+    if (r + 1 < r1) frame_load<LOGM>(xc + (prm.frame0 + r + 1) * (int64_t)prm.hop, ux);
+#endif
 
     // ---- untangle -> fx[0..M), |fx|, min / max / sum of squares
     float lmin = 3.402823466e+38f, lmax = 0.f, lsum = 0.f;
@@ -497,15 +609,15 @@ __global__ void __launch_bounds__(Plan<LOGM>::T, 512 / Plan<LOGM>::T) analyze_ke
       const float wmin = __uint_as_float(warp_umin(__float_as_uint(lmin)));
       const float wmax = __uint_as_float(warp_umax(__float_as_uint(lmax)));
       const double wsum = warp_sum((double)lsum);
-      if (lane == 0) { redf[warp] = wmin; redf[8 + warp] = wmax; redd[warp] = wsum; }
+      if (lane == 0) { redf[warp] = wmin; redf[16 + warp] = wmax; redd[warp] = wsum; }
     }
     __syncthreads();
-    float miny = redf[0], ymax = redf[8];
+    float miny = redf[0], ymax = redf[16];
     double sumsq = redd[0];
 #pragma unroll
     for (int w = 1; w < NW; ++w) {
       miny = fminf(miny, redf[w]);
-      ymax = fmaxf(ymax, redf[8 + w]);
+      ymax = fmaxf(ymax, redf[16 + w]);
       sumsq += redd[w];
     }
     // PeakFinder.__init__ :57-70 and findpos :164,174 (miny / ymax are powers here)
@@ -575,7 +687,7 @@ __global__ void __launch_bounds__(Plan<LOGM>::T, 512 / Plan<LOGM>::T) analyze_ke
       kmin = warp_umin(kmin);
       kmax = warp_umax(kmax);
       if (lane == 31) redu[warp] = (unsigned)incl;
-      if (lane == 0) { redu[8 + warp] = kmin; redu[16 + warp] = kmax; }
+      if (lane == 0) { redu[16 + warp] = kmin; redu[32 + warp] = kmax; }
       __syncthreads();
       int pos = incl - cnt;
 #pragma unroll
@@ -583,8 +695,8 @@ __global__ void __launch_bounds__(Plan<LOGM>::T, 512 / Plan<LOGM>::T) analyze_ke
         const int cw = (int)redu[w];
         pos += (w < warp) ? cw : 0;
         C += cw;
-        lo = redu[8 + w] < lo ? redu[8 + w] : lo;
-        hi = redu[16 + w] > hi ? redu[16 + w] : hi;
+        lo = redu[16 + w] < lo ? redu[16 + w] : lo;
+        hi = redu[32 + w] > hi ? redu[32 + w] : hi;
       }
       for (unsigned rem = cbits; rem;) {
         const int i = __ffs((int)rem) - 1;
@@ -691,7 +803,7 @@ __global__ void __launch_bounds__(Plan<LOGM>::T, 512 / Plan<LOGM>::T) analyze_ke
       int k = 0;
       if (p < nk) {
         k = pk[p];
-        valid = peak_epilogue(k, M, cur, prev, famp, prm.fbin, prm.wfbin, prm.dt, inv_2pidt, inv_dt, prm.fstep, v);
+        valid = peak_epilogue(k, M, cur, prev, famp, prm.fbin, prm.wfbin, prm.dt, inv_2pidt, inv_dt, pi_fstep, v);
       }
       const int64_t pos = ob + round_pos<NW>(valid, wsB, round, outbase);
       if (valid) {
@@ -792,8 +904,7 @@ __global__ void __launch_bounds__(Plan<LOGM>::T) harmonic_kernel(HParams prm) {
   using S = Smem<LOGM>;
   constexpr int M = P::M, T = P::T, NW = P::NW;
   PVK_SMEM(smem);
-  float2 *bufs[2] = {reinterpret_cast<float2 *>(smem + S::OFF_BUF0),
-                     reinterpret_cast<float2 *>(smem + S::OFF_BUF1)};
+  constexpr int BUF_STRIDE = S::OFF_BUF1 - S::OFF_BUF0;
   float *famp = reinterpret_cast<float *>(smem + S::OFF_FAMP);
   double *redd = reinterpret_cast<double *>(smem + S::OFF_RED);      // 8 doubles
   double *redc = reinterpret_cast<double *>(smem + S::OFF_CKEY);     // 8 doubles (candidate area is free here)
@@ -808,11 +919,11 @@ __global__ void __launch_bounds__(Plan<LOGM>::T) harmonic_kernel(HParams prm) {
 #if PVK_TWREG
   if constexpr (P::NPASS > 1) Pass<LOGM, 1>::load_tw(twp, treg);
 #endif
-  int cb = 0;                                                 // bufs[cb] = spectrum of the last processed frame
+  int cb = 0;                                                 // PVK_BUF(cb) = spectrum of the last processed frame
   {
     int64_t p = r0 - 1;
     while (p >= 0 && !f0_valid(__ldg(prm.f0 + p))) --p;       // uniform across the CTA
-    float2 *pb = bufs[cb];
+    float2 *pb = PVK_BUF(cb);
     if (p < 0) {
       for (int i = tid; i < P::MP; i += T) pb[i] = make_float2(0.f, 0.f);   // oldfft = zeros (:121)
     } else {
@@ -832,8 +943,8 @@ __global__ void __launch_bounds__(Plan<LOGM>::T) harmonic_kernel(HParams prm) {
       if (tid == 0) { prm.residual[r] = __longlong_as_double(0x7ff8000000000000LL); prm.nharm[r] = 0; }
       continue;
     }
-    float2 *cur = bufs[cb ^ 1];
-    const float2 *prev = bufs[cb];
+    float2 *cur = PVK_BUF(cb ^ 1);
+    const float2 *prev = PVK_BUF(cb);
     const float *xf = prm.x + r * (int64_t)prm.hop;
     const bool al8 = ((reinterpret_cast<uintptr_t>(xf) & 7) == 0);
     fft_frame<LOGM>(xf, al8, prm.win, twp, treg, cur);
