@@ -188,8 +188,11 @@ int pvk_track_stats(const int32_t *tid, const int32_t *ntracks, int64_t nclips, 
                     int npks, int64_t *stats, void *stream);
 
 /* Pack per-track value runs (= RegPartial.f/mag/ph/realph lists, :616-626, with
- * start_idx = tstart, :598) from the frame tables of ONE clip.  ntracks must be the value
- * pvk_track reported.  Outputs: tstart / tlen int32 [ntracks] (= ss.st and
+ * start_idx = tstart, :598) from the frame tables of ONE clip.  ntracks is the value
+ * pvk_track reported -- or any smaller capacity of the index arrays (a pack launched before the
+ * count has been read back): ids >= ntracks are skipped, nothing is written outside
+ * tstart/tlen[0..ntracks), toff[0..ntracks] and the first nframes*npks packed slots, and the
+ * partials below ntracks come out exactly as in a full pack.  Outputs: tstart / tlen int32 [ntracks] (= ss.st and
  * ss.end - ss.st + 1, :827-828,950), toff int64 [ntracks+1] exclusive offsets, packed
  * float64 arrays of length sum(tlen) (pph may be NULL).  workspace: scratch of
  * pvk_track_pack_workspace_bytes(ntracks) bytes. */

@@ -208,11 +208,10 @@ template <int LOGM, int Q> struct Pass {
   }
 };
 
-// Two consecutive signal samples.  Build knobs, both OFF by default because they measured neutral
-// to slightly negative on B200 (gpurun_out/tune_r2b.txt: 0.482 ms plain vs 0.495-0.500 ms):
-// PVK_STREAM loads past L1 (ld.global.nc.L1::no_allocate, keeps the window / twiddle tables in the
-// small L1 left beside 8 x 26 KB of shared memory); PVK_PREFETCH requests the samples of row r + 1
-// right after the FFT of row r (32 more live registers during the peak picking).
+// Two consecutive signal samples.  Build knob PVK_STREAM (off: it measured neutral on B200,
+// profiles/r2_tune_analyze.txt): load past L1 (ld.global.nc.L1::no_allocate), which keeps the window
+// and twiddle tables in the small L1 left beside 8 x 26 KB of shared memory.  Requesting the samples
+// of row r + 1 one phase early (32 more live registers during the peak picking) was neutral too.
 __device__ __forceinline__ float2 ldg_stream2(const float *p, bool al8) {
 #if defined(PVK_EMU) || !defined(PVK_STREAM)
   if (al8) return __ldg(reinterpret_cast<const float2 *>(p));
@@ -367,6 +366,7 @@ __device__ __noinline__ void peak_phase_freq_slow(float2 c, float2 p, int k, con
 // 1e-5 of a tie (fp32 moves a candidate by ~5e-8 of their spacing), the frequency is within 1e-4
 // frame rates of zero (the freq > 0 filter, :193), or the previous bin is zero / the product under-
 // or overflows (numpy's x/0 semantics), the exact fp64 path above is taken instead.
+constexpr double RINT_MAGIC_A = 6755399441055744.0;             // 1.5 * 2^52: (x + M) - M == rint(x)
 __device__ __forceinline__ void peak_phase_freq_fast(int k, const float2 *cur, const float2 *prev,
                                                      const double *__restrict__ fbin,
                                                      const double *__restrict__ wfbin, double dt, double inv,
@@ -382,14 +382,15 @@ __device__ __forceinline__ void peak_phase_freq_fast(int k, const float2 *cur, c
   const double fb = __ldg(fbin + k);
   if (ok) {
     const double base = (double)atan2f(qi, qr) + __ldg(wfbin + k);   // :140
-    const double e1 = fb - base * inv;                        // df of m = 1; m = 0 / 2 are +- step away
-    const double a0 = fabs(e1 + step), a1 = fabs(e1), a2 = fabs(e1 - step);
-    const int best = a0 <= a1 ? (a0 <= a2 ? 0 : 2) : (a1 <= a2 ? 1 : 2);
-    const double lo = fmin(a0, fmin(a1, a2));
-    const double second = best == 0 ? fmin(a1, a2) : (best == 1 ? fmin(a0, a2) : fmin(a0, a1));
-    bf = (base + (best == 0 ? -PI2 : (best == 1 ? 0.0 : PI2))) * inv;   // :142
+    // :141-147 in closed form: the candidates base + 2 pi {-1, 0, 1} are one frame rate (1/dt) apart
+    // in frequency and the one nearest the bin centre wins, i.e. base + 2 pi clamp(rint(t), -1, 1)
+    // with t = df of the middle candidate in frame rates; two candidates tie at |t| = 0.5, where
+    // np.argmin takes the first (left to the exact path)
+    const double t = (fb - base * inv) * dt;
+    const double mr = fmax(-1.0, fmin(1.0, (t + RINT_MAGIC_A) - RINT_MAGIC_A));
+    bf = fma(mr, PI2, base) * inv;                            // :142
     bdf = fb - bf;                                            // :144
-    ok = (second - lo) > 1e-5 * step && fabs(bf) > 1e-4 * step;
+    ok = fabs(fabs(t) - 0.5) > 1e-5 && fabs(bf) > 1e-4 * step;
     thisph = (double)atan2f(c.y, c.x);                        // :188
   }
   if (!ok) {
@@ -521,55 +522,29 @@ __global__ void __launch_bounds__(Plan<LOGM>::T, PVK_MINB(Plan<LOGM>::T)) analyz
   if constexpr (P::NPASS > 1) Pass<LOGM, 1>::load_tw(twp, treg);
 #endif
 
-  // ---- previous spectrum of the first row of this run
-  {
+  // ---- the run starts one row early: row r0 - 1 only leaves its spectrum behind (the "previous"
+  //      spectrum of row r0) and emits nothing -- same code, one copy of the FFT in the instruction
+  //      cache.  Global frame 0 has the all-zero previous spectrum instead (PVAnalysis.py:121).
+  const bool zero_start = (r0 == 0 && prm.prev_zero);
+  if (zero_start) {
     float2 *pb = PVK_BUF((r0 & 1) ^ 1);
-    if (r0 == 0 && prm.prev_zero) {
-      for (int i = tid; i < P::MP; i += T) pb[i] = make_float2(0.f, 0.f);
-      __syncthreads();
-    } else {
-      const int64_t s0 = (prm.frame0 + r0 - 1) * (int64_t)prm.hop;
-      const float *xf = xc + s0;
-      const bool al8 = ((reinterpret_cast<uintptr_t>(xf) & 7) == 0);
-      fft_frame<LOGM>(xf, al8, prm.win, twp, treg, pb);
-      // untangle only (no magnitudes needed)
-      for (int k = tid; k < M / 2; k += T) {
-        if (k == 0) {
-          const float2 z0 = pb[PADC(0)], zh = pb[PADC(M / 2)];
-          pb[PADC(0)] = make_float2(z0.x + z0.y, 0.f);
-          pb[PADC(M / 2)] = make_float2(zh.x, -zh.y);
-        } else {
-          const float2 a = pb[PADC(k)], bq = pb[PADC(M - k)];
-          const float2 e = make_float2(0.5f * (a.x + bq.x), 0.5f * (a.y - bq.y));
-          const float2 o = make_float2(0.5f * (a.y + bq.y), -0.5f * (a.x - bq.x));
-          const float2 wo = cmul(o, __ldg(twr + k));
-          pb[PADC(k)] = make_float2(e.x + wo.x, e.y + wo.y);
-          pb[PADC(M - k)] = make_float2(e.x - wo.x, -(e.y - wo.y));
-        }
-      }
-      __syncthreads();
-    }
+    for (int i = tid; i < P::MP; i += T) pb[i] = make_float2(0.f, 0.f);
+    __syncthreads();
   }
-
-  float2 ux[1 << P::lr(0)];
-#ifdef PVK_PREFETCH
-  if (r0 < r1) frame_load<LOGM>(xc + (prm.frame0 + r0) * (int64_t)prm.hop, ux);
-#endif
-  for (int64_t r = r0; r < r1; ++r) {
+  for (int64_t r = zero_start ? r0 : r0 - 1; r < r1; ++r) {
+    const bool emit = r >= r0;
     float2 *cur = PVK_BUF(r & 1);
     const float2 *prev = PVK_BUF((r & 1) ^ 1);
     const int64_t row = clip * prm.nframes + r;
-#ifndef PVK_PREFETCH
-    frame_load<LOGM>(xc + (prm.frame0 + r) * (int64_t)prm.hop, ux);
-    fft_frame_regs<LOGM>(ux, prm.win, twp, treg, cur);
-#else
-    fft_frame_regs<LOGM>(ux, prm.win, twp, treg, cur);
-    if (r + 1 < r1) frame_load<LOGM>(xc + (prm.frame0 + r + 1) * (int64_t)prm.hop, ux);
-#endif
+    {
+      float2 ux[1 << P::lr(0)];
+      frame_load<LOGM>(xc + (prm.frame0 + r) * (int64_t)prm.hop, ux);
+      fft_frame_regs<LOGM>(ux, prm.win, twp, treg, cur);
+    }
 
     // ---- untangle -> fx[0..M), |fx|, min / max / sum of squares
     float lmin = 3.402823466e+38f, lmax = 0.f, lsum = 0.f;
-    float2 *so = prm.spec_out ? prm.spec_out + row * M : nullptr;
+    float2 *so = (prm.spec_out && emit) ? prm.spec_out + row * M : nullptr;
     constexpr int UI = (M / 2) / T;                            // pairs per thread (0: fewer pairs than threads)
 #pragma unroll
     for (int it = 0; it < (UI > 0 ? UI : 1); ++it) {
@@ -612,6 +587,7 @@ __global__ void __launch_bounds__(Plan<LOGM>::T, PVK_MINB(Plan<LOGM>::T)) analyz
       if (lane == 0) { redf[warp] = wmin; redf[16 + warp] = wmax; redd[warp] = wsum; }
     }
     __syncthreads();
+    if (!emit) continue;                                       // warm-up row: only its spectrum is needed
     float miny = redf[0], ymax = redf[16];
     double sumsq = redd[0];
 #pragma unroll

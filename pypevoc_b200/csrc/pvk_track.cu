@@ -938,7 +938,9 @@ __global__ void track_fix_kernel(int32_t *__restrict__ tid, const int32_t *__res
 #define PVK_PACK_STRIP 64
 #endif
 constexpr int PACK_STRIP = PVK_PACK_STRIP;
-__global__ void pack_count_kernel(const int32_t *__restrict__ tid, int64_t F, int K,
+// Ids >= ntracks (the capacity of tstart / tlen: a speculative pack is sized by an upper bound
+// before the real count is known, pv.track_pack_device) are skipped, never written.
+__global__ void pack_count_kernel(const int32_t *__restrict__ tid, int64_t F, int K, int64_t ntracks,
                                   int32_t *__restrict__ tstart, int32_t *__restrict__ tlen) {
   const int64_t nstrips = (F + PACK_STRIP - 1) / PACK_STRIP;
   const int64_t n = nstrips * K;
@@ -957,14 +959,14 @@ __global__ void pack_count_kernel(const int32_t *__restrict__ tid, int64_t F, in
         if (jb + u < j1) {
           const int v = v8[u];
           if (v != cur) {
-            if (cur >= 0) { atomicAdd(&tlen[cur], cnt); atomicMin(&tstart[cur], (int32_t)first); }
+            if (cur >= 0 && cur < ntracks) { atomicAdd(&tlen[cur], cnt); atomicMin(&tstart[cur], (int32_t)first); }
             cur = v; cnt = 0; first = jb + u;
           }
           ++cnt;
         }
       }
     }
-    if (cur >= 0) { atomicAdd(&tlen[cur], cnt); atomicMin(&tstart[cur], (int32_t)first); }
+    if (cur >= 0 && cur < ntracks) { atomicAdd(&tlen[cur], cnt); atomicMin(&tstart[cur], (int32_t)first); }
   }
 }
 
@@ -977,6 +979,7 @@ __global__ void pack_count_kernel(const int32_t *__restrict__ tid, int64_t F, in
 __global__ void pack_scatter_tiled_kernel(const double *__restrict__ f, const double *__restrict__ mag,
                                           const double *__restrict__ ph, const double *__restrict__ realph,
                                           const int32_t *__restrict__ tid, int64_t F, int K, int ROWS,
+                                          int64_t ntracks, int64_t npts_cap,
                                           const int32_t *__restrict__ tstart, const int64_t *__restrict__ toff,
                                           double *__restrict__ pf, double *__restrict__ pmag,
                                           double *__restrict__ pph, double *__restrict__ prealph) {
@@ -994,7 +997,10 @@ __global__ void pack_scatter_tiled_kernel(const double *__restrict__ f, const do
     for (int e = t; e < n; e += T) {
       const int r = e / K, c = e - r * K;
       const int v = tid[base + e];
-      pos[r * KP + c] = v >= 0 ? (int32_t)(toff[v] + (j0 + r - tstart[v])) : -1;
+      // ids beyond the capacity of the index arrays and positions beyond the packed arrays are dropped
+      int64_t q = -1;
+      if (v >= 0 && v < ntracks) { q = toff[v] + (j0 + r - tstart[v]); if (q >= npts_cap) q = -1; }
+      pos[r * KP + c] = (int32_t)q;
     }
     const double *src[4] = {f, mag, ph, realph};
     double *dst[4] = {pf, pmag, pph, prealph};
@@ -1208,7 +1214,7 @@ extern "C" int pvk_track_spans(const int32_t *tid, int64_t nframes, int npks, in
   if (nframes == 0) return PVK_OK;
   PVK_REQUIRE(tid != nullptr, "pvk_track_spans: tid is NULL");
   PVK_LAUNCH(pack_count_kernel, dim3(grid_for((nframes + PACK_STRIP - 1) / PACK_STRIP * npks, 128)), dim3(128), 0,
-             stream, tid, nframes, npks, tstart, tlen);
+             stream, tid, nframes, npks, ntracks, tstart, tlen);
   PVK_CHECK_LAUNCH("pvk_track_spans");
   return PVK_OK;
 }
@@ -1253,7 +1259,7 @@ extern "C" int pvk_track_pack(const double *f, const double *mag, const double *
   cudaMemsetAsync(tlen, 0, 4 * (size_t)ntracks, (cudaStream_t)stream);
   cudaMemsetAsync(tstart, 0x7f, 4 * (size_t)ntracks, (cudaStream_t)stream);   // 0x7f7f7f7f: "no frame yet"
   PVK_LAUNCH(pack_count_kernel, dim3(grid_for((nframes + PACK_STRIP - 1) / PACK_STRIP * npks, 128)), dim3(128), 0,
-             stream, tid, nframes, npks, tstart, tlen);
+             stream, tid, nframes, npks, ntracks, tstart, tlen);
   PVK_CHECK_LAUNCH("pvk_track_pack(count)");
   {
     const int64_t nt = scan_tiles(ntracks);
@@ -1277,7 +1283,7 @@ extern "C" int pvk_track_pack(const double *f, const double *mag, const double *
     }
     int64_t g = ntiles < 148 * 16 ? ntiles : 148 * 16;
     PVK_LAUNCH(pack_scatter_tiled_kernel, dim3((unsigned)g), dim3(256), smem, stream, f, mag, ph, realph, tid, nframes,
-               npks, rows, tstart, toff, pf, pmag, pph, prealph);
+               npks, rows, ntracks, n, tstart, toff, pf, pmag, pph, prealph);
   }
   (void)n;
   PVK_CHECK_LAUNCH("pvk_track_pack(scatter)");

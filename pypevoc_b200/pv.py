@@ -1108,7 +1108,10 @@ class SinSum(object):
         if self._trk is None:
             t = self._tables
             if t["f"].shape[0] == 0:
-                self._trk = dict(tid=torch.zeros((0, 1), dtype=torch.int32, device=self._dev), link=None, ntracks=0)
+                # (0, npks): a rank without frames still takes part in the numbering all_gather of a
+                # sharded run with 2*npks + 4 integers like everybody else (dist.StitchHandle)
+                self._trk = dict(tid=torch.zeros((0, int(t["f"].shape[1])), dtype=torch.int32, device=self._dev),
+                                 link=None, ntracks=0)
             else:
                 tr, pk = track_pack_device(t["f"], t["mag"], t["ph"], t["realph"], self._maxpitchjmp,
                                            after_link=self._after_link)

@@ -47,6 +47,45 @@ def _worker(rank, world, port, result_dir, name):
     dist.destroy_process_group()
 
 
+def _worker_short(rank, world, port, result_dir, name, nrows):
+    """Too few frames to shard (F < 4 * world): rank 0 owns everything, the other ranks contribute
+    empty [0, K] tables -- and still 2K + 4 integers each to the numbering all_gather."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import pv_oracle as orc
+    from pypevoc_b200 import dist as D
+    from golden_util import case_golden
+    g = case_golden(name)
+    K = g["f"].shape[1]
+    nfft, hop = CASE[name]
+    plans = D.plan_segments((nrows - 1) * hop + nfft + 1, nfft, hop, world)
+    p = plans[rank]
+    assert plans[0]["nown"] == nrows and all(q["nown"] == 0 for q in plans[1:])
+    f = np.ascontiguousarray(g["f"][p["w0"]:p["w1"]]).reshape(-1, K)
+    mag = np.ascontiguousarray(g["mag"][p["w0"]:p["w1"]]).reshape(-1, K)
+    tid = orc.track(f, mag)["tid"] if len(f) else np.zeros((0, K), dtype=np.int32)
+    st = D.stitch(torch.from_numpy(tid), p, plans)
+    _, finish = D.gather_track_table(st["tid_own"], plans, async_op=False)
+    np.savez(os.path.join(result_dir, "r%d.npz" % rank), tid=finish().numpy(), ntracks=st["ntracks"], max_end=st["max_end"])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_stitch_unsharded_plan_with_empty_ranks(tmp_path):
+    from oracle import pv_oracle as orc
+    from golden_util import case_golden
+    world, name, nrows = 3, "cfg3_clip", 9
+    port = 29650 + (os.getpid() % 200)
+    mp.spawn(_worker_short, args=(world, port, str(tmp_path), name, nrows), nprocs=world, join=True)
+    g = case_golden(name)
+    ref = orc.track(g["f"][:nrows], g["mag"][:nrows])
+    for r in range(world):
+        z = np.load(os.path.join(str(tmp_path), "r%d.npz" % r))
+        assert np.array_equal(z["tid"], ref["tid"]), r
+        assert int(z["ntracks"]) == len(ref["st"]) and int(z["max_end"]) == int(np.max(ref["end"]))
+
+
 @pytest.mark.parametrize("world,name", [(2, "cfg3_clip"), (3, "cfg3_clip"), (2, "metric_1s")])
 def test_stitch_matches_unsharded_tracking(tmp_path, world, name):
     from golden_util import case_golden

@@ -172,3 +172,44 @@ def test_emu_large_row_link_kernel(K, mode):
     ref = orc.track(f, mag)
     assert np.array_equal(tr["tid"][0], ref["tid"])
     assert int(tr["ntracks"][0]) == int(ref["tid"].max()) + 1
+
+
+def test_emu_pack_respects_capacity():
+    """A pack sized for fewer partials than the table holds (the speculative pack of
+    pv.track_pack_device above its cap) writes nothing out of bounds and packs the partials below
+    the capacity exactly as a full pack does (ids were not bound-checked)."""
+    import ctypes as C
+    rng = np.random.RandomState(5)
+    F, K = 70, 12
+    f = np.zeros((F, K)); mag = np.zeros((F, K))
+    for j in range(F):                                        # many short partials: births in most frames
+        n = rng.randint(3, K + 1)
+        cols = np.sort(rng.choice(K, n, replace=False))
+        f[j, cols] = np.sort(rng.uniform(100, 8000, n)); mag[j, cols] = rng.uniform(0.1, 1.0, n)
+    ph = rng.uniform(-3, 3, (F, K)); rph = rng.uniform(-3, 3, (F, K))
+    tr = eh.track(f, mag)
+    tid = np.ascontiguousarray(tr["tid"][0])
+    nt = int(tr["ntracks"][0])
+    full = eh.track_pack(f, mag, ph, rph, tid, None, nt)
+    cap = nt // 3
+    assert cap >= 4
+    L = eh.lib()
+    G = 64                                                    # canary elements either side
+    tstart = np.full(cap + 2 * G, -77, dtype=np.int32); tlen = np.full(cap + 2 * G, -77, dtype=np.int32)
+    toff = np.full(cap + 1 + 2 * G, -77, dtype=np.int64)
+    packed = [np.full(F * K + 2 * G, -77.0) for _ in range(4)]
+    wsb = L.pvk_track_pack_workspace_bytes(cap)
+    ws = np.zeros(max(wsb, 8), dtype=np.uint8)
+    at = lambda a: C.c_void_p(a.ctypes.data + G * a.itemsize)  # noqa: E731
+    arrs = [np.ascontiguousarray(a) for a in (f, mag, ph, rph)]
+    eh.check(L.pvk_track_pack(eh.ptr(arrs[0]), eh.ptr(arrs[1]), eh.ptr(arrs[2]), eh.ptr(arrs[3]), eh.ptr(tid), F, K, cap,
+                              at(tstart), at(tlen), at(toff), at(packed[0]), at(packed[1]), at(packed[2]), at(packed[3]),
+                              eh.ptr(ws), int(wsb), None))
+    for a in (tstart, tlen, toff) + tuple(packed):
+        assert np.all(a[:G] == -77) and np.all(a[-G:] == -77)
+    assert np.array_equal(tstart[G:G + cap], full["tstart"][:cap]) and np.array_equal(tlen[G:G + cap], full["tlen"][:cap])
+    assert np.array_equal(toff[G:G + cap + 1], full["toff"][:cap + 1])
+    n = int(full["toff"][cap])
+    for q, k in enumerate(("pf", "pmag", "pph", "prealph")):
+        assert np.array_equal(packed[q][G:G + n], full[k][:n])
+        assert np.all(packed[q][G + n:] == -77)

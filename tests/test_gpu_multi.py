@@ -13,7 +13,18 @@ sys.path.insert(0, ROOT)
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, result_dir, streamed, peer=False):
+def _signal(short):
+    from pypevoc_b200 import signals
+    sr = 44100
+    if short:                                              # 7 frames < 4 * world: rank 0 owns everything
+        return signals.harm(sr, (2048 + 6 * 512 + 100) / float(sr), 220, 90, 0.5, 0.02, 9), sr
+    x = signals.harm(sr, 6.0, 220, 90, 0.5, 0.02, 9)
+    x[int(2.2 * sr):int(2.6 * sr)] = 0.0
+    x[int(5.3 * sr):] = 0.0                               # the signal's last point lies before the last frames
+    return x, sr
+
+
+def _worker(rank, world, port, result_dir, streamed, peer=False, short=False):
     import torch
     import torch.distributed as dist
     if peer:
@@ -22,11 +33,9 @@ def _worker(rank, world, port, result_dir, streamed, peer=False):
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world)
-    from pypevoc_b200 import signals, dist as D
-    sr, nfft, hop, npks = 44100, 2048, 512, 50
-    x = signals.harm(sr, 6.0, 220, 90, 0.5, 0.02, 9)
-    x[int(2.2 * sr):int(2.6 * sr)] = 0.0
-    x[int(5.3 * sr):] = 0.0                               # the signal's last point lies before the last frames
+    from pypevoc_b200 import dist as D
+    nfft, hop, npks = 2048, 512, 50
+    x, sr = _signal(short)
     plans = D.plan_segments(len(x), nfft, hop, world)
     p = plans[rank]
     xl = torch.from_numpy(np.ascontiguousarray(x[p["sample0"]:p["sample0"] + p["nsamp"]]))
@@ -47,26 +56,23 @@ def _worker(rank, world, port, result_dir, streamed, peer=False):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("streamed,peer", [(False, False), (True, False), (False, True)])
-def test_sharded_pv_over_nccl(tmp_path, streamed, peer):
+@pytest.mark.parametrize("streamed,peer,short", [(False, False, False), (True, False, False), (False, True, False),
+                                                 (False, False, True), (False, True, True)])
+def test_sharded_pv_over_nccl(tmp_path, streamed, peer, short):
     import torch
     import torch.multiprocessing as mp
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
         pytest.skip("needs at least 2 GPUs")
-    if peer and os.environ.get("PVK_TEST_PEER") != "1":
-        pytest.skip("experimental peer-memory gather: set PVK_TEST_PEER=1 to run it (unverified on real peers)")
-    from pypevoc_b200 import PV, signals
-    sr, nfft, hop, npks = 44100, 2048, 512, 50
-    x = signals.harm(sr, 6.0, 220, 90, 0.5, 0.02, 9)
-    x[int(2.2 * sr):int(2.6 * sr)] = 0.0
-    x[int(5.3 * sr):] = 0.0
+    from pypevoc_b200 import PV
+    nfft, hop, npks = 2048, 512, 50
+    x, sr = _signal(short)
     pv0 = PV(x, sr, nfft=nfft, hop=hop, npks=npks, progress=False)
     pv0.run_pv()
     ss0 = pv0.toSinSum()
     w0 = ss0.synth(sr, hop)
-    port = 29700 + (os.getpid() % 200) + (50 if streamed else 0) + (25 if peer else 0)
-    mp.spawn(_worker, args=(world, port, str(tmp_path), streamed, peer), nprocs=world, join=True)
+    port = 29700 + (os.getpid() % 200) + (50 if streamed else 0) + (25 if peer else 0) + (12 if short else 0)
+    mp.spawn(_worker, args=(world, port, str(tmp_path), streamed, peer, short), nprocs=world, join=True)
     sig = np.zeros_like(w0)
     covered = 0
     for r in range(world):
