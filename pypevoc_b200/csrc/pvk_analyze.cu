@@ -445,13 +445,14 @@ template <int LOGM> struct Smem {
   static constexpr int OFF_FAMP = OFF_BUF1 + P::MP * 8;
   static constexpr int OFF_CKEY = OFF_FAMP + (P::M + P::M / 4 + 4) * 4;   // candidate keys (compact, bin order)
   static constexpr int OFF_HIST = OFF_CKEY + (PVK_CKEY ? P::M * 4 : 0);
-  static constexpr int OFF_RED = (OFF_HIST + 256 * 4 + 7) / 8 * 8;   // doubles: one sum per warp (<= 16 warps)
+  static constexpr int OFF_RED = (OFF_HIST + 3 * 128 * 4 + 7) / 8 * 8;   // doubles: one sum per warp (<= 16 warps)
   static constexpr int OFF_REDF = OFF_RED + 16 * 8;                  // floats: 16 min, 16 max
   static constexpr int OFF_REDU = OFF_REDF + 32 * 4;                 // uints: 16 cnt, 16 kmin, 16 kmax
   static constexpr int OFF_BC = OFF_REDU + 48 * 4;                   // 8 broadcast ints
   static constexpr int OFF_WS = OFF_BC + 8 * 4;                      // 2 x (2 x 16) warp sums
   static constexpr int OFF_CBIN = OFF_WS + 64 * 4;                   // candidate bins (uint16, compact)
-  static constexpr int OFF_PK = OFF_CBIN + P::M * 2;                 // 2 x npks uint16
+  static constexpr int OFF_SELW = OFF_CBIN + P::M * 2;               // 2 x M/32 ballot words
+  static constexpr int OFF_PK = OFF_SELW + 2 * (P::M / 32) * 4;      // 2 x npks uint16
   static int bytes(int npks) { return OFF_PK + 2 * ((npks + 7) / 8 * 8) * 2; }
 };
 
@@ -494,16 +495,17 @@ __global__ void __launch_bounds__(Plan<LOGM>::T, PVK_MINB(Plan<LOGM>::T)) analyz
 #define PVK_KEY(e) ((cbin[e] & 0x8000) ? 0u : __float_as_uint(famp[FA(cbin[e])]))
 #define PVK_BIN(v) ((v) & 0x7fff)
 #endif
-  int *hist = reinterpret_cast<int *>(smem + S::OFF_HIST);
+  unsigned *hist = reinterpret_cast<unsigned *>(smem + S::OFF_HIST);   // 3 x 128 words (256 16-bit buckets each)
   double *redd = reinterpret_cast<double *>(smem + S::OFF_RED);
   float *redf = reinterpret_cast<float *>(smem + S::OFF_REDF);
   unsigned *redu = reinterpret_cast<unsigned *>(smem + S::OFF_REDU);
-  int *bc = reinterpret_cast<int *>(smem + S::OFF_BC);
   int *wsA = reinterpret_cast<int *>(smem + S::OFF_WS);
   int *wsB = wsA + 32;
   unsigned short *cbin = reinterpret_cast<unsigned short *>(smem + S::OFF_CBIN);
   unsigned short *pk1 = reinterpret_cast<unsigned short *>(smem + S::OFF_PK);
   unsigned short *pk2 = pk1 + (prm.npks + 7) / 8 * 8;
+  unsigned *selw = reinterpret_cast<unsigned *>(smem + S::OFF_SELW);   // selection / tie ballots, one word per 32 candidates
+  unsigned *tiew = selw + M / 32;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t clip = blockIdx.x / prm.nruns;
@@ -579,6 +581,7 @@ __global__ void __launch_bounds__(Plan<LOGM>::T, PVK_MINB(Plan<LOGM>::T)) analyz
       lmax = fmaxf(lmax, fmaxf(pa, pb));
       lsum += pa + pb;
     }
+    for (int w = tid; w < 3 * 128; w += T) hist[w] = 0u;        // the select's histograms (read after >= 2 barriers)
     {
       // powers are >= 0: their bit patterns order like the values, so one REDUX each
       const float wmin = __uint_as_float(warp_umin(__float_as_uint(lmin)));
@@ -688,39 +691,54 @@ __global__ void __launch_bounds__(Plan<LOGM>::T, PVK_MINB(Plan<LOGM>::T)) analyz
     }
     __syncthreads();
 
-    // ---- top-K by (key desc, bin asc): exact radix select of the K-th largest key
-    const unsigned short *sel = cbin;
-    int ns = C;
-    if (C > K) {
-      int rr = K;
-      bool exact_ties = false;
+    // ---- top-K by (key desc, bin asc): exact radix select of the K-th largest key, 8 bits per
+    //      level.  One barrier per level: all threads fill a 256-bucket histogram (16-bit counters,
+    //      two per word), then EVERY warp scans it (same result in each, no broadcast through shared
+    //      memory).  Three histograms rotate; all are zero at this point (cleared during the
+    //      untangle) and level L >= 2 clears the one level L + 1 will use, whose last readers (the
+    //      scans of level L - 2) finished before the barrier of level L - 1.
+    int rr = K;
+    bool exact_ties = false;
+    const bool need_sel = C > K;
+    if (need_sel) {
       for (int level = 0; level < 4; ++level) {
+        unsigned *h = hist + (level % 3) * 128;
         const unsigned range = hi - lo;
         const int bl = 32 - __clz((int)range);
         const int sh = bl > 8 ? bl - 8 : 0;
-        for (int h = tid; h < 256; h += T) hist[h] = 0;
-        __syncthreads();
         for (int e = tid; e < C; e += T) {
           const unsigned key = PVK_KEY(e);
-          if (key >= lo && key <= hi) atomicAdd(&hist[(key - lo) >> sh], 1);
-        }
-        __syncthreads();
-        if (warp == 0) {
-          int c[8], s = 0;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) { c[q] = hist[255 - 8 * lane - q]; s += c[q]; }
-          const int incl = warp_scan_incl(s);
-          int above = incl - s;
-          if (above < rr && rr <= incl) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              if (above < rr && rr <= above + c[q]) { bc[0] = 255 - 8 * lane - q; bc[1] = above; bc[2] = c[q]; }
-              above += c[q];
-            }
+          if (key >= lo && key <= hi) {
+            const unsigned b = (key - lo) >> sh;
+            atomicAdd(&h[b >> 1], 1u << ((b & 1u) * 16u));
           }
         }
+        if (level >= 2) {
+          unsigned *hn = hist + ((level + 1) % 3) * 128;
+          for (int w = tid; w < 128; w += T) hn[w] = 0u;
+        }
         __syncthreads();
-        const int b = bc[0], nabove = bc[1], cb = bc[2];
+        // lane l owns buckets 255 - 8 l - q, q = 0 .. 7 (descending keys) = words 127 - 4 l - j, high half first
+        int c[8], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const unsigned w = h[127 - 4 * lane - j];
+          c[2 * j] = (int)(w >> 16); c[2 * j + 1] = (int)(w & 0xffffu);
+          sum += c[2 * j] + c[2 * j + 1];
+        }
+        const int incl = warp_scan_incl(sum);
+        int above = incl - sum;
+        const bool mine = above < rr && rr <= incl;               // exactly one lane
+        int bq = 0, ab = 0, cq = 0;
+        if (mine) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if (above < rr && rr <= above + c[q]) { bq = 255 - 8 * lane - q; ab = above; cq = c[q]; }
+            above += c[q];
+          }
+        }
+        const int src = __ffs((int)__ballot_sync(FULL, mine)) - 1;
+        const int b = __shfl_sync(FULL, bq, src), nabove = __shfl_sync(FULL, ab, src), cb = __shfl_sync(FULL, cq, src);
         lo = lo + ((unsigned)b << sh);
         const unsigned hi2 = lo + ((1u << sh) - 1u);
         hi = hi2 < hi ? hi2 : hi;
@@ -728,21 +746,74 @@ __global__ void __launch_bounds__(Plan<LOGM>::T, PVK_MINB(Plan<LOGM>::T)) analyz
         if (cb == rr) break;
         if (sh == 0) { exact_ties = true; break; }
       }
-      // selected = key above the boundary bucket, or inside it (only its first rr entries in bin
-      // order when the bucket is a run of exactly equal keys); compacted in bin order into pk1
-      int base = 0, tbase = 0;
-      for (int e0 = 0, round = 0; e0 < C; e0 += T, ++round) {
+    }
+
+    // ---- selected entries, compacted in bin order into pk1.  Selected = key above the boundary
+    //      bucket, or inside it (only its first rr entries in bin order when the bucket is a run of
+    //      exactly equal keys).  Entry e = round * T + tid; the warps' ballots go to shared memory
+    //      (word q = e / 32), ONE barrier, then the position of an entry is the number of set bits
+    //      before it (a warp scan over the words).
+    const unsigned short *sel = cbin;
+    int ns = C;
+    if (need_sel) {
+      constexpr int NCH = (M + 1023) / 1024;                       // chunks of 32 mask words
+      const int nwords = (C + 31) >> 5;
+      // exclusive prefix of the set bits of words[0 .. nwords): value for word q in lane q % 32 of chunk q / 32
+      auto word_prefix = [&](const unsigned *words, int (&excl)[NCH]) -> int {
+        int total = 0;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const int q = c * 32 + lane;
+          const int v = q < nwords ? __popc(words[q]) : 0;
+          const int incl = warp_scan_incl(v);
+          excl[c] = total + incl - v;
+          total += __shfl_sync(FULL, incl, 31);
+        }
+        return total;
+      };
+      auto prefix_of = [&](const int (&excl)[NCH], int q) -> int {
+        int val = 0;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const int t = __shfl_sync(FULL, excl[c], q & 31);
+          if ((q >> 5) == c) val = t;
+        }
+        return val;
+      };
+      unsigned flags = 0, ties = 0;                                // bit j: my entry of round j is selected / a tie
+      for (int e0 = 0, j = 0; e0 < C; e0 += T, ++j) {
         const int e = e0 + tid;
         const unsigned key = e < C ? PVK_KEY(e) : 0u;
         const bool inA = e < C && key > hi;
         const bool inB = e < C && key >= lo && key <= hi;
-        bool s = inA || inB;
-        if (exact_ties) {
-          const int tpos = round_pos<NW>(inB, wsA, round, tbase);
-          s = inA || (inB && tpos < rr);
+        const bool s = inA || (inB && !exact_ties);
+        const unsigned ms = __ballot_sync(FULL, s), mt = __ballot_sync(FULL, inB);
+        if (lane == 0) { selw[(e0 >> 5) + warp] = ms; tiew[(e0 >> 5) + warp] = mt; }
+        if (s) flags |= 1u << j;
+        if (inB) ties |= 1u << j;
+      }
+      __syncthreads();
+      if (exact_ties) {                                            // rare: the first rr ties in bin order join
+        int excl[NCH];
+        word_prefix(tiew, excl);
+        for (int e0 = 0, j = 0; e0 < C; e0 += T, ++j) {
+          const int q = (e0 >> 5) + warp;
+          const int tpos = prefix_of(excl, q) + __popc(tiew[q < nwords ? q : 0] & lanemask_lt());
+          const bool s = ((ties >> j) & 1u) && tpos < rr;
+          const unsigned ms = __ballot_sync(FULL, s);
+          if (lane == 0 && q < nwords) atomicOr(&selw[q], ms);
+          if (s) flags |= 1u << j;
         }
-        const int pos = round_pos<NW>(s, wsB, round, base);
-        if (s) pk1[pos] = PVK_BIN(cbin[e]);
+        __syncthreads();
+      }
+      {
+        int excl[NCH];
+        word_prefix(selw, excl);
+        for (int e0 = 0, j = 0; e0 < C; e0 += T, ++j) {
+          const int q = (e0 >> 5) + warp;
+          const int pos = prefix_of(excl, q) + __popc(selw[q < nwords ? q : 0] & lanemask_lt());
+          if ((flags >> j) & 1u) pk1[pos] = PVK_BIN(cbin[e0 + tid]);
+        }
       }
       sel = pk1;
       ns = K;

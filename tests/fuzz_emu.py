@@ -122,7 +122,7 @@ def check_analyze(eh, orc, pu, case):
     got = {k: o[k][0] for k in ("f", "mag", "ph", "realph", "binno", "totalmag", "npk")}
     oo = orc.analyze(np.zeros(1), sr, nfft=nfft, hop=hop, npks=npks, pkthresh=th, fx_given=o["fx"][0].astype(np.complex64))
     for k in ("ph", "realph"):                               # +-pi on an exactly real negative bin
-        flip = np.abs(np.abs(got[k] - oo[k]) - 2 * np.pi) < 1e-9
+        flip = np.abs(np.abs(got[k] - oo[k]) - 2 * np.pi) < 1e-6
         got[k] = np.where(flip, oo[k], got[k])
     pu.compare_exact_on_spectrum(got, oo)
 
