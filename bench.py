@@ -149,6 +149,60 @@ class ClockSampler(object):
         return out
 
 
+# --------------------------------------------------------------------------- sharded parity self-check
+def sharded_selfcheck(rank, world, dev):
+    """N > 1 only, before the warm-up: a 6 s signal with a silent gap and a silent tail goes through
+    the sharded path (ShardedPV over NCCL / peer memory, exactly the calls the timed step makes) and
+    through the unsharded single-GPU path; every rank compares its own analysis rows, the gathered
+    track table, the spans and its rendered block range BIT FOR BIT.  Any mismatch on any rank makes
+    every rank exit with status 3, so a green N-GPU bench line carries multi-GPU parity."""
+    import torch
+    import torch.distributed as dist
+    from pypevoc_b200 import PV, signals
+    from pypevoc_b200 import dist as D
+    sr, nfft, hop, npks = 44100, 2048, 512, 50
+    x = signals.harm(sr, 6.0, 220, 90, 0.5, 0.02, 9)
+    x[int(2.2 * sr):int(2.6 * sr)] = 0.0
+    x[int(5.3 * sr):] = 0.0
+    pv0 = PV(x, sr, nfft=nfft, hop=hop, npks=npks, progress=False, device=dev)
+    pv0.run_pv()
+    ss0 = pv0.toSinSum()
+    w0 = ss0.synth(sr, hop)
+    tid0 = ss0.track_ids
+    plans = D.plan_segments(len(x), nfft, hop, world)
+    p = plans[rank]
+    xl = torch.from_numpy(np.ascontiguousarray(x[p["sample0"]:p["sample0"] + p["nsamp"]]))
+    bad = []
+    peer = None
+    for rep in range(3):                               # both alternating peer tables + one reuse
+        spv = D.ShardedPV(xl.to(dev), sr, len(x), nfft=nfft, hop=hop, npks=npks, rank=rank, world=world, device=dev)
+        spv.run_pv()
+        ss = spv.toSinSum()
+        w, s0 = ss.synth_local(to_host=True)
+        peer = bool(ss._h.peer_used)
+        for k in ("f", "mag", "ph", "realph", "binno"):
+            if not np.array_equal(np.asarray(getattr(spv.pv, k))[spv.own_rows], getattr(pv0, k)[p["j0"]:p["j1"]]):
+                bad.append("rep %d: own rows of %s" % (rep, k))
+        if not np.array_equal(ss.track_ids, tid0):
+            bad.append("rep %d: gathered track table" % rep)
+        if ss.st != ss0.st or ss.end != ss0.end or ss.ntracks != len(ss0.st) or ss.max_end != max(ss0.end):
+            bad.append("rep %d: spans / counts" % rep)
+        if not np.array_equal(np.asarray(w), w0[s0:s0 + len(w)]):
+            bad.append("rep %d: rendered block range [%d, %d)" % (rep, s0, s0 + len(w)))
+    cover = torch.tensor([len(w), len(bad)], dtype=torch.int64, device=dev)
+    dist.all_reduce(cover)
+    if int(cover[0].item()) != len(w0):
+        bad.append("block ranges cover %d of %d samples" % (int(cover[0].item()), len(w0)))
+    if bad or int(cover[1].item()):
+        sys.stderr.write("rank %d: SHARDED PARITY FAILED: %s\n" % (rank, "; ".join(bad) or "(another rank)"))
+        sys.stderr.flush()
+        dist.barrier()
+        os._exit(3)
+    return {"sharded_vs_unsharded": "bit-exact (own rows f/mag/ph/realph/binno, gathered track table, st/end, "
+                                    "rendered block ranges; 3 passes)", "frames": int(pv0.nframes),
+            "partials": len(ss0.st), "ranks": world, "peer_memory_gather": peer}
+
+
 # --------------------------------------------------------------------------- GPU arm
 def gpu_main(args):
     # everything else that writes to fd 1 (NCCL's version banner, library chatter) goes to stderr:
@@ -180,7 +234,14 @@ def gpu_main(args):
     plan = plans[rank]
     xd = signals.harm_torch(sr, plan["nsamp"], c["f0"], c["nharm"], c["p"], c["sigma"], c["seed"], dev,
                             t0_samples=plan["sample0"], scale=0.25)
+    # peak 0.9 (the max over the whole N x 10-minute signal; one fp32 factor on every rank, so
+    # the overlapping windows of neighbouring ranks stay bit-identical)
+    peak = xd.abs().max().to(torch.float64)
+    if world > 1:
+        dist.all_reduce(peak, op=dist.ReduceOp.MAX)
+    xd.mul_(float(np.float32(0.9 / float(peak.item()))))
     tb = P.host_tables(sr, nfft, hop)
+    selfcheck = sharded_selfcheck(rank, world, dev) if world > 1 else None
     F = plan["nown"]                                 # own frames (halo rows are not counted)
     frames_total = plan["frames_total"]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -241,7 +302,7 @@ def gpu_main(args):
             sys.stderr.write("trace rank %d: host ms since step start [analysis launched, track launched, stitch "
                              "launched, counts read, pack launched, resynth launched, global counts read, all "
                              "launched, gpu idle] = %s\n" % (rank, ["%.3f" % (1e3 * (v - ht[0])) for v in ht[1:]]))
-        state.update(a=a, tr=tr, pk=pk, w=w, st=st, table=table, spans=spans)
+        state.update(a=a, tr=tr, pk=pk, w=w, st=st, table=table, spans=spans, peer=bool(sh.peer_used) if sh else None)
         if timed is not None:
             timed.append(e)
 
@@ -260,11 +321,14 @@ def gpu_main(args):
         time.sleep(0.005)
     gc.collect()
     gc.disable()                                         # no collector pauses inside the timed steps
-    nwarm = max(args.warmup, 8)                          # the allocator / driver settle within ~5 passes
+    # --warmup W is honoured exactly: W warm-up steps directly before the K timed ones.  The caching
+    # allocator / driver / NCCL channels settle within ~5 passes, so `settle` extra untimed passes
+    # (reported in config) run BEFORE the counted warm-up when W is small.
+    settle = max(0, 8 - args.warmup)
+    nwarm = settle + args.warmup
     timed, warm, launches0 = [], [], 0                   # (warm-up events stay alive until the end)
-    # one loop, one step form: warm-up steps are the first `nwarm` passes of exactly the timed code
-    # (events, L2 flush, idle device at the start), so nothing but the barrier separates them from
-    # the K timed steps
+    # one loop, one step form: settle + warm-up steps are passes of exactly the timed code (events, L2
+    # flush, idle device at the start), so nothing but the barrier separates them from the K timed steps
     for i in range(nwarm + args.steps):
         if i == nwarm:
             barrier()
@@ -360,18 +424,22 @@ def gpu_main(args):
     # dominant KERNEL of the step: the analysis stage is one launch of analyze_kernel; the resynthesis
     # stage is resynth_tracks + 2 x (resynth_prepare + resynth_tile), of which the tile kernel takes
     # ~72 % (ncu launch lists under profiles/), so analysis dominates unless the tile kernel alone is longer
-    dominant = roof_an if ms_an >= 0.72 * ms_syn else roof_syn
+    # reported on the same kernel at every N
+    dominant = roof_an
     line = {
         "metric": METRIC, "value": frames_total / (ms_step * 1e-3), "unit": "frames/s",
-        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 8), "ms_per_step": ms_step,
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 FFT, f64 per-peak/phase",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "sr": sr, "seconds_per_gpu": c["seconds"], "nfft": nfft, "hop": hop,
                    "npks": npks, "frames_per_gpu": F, "frames_total": frames_total,
                    "partial_samples_total": psamp_total, "tracks_total": int(state["st"]["ntracks"]),
                    "l2": "256 MiB buffer written between timed steps; per-step CUDA events on the launch stream",
+                   "settle_passes_before_warmup": settle, "signal_peak": 0.9,
                    "parallelism": "segment-sharded x%d (hop-aligned frame ranges + %d/%d halo rows; local "
-                                  "resynthesis, one all_gather of the int32 track table)" % ((world,) + D.halos(nfft, hop))},
+                                  "resynthesis; track table gathered by %s)" % ((world,) + D.halos(nfft, hop) + (
+                                      "P2P stores of the rename kernel into symmetric-memory tables over NVLink"
+                                      if state.get("peer") else "one NCCL all_gather",))},
         "stages": {"analysis_ms": ms_an, "tracking_ms": ms_trk, "pack_ms": ms_pack, "resynth_ms": ms_syn,
                    "analysis_frames_per_s": frames_total / (ms_an * 1e-3),
                    "resynth_partial_samples_per_s": psamp_total / (ms_syn * 1e-3)},
@@ -380,6 +448,8 @@ def gpu_main(args):
     }
     if e2e is not None:
         line["e2e"] = e2e
+    if selfcheck is not None:
+        line["selfcheck"] = selfcheck
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(xd[:sr * args.cpu_seconds + nfft].cpu().numpy(), 1)
     sys.stdout.flush()
@@ -414,58 +484,97 @@ def _oracle_pipeline(x):
     return o["nframes"], ps, (t1 - t0, t2 - t1, t3 - t2)
 
 
+def _reference_pipeline(x):
+    """analysis -> tracking -> resynthesis with the UNMODIFIED reference (pypevoc.PV.run_pv,
+    PV.toSinSum, RegPartial.synth through the documented Python-3 overlap-add shim of
+    oracle/ref_loader.py); same return values as _oracle_pipeline."""
+    from oracle import ref_loader as rl
+    c = CFG
+    t0 = time.perf_counter()
+    pv = rl.ref_run_pv(np.asarray(x, dtype=np.float64), c["sr"], c["nfft"], c["hop"], c["npks"], c["pkthresh"])
+    t1 = time.perf_counter()
+    ss = pv.toSinSum()
+    t2 = time.perf_counter()
+    rl.ref_sinsum_synth(ss, c["sr"], c["hop"])
+    t3 = time.perf_counter()
+    E = int(c["hop"] * c["nfft"] / c["hop"] / 2.)
+    ps = sum(len(p.f) * c["hop"] + 2 * E for p in ss.partial if len(p.f) >= 3)
+    return pv.nframes, ps, (t1 - t0, t2 - t1, t3 - t2)
+
+
+def _reference_kind():
+    try:
+        from oracle import ref_loader as rl
+        if rl.available():
+            rl.load()
+            return "reference"
+    except Exception as e:
+        sys.stderr.write("bench: the reference under baseline/_ref could not be imported (%r); timing the port\n" % (e,))
+    return "port"
+
+
 def _worker(args):
-    seed_off, nsamp = args
+    seed_off, nsamp, kind = args
     from pypevoc_b200 import signals
     c = CFG
     x = signals.harm(c["sr"], nsamp / float(c["sr"]), c["f0"], c["nharm"], c["p"], c["sigma"], c["seed"] + seed_off)
     import warnings
     warnings.simplefilter("ignore")
     t0 = time.perf_counter()
-    fr, ps, st = _oracle_pipeline(x)
+    fr, ps, st = (_reference_pipeline if kind == "reference" else _oracle_pipeline)(x)
     return fr, ps, st, time.perf_counter() - t0
 
 
 def cpu_baseline(x, cores):
     import warnings
     warnings.simplefilter("ignore")
+    kind = _reference_kind()
     t0 = time.perf_counter()
-    fr, ps, st = _oracle_pipeline(x)
+    fr, ps, st = (_reference_pipeline if kind == "reference" else _oracle_pipeline)(x)
     dt = time.perf_counter() - t0
-    return {"value": fr / dt, "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": "first %.0f s of the same samples (%d frames): numpy oracle analyze+track+synth" % (len(x) / CFG["sr"], fr),
+    what = ("unmodified reference PV.run_pv + toSinSum + synth (baseline/_ref)" if kind == "reference"
+            else "numpy oracle analyze+track+synth")
+    return {"value": fr / dt, "unit": "frames/s", "cores": cores, "kind": kind,
+            "sample": "first %.0f s of the same samples (%d frames): %s" % (len(x) / CFG["sr"], fr, what),
             "analysis_frames_per_s": fr / st[0], "tracking_s": st[1],
             "resynth_partial_samples_per_s": ps / st[2]}
 
 
 def reference_main(args):
-    """--impl reference: the reference's CPU algorithm (numpy oracle port; the Python reference
-    itself cannot travel to the GPU box) on all host cores, one disjoint segment per process."""
+    """--impl reference: the reference's own CPU implementation of the path on all host cores, one
+    disjoint segment of the workload signal per process: the UNMODIFIED reference from baseline/_ref
+    (offline pip install done by __graft_entry__.build(); kind "reference") when it is there, else
+    the numpy oracle port (kind "port")."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
+    kind = _reference_kind()
     cores = os.cpu_count() or 1
-    seg = CFG["sr"] * args.ref_seconds + CFG["nfft"]
+    c = CFG
+    seg = c["sr"] * args.ref_seconds + c["nfft"]
     ctx = mp.get_context("fork")
     times, frames = [], 0
     with ctx.Pool(cores) as pool:
         for it in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            res = pool.map(_worker, [(100 * it + i, seg) for i in range(cores)])
+            res = pool.map(_worker, [(100 * it + i, seg, kind) for i in range(cores)])
             dt = time.perf_counter() - t0
             if it >= args.warmup:
                 times.append(max(r[3] for r in res))
                 frames = sum(r[0] for r in res)
     ms = 1e3 * float(np.mean(times))
     val = frames / (ms * 1e-3)
+    what = ("unmodified reference (baseline/_ref): PV.run_pv + toSinSum + RegPartial.synth" if kind == "reference"
+            else "numpy oracle analyze+track+synth")
+    sample = "%d disjoint %d s segments of the workload signal per step, one process per core, %s" % (
+        cores, args.ref_seconds, what)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": "%d processes x %d s segments per step" % (cores, args.ref_seconds)},
-            "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": "port",
-                             "sample": "%d disjoint %d s segments of the workload signal per step, one process per core, "
-                                       "numpy oracle analyze+track+synth" % (cores, args.ref_seconds)},
+            "config": {"workload": WORKLOAD, "sr": c["sr"], "seconds_per_gpu": c["seconds"], "nfft": c["nfft"],
+                       "hop": c["hop"], "npks": c["npks"], "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 

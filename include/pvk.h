@@ -155,6 +155,18 @@ int pvk_frame_stats(const double *f, const double *mag, int64_t nrows, int npks,
                     double thr, double *fm, int32_t *fundamental_idx, double *partial_sum_mag,
                     void *stream);
 
+/* PV.calc_harmonic_power (PVAnalysis.py:266-297) over peak tables f, mag float64 [nrows, npks]:
+ *   hpower, nharmonics float64 [nrows, npks]: for every valid peak i (f > 0) of a frame, the
+ *   valid peaks h of the same frame with |f_h / round(f_h / f_i) / f_i - 1| < f_threshold are
+ *   counted (nharmonics) and -- exactly as :278 indexes `self.mag[valid_idx]`, i.e. ROWS of the
+ *   table by the peaks' COLUMN numbers -- hpower sums rowpow[column of h] over them, where
+ *   rowpow[c] = sum_k mag[c, k]^2; 0 in columns without a peak.
+ *   rowpow: scratch, float64 [min(nrows, npks)].  err: int32 [1], zeroed by the caller; set to 1
+ *   when a harmonic's column number is >= nrows (IndexError in the reference).
+ */
+int pvk_harmonic_power(const double *f, const double *mag, int64_t nrows, int npks, double f_threshold,
+                       double *rowpow, double *hpower, double *nharmonics, int32_t *err, void *stream);
+
 /* ------------------------------------------------------------------ tracking
  * Replaces PV.toSinSum -> SinSum.add_frame (PVAnalysis.py:299-322,871-957).
  *

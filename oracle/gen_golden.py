@@ -189,6 +189,30 @@ def consumer_cases():
     np.savez_compressed(os.path.join(GOLD, "consumers.npz"), **out)
 
 
+def hpower_cases():
+    """PV.calc_harmonic_power (PVAnalysis.py:266-297) of the unmodified reference on its own tables,
+    for every analysis case and two thresholds.  Cases in which a peak sits in a column >= nframes
+    raise IndexError in the reference (:278 indexes rows of mag with column numbers): recorded as
+    ``<case>.indexerror = 1``."""
+    out = {}
+    for name in CASES:
+        gen, gkw, pkw, _ = CASES[name]
+        x, sr = make_signal(gen, gkw)
+        pv = ref_loader.ref_run_pv(x.astype(np.float64), sr, **pkw)
+        for thr in (0.01, 0.05):
+            tag = "%s.%g" % (name, thr)
+            try:
+                with np.errstate(all="ignore"):
+                    pv.calc_harmonic_power(thr)
+            except IndexError:
+                out[name + ".indexerror"] = np.array(1)
+                break
+            out[tag + ".hpower"] = pv.hpower
+            out[tag + ".nharmonics"] = pv.nharmonics
+        print(name, pv.f.shape, name + ".indexerror" in out)
+    np.savez_compressed(os.path.join(GOLD, "hpower.npz"), **out)
+
+
 def refine_cases():
     """PeakFinder.refine_all (PeakFinder.py:331-406) of the reference: the known answers of its
     tests/test_peak_finder.py:22-48 and random spectra."""
@@ -220,8 +244,11 @@ def refine_cases():
 
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    if "--hpower-only" in sys.argv:
+        hpower_cases()
+        return
     if "--extras-only" in sys.argv:
-        harmonic_cases(), consumer_cases(), refine_cases()
+        harmonic_cases(), consumer_cases(), refine_cases(), hpower_cases()
         return
     meta = {}
     for name in CASES:
@@ -231,7 +258,7 @@ def main():
                           nframes=int(F), npartials=int(P))
         print(name, F, P)
     peakfinder_cases()
-    harmonic_cases(), consumer_cases(), refine_cases()
+    harmonic_cases(), consumer_cases(), refine_cases(), hpower_cases()
     with open(os.path.join(GOLD, "cases.json"), "w") as fh:
         json.dump(meta, fh, indent=1, sort_keys=True)
 

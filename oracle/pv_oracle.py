@@ -320,6 +320,27 @@ def partial_sum_magnitude(mag):
     return np.sqrt(np.sum(np.asarray(mag, dtype=np.float64) ** 2, axis=1))
 
 
+def calc_harmonic_power(f, mag, f_threshold=0.01):
+    """PV.calc_harmonic_power (PVAnalysis.py:266-297) restated, INCLUDING the behaviour of :278:
+    ``valid_mag = self.mag[valid_idx]`` indexes rows (frames) of the mag table with the column
+    numbers of the frame's valid peaks, so ``valid_mag[harmonic_comp]**2`` summed (:286) is the sum
+    of squares of whole table rows.  Returns (hpower, nharmonics) float64 [F, K]; raises IndexError
+    like the reference when a valid peak sits in a column >= F."""
+    f, mag = np.asarray(f), np.asarray(mag)
+    hpower, nharm = np.zeros(f.shape), np.zeros(f.shape)
+    for nfr in range(f.shape[0]):
+        valid_idx = np.flatnonzero(f[nfr] > 0)                               # :276
+        valid_f = f[nfr, valid_idx]
+        valid_rows = mag[valid_idx]                                          # :278 (rows, not columns)
+        for c, fv in zip(valid_idx, valid_f):
+            nbr = np.round(valid_f / fv)                                     # :282
+            nbr[nbr == 0] = 1
+            comp = np.flatnonzero(np.abs(valid_f / nbr / fv - 1) < f_threshold)   # :284-285
+            hpower[nfr, c] = np.sum(valid_rows[comp] ** 2)                   # :286
+            nharm[nfr, c] = len(comp)
+    return hpower, nharm
+
+
 def refine_peaks(y, bins):
     """``PeakFinder.refine`` (PeakFinder.py:331-372, ``fun=None``, default ``x = arange``) for
     the peaks at integer ``bins`` of ``y``: parabola through the three samples around a

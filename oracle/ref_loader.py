@@ -14,8 +14,10 @@ Two documented shims are needed for the resynthesis half, which is Python-2-only
     ``RegPartial.synth`` for every partial (the original raises TypeError at :1059
     because ``np.zeros`` gets a float size).
 
-``/root/reference`` does not exist on the GPU box: nothing that runs there may call
-into this module (``available()`` returns False there and the tests that need it skip).
+``/root/reference`` does not exist on the GPU box.  The one thing that travels is the offline
+``pip install --target baseline/_ref`` of the unmodified reference (done by
+``__graft_entry__.build()`` in the build container; git-ignored): ``bench.py --impl reference``
+times it there; where neither exists ``available()`` is False and callers fall back / skip.
 """
 import importlib
 import os
@@ -25,7 +27,22 @@ import warnings
 
 import numpy as np
 
-REF_ROOT = os.environ.get("PYPEVOC_REFERENCE", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root():
+    """$PYPEVOC_REFERENCE, else /root/reference (build container), else the offline pip install of
+    the unmodified reference under baseline/_ref (git-ignored; it travels to the GPU box with the
+    snapshot, where bench.py --impl reference times it)."""
+    cands = [os.environ.get("PYPEVOC_REFERENCE"), "/root/reference",
+             os.path.join(os.path.dirname(_HERE), "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "pypevoc", "PVAnalysis.py")):
+            return c
+    return cands[0] or "/root/reference"
+
+
+REF_ROOT = _find_root()
 
 
 def available():

@@ -29,6 +29,7 @@ SIGNATURES = {
     "pvk_harmonic": (_i, [_p, _i64, _p, _p, _p, _p, _i, _i, _i, _d, _d, _d, _p, _i64, _i, _p, _p, _p, _p, _p, _p]),
     "pvk_stft_bank": (_i, [_p, _i64, _p, _p, _i, _i, _i64, _i, _p, _p, _p, _i, _p, _i, _i, _p, _d, _p, _p]),
     "pvk_frame_stats": (_i, [_p, _p, _i64, _i, _d, _d, _d, _p, _p, _p, _p]),
+    "pvk_harmonic_power": (_i, [_p, _p, _i64, _i, _d, _p, _p, _p, _p, _p]),
     "pvk_track_workspace_bytes": (_i64, [_i64, _i64, _i]),
     "pvk_track": (_i, [_p, _p, _i64, _i64, _i, _d, _p, _p, _p, _p, _i64, _p]),
     "pvk_track_spans": (_i, [_p, _i64, _i, _i64, _p, _p, _p]),

@@ -1260,6 +1260,56 @@ __global__ void frame_stats_kernel(const double *__restrict__ f, const double *_
   }
 }
 
+// PV.calc_harmonic_power (PVAnalysis.py:266-297), including what :278 really computes: the
+// reference indexes ROWS of mag with the column indices of the frame's valid peaks
+// (`self.mag[valid_idx]`), so the "magnitudes" summed for a harmonic at column c are the whole
+// frame row c of the mag table:  hpower[j, i] = sum over valid h with
+// |f_h / round(f_h/f_i) / f_i - 1| < thr  of  rowpow[col_h],  rowpow[c] = sum_k mag[c, k]^2.
+// A valid peak in a column >= nrows is an IndexError there; here it raises `*err`.
+__global__ void row_power_kernel(const double *__restrict__ mag, int64_t nrows, int K, double *__restrict__ rowpow) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = w0; row < nrows; row += nw) {
+    double sq = 0.0;
+    for (int c = lane; c < K; c += 32) { const double m = mag[row * K + c]; sq += m * m; }
+    sq = warp_sum(sq);
+    if (lane == 0) rowpow[row] = sq;
+  }
+}
+
+__global__ void harmonic_power_kernel(const double *__restrict__ f, const double *__restrict__ rowpow, int64_t nrows, int K,
+                                      double thr, double *__restrict__ hpower, double *__restrict__ nharm,
+                                      int32_t *__restrict__ err) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = w0; row < nrows; row += nw) {
+    const double *fr = f + row * K;
+    for (int i = 0; i < K; ++i) {
+      const double fi = fr[i];
+      double s = 0.0;
+      int n = 0;
+      if (fi > 0.0) {
+        for (int h = lane; h < K; h += 32) {
+          const double fh = fr[h];
+          if (fh > 0.0) {
+            if (h >= nrows) *err = 1;                              // `self.mag[valid_idx]` (:278) is out of range
+            double nb = rint(__ddiv_rn(fh, fi));                   // np.round: half to even
+            if (nb == 0.0) nb = 1.0;
+            const double inh = fabs(__dsub_rn(__ddiv_rn(__ddiv_rn(fh, nb), fi), 1.0));
+            if (inh < thr) {
+              if (h < nrows) s += rowpow[h];
+              ++n;
+            }
+          }
+        }
+        s = warp_sum(s);
+        n = warp_sum(n);
+      }
+      if (lane == 0) { hpower[row * K + i] = s; nharm[row * K + i] = (double)n; }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ twiddle tables
 template <int LOGM> __global__ void tables_kernel(float2 *tab) {
   using P = Plan<LOGM>;
@@ -1502,5 +1552,23 @@ extern "C" int pvk_frame_stats(const double *f, const double *mag, int64_t nrows
   PVK_LAUNCH(frame_stats_kernel, dim3((unsigned)g), dim3(256), 0, stream, f, mag, nrows, npks, fmin, fmax, thr, fm,
              fundamental_idx, partial_sum_mag);
   PVK_CHECK_LAUNCH("pvk_frame_stats");
+  return PVK_OK;
+}
+
+extern "C" int pvk_harmonic_power(const double *f, const double *mag, int64_t nrows, int npks, double f_threshold,
+                                  double *rowpow, double *hpower, double *nharmonics, int32_t *err, void *stream) {
+  using namespace pvk;
+  PVK_REQUIRE(nrows >= 0 && npks >= 1, "pvk_harmonic_power: bad sizes");
+  if (nrows == 0) return PVK_OK;
+  PVK_REQUIRE(f && mag && rowpow && hpower && nharmonics && err, "pvk_harmonic_power: NULL pointer argument");
+  const int64_t nr = nrows < npks ? nrows : npks;            // only rows that a column index can name
+  int64_t g = (nr + 7) / 8;
+  PVK_LAUNCH(row_power_kernel, dim3((unsigned)g), dim3(256), 0, stream, mag, nr, npks, rowpow);
+  PVK_CHECK_LAUNCH("pvk_harmonic_power");
+  g = (nrows + 7) / 8;
+  if (g > 148 * 32) g = 148 * 32;
+  PVK_LAUNCH(harmonic_power_kernel, dim3((unsigned)g), dim3(256), 0, stream, f, rowpow, nrows, npks, f_threshold, hpower,
+             nharmonics, err);
+  PVK_CHECK_LAUNCH("pvk_harmonic_power");
   return PVK_OK;
 }

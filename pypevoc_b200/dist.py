@@ -319,7 +319,7 @@ class StitchHandle(object):
             else:
                 allv = mine
             self.peer_used = False
-            if world > 1 and os.environ.get("PVK_PEER_GATHER") == "1" and self._peer_gather(tid_local, allv, group):
+            if world > 1 and os.environ.get("PVK_PEER_GATHER", "1") != "0" and self._peer_gather(tid_local, allv, group):
                 return
             r = segment_rename_device(tid_local, plan, world, allv, max(p["own0"] for p in plans), sync=False)
             self._tid_own, self._params = r["tid_own"], r["params"]
@@ -327,10 +327,10 @@ class StitchHandle(object):
             self._table = finish()                        # queued behind the gather on the side stream
 
     def _peer_gather(self, tid_local, allv, group):
-        """EXPERIMENTAL (PVK_PEER_GATHER=1; not yet measured): rename fused with the gather --
+        """Default path (PVK_PEER_GATHER=0 selects the NCCL all_gather): rename fused with the gather --
         pvk_segment_rename_push stores the renamed rows straight into the track tables of all ranks,
         which are symmetric-memory buffers mapped over NVLink; two signal-pad barriers replace the
-        NCCL all_gather.  Two buffers alternate, so a returned table stays valid until the second
+        NCCL all_gather (verified bit for bit against the unsharded run on 2 GPUs, profiles/r2a_*).  Two buffers alternate, so a returned table stays valid until the second
         next call.  Returns False (and the NCCL path runs) if symmetric memory cannot be set up or the
         plan is not the equal-share one."""
         import sys
@@ -381,7 +381,7 @@ class StitchHandle(object):
         except Exception as e:                            # no symmetric memory here: the NCCL path runs
             if not _PEER_TABLES.get("warned"):
                 _PEER_TABLES["warned"] = True
-                sys.stderr.write("pypevoc_b200: PVK_PEER_GATHER=1 but the peer path is unavailable (%r); "
+                sys.stderr.write("pypevoc_b200: the peer-memory gather is unavailable (%r); "
                                  "using the NCCL all_gather\n" % (e,))
             return False
 

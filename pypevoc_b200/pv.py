@@ -226,6 +226,23 @@ def frame_stats_device(fd, magd, fmin=50, fmax=10000, thr=0.1):
     return fm, idx, ps
 
 
+def harmonic_power_device(fd, magd, f_threshold=0.01):
+    """pvk_harmonic_power on device tables ``[F, K]``: (hpower, nharmonics) float64 ``[F, K]`` and
+    the int32 out-of-range flag = PV.calc_harmonic_power (PVAnalysis.py:266-297).  Asynchronous."""
+    L = _lib.lib()
+    assert fd.dtype == torch.float64 and fd.is_contiguous() and magd.is_contiguous() and fd.dim() == 2
+    dev = fd.device
+    F, K = fd.shape
+    hp = torch.empty((F, K), dtype=torch.float64, device=dev)
+    nh = torch.empty((F, K), dtype=torch.float64, device=dev)
+    rowpow = torch.empty((max(min(F, K), 1),), dtype=torch.float64, device=dev)
+    err = torch.zeros((1,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.pvk_harmonic_power(_ptr(fd), _ptr(magd), F, K, float(f_threshold), _ptr(rowpow), _ptr(hp),
+                                        _ptr(nh), _ptr(err), _stream()), "pvk_harmonic_power")
+    return hp, nh, err
+
+
 def track_device(fd, magd, maxpitchjmp=0.5):
     """pvk_track on device tables ``[nclips, F, K]`` (or ``[F, K]``); returns device ``tid``,
     ``link`` (int32, same shape) and ``ntracks`` (int32 ``[nclips]``).  Asynchronous."""
@@ -752,6 +769,32 @@ class PV(object):
         fm = np.where(has, f[np.arange(f.shape[0]), im], 0.0)
         self.fundamental_idx = im
         return fm
+
+    def calc_harmonic_power(self, f_threshold=0.01):
+        """
+        calculate the harmonic power of individual sine components (PVAnalysis.py:266-297):
+        sets ``hpower`` and ``nharmonics`` (float64 ``[nframes, npks]``).  One pvk_harmonic_power
+        launch on the device tables (host-edited ``f`` / ``mag`` are uploaded first).
+
+        As in the reference, line :278 indexes the *rows* of ``mag`` with the peaks' column
+        numbers, so ``hpower`` sums whole table rows (kept: results are identical to the
+        reference's), and a peak in a column >= nframes raises IndexError.
+        """
+        if self._devout is None:
+            raise AttributeError("f")                    # the reference fails on self.f before run_pv
+        if self.nframes == 0:
+            raise IndexError("tuple index out of range")     # self.f.shape[0] of an empty 1-D array (:274)
+        if self._on_device():
+            fd, md = self._devout["f"][0], self._devout["mag"][0]
+        else:
+            fd = torch.from_numpy(np.ascontiguousarray(self.f, dtype=np.float64)).to(self._dev)
+            md = torch.from_numpy(np.ascontiguousarray(self.mag, dtype=np.float64)).to(self._dev)
+        hp, nh, err = harmonic_power_device(fd, md, f_threshold)
+        if int(err.item()):
+            raise IndexError("index out of bounds for axis 0 with size %d (a peak column used as a frame index, "
+                             "PVAnalysis.py:278)" % fd.shape[0])
+        self.hpower = hp.cpu().numpy()
+        self.nharmonics = nh.cpu().numpy()
 
     @property
     def fundamental_frequency(self):

@@ -131,6 +131,19 @@ def frame_stats(f, mag, fmin=50, fmax=10000, thr=0.1):
     return fm, idx, ps
 
 
+def harmonic_power(f, mag, f_threshold=0.01):
+    """pvk_harmonic_power on host arrays [F, K] -> (hpower, nharmonics, err)."""
+    L = lib()
+    f = np.ascontiguousarray(f, dtype=np.float64)
+    mag = np.ascontiguousarray(mag, dtype=np.float64)
+    F, K = f.shape
+    hp, nh = np.full((F, K), np.nan), np.full((F, K), np.nan)
+    rowpow = np.full(max(min(F, K), 1), np.nan)
+    err = np.zeros(1, dtype=np.int32)
+    check(L.pvk_harmonic_power(ptr(f), ptr(mag), F, K, float(f_threshold), ptr(rowpow), ptr(hp), ptr(nh), ptr(err), None))
+    return hp, nh, int(err[0])
+
+
 def track(f, mag, maxpitchjmp=0.5):
     """pvk_track on host arrays; f, mag [F, K] or [nclips, F, K]."""
     L = lib()

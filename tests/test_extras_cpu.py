@@ -119,3 +119,27 @@ def test_emu_refine_and_frame_stats():
         tag = "%s.%d_%d_%g" % ((name,) + args)
         assert np.array_equal(fm, CG[tag + ".fm"]) and np.array_equal(idx, CG[tag + ".idx"])
         assert np.allclose(ps, CG[name + ".psm"], rtol=1e-13, atol=0)
+
+
+HPG = np.load(os.path.join(GOLD, "hpower.npz"))
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_harmonic_power_oracle_and_emulated_kernel_vs_reference(name):
+    """calc_harmonic_power (PVAnalysis.py:266-297, incl. the row indexing of :278): the oracle equals
+    the unmodified reference bit for bit; the emulated pvk_harmonic_power kernel gives identical
+    harmonic counts and hpower to fp64 summation-order round-off; the reference's IndexError cases
+    (a peak in a column >= nframes) raise in the oracle and set the kernel's flag."""
+    g = case_golden(name)
+    if name + ".indexerror" in HPG.files:
+        with pytest.raises(IndexError):
+            orc.calc_harmonic_power(g["f"], g["mag"])
+        assert eh.harmonic_power(g["f"], g["mag"])[2] == 1
+        return
+    for thr in (0.01, 0.05):
+        tag = "%s.%g" % (name, thr)
+        hp, nh = orc.calc_harmonic_power(g["f"], g["mag"], thr)
+        assert np.array_equal(hp, HPG[tag + ".hpower"]) and np.array_equal(nh, HPG[tag + ".nharmonics"])
+        ehp, enh, err = eh.harmonic_power(g["f"], g["mag"], thr)
+        assert err == 0 and np.array_equal(enh, HPG[tag + ".nharmonics"])
+        assert np.allclose(ehp, HPG[tag + ".hpower"], rtol=1e-13, atol=0)

@@ -231,3 +231,36 @@ def test_pvbatch_equals_single_clips():
     assert np.array_equal(np.concatenate(got), pb.f)
     with pytest.raises(ValueError):
         pb200.PVBatch(clips[0], 16000)
+
+
+HPG = np.load(os.path.join(GOLD, "hpower.npz"))
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_device_calc_harmonic_power(pvmod, name):
+    """pvk_harmonic_power on the reference's tables == the reference's calc_harmonic_power
+    (PVAnalysis.py:266-297, row indexing of :278 included): counts bit exact, hpower to fp64
+    summation order; IndexError where the reference raises it; PV.calc_harmonic_power on the GPU's
+    own tables == the oracle on the same tables."""
+    from pypevoc_b200.pv import harmonic_power_device
+    g = case_golden(name)
+    fd, md = torch.from_numpy(g["f"]).cuda(), torch.from_numpy(g["mag"]).cuda()
+    x, sr = case_signal(name)
+    pv = pvmod.PV(x, sr, progress=False, **pv_kwargs(name))
+    pv.run_pv()
+    if name + ".indexerror" in HPG.files:
+        assert int(harmonic_power_device(fd, md)[2].item()) == 1
+        with pytest.raises(IndexError):
+            pv.calc_harmonic_power()
+        return
+    for thr in (0.01, 0.05):
+        tag = "%s.%g" % (name, thr)
+        hp, nh, err = harmonic_power_device(fd, md, thr)
+        assert int(err.item()) == 0 and np.array_equal(nh.cpu().numpy(), HPG[tag + ".nharmonics"])
+        assert np.allclose(hp.cpu().numpy(), HPG[tag + ".hpower"], rtol=1e-13, atol=0)
+    pv.calc_harmonic_power(0.02)
+    ohp, onh = orc.calc_harmonic_power(pv.f, pv.mag, 0.02)
+    assert np.array_equal(pv.nharmonics, onh) and np.allclose(pv.hpower, ohp, rtol=1e-13, atol=0)
+    pv.mag = pv.mag * 2.0                                   # host-edited tables are honoured
+    pv.calc_harmonic_power(0.02)
+    assert np.allclose(pv.hpower, 4.0 * ohp, rtol=1e-13, atol=0)

@@ -27,8 +27,8 @@ def _signal(short):
 def _worker(rank, world, port, result_dir, streamed, peer=False, short=False):
     import torch
     import torch.distributed as dist
-    if peer:
-        os.environ["PVK_PEER_GATHER"] = "1"               # experimental fused rename + gather over peer memory
+    # peer: fused rename + gather over peer memory (the default); otherwise the NCCL all_gather
+    os.environ["PVK_PEER_GATHER"] = "1" if peer else "0"
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -80,7 +80,10 @@ def test_sharded_pv_over_nccl(tmp_path, streamed, peer, short):
         assert np.array_equal(z["table"], ss0.track_ids), r
         assert z["st"].tolist() == ss0.st and z["end"].tolist() == ss0.end
         assert int(z["ntracks"]) == len(ss0.st) and int(z["max_end"]) == max(ss0.end)
-        assert np.array_equal(z["f"], pv0.f[int(z["j0"]):int(z["j1"])])
+        if int(z["j1"]) > int(z["j0"]):
+            assert np.array_equal(z["f"], pv0.f[int(z["j0"]):int(z["j1"])])
+        else:                                              # a rank without frames: f.shape == (0,) as in the reference
+            assert z["f"].size == 0
         s0, w = int(z["s0"]), z["w"]
         sig[s0:s0 + len(w)] = w
         covered += len(w)
