@@ -110,7 +110,17 @@ struct __align__(16) TrackFade {
 
 constexpr double INV_2PI = 0.15915494309189535;
 constexpr double TWO_PI = 6.283185307179586;
-constexpr double RINT_MAGIC = 6755399441055744.0;                 // 1.5 * 2^52: (x + M) - M == rint(x)
+
+
+// Fractional part of a phase `th` (cycles, |th| < 2^28) as an fp32 angle in [0, 2 pi): adding
+// 1.5 * 2^29 leaves round(th * 2^23) mod 2^23 in the low mantissa bits (exact reduction mod 1, rounded
+// to 2^-23 cycles = 7.5e-7 rad), which become the mantissa of a float in [2^23, 2^24); one DADD, one
+// LOP3 and one FFMA -- no fp64 -> fp32 conversion (a quarter-rate XU instruction next to the MUFUs).
+__device__ __forceinline__ float frac_angle(double th) {
+  const unsigned lo = (unsigned)__double_as_longlong(th + 805306368.0);
+  const float x = __uint_as_float((lo & 0x7fffffu) | 0x4b000000u);
+  return fmaf(x, 7.4901405e-7f, -6.2831855f);                    // (x - 2^23) * 2 pi / 2^23
+}
 
 // body of partial v (nfr frames) inside block b (PVAnalysis.py:701-736), in cycles
 __device__ __forceinline__ void make_body(const RParams &p, int64_t b, int v, int nfr, BodyItem &it) {
@@ -242,8 +252,7 @@ __device__ __forceinline__ void render_bodies(const RParams &p, const BodyItem *
       const float tB = __int_as_float((int)(__double_as_longlong(cw.y) & 0xffffffffLL));
       const float tC2 = __int_as_float((int)(__double_as_longlong(cw.y) >> 32));
       const double th = fma(fma(cw.x, qcd, ab.y), qcd, ab.x);     // cycles at the chunk centre
-      const double fr = th - ((th + RINT_MAGIC) - RINT_MAGIC);    // exact reduction to [-0.5, 0.5]
-      const float t0 = TWO_PI_F * (float)fr;
+      const float t0 = frac_angle(th);                            // exact reduction mod 1 cycle
       const float t1 = fmaf(tC2, qcf, tB);
       const float t2 = 0.5f * tC2;
       const float a0 = fmaf(am.y, qcf, am.x);
@@ -315,7 +324,7 @@ __device__ __forceinline__ void render_fades(const RParams &p, int64_t b, int qs
           // whole chunk inside the fade: linear phase and linear envelope angle in fp32
           const double qcd = (double)(qs + RS / 2);
           const double th = fma(B, qcd, A);
-          const float t0 = TWO_PI_F * (float)(th - ((th + RINT_MAGIC) - RINT_MAGIC));
+          const float t0 = frac_angle(th);
           const float t1 = TWO_PI_F * (float)B;
           const float e1 = 3.14159265358979f * p.einv;
           const float e0 = e1 * (float)(qs + RS / 2 + eoff);
@@ -401,10 +410,14 @@ __global__ void __launch_bounds__(128, 8) resynth_kernel(RParams p) {
 
 // Tile render kernel (hop a multiple of 32*RS): one WARP renders one tile of 32*RS consecutive
 // samples of a block, lane l the samples [l*RS, (l+1)*RS).  No block barrier, no cross-group
-// reduction, block-level scalar work (row lookup, fade scan) done once per tile.  The staged
-// bodies stream through a per-warp shared-memory buffer in batches of 32, the next batch is in
-// flight (registers) while the current one is rendered.  The finished tile is transposed through
-// the same buffer so that the fp64 stores are coalesced.
+// reduction, block-level scalar work (row lookup, fade scan) done once per tile.  The partial
+// bodies are NOT staged in HBM: the warp walks the block's frame row 32 slots at a time, every
+// lane turns the rendered partial of its slot into closed-form coefficients (make_body) and puts
+// them, compacted in slot order (deterministic sum order), into the warp's shared-memory buffer,
+// from which all lanes render them.  The slot ids of the next group are in flight while the current
+// group is rendered; the dependent loads of make_body (track meta -> 9 table values) are hidden by
+// the other resident warps.  The finished tile is transposed through the same buffer so that the
+// fp64 stores are coalesced.
 constexpr int TILE_BATCH = 32;
 constexpr int TILE_WARP_BYTES = TILE_BATCH * (int)sizeof(BodyItem);   // 2560 >= RS * 33 * 4 for RS <= 16
 constexpr int TILE_WARPS = 4;
@@ -413,45 +426,37 @@ template <int RS>
 __global__ void __launch_bounds__(TILE_WARPS * 32, 8) resynth_tile_kernel(RParams p, int64_t ntiles, int tpb) {
   PVK_SMEM(smem);
   constexpr int TILE = 32 * RS;
-  constexpr int V = (int)(sizeof(BodyItem) / 16);                 // int4 per item
   static_assert(RS * 33 * 4 <= TILE_WARP_BYTES, "transpose buffer");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t tile = (int64_t)blockIdx.x * TILE_WARPS + warp;
   if (tile >= ntiles) return;                                     // warp uniform; the kernel has no block barrier
   BodyItem *items = reinterpret_cast<BodyItem *>(smem + warp * TILE_WARP_BYTES);
-  const int h = p.h;
+  const int h = p.h, K = p.K;
   const int64_t b = p.block0 + tile / tpb;
   const int q0 = (int)(tile % tpb) * TILE;
   const int qs = q0 + lane * RS;
-  const int nbody = p.gcount[b - p.chunk0];
-  const int4 *src = reinterpret_cast<const int4 *>(p.gitems + (b - p.chunk0) * p.K);
-  int4 *dst = reinterpret_cast<int4 *>(items);
 
   float acc[RS];
 #pragma unroll
   for (int m = 0; m < RS; ++m) acc[m] = 0.f;
   const bool fast = !(qs < p.qk && p.qk < qs + RS) && !(qs < p.qkm && p.qkm < qs + RS);
 
-  int4 pre[V];
-  {
-    const int n16 = (nbody < TILE_BATCH ? nbody : TILE_BATCH) * V;
-#pragma unroll
-    for (int v = 0; v < V; ++v) { const int i = lane + 32 * v; if (i < n16) pre[v] = src[i]; }
-  }
-  for (int c0 = 0; c0 < nbody; c0 += TILE_BATCH) {
-    const int n = nbody - c0 < TILE_BATCH ? nbody - c0 : TILE_BATCH;
-#pragma unroll
-    for (int v = 0; v < V; ++v) { const int i = lane + 32 * v; if (i < n * V) dst[i] = pre[v]; }
-    __syncwarp();
-    if (c0 + TILE_BATCH < nbody) {
-      const int rest = nbody - c0 - TILE_BATCH;
-      const int n16 = (rest < TILE_BATCH ? rest : TILE_BATCH) * V;
-      const int4 *s2 = src + (c0 + TILE_BATCH) * V;
-#pragma unroll
-      for (int v = 0; v < V; ++v) { const int i = lane + 32 * v; if (i < n16) pre[v] = s2[i]; }
+  if (b < p.F) {
+    const int32_t *trow = p.tid + b * K;
+    int vnext = lane < K ? trow[lane] : -1;
+    for (int c0 = 0; c0 < K; c0 += 32) {
+      const int v = vnext;
+      const int cn = c0 + 32 + lane;
+      vnext = cn < K ? trow[cn] : -1;
+      const int nfr = v >= 0 ? p.tlen[v] : 0;
+      const bool on = v >= 0 && nfr >= p.minframes;               // :1061
+      const unsigned mk = __ballot_sync(FULL, on);
+      if (mk == 0u) continue;                                      // warp uniform
+      if (on) make_body(p, b, v, nfr, items[__popc(mk & lanemask_lt())]);
+      __syncwarp();
+      render_bodies<RS>(p, items, __popc(mk), 0, 1, qs, fast, acc);
+      __syncwarp();
     }
-    render_bodies<RS>(p, items, n, 0, 1, qs, fast, acc);
-    __syncwarp();
   }
   render_fades<RS>(p, b, qs, true, 0, 1, acc);
 
@@ -583,6 +588,12 @@ extern "C" int pvk_resynth(const int32_t *tid, int64_t nframes, int npks, int64_
   p.nchp = nch < bd ? nch : bd;
   p.G = bd / p.nchp;
   if (p.G > npks) p.G = npks;
+  if (hop % 256 == 0) {
+    // tile kernels: bodies are built inside the render kernel, one launch over the whole block range
+    p.chunk0 = block0;
+    return hop % 512 == 0 ? launch_resynth_tile<16>(p, nblocks, stream)      // one warp per 512-sample tile
+                          : launch_resynth_tile<8>(p, nblocks, stream);
+  }
   for (int64_t c0 = block0; c0 < block0 + nblocks; c0 += cb) {
     const int64_t n = (c0 + cb <= block0 + nblocks) ? cb : block0 + nblocks - c0;
     p.chunk0 = c0;
@@ -590,10 +601,7 @@ extern "C" int pvk_resynth(const int32_t *tid, int64_t nframes, int npks, int64_
     p.out = out + (c0 - block0) * (int64_t)hop;
     PVK_LAUNCH(resynth_prepare_kernel, dim3((unsigned)((n + 3) / 4)), dim3(128), 0, stream, p, n, gitems, gcount);
     PVK_CHECK_LAUNCH("pvk_resynth(prepare)");
-    int rc;
-    if (hop % 512 == 0) rc = launch_resynth_tile<16>(p, n, stream);          // one warp per 512-sample tile
-    else if (hop % 256 == 0) rc = launch_resynth_tile<8>(p, n, stream);
-    else rc = RS == 16 ? launch_resynth<16>(p, n, bd, stream) : launch_resynth<8>(p, n, bd, stream);
+    const int rc = RS == 16 ? launch_resynth<16>(p, n, bd, stream) : launch_resynth<8>(p, n, bd, stream);
     if (rc != PVK_OK) return rc;
   }
   return PVK_OK;
