@@ -37,6 +37,12 @@ if ROOT not in sys.path:
 # nfft 2048 and survive the salience filter: ~40 peaks per frame), 10 minutes long
 CFG = dict(sr=44100, seconds=600, nfft=2048, hop=512, npks=50, pkthresh=0.005,
            f0=220.0, nharm=90, p=0.5, sigma=0.01, seed=1)
+# other BASELINE.json configs (`--workload`; auxiliary lines for profiles/, the driver runs the default):
+#   cfg4  configs[3]: ONE 8-hour signal, nfft 2048 / hop 256 / npks 100, segment-sharded: STRONG scaling
+#   cfg3  configs[2]: 4096 speech-like 3 s clips @ 16 kHz, nfft 512 / hop 128 / npks 20, split by clip: STRONG scaling
+CFG4 = dict(sr=44100, seconds=8 * 3600, nfft=2048, hop=256, npks=100, pkthresh=0.005,
+            f0=200.0, nharm=100, p=0.4, sigma=0.01, seed=4000)
+CFG3 = dict(sr=16000, seconds=3, nclips=4096, nfft=512, hop=128, npks=20, pkthresh=0.005)
 METRIC = "STFT frames/sec (nfft=2048,hop=512,npks=50) + resynth partial-samples/sec"
 WORKLOAD = ("10 min mono 44.1 kHz synthetic harmonic tone+noise (configs[1] length; 220 Hz, 90 harmonics, "
             "sigma 0.01), metric parameters nfft=2048 hop=512 npks=50, analysis + tracking + full resynthesis")
@@ -203,6 +209,120 @@ def sharded_selfcheck(rank, world, dev):
             "partials": len(ss0.st), "ranks": world, "peer_memory_gather": peer}
 
 
+# --------------------------------------------------------------------------- clip batch (configs[2])
+def clips_main(args, world, rank, dev, real_stdout):
+    """--workload cfg3: 4096 speech-like clips split by clip over the ranks (dist.clip_range; no halo,
+    no collective): PVBatch.run_pv -> toSinSum (ONE link + pack over the flattened table) ->
+    synth_device (ONE resynthesis launch), device resident.  Strong scaling."""
+    import torch
+    import torch.distributed as dist
+    from pypevoc_b200 import PVBatch, signals
+    from pypevoc_b200 import pv as P
+    from pypevoc_b200 import dist as D
+    from pypevoc_b200 import _lib
+    c = dict(CFG3, nclips=args.cfg3_clips)
+    sr, nfft, hop, npks = c["sr"], c["nfft"], c["hop"], c["npks"]
+    c0, c1 = D.clip_range(c["nclips"], rank, world)
+    # 64 distinct clips tiled to the batch size (numpy generation of 4096 distinct clips takes minutes;
+    # throughput does not depend on it); clip i of the batch = base[i % 64]
+    base = np.stack([signals.speech_like_clip(1000 + i, sr=sr, dur=float(c["seconds"])) for i in range(64)])
+    xd = torch.from_numpy(base).to(dev)[torch.arange(c0, c1, device=dev) % 64].contiguous()
+    pb = PVBatch(xd, sr, nfft=nfft, hop=hop, npks=npks, pkthresh=c["pkthresh"], device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    state = {}
+
+    def step(timed):
+        e = [ev() for _ in range(4)]
+        state.clear()
+        e[0].record()
+        pb.run_pv()
+        e[1].record()
+        ssb = pb.toSinSum()
+        ssb.ss._ensure_packed()                          # link + pack of all clips; one 24-byte read-back
+        e[2].record()
+        w = ssb.synth_device(sr, hop)
+        e[3].record()
+        state.update(ssb=ssb, w=w)
+        timed.append(e)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+    import gc
+    count = _lib.lib().pvk_launch_count
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    t_wait = time.perf_counter()
+    while sampler.thread is not None and len(sampler.samples) < 5 and time.perf_counter() - t_wait < 2.0:
+        time.sleep(0.005)
+    gc.collect()
+    gc.disable()
+    settle = max(0, 5 - args.warmup)
+    nwarm = settle + args.warmup
+    timed, warm, launches0 = [], [], 0
+    for i in range(nwarm + args.steps):
+        if i == nwarm:
+            barrier()
+            del sampler.samples[:]
+            launches0 = int(count())
+        torch.cuda.synchronize()
+        flush.fill_(1)
+        step(timed if i >= nwarm else warm)
+    barrier()
+    launches = int(count()) - launches0
+    clocks = sampler.stop()
+    gc.enable()
+    st = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(3)] for e in timed])
+    sys.stderr.write("rank %d per-step stage ms [analysis, tracking+pack, resynth]:\n%s\n" % (rank, np.round(st, 3)))
+    ssb = state["ssb"]
+    tl = ssb.ss._ensure_packed()["tlen"].cpu().numpy().astype(np.int64)
+    _, E = P.synth_geometry(0, hop, nfft, hop)
+    F = pb.nframes
+    t = torch.tensor([float(st.sum(axis=1).mean())] + st.mean(axis=0).tolist() +
+                     [float((c1 - c0) * F), float((tl[tl >= 3] * hop + 2 * E).sum()), float(len(tl))],
+                     device=dev, dtype=torch.float64)
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        t[:4] = tmax[:4]
+    ms_step, ms_an, ms_trk, ms_syn, frames_total, psamp_total, tracks_total = [float(v) for v in t.tolist()]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk_, how = peaks()
+    hbm = float(pk_["hbm_gbs"])
+    alg_an = (4 * hop + 20 * npks + 8) * (c1 - c0) * F
+    line = {
+        "metric": "STFT frames/sec (nfft=512,hop=128,npks=20, clip batch) + resynth partial-samples/sec",
+        "value": frames_total / (ms_step * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32 FFT, f64 per-peak/phase", "data": "synthetic",
+        "config": {"workload": "%d synthetic speech-like %d s clips @ %d Hz (configs[2]; 64 distinct clips tiled), nfft=%d "
+                               "hop=%d npks=%d, clip-batched analysis + tracking + full resynthesis"
+                               % (c["nclips"], c["seconds"], sr, nfft, hop, npks),
+                   "sr": sr, "nclips": c["nclips"], "clips_per_gpu": c1 - c0, "frames_per_clip": F, "nfft": nfft, "hop": hop,
+                   "npks": npks, "frames_total": frames_total, "partial_samples_total": psamp_total,
+                   "tracks_total": tracks_total, "guard_rows_per_clip": pb.guard,
+                   "l2": "256 MiB buffer written between timed steps; per-step CUDA events on the launch stream",
+                   "settle_passes_before_warmup": settle,
+                   "parallelism": "clips split x%d (dist.clip_range; independent units, no halo, no collective)" % world},
+        "stages": {"analysis_ms": ms_an, "tracking_pack_ms": ms_trk, "resynth_ms": ms_syn,
+                   "analysis_frames_per_s": frames_total / (ms_an * 1e-3),
+                   "resynth_partial_samples_per_s": psamp_total / (ms_syn * 1e-3)},
+        "roofline": {"kernel": "analyze_kernel<8>", "bound": "hbm", "achieved": alg_an / (ms_an * 1e-3) / 1e9, "peak": hbm,
+                     "unit": "GB/s", "frac": alg_an / (ms_an * 1e-3) / 1e9 / hbm, "traffic": None, "ms": ms_an,
+                     "alg_bytes_per_launch": alg_an, "peak_source": how},
+        "clocks": clocks, "gpu_launches": launches, "e2e": None,
+    }
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # --------------------------------------------------------------------------- GPU arm
 def gpu_main(args):
     # everything else that writes to fd 1 (NCCL's version banner, library chatter) goes to stderr:
@@ -224,13 +344,17 @@ def gpu_main(args):
         dist.init_process_group("nccl")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    c = CFG
+    if args.workload == "cfg3":
+        return clips_main(args, world, rank, dev, real_stdout)
+    strong = args.workload == "cfg4"
+    c = dict(CFG4, seconds=int(round(args.cfg4_hours * 3600))) if strong else CFG
     sr, nfft, hop, npks = c["sr"], c["nfft"], c["hop"], c["npks"]
     nsamp_seg = sr * c["seconds"]
+    nsamp_total = nsamp_seg if strong else world * nsamp_seg
 
     # ---- synthetic signal: rank r owns frames [r*Fseg, (r+1)*Fseg) of an N*10-minute signal and
     #      analyses a window with a few halo rows either side (pypevoc_b200/dist.py)
-    plans = D.plan_segments(world * nsamp_seg, nfft, hop, world)
+    plans = D.plan_segments(nsamp_total, nfft, hop, world)
     plan = plans[rank]
     xd = signals.harm_torch(sr, plan["nsamp"], c["f0"], c["nharm"], c["p"], c["sigma"], c["seed"], dev,
                             t0_samples=plan["sample0"], scale=0.25)
@@ -253,6 +377,7 @@ def gpu_main(args):
     def step(timed=None):
         """One pass of the hot path over this rank's segment (device resident)."""
         e = [ev() for _ in range(5)] if timed is not None else None
+        state.clear()                                     # (the previous step's tensors go back to the allocator)
         ht = [time.perf_counter()] if trace else None     # PVK_BENCH_TRACE=1: host-side launch timeline
         if e: e[0].record()
         a = P.analyze_device(xd, sr, nfft, hop, npks, c["pkthresh"], tb, frame0=plan["frame0"],
@@ -356,7 +481,7 @@ def gpu_main(args):
 
     # ---- end to end through the public API with host buffers (pinned), per rank
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not strong:
         xh = torch.empty(plan["nsamp"], dtype=torch.float32).pin_memory()
         xh.copy_(xd)
         hostbuf = {}
@@ -372,7 +497,7 @@ def gpu_main(args):
                 assert pv.f.shape == (pv.nframes, npks) and w.dtype == np.float64   # host views (synchronises)
                 nb = pv.d2h_bytes + ss.d2h_bytes
             else:
-                spv = D.ShardedPV(xh, sr, world * nsamp_seg, nfft=nfft, hop=hop, npks=npks, pkthresh=c["pkthresh"],
+                spv = D.ShardedPV(xh, sr, nsamp_total, nfft=nfft, hop=hop, npks=npks, pkthresh=c["pkthresh"],
                                   rank=rank, world=world, device=dev)
                 spv.run_pv(hostbuf=hostbuf)
                 ss = spv.toSinSum()
@@ -429,9 +554,14 @@ def gpu_main(args):
     line = {
         "metric": METRIC, "value": frames_total / (ms_step * 1e-3), "unit": "frames/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 FFT, f64 per-peak/phase",
-        "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sr": sr, "seconds_per_gpu": c["seconds"], "nfft": nfft, "hop": hop,
+        "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+        "dtype": "f32 FFT, f64 per-peak/phase", "data": "synthetic",
+        "config": {"workload": WORKLOAD if not strong else (
+                       "%g h mono 44.1 kHz synthetic harmonic tone+noise (configs[3]; 200 Hz, 100 harmonics, sigma 0.01), "
+                       "nfft=2048 hop=256 npks=100, ONE signal segment-sharded over the GPUs, analysis + tracking + "
+                       "full resynthesis" % args.cfg4_hours),
+                   "sr": sr, "seconds_per_gpu": c["seconds"] if not strong else c["seconds"] / float(world),
+                   "nfft": nfft, "hop": hop,
                    "npks": npks, "frames_per_gpu": F, "frames_total": frames_total,
                    "partial_samples_total": psamp_total, "tracks_total": int(state["st"]["ntracks"]),
                    "l2": "256 MiB buffer written between timed steps; per-step CUDA events on the launch stream",
@@ -450,7 +580,10 @@ def gpu_main(args):
         line["e2e"] = e2e
     if selfcheck is not None:
         line["selfcheck"] = selfcheck
-    if world == 1 and not args.no_cpu:
+    if strong:
+        line["metric"] = "STFT frames/sec (nfft=2048,hop=256,npks=100) + resynth partial-samples/sec"
+        line["e2e"] = None
+    if world == 1 and not args.no_cpu and not strong:
         line["cpu_baseline"] = cpu_baseline(xd[:sr * args.cpu_seconds + nfft].cpu().numpy(), 1)
     sys.stdout.flush()
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
@@ -589,6 +722,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=int, default=15)
     ap.add_argument("--ref-seconds", type=int, default=8)
+    ap.add_argument("--workload", default="metric", choices=["metric", "cfg3", "cfg4"])
+    ap.add_argument("--cfg4-hours", type=float, default=8.0)
+    ap.add_argument("--cfg3-clips", type=int, default=4096)
     args = ap.parse_args()
     if args.impl == "reference":
         reference_main(args)

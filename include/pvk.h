@@ -102,6 +102,23 @@ int pvk_analyze_ex(const float *x, int64_t nclips, int64_t clip_stride, int64_t 
                    double *binno, int32_t *npk, double *totalmag, float *spec_out,
                    double *fine_pos, double *fine_val, void *stream);
 
+/*
+ * pvk_analyze_ex for clip batches that continue into tracking and resynthesis (BASELINE
+ * configs[2]; SURVEY 8b "pvk_analyze_batch", PVAnalysis.py:213-264 once per clip): clip c writes
+ * its rows at row index c * out_rows_per_clip + r of every output table, out_rows_per_clip >=
+ * nframes.  The rows in between are the caller's guard rows: kept all-zero they end every
+ * partial at a clip boundary, so ONE pvk_track / pvk_track_pack / pvk_resynth over the flattened
+ * [nclips * out_rows_per_clip, npks] tables links, packs and renders all clips at once, each
+ * exactly like a PV of its own (ids are numbered clip after clip).
+ */
+int pvk_analyze_batch(const float *x, int64_t nclips, int64_t clip_stride, int64_t nsamp,
+                      const float *win_scaled, const double *fbin, const double *wfbin,
+                      const void *tables, int nfft, int hop, int npks, double pkthresh,
+                      double dt, double fstep, int64_t frame0, int64_t nframes, int prev_zero,
+                      int run_frames, double *f, double *mag, double *ph, double *realph,
+                      double *binno, int32_t *npk, double *totalmag, float *spec_out,
+                      double *fine_pos, double *fine_val, int64_t out_rows_per_clip, void *stream);
+
 /* ------------------------------------------------------------------ f0-guided analysis
  * Replaces PVHarmonic.run_pv / PVHarmonic.calc_pv_frame (PVAnalysis.py:419-538) for one
  * signal: frame r (starting at sample r*hop) is processed when f0[r] > 0 and not NaN (:509);
@@ -198,6 +215,13 @@ int pvk_track_spans(const int32_t *tid, int64_t nframes, int npks, int64_t ntrac
  * holding a point (= max(ss.end), :1059; -1 = none) | number of partials (copy of ntracks). */
 int pvk_track_stats(const int32_t *tid, const int32_t *ntracks, int64_t nclips, int64_t nframes,
                     int npks, int64_t *stats, void *stream);
+
+/* Clip batches flattened with pvk_analyze_batch (rows_per_clip rows per clip, zero guard rows):
+ * from the packed tracks' first frames / lengths, count[c] = partials of clip c (their ids are the
+ * exclusive scan of count, clip after clip) and last[c] = last local frame of clip c holding a
+ * point (-1: none) = max(SinSum.end) of that clip (PVAnalysis.py:1059).  int32 [nclips] each. */
+int pvk_clip_spans(const int32_t *tstart, const int32_t *tlen, int64_t ntracks, int64_t rows_per_clip,
+                   int64_t nclips, int32_t *count, int32_t *last, void *stream);
 
 /* Pack per-track value runs (= RegPartial.f/mag/ph/realph lists, :616-626, with
  * start_idx = tstart, :598) from the frame tables of ONE clip.  ntracks is the value

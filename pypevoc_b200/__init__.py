@@ -4,6 +4,6 @@ Drop-in for ``pypevoc.PV`` / ``pypevoc.SinSum`` (reference pypevoc/__init__.py:1
 
     from pypevoc_b200 import PV
 """
-from .pv import PV, PVBatch, PVHarmonic, SinSum, RegPartial, Progress  # noqa: F401
+from .pv import PV, PVBatch, PVHarmonic, SinSum, SinSumBatch, RegPartial, Progress  # noqa: F401
 
-__all__ = ["PV", "PVBatch", "PVHarmonic", "SinSum", "RegPartial", "Progress"]
+__all__ = ["PV", "PVBatch", "PVHarmonic", "SinSum", "SinSumBatch", "RegPartial", "Progress"]

@@ -26,6 +26,8 @@ SIGNATURES = {
                          _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "pvk_analyze_ex": (_i, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _i, _i, _i, _d, _d, _d, _i64, _i64,
                             _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "pvk_analyze_batch": (_i, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _i, _i, _i, _d, _d, _d, _i64, _i64,
+                               _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "pvk_harmonic": (_i, [_p, _i64, _p, _p, _p, _p, _i, _i, _i, _d, _d, _d, _p, _i64, _i, _p, _p, _p, _p, _p, _p]),
     "pvk_stft_bank": (_i, [_p, _i64, _p, _p, _i, _i, _i64, _i, _p, _p, _p, _i, _p, _i, _i, _p, _d, _p, _p]),
     "pvk_frame_stats": (_i, [_p, _p, _i64, _i, _d, _d, _d, _p, _p, _p, _p]),
@@ -34,6 +36,7 @@ SIGNATURES = {
     "pvk_track": (_i, [_p, _p, _i64, _i64, _i, _d, _p, _p, _p, _p, _i64, _p]),
     "pvk_track_spans": (_i, [_p, _i64, _i, _i64, _p, _p, _p]),
     "pvk_track_stats": (_i, [_p, _p, _i64, _i64, _i, _p, _p]),
+    "pvk_clip_spans": (_i, [_p, _p, _i64, _i64, _i64, _p, _p, _p]),
     "pvk_track_pack_workspace_bytes": (_i64, [_i64]),
     "pvk_track_pack": (_i, [_p, _p, _p, _p, _p, _i64, _i, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "pvk_segment_summary": (_i, [_p, _i, _i64, _i64, _i64, _p, _p]),

@@ -37,6 +37,7 @@ struct AParams {
   int hop, npks;
   double pkthresh, dt, fstep;
   int64_t frame0, nframes;
+  int64_t out_rows;              // rows per clip of the output tables (>= nframes; the rest are the caller's guard rows)
   int prev_zero, run;
   int64_t nruns;
   double *f, *mag, *ph, *realph, *binno;
@@ -537,7 +538,7 @@ __global__ void __launch_bounds__(Plan<LOGM>::T, PVK_MINB(Plan<LOGM>::T)) analyz
     const bool emit = r >= r0;
     float2 *cur = PVK_BUF(r & 1);
     const float2 *prev = PVK_BUF((r & 1) ^ 1);
-    const int64_t row = clip * prm.nframes + r;
+    const int64_t row = clip * prm.out_rows + r;
     {
       float2 ux[1 << P::lr(0)];
       frame_load<LOGM>(xc + (prm.frame0 + r) * (int64_t)prm.hop, ux);
@@ -1431,13 +1432,15 @@ extern "C" int pvk_analyze_init(int nfft, void *tables, void *stream) {
   return PVK_ERR_ARG;
 }
 
-extern "C" int pvk_analyze_ex(const float *x, int64_t nclips, int64_t clip_stride, int64_t nsamp,
-                              const float *win_scaled, const double *fbin, const double *wfbin,
-                              const void *tables, int nfft, int hop, int npks, double pkthresh,
-                              double dt, double fstep, int64_t frame0, int64_t nframes, int prev_zero,
-                              int run_frames, double *f, double *mag, double *ph, double *realph,
-                              double *binno, int32_t *npk, double *totalmag, float *spec_out,
-                              double *fine_pos, double *fine_val, void *stream) {
+extern "C" int pvk_analyze_batch(const float *x, int64_t nclips, int64_t clip_stride, int64_t nsamp,
+                                 const float *win_scaled, const double *fbin, const double *wfbin,
+                                 const void *tables, int nfft, int hop, int npks, double pkthresh,
+                                 double dt, double fstep, int64_t frame0, int64_t nframes, int prev_zero,
+                                 int run_frames, double *f, double *mag, double *ph, double *realph,
+                                 double *binno, int32_t *npk, double *totalmag, float *spec_out,
+                                 double *fine_pos, double *fine_val, int64_t out_rows_per_clip, void *stream) {
+  PVK_REQUIRE(out_rows_per_clip >= nframes, "pvk_analyze_batch: out_rows_per_clip=%lld < nframes=%lld",
+              (long long)out_rows_per_clip, (long long)nframes);
   const int l = log2_exact(nfft);
   PVK_REQUIRE(l >= 0 && nfft >= PVK_MIN_NFFT && nfft <= PVK_MAX_NFFT,
               "pvk_analyze: nfft=%d must be a power of two in [%d, %d]", nfft, PVK_MIN_NFFT, PVK_MAX_NFFT);
@@ -1459,6 +1462,7 @@ extern "C" int pvk_analyze_ex(const float *x, int64_t nclips, int64_t clip_strid
   prm.fbin = fbin; prm.wfbin = wfbin; prm.hop = hop; prm.npks = npks;
   prm.pkthresh = pkthresh; prm.dt = dt; prm.fstep = fstep;
   prm.frame0 = frame0; prm.nframes = nframes; prm.prev_zero = prev_zero ? 1 : 0;
+  prm.out_rows = out_rows_per_clip;
   prm.run = 0; prm.nruns = 0;                              // chosen by launch_analyze
   prm.f = f; prm.mag = mag; prm.ph = ph; prm.realph = realph; prm.binno = binno;
   prm.npk = npk; prm.totalmag = totalmag;
@@ -1469,6 +1473,18 @@ extern "C" int pvk_analyze_ex(const float *x, int64_t nclips, int64_t clip_strid
   PVK_DISPATCH_LOGM(l - 1, CALL)
 #undef CALL
   return PVK_ERR_ARG;
+}
+
+extern "C" int pvk_analyze_ex(const float *x, int64_t nclips, int64_t clip_stride, int64_t nsamp,
+                              const float *win_scaled, const double *fbin, const double *wfbin,
+                              const void *tables, int nfft, int hop, int npks, double pkthresh,
+                              double dt, double fstep, int64_t frame0, int64_t nframes, int prev_zero,
+                              int run_frames, double *f, double *mag, double *ph, double *realph,
+                              double *binno, int32_t *npk, double *totalmag, float *spec_out,
+                              double *fine_pos, double *fine_val, void *stream) {
+  return pvk_analyze_batch(x, nclips, clip_stride, nsamp, win_scaled, fbin, wfbin, tables, nfft, hop, npks, pkthresh,
+                           dt, fstep, frame0, nframes, prev_zero, run_frames, f, mag, ph, realph, binno, npk, totalmag,
+                           spec_out, fine_pos, fine_val, nframes, stream);
 }
 
 extern "C" int pvk_analyze(const float *x, int64_t nclips, int64_t clip_stride, int64_t nsamp,

@@ -1048,6 +1048,21 @@ __global__ void track_stats_kernel(const int32_t *__restrict__ tid, const int32_
   if (blockIdx.x == 0 && threadIdx.x == 0) stats[2 * gridDim.y + clip] = ntracks[clip];
 }
 
+// Clip batches flattened into one table of rows_per_clip rows per clip (pvk_analyze_batch): per
+// clip, the number of partials that start in it and the last LOCAL frame holding a point of one of
+// them (-1: none).  Partials never cross a clip (zero guard rows), ids ascend clip after clip.
+__global__ void clip_spans_kernel(const int32_t *__restrict__ tstart, const int32_t *__restrict__ tlen, int64_t ntracks,
+                                  int64_t rows_per_clip, int64_t nclips, int32_t *__restrict__ count,
+                                  int32_t *__restrict__ last) {
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < ntracks; v += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = tstart[v];
+    const int64_t c = s / rows_per_clip;
+    if (s < 0 || c >= nclips) continue;
+    atomicAdd(&count[c], 1);
+    atomicMax(&last[c], (int)(s - c * rows_per_clip) + tlen[v] - 1);
+  }
+}
+
 static inline int grid_for(int64_t n, int block) {
   int64_t g = (n + block - 1) / block;
   const int64_t cap = 148 * 16;
@@ -1231,6 +1246,20 @@ extern "C" int pvk_track_stats(const int32_t *tid, const int32_t *ntracks, int64
   PVK_LAUNCH(track_stats_kernel, dim3((unsigned)g, (unsigned)nclips), dim3(256), 0, stream, tid, ntracks, nframes, npks,
              reinterpret_cast<long long *>(stats));
   PVK_CHECK_LAUNCH("pvk_track_stats");
+  return PVK_OK;
+}
+
+extern "C" int pvk_clip_spans(const int32_t *tstart, const int32_t *tlen, int64_t ntracks, int64_t rows_per_clip,
+                              int64_t nclips, int32_t *count, int32_t *last, void *stream) {
+  PVK_REQUIRE(ntracks >= 0 && rows_per_clip >= 1 && nclips >= 0, "pvk_clip_spans: bad sizes");
+  if (nclips == 0) return PVK_OK;
+  PVK_REQUIRE(count && last && (ntracks == 0 || (tstart && tlen)), "pvk_clip_spans: NULL pointer argument");
+  cudaMemsetAsync(count, 0, 4 * (size_t)nclips, (cudaStream_t)stream);
+  cudaMemsetAsync(last, 0xff, 4 * (size_t)nclips, (cudaStream_t)stream);                 // -1
+  if (ntracks == 0) return PVK_OK;
+  PVK_LAUNCH(clip_spans_kernel, dim3(grid_for(ntracks, 256)), dim3(256), 0, stream, tstart, tlen, ntracks, rows_per_clip,
+             nclips, count, last);
+  PVK_CHECK_LAUNCH("pvk_clip_spans");
   return PVK_OK;
 }
 

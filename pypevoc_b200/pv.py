@@ -126,14 +126,16 @@ def host_tables(sr, nfft, hop, wind=np.hanning):
 
 
 def analyze_device(xd, sr, nfft, hop, npks, pkthresh, tb, frame0=0, nframes=None, prev_zero=True,
-                   run_frames=0, spectra=False, out=None, refine=False):
+                   run_frames=0, spectra=False, out=None, refine=False, out_rows=None):
     """Launch pvk_analyze on a device signal.
 
     ``xd``: float32 CUDA tensor, ``[nsamp]`` or ``[nclips, nsamp]``.  Returns a dict of device
     tensors ``f mag ph realph binno`` (float64 ``[nclips, nframes, npks]``), ``npk`` (int32),
     ``totalmag`` (float64) and optionally ``fx`` (complex64 ``[nclips, nframes, nfft/2]``);
     ``refine=True`` adds ``fine_pos`` / ``fine_val`` (PeakFinder.refine of every emitted peak,
-    PeakFinder.py:331-372).  Asynchronous on the current stream.
+    PeakFinder.py:331-372).  ``out_rows`` (>= nframes; pvk_analyze_batch): the tables get
+    ``out_rows`` rows per clip, the rows beyond ``nframes`` are zero guard rows (clip batches that
+    go on to tracking / resynthesis as ONE flattened table).  Asynchronous on the current stream.
     """
     L = _lib.lib()
     if xd.dim() == 1:
@@ -151,25 +153,30 @@ def analyze_device(xd, sr, nfft, hop, npks, pkthresh, tb, frame0=0, nframes=None
             wfbin=torch.from_numpy(np.ascontiguousarray(tb["wfbin"], dtype=np.float64)).to(dev))
     dtb = tb[key]
     tables = _analysis_tables(nfft, dev)
+    rows = int(nframes if out_rows is None else out_rows)
+    assert rows >= nframes and not (spectra and rows != nframes)
     if out is None:
         out = {}
         for k in ("f", "mag", "ph", "realph", "binno"):
-            out[k] = torch.empty((nclips, nframes, npks), dtype=torch.float64, device=dev)
-        out["npk"] = torch.empty((nclips, nframes), dtype=torch.int32, device=dev)
-        out["totalmag"] = torch.empty((nclips, nframes), dtype=torch.float64, device=dev)
+            out[k] = torch.empty((nclips, rows, npks), dtype=torch.float64, device=dev)
+        out["npk"] = torch.empty((nclips, rows), dtype=torch.int32, device=dev)
+        out["totalmag"] = torch.empty((nclips, rows), dtype=torch.float64, device=dev)
+        if rows > nframes:                                    # guard rows: zero (memset-like strided fills)
+            for v in out.values():
+                v[:, nframes:].zero_()
     spec = torch.empty((nclips, nframes, nfft // 2), dtype=torch.complex64, device=dev) if spectra else None
     if refine and "fine_pos" not in out:
         out["fine_pos"] = torch.empty((nclips, nframes, npks), dtype=torch.float64, device=dev)
         out["fine_val"] = torch.empty((nclips, nframes, npks), dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(L.pvk_analyze_ex(
+        _lib.check(L.pvk_analyze_batch(
             _ptr(xd), nclips, xd.stride(0), nsamp, _ptr(dtb["win"]), _ptr(dtb["fbin"]), _ptr(dtb["wfbin"]),
             _ptr(tables), int(nfft), int(hop), int(npks), float(pkthresh), float(tb["dt"]), float(tb["fstep"]),
             int(frame0), int(nframes), 1 if prev_zero else 0, int(run_frames),
             _ptr(out["f"]), _ptr(out["mag"]), _ptr(out["ph"]), _ptr(out["realph"]), _ptr(out["binno"]),
             _ptr(out["npk"]), _ptr(out["totalmag"]), _ptr(spec),
             _ptr(out["fine_pos"]) if refine else None, _ptr(out["fine_val"]) if refine else None,
-            _stream()), "pvk_analyze")
+            rows, _stream()), "pvk_analyze")
     if spectra:
         out["fx"] = spec
     return out
@@ -484,7 +491,7 @@ class PV(object):
 
     def _get(self, name):
         if name not in self._host:
-            if self._devout is None:
+            if self._devout is None and self._hostbuf is None:
                 raise AttributeError(name)
             self._host[name] = self._fetch(name)
         return self._host[name]
@@ -500,6 +507,8 @@ class PV(object):
             if name == "totalmag":
                 return [v for v in hb]
             return hb if self.nframes else np.array([])
+        if d is None:
+            raise AttributeError("%s was not kept by the last (chunked) run_pv" % name)
         if name == "totalmag":
             return [v for v in d["totalmag"][0].cpu().numpy()]
         if name not in d:
@@ -565,7 +574,7 @@ class PV(object):
         return nbytes
 
     # -- analysis ----------------------------------------------------------------------
-    def run_pv(self, run_frames=0, hostbuf=None, chunks=8, refine=False):
+    def run_pv(self, run_frames=0, hostbuf=None, chunks=8, refine=False, device_budget=None):
         """STFT + peak picking + instantaneous frequency for every frame (PVAnalysis.py:213-264)
         in one kernel launch.  Results appear as the reference's attributes ``f mag ph realph
         binno`` (float64 ``[nframes, npks]``), ``t``, ``nframes``, ``totalmag`` (list).
@@ -579,10 +588,27 @@ class PV(object):
         ``refine=True`` additionally evaluates ``PeakFinder.refine`` (PeakFinder.py:331-372) for
         every peak: attributes ``fine_pos`` (fractional bin) and ``fine_val`` (interpolated
         |fx|), float64 ``[nframes, npks]``, columns aligned with ``binno``.  The reference's PV
-        never refines (PVAnalysis.py:175-178), so this is an opt-in extra."""
+        never refines (PVAnalysis.py:175-178), so this is an opt-in extra.
+
+        ``device_budget`` (bytes; needs a pinned host signal and ``hostbuf``): signals whose samples
+        and peak tables exceed a device-memory budget (the reference reads the whole file,
+        AudioInterface.py:15-37, and keeps every table on the host).  The frames are analysed in
+        frame-aligned chunks sized so that two chunks (signal slice + tables) fit the budget; every
+        chunk re-computes the frame before its first one as warm-up (the previous spectrum), results
+        stream into the pinned host tables and nothing but the two chunk buffers stays on the device.
+        Bit-identical to the one-shot run.  ``toSinSum`` then uploads the host tables."""
         self._hostbuf = None
         self._d2h_event = None
         self._stats = None
+        if device_budget is not None:
+            if hostbuf is None or self._xh_pinned is None:
+                raise ValueError("run_pv(device_budget=...) needs a pinned float32 host signal and hostbuf={}")
+            self._run_pv_chunked(hostbuf, int(device_budget), run_frames, refine=refine)
+            self._host = {}
+            self._host["t"] = (np.arange(self.nframes) * self.hop + self.nfft / 2.0) / self.sr   # :247
+            if self.progress:
+                self.progress.update(self.nsamp)
+            return
         if hostbuf is not None:
             self._run_pv_streamed(hostbuf, int(chunks), run_frames, refine=refine)
         else:
@@ -647,11 +673,70 @@ class PV(object):
                     _mark("tables d2h %d" % i, d2h)
             if upload:
                 self._xd_t = xd
+                xd.record_stream(h2d)
+            for t in out.values():                                # read by the copy stream: the allocator
+                t.record_stream(d2h)                              # must not recycle them before it is done
             self._d2h_event = torch.cuda.Event()
             self._d2h_event.record(d2h)
         self._devout = out
         self._hostbuf = hostbuf
         self.d2h_bytes = F * (5 * K + 1) * 8
+
+    def _run_pv_chunked(self, hostbuf, budget, run_frames, refine=False):
+        dev, K, hop, nfft = self._dev, self.npeaks, self.hop, self.nfft
+        F = n_frames(self.nsamp, nfft, hop)
+        names = ("f", "mag", "ph", "realph", "binno") + (("fine_pos", "fine_val") if refine else ())
+        per_frame = hop * 4 + (len(names) * K + 1) * 8 + 4
+        Fc = int(max(64, (budget // 2 - (nfft + hop) * 4) // per_frame))
+        Fc = min(Fc, max(F, 1))
+        cur = torch.cuda.current_stream(dev)
+        h2d, d2h = _side_streams(dev)
+        with torch.cuda.device(dev):
+            hb = {k: _pinned(hostbuf, k, (F, K), torch.float64) for k in names}
+            hb["totalmag"] = _pinned(hostbuf, "totalmag", (F,), torch.float64)
+            bufs = []
+            for _ in range(2 if F > Fc else 1):
+                o = {k: torch.empty((1, Fc, K), dtype=torch.float64, device=dev) for k in names}
+                o["npk"] = torch.empty((1, Fc), dtype=torch.int32, device=dev)
+                o["totalmag"] = torch.empty((1, Fc), dtype=torch.float64, device=dev)
+                bufs.append(dict(x=torch.empty((Fc * hop + nfft,), dtype=torch.float32, device=dev), out=o, free=None))
+            h2d.wait_stream(cur)
+            d2h.wait_stream(cur)
+            last = None
+            for i, j0 in enumerate(range(0, F, Fc)):
+                j1 = min(F, j0 + Fc)
+                b = bufs[i & 1]
+                s0 = (j0 - 1) * hop if j0 > 0 else 0                     # one warm-up frame before the chunk
+                s1 = (j1 - 1) * hop + nfft
+                with torch.cuda.stream(h2d):
+                    if b["free"] is not None:
+                        h2d.wait_event(b["free"])                       # the buffer's previous tables are on the host
+                    b["x"][:s1 - s0].copy_(self._xh_pinned[s0:s1], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(h2d)
+                cur.wait_event(ev)
+                view = {k: v[:, :j1 - j0] for k, v in b["out"].items()}
+                analyze_device(b["x"][:s1 - s0], self.sr, nfft, hop, K, self.peakthresh, self._tb,
+                               frame0=1 if j0 > 0 else 0, nframes=j1 - j0, prev_zero=(j0 == 0), run_frames=run_frames,
+                               out=view, refine=refine)
+                ev2 = torch.cuda.Event()
+                ev2.record(cur)
+                with torch.cuda.stream(d2h):
+                    d2h.wait_event(ev2)
+                    for k in names:
+                        hb[k][j0:j1].copy_(b["out"][k][0, :j1 - j0], non_blocking=True)
+                    hb["totalmag"][j0:j1].copy_(b["out"]["totalmag"][0, :j1 - j0], non_blocking=True)
+                    b["free"] = torch.cuda.Event()
+                    b["free"].record(d2h)
+                    last = b["free"]
+                for t in [b["x"]] + list(b["out"].values()):
+                    t.record_stream(h2d), t.record_stream(d2h)
+            self._d2h_event = last
+        self._devout = None
+        self._hostbuf = hostbuf
+        self.nframes = F
+        self.chunk_frames = Fc
+        self.d2h_bytes = F * (len(names) * K + 1) * 8
 
     def dphase2freq(self, dph, nbin):
         '''"instantaneous frequency" for the phase difference dph at bin nbin (host helper with
@@ -695,11 +780,21 @@ class PV(object):
         the GPU.  As in the reference the argument is not forwarded: add_frame's default
         maxpitchjmp=0.5 semitones is what is applied (PVAnalysis.py:320-321,871).
         '''
-        if self._devout is None:
+        if self._devout is None and self._hostbuf is None:
             raise RuntimeError("run_pv() has not been called")
         ss = SinSum(self.sr, nfft=self.nfft, hop=self.hop, device=self._dev)
-        d = self.device_tables
-        ss._set_device_tables(d["f"], d["mag"], d["ph"], d["realph"])
+        # the reference tracks self.f / mag / ph / realph (:320): a table the caller has read (and
+        # may have edited in place) or assigned is uploaded again; untouched ones stay on the device
+        tabs = []
+        for k in ("f", "mag", "ph", "realph"):
+            if k in self._host or self._devout is None:
+                a = np.asarray(self._get(k), dtype=np.float64)
+                if a.ndim != 2:
+                    a = a.reshape(0, self.npeaks)
+                tabs.append(torch.from_numpy(np.ascontiguousarray(a)).to(self._dev))
+            else:
+                tabs.append(self._devout[k][0])
+        ss._set_device_tables(*tabs)
         return ss
 
     # -- consumers (host side views over the peak tables, PVAnalysis.py:324-417) ---------
@@ -825,19 +920,24 @@ class PV(object):
 
 class PVBatch(object):
     """Clip batch (BASELINE configs[2]): ``nclips`` independent signals of equal length
-    analysed by ONE pvk_analyze launch and linked by ONE pvk_track launch (every clip starts from
-    the all-zero previous spectrum and its own partial numbering, exactly as a ``PV`` per clip).
+    analysed by ONE pvk_analyze_batch launch; tracking, packing and resynthesis of all clips run as
+    ONE pvk_track / pvk_track_pack / pvk_resynth over the flattened peak table, in which a few
+    all-zero guard rows after every clip end all partials at the clip boundary (every clip starts
+    from the all-zero previous spectrum and its own partial numbering, exactly as a ``PV`` per clip:
+    PVAnalysis.py:213-264, 299-322, 1053-1070 once per clip).
 
         pb = PVBatch(x, sr, nfft=512, hop=128, npks=20)      # x: [nclips, nsamp] numpy / torch
         pb.run_pv()
         pb.f, pb.mag, pb.ph, pb.realph, pb.binno               # float64 [nclips, nframes, npks]
+        ssb = pb.toSinSum(); w = ssb.synth(sr, pb.hop)         # list of nclips float64 signals
         pb.track()["tid"]                                      # int32 CUDA [nclips, nframes, npks]
         pv3 = pb[3]                                            # a PV over clip 3 sharing the device tables
 
     Across GPUs a batch shards by clip with no halo and no collective
     (``dist.clip_range(nclips, rank, world)``)."""
 
-    def __init__(self, x, sr, nfft=1024, hop=None, npks=20, pkthresh=0.005, wind=np.hanning, device=None):
+    def __init__(self, x, sr, nfft=1024, hop=None, npks=20, pkthresh=0.005, wind=np.hanning, device=None,
+                 max_edge=1.0):
         self._dev = _device(device)
         if isinstance(x, torch.Tensor):
             xd = x.detach()
@@ -852,25 +952,33 @@ class PVBatch(object):
         proto = PV(self._xd[0] if self.nclips else torch.zeros(1), sr, progress=False, device=self._dev, **self._kw)
         self.sr, self.nfft, self.hop, self.npeaks, self.peakthresh = sr, proto.nfft, proto.hop, proto.npeaks, pkthresh
         self._tb = proto._tb
+        # guard rows after every clip: fade-out tails (ceil(dfr*edge) blocks + 1) of one clip and the
+        # fade-in heads (ceil(dfr*edge) blocks) of the next must not meet
+        self.max_edge = float(max_edge)
+        self.guard = 2 * int(np.ceil(self.nfft / float(self.hop) / 2. * self.max_edge)) + 3
         self._devout = None
         self._trk = None
+        self._ssb = None
         self._host = {}
         self.nframes = 0
 
     def run_pv(self, run_frames=0):
+        F = n_frames(self.nsamp, self.nfft, self.hop)
         self._devout = analyze_device(self._xd, self.sr, self.nfft, self.hop, self.npeaks, self.peakthresh, self._tb,
-                                      run_frames=run_frames)
-        self.nframes = int(self._devout["f"].shape[1])
+                                      run_frames=run_frames, nframes=F, out_rows=F + self.guard if F else 0)
+        self.nframes = F
+        self.rows_per_clip = F + self.guard if F else 0
         self._host = {"t": (np.arange(self.nframes) * self.hop + self.nfft / 2.0) / self.sr}
         self._trk = None
+        self._ssb = None
 
     @property
     def device_tables(self):
         """Device tensors of the last run_pv: f mag ph realph binno float64 [nclips, nframes, npks],
-        npk int32 and totalmag float64 [nclips, nframes]."""
+        npk int32 and totalmag float64 [nclips, nframes] (views of the guard-row padded tables)."""
         if self._devout is None:
             raise RuntimeError("run_pv() has not been called")
-        return dict(self._devout)
+        return {k: v[:, :self.nframes] for k, v in self._devout.items()}
 
     def __getattr__(self, name):
         if name in ("f", "mag", "ph", "realph", "binno", "totalmag", "t"):
@@ -879,15 +987,30 @@ class PVBatch(object):
                 dev = self.__dict__.get("_devout")
                 if dev is None:
                     raise AttributeError(name)
-                host[name] = dev[name].cpu().numpy()
+                host[name] = dev[name][:, :self.nframes].cpu().numpy()
             return host[name]
         raise AttributeError(name)
 
+    def toSinSum(self, maxpitchjmp=0.5):
+        """Tracking of every clip (PVAnalysis.py:299-322 per clip; as there, the argument is not
+        forwarded) -> :class:`SinSumBatch`."""
+        if self._devout is None:
+            raise RuntimeError("run_pv() has not been called")
+        if self._ssb is None:
+            self._ssb = SinSumBatch(self)
+        return self._ssb
+
     def track(self, maxpitchjmp=0.5):
-        """pvk_track over all clips: dict(tid, link int32 [nclips, nframes, npks], ntracks int32 [nclips])."""
+        """Per-clip view of the batch tracking: dict(tid int32 CUDA [nclips, nframes, npks] with every
+        clip's own numbering (-1 = no peak), ntracks int32 CUDA [nclips])."""
         if self._trk is None:
-            d = self.device_tables
-            self._trk = track_device(d["f"], d["mag"], maxpitchjmp)
+            ssb = self.toSinSum()
+            base, _ = ssb.clip_spans()
+            R, F, K = self.rows_per_clip, self.nframes, self.npeaks
+            tid = ssb.ss._ensure_tracks()["tid"].view(self.nclips, R, K)[:, :F]
+            b = torch.from_numpy(base[:-1].astype(np.int32)).to(self._dev).view(-1, 1, 1)
+            self._trk = dict(tid=torch.where(tid >= 0, tid - b, tid),
+                             ntracks=torch.from_numpy(np.diff(base).astype(np.int32)).to(self._dev))
         return self._trk
 
     def __len__(self):
@@ -902,10 +1025,88 @@ class PVBatch(object):
             raise IndexError(i)
         pv = PV(self._xd[i], self.sr, progress=False, device=self._dev, **self._kw)
         if self._devout is not None:
-            pv._devout = {k: v[i:i + 1] for k, v in self._devout.items()}
+            pv._devout = {k: v[i:i + 1, :self.nframes] for k, v in self._devout.items()}
             pv.nframes = self.nframes
             pv._host = {"t": self._host["t"]}
         return pv
+
+
+class SinSumBatch(object):
+    """Partials of every clip of a :class:`PVBatch`: ONE link / pack / resynthesis over the
+    flattened, guard-row separated peak table (``ss``: the SinSum of that table; partial ids run
+    clip after clip, frame indices are rows of the flattened table)."""
+
+    def __init__(self, pb):
+        self._pb = pb
+        R, K = pb.rows_per_clip, pb.npeaks
+        d = pb._devout
+        self.ss = SinSum(pb.sr, nfft=pb.nfft, hop=pb.hop, device=pb._dev)
+        self.ss._set_device_tables(*(d[k].view(pb.nclips * R, K) for k in ("f", "mag", "ph", "realph")))
+        self._spans = None
+        self.sr, self.nfft, self.hop = pb.sr, pb.nfft, pb.hop
+
+    def clip_spans(self):
+        """(base, last): base int64 [nclips + 1] -- clip c owns the partials base[c] .. base[c+1] of
+        ``ss`` -- and last int64 [nclips] = max(SinSum.end) of clip c in its own frame numbering (-1:
+        the clip has no partial).  One pvk_clip_spans launch + a read-back of 2 ints per clip."""
+        if self._spans is None:
+            pb = self._pb
+            pk = self.ss._ensure_packed()
+            nt = int(pk["tstart"].shape[0])
+            cnt = torch.empty((max(pb.nclips, 1),), dtype=torch.int32, device=pb._dev)
+            last = torch.empty((max(pb.nclips, 1),), dtype=torch.int32, device=pb._dev)
+            with torch.cuda.device(pb._dev):
+                _lib.check(_lib.lib().pvk_clip_spans(_ptr(pk["tstart"]), _ptr(pk["tlen"]), nt, max(pb.rows_per_clip, 1),
+                                                     pb.nclips, _ptr(cnt), _ptr(last), _stream()), "pvk_clip_spans")
+            both = torch.stack([cnt, last]).cpu().numpy().astype(np.int64)[:, :pb.nclips]
+            self._spans = (np.concatenate([[0], np.cumsum(both[0])]), both[1])
+        return self._spans
+
+    @property
+    def ntracks(self):
+        """Number of partials of every clip (numpy int64 [nclips])."""
+        return np.diff(self.clip_spans()[0])
+
+    def __len__(self):
+        return self._pb.nclips
+
+    def synth_device(self, sr, hop, edge=1.0, minframes=3):
+        """Render all clips in one pvk_resynth: float64 CUDA tensor [nclips, rows_per_clip * hop]; row c
+        holds clip c's signal from its sample 0 (then the silence of the guard rows)."""
+        pb = self._pb
+        if int(hop) != hop:
+            raise TypeError("hop must be an integer number of samples")
+        if edge > pb.max_edge:
+            raise ValueError("edge=%r exceeds the guard rows of this batch (PVBatch(max_edge=%r))" % (edge, pb.max_edge))
+        hop = int(hop)
+        pk = self.ss._ensure_packed()
+        tr = self.ss._trk
+        nout = pb.nclips * pb.rows_per_clip * hop
+        if tr["ntracks"] == 0 or nout == 0:
+            return torch.zeros((pb.nclips, pb.rows_per_clip * hop), dtype=torch.float64, device=pb._dev)
+        out = resynth_device(tr["tid"], pk, sr, hop, self.nfft, self.hop, edge=edge, minframes=minframes, nout=nout)
+        return out.view(pb.nclips, pb.rows_per_clip * hop)
+
+    def clip_lengths(self, hop, edge=1.0):
+        """Length of every clip's resynthesis, (max(end) + 2) * hop + edgsamp (PVAnalysis.py:1055-1059,
+        1070); 0 for a clip without partials (where the reference raises ValueError)."""
+        _, last = self.clip_spans()
+        n = np.array([synth_geometry(int(e), int(hop), self.nfft, self.hop, edge)[0] for e in last], dtype=np.int64)
+        return np.where(last >= 0, n, 0)
+
+    def synth(self, sr, hop, edge=1.0, minframes=3, to_host=True):
+        """SinSum.synth of every clip (PVAnalysis.py:1053-1070): list of ``nclips`` float64 signals
+        (numpy, or CUDA views with ``to_host=False``), each of its own length."""
+        w = self.synth_device(sr, hop, edge, minframes)
+        n = self.clip_lengths(hop, edge)
+        if to_host:
+            wh = w.cpu().numpy()
+            return [wh[c, :n[c]] for c in range(len(n))]
+        return [w[c, :n[c]] for c in range(len(n))]
+
+    def __getitem__(self, i):
+        """``SinSum`` of clip ``i`` alone (its own link / pack; for the reference's per-partial accessors)."""
+        return self._pb[i].toSinSum()
 
 
 class PVHarmonic(PV):

@@ -213,3 +213,42 @@ def test_emu_pack_respects_capacity():
     for q, k in enumerate(("pf", "pmag", "pph", "prealph")):
         assert np.array_equal(packed[q][G:G + n], full[k][:n])
         assert np.all(packed[q][G + n:] == -77)
+
+
+def test_emu_clip_batch_flattened_with_guard_rows():
+    """Clip batches (BASELINE configs[2]): pvk_analyze_batch writes every clip's rows into one table
+    with zero guard rows between the clips; ONE pvk_track / pvk_track_pack / pvk_resynth over the
+    flattened table equals the per-clip runs -- ids up to the clip's base, signals bit for bit."""
+    from pypevoc_b200 import signals
+    sr, nfft, hop, npks = 16000, 512, 128, 20
+    clips = np.stack([signals.speech_like_clip(s, sr=sr, dur=0.5) for s in (3, 4, 5)])
+    F = -(-(clips.shape[1] - nfft) // hop)
+    dfr = nfft / hop / 2.0
+    E = int(dfr * hop)
+    G = 2 * (-(-E // hop)) + 3
+    b = eh.analyze(clips, sr, nfft, hop, npks, out_rows=F + G)
+    flat = {k: b[k].reshape(-1, npks) for k in ("f", "mag", "ph", "realph")}
+    trb = eh.track(flat["f"], flat["mag"])
+    ntb = int(trb["ntracks"][0])
+    pkb = eh.track_pack(flat["f"], flat["mag"], flat["ph"], flat["realph"], trb["tid"][0], None, ntb)
+    wb = eh.resynth(trb["tid"][0], pkb, sr, hop, nfft, hop, nout=clips.shape[0] * (F + G) * hop)
+    base = 0
+    for c in range(clips.shape[0]):
+        a = eh.analyze(clips[c], sr, nfft, hop, npks)
+        for k in ("f", "mag", "ph", "realph", "binno"):
+            assert np.array_equal(a[k][0], b[k][c, :F]), k
+            assert not b[k][c, F:].any()
+        tr = eh.track(a["f"][0], a["mag"][0])
+        nt = int(tr["ntracks"][0])
+        tb = trb["tid"][0][c * (F + G):c * (F + G) + F]
+        assert np.array_equal(np.where(tb >= 0, tb - base, -1), tr["tid"][0])
+        assert (trb["tid"][0][c * (F + G) + F:(c + 1) * (F + G)] == -1).all()
+        pk = eh.track_pack(a["f"][0], a["mag"][0], a["ph"][0], a["realph"][0], tr["tid"][0], None, nt)
+        assert np.array_equal(pkb["tstart"][base:base + nt] - c * (F + G), pk["tstart"])
+        assert np.array_equal(pkb["tlen"][base:base + nt], pk["tlen"])
+        w = eh.resynth(tr["tid"][0], pk, sr, hop, nfft, hop)
+        s0 = c * (F + G) * hop
+        assert np.array_equal(wb[s0:s0 + len(w)], w)
+        assert not wb[s0 + len(w):(c + 1) * (F + G) * hop - E].any()     # (the next clip's fade-in heads come after)
+        base += nt
+    assert base == ntb

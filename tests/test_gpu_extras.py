@@ -211,6 +211,10 @@ def test_pvbatch_equals_single_clips():
     pb.run_pv()
     assert len(pb) == 5 and pb.f.shape == (5, pb.nframes, 20)
     tr = pb.track()
+    ssb = pb.toSinSum()
+    wb = ssb.synth(16000, 128)                       # ONE link / pack / resynthesis over the flattened table
+    wb200 = ssb.synth(16000, 200, edge=0.5, minframes=2)
+    assert len(ssb) == 5 and len(wb) == 5
     for i in range(5):
         pv = pb200.PV(clips[i], 16000, nfft=512, hop=128, npks=20, progress=False)
         pv.run_pv()
@@ -222,6 +226,9 @@ def test_pvbatch_equals_single_clips():
         view = pb[i]
         assert np.array_equal(view.f, pv.f) and np.array_equal(view.t, pv.t)
         assert np.array_equal(view.toSinSum().synth(16000, 128), ss.synth(16000, 128))
+        assert int(tr["ntracks"][i]) == len(ss.st) == int(ssb.ntracks[i])
+        assert wb[i].shape == ss.synth(16000, 128).shape and np.array_equal(wb[i], ss.synth(16000, 128))
+        assert np.array_equal(wb200[i], ss.synth(16000, 200, edge=0.5, minframes=2))
     got = []
     for r in range(3):
         c0, c1 = D.clip_range(5, r, 3)
@@ -231,6 +238,16 @@ def test_pvbatch_equals_single_clips():
     assert np.array_equal(np.concatenate(got), pb.f)
     with pytest.raises(ValueError):
         pb200.PVBatch(clips[0], 16000)
+    with pytest.raises(ValueError):
+        ssb.synth(16000, 128, edge=2.0)               # beyond the guard rows (PVBatch(max_edge=...))
+    # a silent clip in the batch: no partials, empty signal, neighbours untouched
+    mixed = clips[:3].copy()
+    mixed[1] = 0.0
+    pm = pb200.PVBatch(mixed, 16000, nfft=512, hop=128, npks=20)
+    pm.run_pv()
+    wm = pm.toSinSum().synth(16000, 128)
+    assert wm[1].size == 0 and np.array_equal(wm[0], wb[0]) and np.array_equal(wm[2], wb[2])
+    assert pm.toSinSum().ntracks.tolist()[1] == 0
 
 
 HPG = np.load(os.path.join(GOLD, "hpower.npz"))

@@ -381,3 +381,50 @@ def test_sharded_pipeline_equals_unsharded(pvmod, world):
     w = np.concatenate(sig)
     assert w.shape == w0.shape
     assert np.array_equal(w, w0)
+
+
+def test_chunked_run_pv_under_a_device_budget_is_bit_identical(pvmod):
+    """run_pv(device_budget=...) (signals larger than a device-memory budget; the reference reads
+    the whole file, AudioInterface.py:15-37): frame-aligned chunks with one warm-up frame each,
+    tables streamed into pinned host memory -- equal to the one-shot run bit for bit, and toSinSum
+    (which uploads the host tables) gives the same partials and the same resynthesis."""
+    from pypevoc_b200 import signals
+    sr = 44100
+    x = signals.harm(sr, 4.0, 220, 60, 0.5, 0.02, 21)
+    x[int(1.5 * sr):int(1.7 * sr)] = 0.0
+    pv0 = pvmod.PV(x, sr, nfft=2048, hop=512, npks=40, progress=False)
+    pv0.run_pv(refine=True)
+    ss0 = pv0.toSinSum()
+    w0 = ss0.synth(sr, 512)
+    xh = torch.from_numpy(x).pin_memory()
+    for budget in (1 << 20, 3 << 20, 1 << 30):              # 64-frame chunks ... one chunk
+        pv = pvmod.PV(xh, sr, nfft=2048, hop=512, npks=40, progress=False)
+        hb = {}
+        pv.run_pv(hostbuf=hb, device_budget=budget, refine=True)
+        assert pv.nframes == pv0.nframes and pv._devout is None
+        if budget == 1 << 20:
+            assert pv.chunk_frames == 64 and pv.nframes > 4 * 64
+        for k in ("f", "mag", "ph", "realph", "binno", "fine_pos", "fine_val", "t"):
+            assert np.array_equal(getattr(pv, k), getattr(pv0, k)), (budget, k)
+        assert np.array_equal(np.asarray(pv.totalmag), np.asarray(pv0.totalmag))
+        ss = pv.toSinSum()
+        assert np.array_equal(ss.track_ids, ss0.track_ids)
+        assert np.array_equal(ss.synth(sr, 512), w0)
+    with pytest.raises(ValueError):
+        pvmod.PV(x, sr, nfft=2048, hop=512, npks=40, progress=False).run_pv(hostbuf={}, device_budget=1 << 20)
+
+
+def test_tosinsum_honours_host_edited_tables(pvmod):
+    """The reference tracks self.f / self.mag (PVAnalysis.py:320): edits made on the host arrays
+    (in place or by assignment) change the partials here too."""
+    from pypevoc_b200 import signals
+    x, sr = signals.two_sines()
+    pv = pvmod.PV(x, sr, nfft=2048, hop=512, npks=10, progress=False)
+    pv.run_pv()
+    n0 = len(pv.toSinSum().st)
+    keep = pv.f < 800.0
+    pv.mag[~keep] = 0.0                                      # in-place edit of a table that was read
+    pv.f = np.where(keep, pv.f, 0.0)                         # assignment
+    ss = pv.toSinSum()
+    tr = orc.track(pv.f, pv.mag)
+    assert np.array_equal(ss.track_ids, tr["tid"]) and len(ss.st) < n0
