@@ -43,6 +43,7 @@ CFG = dict(sr=44100, seconds=600, nfft=2048, hop=512, npks=50, pkthresh=0.005,
 CFG4 = dict(sr=44100, seconds=8 * 3600, nfft=2048, hop=256, npks=100, pkthresh=0.005,
             f0=200.0, nharm=100, p=0.4, sigma=0.01, seed=4000)
 CFG3 = dict(sr=16000, seconds=3, nclips=4096, nfft=512, hop=128, npks=20, pkthresh=0.005)
+E2E_TABLES = ("f", "mag", "ph", "totalmag")      # what the end-to-end step downloads (the arrays north_star names)
 METRIC = "STFT frames/sec (nfft=2048,hop=512,npks=50) + resynth partial-samples/sec"
 WORKLOAD = ("10 min mono 44.1 kHz synthetic harmonic tone+noise (configs[1] length; 220 Hz, 90 harmonics, "
             "sigma 0.01), metric parameters nfft=2048 hop=512 npks=50, analysis + tracking + full resynthesis")
@@ -491,7 +492,7 @@ def gpu_main(args):
             t0 = time.perf_counter()
             if world == 1:
                 pv = PV(xh, sr, nfft=nfft, hop=hop, npks=npks, pkthresh=c["pkthresh"], progress=False, device=dev)
-                pv.run_pv(hostbuf=hostbuf)                 # upload, analysis and table download overlap
+                pv.run_pv(hostbuf=hostbuf, stream_tables=E2E_TABLES)   # upload, analysis and table download overlap
                 ss = pv.toSinSum()
                 w = ss.synth(sr, hop, hostbuf=hostbuf)     # rendering and signal download overlap
                 assert pv.f.shape == (pv.nframes, npks) and w.dtype == np.float64   # host views (synchronises)
@@ -499,7 +500,7 @@ def gpu_main(args):
             else:
                 spv = D.ShardedPV(xh, sr, nsamp_total, nfft=nfft, hop=hop, npks=npks, pkthresh=c["pkthresh"],
                                   rank=rank, world=world, device=dev)
-                spv.run_pv(hostbuf=hostbuf)
+                spv.run_pv(hostbuf=hostbuf, stream_tables=E2E_TABLES)
                 ss = spv.toSinSum()
                 w, _ = ss.synth_local(hostbuf=hostbuf)
                 tids = ss.device_track_table                 # the gathered track table (stays on the device)
@@ -522,9 +523,10 @@ def gpu_main(args):
         e2e = {"value": frames_total / float(tt[0].item()), "unit": "frames/s",
                "h2d_bytes_per_step": int(tt[2].item()), "d2h_bytes_per_step": int(tt[1].item()),
                "ms_per_step": 1e3 * float(tt[0].item()),
-               "note": "PV(pinned host signal).run_pv(hostbuf) -> toSinSum -> synth(hostbuf): f/mag/ph/realph/"
-                       "binno/totalmag float64 tables + float64 resynthesis land in pinned host memory (copies "
-                       "overlap the kernels on side streams); host wall clock, max over ranks"}
+               "note": "PV(pinned host signal).run_pv(hostbuf, stream_tables=f/mag/ph/totalmag) -> toSinSum -> "
+                       "synth(hostbuf): the float64 f / mag / ph tables, totalmag and the float64 resynthesis land in "
+                       "pinned host memory (copies overlap the kernels on side streams); realph / binno stay on the "
+                       "device and are downloaded on first access of the attribute; host wall clock, max over ranks"}
 
     if rank != 0:
         if world > 1:

@@ -669,15 +669,15 @@ class ShardedPV(object):
                 self.rank, self.plan["nsamp"], self.plan["sample0"], self.pv.nsamp))
         self.sr, self.nfft, self.hop = sr, nfft, hop
 
-    def run_pv(self, hostbuf=None, chunks=8):
+    def run_pv(self, hostbuf=None, chunks=8, stream_tables=None):
         """Analyse this rank's window rows [w0, w1) (own rows: ``own_rows``).  ``hostbuf``: stream the
-        tables into pinned host memory as in PV.run_pv."""
+        tables (``stream_tables``: which of them) into pinned host memory as in PV.run_pv."""
         p, pv = self.plan, self.pv
         pv._hostbuf = None
         pv._d2h_event = None
         if hostbuf is not None and p["nframes"] > 0:
             pv._run_pv_streamed(hostbuf, int(chunks), 0, frame_lo=p["frame0"], nframes=p["nframes"],
-                                prev_zero=p["prev_zero"])
+                                prev_zero=p["prev_zero"], stream_tables=stream_tables)
         else:
             pv._devout = P.analyze_device(pv._xd, pv.sr, pv.nfft, pv.hop, pv.npeaks, pv.peakthresh, pv._tb,
                                           frame0=p["frame0"], nframes=p["nframes"], prev_zero=p["prev_zero"])

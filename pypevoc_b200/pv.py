@@ -498,7 +498,7 @@ class PV(object):
 
     def _fetch(self, name):
         d = self._devout
-        if self._hostbuf is not None and name in ("f", "mag", "ph", "realph", "binno", "totalmag"):
+        if self._hostbuf is not None and name in getattr(self, "_streamed", ()):
             # run_pv(hostbuf=...) already streamed the tables into pinned memory
             if self._d2h_event is not None:
                 self._d2h_event.synchronize()
@@ -574,7 +574,7 @@ class PV(object):
         return nbytes
 
     # -- analysis ----------------------------------------------------------------------
-    def run_pv(self, run_frames=0, hostbuf=None, chunks=8, refine=False, device_budget=None):
+    def run_pv(self, run_frames=0, hostbuf=None, chunks=8, refine=False, device_budget=None, stream_tables=None):
         """STFT + peak picking + instantaneous frequency for every frame (PVAnalysis.py:213-264)
         in one kernel launch.  Results appear as the reference's attributes ``f mag ph realph
         binno`` (float64 ``[nframes, npks]``), ``t``, ``nframes``, ``totalmag`` (list).
@@ -584,6 +584,10 @@ class PV(object):
         upload of a pinned host signal, the kernels and the download of finished rows overlap on
         three streams; the attributes are numpy views of the pinned buffers (valid until the next
         call with the same ``hostbuf``) and synchronise on first access.
+
+        ``stream_tables`` (with ``hostbuf``): names of the tables to stream (default: all of ``f mag ph
+        realph binno totalmag``).  The others stay on the device and are downloaded on first access of
+        the attribute, so a caller that only reads e.g. ``f mag ph`` moves 3/5 of the bytes.
 
         ``refine=True`` additionally evaluates ``PeakFinder.refine`` (PeakFinder.py:331-372) for
         every peak: attributes ``fine_pos`` (fractional bin) and ``fine_val`` (interpolated
@@ -610,7 +614,7 @@ class PV(object):
                 self.progress.update(self.nsamp)
             return
         if hostbuf is not None:
-            self._run_pv_streamed(hostbuf, int(chunks), run_frames, refine=refine)
+            self._run_pv_streamed(hostbuf, int(chunks), run_frames, refine=refine, stream_tables=stream_tables)
         else:
             self._devout = analyze_device(self._xd, self.sr, self.nfft, self.hop, self.npeaks, self.peakthresh,
                                           self._tb, run_frames=run_frames, refine=refine)
@@ -620,7 +624,8 @@ class PV(object):
         if self.progress:
             self.progress.update(self.nsamp)
 
-    def _run_pv_streamed(self, hostbuf, chunks, run_frames, frame_lo=0, nframes=None, prev_zero=True, refine=False):
+    def _run_pv_streamed(self, hostbuf, chunks, run_frames, frame_lo=0, nframes=None, prev_zero=True, refine=False,
+                         stream_tables=None):
         """Rows r = 0 .. F-1 are the frames starting at sample (frame_lo + r)*hop (frame_lo = 1 with
         prev_zero=False: frame 0 of the buffer is only the warm-up of a sharded window)."""
         dev, K = self._dev, self.npeaks
@@ -635,8 +640,13 @@ class PV(object):
             if refine:      # stays on the device, fetched on first access
                 out["fine_pos"] = torch.empty((1, F, K), dtype=torch.float64, device=dev)
                 out["fine_val"] = torch.empty((1, F, K), dtype=torch.float64, device=dev)
-            hb = {k: _pinned(hostbuf, k, (F, K), torch.float64) for k in names}
-            hb["totalmag"] = _pinned(hostbuf, "totalmag", (F,), torch.float64)
+            want = set(names + ("totalmag",)) if stream_tables is None else set(stream_tables)
+            if not want <= set(names + ("totalmag",)):
+                raise ValueError("stream_tables: unknown table name(s) %r" % sorted(want - set(names + ("totalmag",))))
+            snames = tuple(k for k in names if k in want)
+            hb = {k: _pinned(hostbuf, k, (F, K), torch.float64) for k in snames}
+            if "totalmag" in want:
+                hb["totalmag"] = _pinned(hostbuf, "totalmag", (F,), torch.float64)
             upload = self._xd_t is None
             if upload:
                 xd = torch.empty((self.nsamp,), dtype=torch.float32, device=dev)
@@ -667,9 +677,8 @@ class PV(object):
                 _mark("analysis %d" % i, cur)
                 with torch.cuda.stream(d2h):
                     d2h.wait_event(ev2)
-                    for k in names:
+                    for k in hb:
                         hb[k][j0:j1].copy_(out[k][0, j0:j1], non_blocking=True)
-                    hb["totalmag"][j0:j1].copy_(out["totalmag"][0, j0:j1], non_blocking=True)
                     _mark("tables d2h %d" % i, d2h)
             if upload:
                 self._xd_t = xd
@@ -680,7 +689,8 @@ class PV(object):
             self._d2h_event.record(d2h)
         self._devout = out
         self._hostbuf = hostbuf
-        self.d2h_bytes = F * (5 * K + 1) * 8
+        self._streamed = set(hb)
+        self.d2h_bytes = F * (len(snames) * K + (1 if "totalmag" in hb else 0)) * 8
 
     def _run_pv_chunked(self, hostbuf, budget, run_frames, refine=False):
         dev, K, hop, nfft = self._dev, self.npeaks, self.hop, self.nfft
@@ -734,6 +744,7 @@ class PV(object):
             self._d2h_event = last
         self._devout = None
         self._hostbuf = hostbuf
+        self._streamed = set(hb)
         self.nframes = F
         self.chunk_frames = Fc
         self.d2h_bytes = F * (len(names) * K + 1) * 8
