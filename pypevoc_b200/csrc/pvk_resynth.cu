@@ -588,11 +588,12 @@ extern "C" int pvk_resynth(const int32_t *tid, int64_t nframes, int npks, int64_
   p.nchp = nch < bd ? nch : bd;
   p.G = bd / p.nchp;
   if (p.G > npks) p.G = npks;
-  if (hop % 256 == 0) {
+  if (hop % 128 == 0) {
     // tile kernels: bodies are built inside the render kernel, one launch over the whole block range
     p.chunk0 = block0;
-    return hop % 512 == 0 ? launch_resynth_tile<16>(p, nblocks, stream)      // one warp per 512-sample tile
-                          : launch_resynth_tile<8>(p, nblocks, stream);
+    if (hop % 512 == 0) return launch_resynth_tile<16>(p, nblocks, stream);   // one warp per 512-sample tile
+    if (hop % 256 == 0) return launch_resynth_tile<8>(p, nblocks, stream);
+    return launch_resynth_tile<4>(p, nblocks, stream);                        // 128-sample tiles (16 kHz clip batches)
   }
   for (int64_t c0 = block0; c0 < block0 + nblocks; c0 += cb) {
     const int64_t n = (c0 + cb <= block0 + nblocks) ? cb : block0 + nblocks - c0;

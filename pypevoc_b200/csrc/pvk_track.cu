@@ -20,83 +20,8 @@ namespace pvk {
 
 constexpr int LINK_NONE = -1;    // slot is not a point
 // link <= -2: new partial, rank among the frame's new partials = -2 - link
-#ifndef PVK_TRACK_CHUNK
-#define PVK_TRACK_CHUNK 128
-#endif
-constexpr int TRACK_CHUNK = PVK_TRACK_CHUNK; // frames per chain-resolution chunk
 
 // ------------------------------------------------------------------ link
-// Load the two peak rows of one frame pair into the warp's shared memory (invalid slots get
-// magnitude -1), order the current peaks by descending magnitude (ord) and rank the previous ones
-// (prank), for K <= 32*S: a lane ranks its S slots in ONE pass over the row (one shared-memory
-// read per compared magnitude).  Returns nc; chi / phi = 1 + highest valid column.
-template <int S>
-__device__ __forceinline__ int link_prepare_s(const double *__restrict__ f, const double *__restrict__ mag,
-                                              int64_t row, bool has_prev, int K, int32_t *__restrict__ link,
-                                              double *cf, double *cm, double *pf, double *pm, short *ord,
-                                              short *prank, int &chi_out, int &phi_out) {
-  const int lane = threadIdx.x & 31;
-  int chi = 0, phi = 0;
-#pragma unroll
-  for (int s = 0; s < S; ++s) {
-    const int i = lane + 32 * s;
-    if (i < K) {
-      const double a = f[row * K + i], b = mag[row * K + i];
-      const bool v = a > 0.0 && b > 0.0;                        // :876
-      cf[i] = a; cm[i] = v ? b : -1.0;
-      if (v) chi = i + 1; else link[row * K + i] = LINK_NONE;
-      if (has_prev) {
-        const double c = f[(row - 1) * K + i], d = mag[(row - 1) * K + i];
-        const bool vp = c > 0.0 && d > 0.0;
-        pf[i] = c; pm[i] = vp ? d : -1.0;
-        if (vp) phi = i + 1;
-      }
-    }
-  }
-#pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) {
-    chi = max(chi, __shfl_xor_sync(FULL, chi, o));
-    phi = max(phi, __shfl_xor_sync(FULL, phi, o));
-  }
-  __syncwarp();
-  // order of the current peaks: magnitude descending (:874-875)
-  int nc = 0;
-  {
-    double mi[S];
-    int r[S];
-#pragma unroll
-    for (int s = 0; s < S; ++s) { const int i = lane + 32 * s; mi[s] = i < chi ? cm[i] : -1.0; r[s] = 0; }
-    for (int i2 = 0; i2 < chi; ++i2) {
-      const double m2 = cm[i2];
-#pragma unroll
-      for (int s = 0; s < S; ++s) r[s] += (m2 > mi[s] || (m2 == mi[s] && i2 > lane + 32 * s)) ? 1 : 0;
-    }
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-      const bool vi = mi[s] > 0.0;
-      if (vi) ord[r[s]] = (short)(lane + 32 * s);
-      nc += __popc(__ballot_sync(FULL, vi));
-    }
-  }
-  // rank of the previous peaks in descending magnitude (:891-900)
-  {
-    double mi[S];
-    int r[S];
-#pragma unroll
-    for (int s = 0; s < S; ++s) { const int i = lane + 32 * s; mi[s] = i < phi ? pm[i] : -1.0; r[s] = 0; }
-    for (int i2 = 0; i2 < phi; ++i2) {
-      const double m2 = pm[i2];
-#pragma unroll
-      for (int s = 0; s < S; ++s) r[s] += (m2 > mi[s] || (m2 == mi[s] && i2 < lane + 32 * s)) ? 1 : 0;
-    }
-#pragma unroll
-    for (int s = 0; s < S; ++s) { const int i = lane + 32 * s; if (i < phi) prank[i] = (short)(mi[s] > 0.0 ? r[s] : 0); }
-  }
-  __syncwarp();
-  chi_out = chi; phi_out = phi;
-  return nc;
-}
-
 // abs(17.312*(fc/pf - 1.0)): dpitch2st :62-68 as called at :914
 __device__ __forceinline__ double stonediff(double fc, double pfv) {
   return fabs(__dmul_rn(17.312, __dsub_rn(__ddiv_rn(fc, pfv), 1.0)));
@@ -309,363 +234,240 @@ __global__ void track_link_kernel(const double *__restrict__ f, const double *__
   }
 }
 
-// ---- wide rows, 128 < K <= 512: the propose / commit schedule of the fast kernel below (every
-// current peak proposes its nearest unused previous peak at once, the longest conflict-free
-// prefix of the magnitude order is committed per round) without stored candidate lists: a
-// proposal is found by scanning the peak's binary-searched window of the previous row and is
-// kept across rounds until its target gets taken.  Ranks come from warp bitonic sorts.  Rows
-// whose previous row has holes or is out of order take the sequential loop.
-__host__ __device__ constexpr int link_wide_smem_per_warp(int S) {
-  // cf cm pf pm skey (double) | pf32 | winner | usedw (32 words) | ord prank sidx (short)
-  return 32 * S * (5 * 8 + 4 + 4 + 3 * 2) + 32 * 4;
+// ---- rows of up to 512 peaks: the greedy loop without ranking either row.
+// The sequential loop (:903-950) hands every current peak, in descending magnitude order, its
+// nearest still-unused previous peak (if within maxpitchjmp).  Only peaks that compete for the same
+// previous peak need to know who comes first, and that is a direct magnitude comparison:
+//   * lane owns the current peaks in COLUMNS lane + 32 s; the previous peaks within maxpitchjmp of
+//     one (exact fp64 distance) form a bit mask over a window of <= 32 consecutive columns that
+//     starts at a binary-searched column (previous rows come out of the analysis in ascending
+//     frequency order; other rows scan from column 0);
+//   * a round: every unresolved peak proposes its nearest unused candidate (distance ties: larger
+//     previous magnitude, then lower column = lower rank, :891-900,:914-922); a proposed previous
+//     peak goes to the proposer that comes first in the order (atomicMax on the magnitude's bit
+//     pattern, then on the column among equal magnitudes: ties -> higher column first, :874-875).
+//     Everybody that comes before the EARLIEST LOSER keeps what it proposed (an earlier peak is
+//     never affected by a later one, and losing somebody else's target does not change one's own
+//     arg-min); the loser and everybody after it try again; a peak without unused candidates is a
+//     new partial.  "Before the loser" is a magnitude comparison with the loser.  Conflict-free rows
+//     finish in one round.
+//   * new partials are numbered by descending magnitude among themselves (:941).
+// Same result as the loop, bit for bit (tests/fuzz_emu.py).  Rows with a window wider than 32
+// columns (previous row with holes / out of order and more than 32 columns) take the loop itself.
+__host__ __device__ constexpr int link_claim_smem_per_warp(int S) {
+  // cf cm pf pm (double) | claim magnitudes = sort keys (8) | pf32 (4) | claim columns (4) | ord prank sidx (short) | usedw
+  return 32 * S * (4 * 8 + 8 + 4 + 4 + 3 * 2) + 32 * 4;
 }
 
 template <int S>
-__global__ void track_link_wide_kernel(const double *__restrict__ f, const double *__restrict__ mag,
-                                       int64_t nrows, int64_t F, int K, double maxjump,
-                                       int32_t *__restrict__ link, int32_t *__restrict__ newcount) {
+__global__ void track_link_claim_kernel(const double *__restrict__ f, const double *__restrict__ mag,
+                                        int64_t nrows, int64_t F, int K, double maxjump,
+                                        int32_t *__restrict__ link, int32_t *__restrict__ newcount) {
   PVK_SMEM(smem);
   constexpr int KM = 32 * S;
   const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned char *base = smem + (size_t)warp * link_wide_smem_per_warp(S);
+  unsigned char *base = smem + (size_t)warp * link_claim_smem_per_warp(S);
   double *cf = reinterpret_cast<double *>(base);
   double *cm = cf + KM;
   double *pf = cm + KM;
   double *pm = pf + KM;
-  double *skey = pm + KM;
-  float *pf32 = reinterpret_cast<float *>(skey + KM);
-  int *winner = reinterpret_cast<int *>(pf32 + KM);
-  unsigned *usedw = reinterpret_cast<unsigned *>(winner + KM);
-  short *ord = reinterpret_cast<short *>(usedw + 32);
+  unsigned long long *claim_m = reinterpret_cast<unsigned long long *>(pm + KM);   // [KM]; the loop's sort keys too
+  float *pf32 = reinterpret_cast<float *>(claim_m + KM);          // [KM] previous frequencies, -1 = not a point
+  int *claim_c = reinterpret_cast<int *>(pf32 + KM);              // [KM]
+  short *ord = reinterpret_cast<short *>(claim_c + KM);
   short *prank = ord + KM;
   short *sidx = prank + KM;
-  const float eps32 = (float)(maxjump / 17.312 * (1.0 + 1e-4) + 1e-6);   // guard band as in the fast kernel
+  unsigned *usedw = reinterpret_cast<unsigned *>(sidx + KM);      // [32]
+  // fp32 pre-test window: |fc - fp| < eps32 * fp is implied by |17.312 (fc/fp - 1)| < maxjump
+  // (slack 1e-4 relative + 1e-6 absolute >> fp32 rounding of fc and fp); the exact fp64 test decides
+  const float eps32 = (float)(maxjump / 17.312 * (1.0 + 1e-4) + 1e-6);
 
   for (int64_t row = (int64_t)blockIdx.x * W + warp; row < nrows; row += (int64_t)gridDim.x * W) {
     const bool has_prev = (row % F) > 0;
     int32_t *lrow = link + row * K;
-    int nc = 0, phi = 0;
+    int phi = 0;
+    double mine[S], fmine[S];
 #pragma unroll
     for (int s = 0; s < S; ++s) {
       const int i = lane + 32 * s;
-      bool v = false;
-      double cmv = -1.0, pmv = -1.0;
+      double cmv = -1.0, pmv = -1.0, cfv = 0.0;
+      float p32 = -1.f;
       if (i < K) {
         const double a = f[row * K + i], b = mag[row * K + i];
-        v = a > 0.0 && b > 0.0;                                   // :876
-        cf[i] = a; cmv = v ? b : -1.0;
+        const bool v = a > 0.0 && b > 0.0;                        // :876
+        cfv = a; cmv = v ? b : -1.0;
         if (!v) lrow[i] = LINK_NONE;
         if (has_prev) {
           const double c = f[(row - 1) * K + i], d = mag[(row - 1) * K + i];
           const bool vp = c > 0.0 && d > 0.0;
           pf[i] = c; pmv = vp ? d : -1.0;
-          pf32[i] = vp ? (float)c : -1.f;
+          p32 = vp ? (float)c : -1.f;
           if (vp) phi = i + 1;
         }
       }
-      cm[i] = cmv; pm[i] = pmv;
-      nc += __popc(__ballot_sync(FULL, v));
+      cf[i] = cfv; cm[i] = cmv; pm[i] = pmv; pf32[i] = p32;
+      mine[s] = cmv; fmine[s] = cfv;
     }
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) phi = max(phi, __shfl_xor_sync(FULL, phi, o));
+    usedw[lane] = 0u;
     __syncwarp();
-    // ---- order of the current peaks (:874-875), ties higher column first
-    for (int i = lane; i < KM; i += 32) { skey[i] = cm[i]; sidx[i] = (short)i; }
-    __syncwarp();
-    warp_sort_desc(skey, sidx, KM, true);
-    for (int t = lane; t < nc; t += 32) ord[t] = sidx[t];
-    __syncwarp();
-    if (!has_prev || phi == 0) {
-      for (int t = lane; t < nc; t += 32) lrow[ord[t]] = -2 - t;  // everything is new (:941)
-      if (lane == 0) newcount[row] = nc;
-      __syncwarp();
-      continue;
-    }
-    // ---- rank of the previous peaks (:891-900), ties lower column first
-    for (int i = lane; i < KM; i += 32) { skey[i] = i < phi ? pm[i] : -1.0; sidx[i] = (short)i; }
-    __syncwarp();
-    warp_sort_desc(skey, sidx, KM, false);
     bool okasc = true;
-    for (int t = lane; t < KM; t += 32) {
-      const int i = sidx[t];
-      if (i < phi) prank[i] = (short)(skey[t] > 0.0 ? t : 0);
-    }
     for (int p = lane; p < phi; p += 32)
       okasc = okasc && pm[p] > 0.0 && (p + 1 >= phi || (pm[p + 1] > 0.0 && pf32[p] <= pf32[p + 1]));
     const bool asc = __all_sync(FULL, okasc);
-    __syncwarp();
-    if (!asc) {                                                   // holes / out of order: sequential loop
-      const int nnew = link_greedy_generic(cf, pf, pm, ord, prank, nc, phi, maxjump, lrow);
-      if (lane == 0) newcount[row] = nnew;
-      __syncwarp();
-      continue;
-    }
-    // ---- per current peak t = lane + 32 s: column, start of its window in the previous row
-    int cidx[S], p0[S], res[S], prop[S];                          // res: -3 unresolved, -2 new, >= 0 matched column
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-      const int t = lane + 32 * s;
-      cidx[s] = 0; p0[s] = 0; prop[s] = -1;
-      res[s] = t < nc ? -3 : -4;
-      if (t < nc) {
-        cidx[s] = ord[t];
-        const float fc32 = (float)cf[cidx[s]];
-        const float flo = fc32 * (1.f - eps32);
-        int q = 0;
-#pragma unroll
-        for (int step = KM / 2; step >= 1; step >>= 1) {
-          const int mid = q + step;
-          if (mid <= phi && pf32[mid - 1] < flo) q = mid;
-        }
-        p0[s] = q;
-      }
-    }
-    if (lane < 32) usedw[lane] = 0u;
-    __syncwarp();
-    bool first = true;
-    for (;;) {
-      for (int p = lane; p < phi; p += 32) winner[p] = 0x7fffffff;
-      __syncwarp();
-#pragma unroll
-      for (int s = 0; s < S; ++s) {
-        if (res[s] == -3) {
-          // a kept proposal stays the arg-min while its target is unused (the unused set only shrinks)
-          const bool rescan = first || (prop[s] >= 0 && ((usedw[prop[s] >> 5] >> (prop[s] & 31)) & 1u));
-          if (rescan) {
-            const double fc = cf[cidx[s]];
-            const float fc32 = (float)fc;
-            const float fhi = fc32 * (1.f + eps32 + 2.f * eps32 * eps32);
-            double bd = 1e300;
-            int br = 0x7fffffff, bp = -1;
-            for (int p = p0[s]; p < phi; ++p) {
-              const float pv = pf32[p];
-              if (pv > fhi) break;
-              if (fabsf(fc32 - pv) < eps32 * pv && !((usedw[p >> 5] >> (p & 31)) & 1u)) {
-                const double d = stonediff(fc, pf[p]);
-                if (d < maxjump) {                                // :923: only these can ever match
-                  const int r = prank[p];
-                  if (d < bd || (d == bd && r < br)) { bd = d; br = r; bp = p; }
-                }
-              }
-            }
-            prop[s] = bp;
-          }
-          if (prop[s] >= 0) atomicMin(&winner[prop[s]], lane + 32 * s);
-        }
-      }
-      first = false;
-      __syncwarp();
-      int L = nc;                                                 // first loser in the order
-#pragma unroll
-      for (int s = S - 1; s >= 0; --s) {
-        const bool lose = res[s] == -3 && prop[s] >= 0 && winner[prop[s]] != lane + 32 * s;
-        const unsigned m = __ballot_sync(FULL, lose);
-        if (m) L = 32 * s + __ffs((int)m) - 1;
-      }
-      bool pending = false;
-#pragma unroll
-      for (int s = 0; s < S; ++s) {
-        if (res[s] == -3) {
-          if (lane + 32 * s < L) {
-            res[s] = prop[s] >= 0 ? prop[s] : -2;
-            if (prop[s] >= 0) atomicOr(&usedw[prop[s] >> 5], 1u << (prop[s] & 31));
-          } else {
-            pending = true;
-          }
-        }
-      }
-      __syncwarp();
-      if (!__any_sync(FULL, pending)) break;
-    }
-    int nnew = 0;                                                 // new partials in processing order (:941)
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-      const bool isnew = res[s] == -2;
-      const unsigned m = __ballot_sync(FULL, isnew);
-      if (res[s] >= 0) lrow[cidx[s]] = res[s];
-      else if (isnew) lrow[cidx[s]] = -2 - (nnew + __popc(m & lanemask_lt()));
-      nnew += __popc(m);
-    }
-    if (lane == 0) newcount[row] = nnew;
-    __syncwarp();
-  }
-}
 
-// Fast link for K <= 32*S (S = slots per lane).  Same result as the generic loop, different
-// schedule: every lane owns the current peaks t = lane + 32*s (t = position in the descending
-// magnitude order), collects the few previous peaks within maxpitchjmp of it (cheap fp64
-// pre-test, exact distance only for survivors), then all peaks propose their nearest unused
-// candidate at once.  A proposal is final when no peak earlier in the order proposed the same
-// previous peak AND every earlier peak is final too, i.e. the longest conflict-free prefix of
-// the order is committed per round (an earlier peak can never be affected by a later one, and
-// removing somebody else's target from the unused set does not change one's own arg-min).
-constexpr int LINK_NC = 8;   // candidates kept per current peak; overflow -> generic loop for that row
-__host__ __device__ constexpr int link_fast_smem_per_warp(int S) {
-  // cf cm pf pm (double) | cand_d | winner | pf32 | usedw | ord prank | cand_p cand_r
-  return 32 * S * 4 * 8 + 32 * S * LINK_NC * 8 + 32 * S * 4 + 32 * S * 4 + 16 + 32 * S * 2 * 2 + 32 * S * LINK_NC * 2 * 2;
-}
-
-template <int S>
-__global__ void track_link_fast_kernel(const double *__restrict__ f, const double *__restrict__ mag,
-                                       int64_t nrows, int64_t F, int K, double maxjump,
-                                       int32_t *__restrict__ link, int32_t *__restrict__ newcount) {
-  PVK_SMEM(smem);
-  constexpr int KM = 32 * S;
-  const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int PER_WARP = link_fast_smem_per_warp(S);
-  unsigned char *base = smem + (size_t)warp * PER_WARP;
-  double *cf = reinterpret_cast<double *>(base);
-  double *cm = cf + KM;
-  double *pf = cm + KM;
-  double *pm = pf + KM;
-  double *cand_d = pm + KM;                                       // [LINK_NC][S][32]
-  int *winner = reinterpret_cast<int *>(cand_d + KM * LINK_NC);   // [KM]
-  float *pf32 = reinterpret_cast<float *>(winner + KM);           // [KM] previous frequencies, -1 = not a point
-  unsigned *usedw = reinterpret_cast<unsigned *>(pf32 + KM);      // [4]
-  short *ord = reinterpret_cast<short *>(usedw + 4);
-  short *prank = ord + KM;
-  short *cand_p = prank + KM;                                     // [LINK_NC][S][32]
-  short *cand_r = cand_p + KM * LINK_NC;
-  // fp32 pre-test window: |fc - fp| < eps32 * fp is implied by |17.312 (fc/fp - 1)| < maxjump
-  // (slack 1e-4 relative + 1e-6 absolute >> fp32 rounding of fc and fp); the exact fp64 test
-  // decides among the survivors
-  const float eps32 = (float)(maxjump / 17.312 * (1.0 + 1e-4) + 1e-6);
-
-  for (int64_t row = (int64_t)blockIdx.x * W + warp; row < nrows; row += (int64_t)gridDim.x * W) {
-    int chi, phi;
-    const int nc = link_prepare_s<S>(f, mag, row, (row % F) > 0, K, link, cf, cm, pf, pm, ord, prank, chi, phi);
-    int32_t *lrow = link + row * K;
-    // previous frequencies in fp32; `asc`: every slot below phi is a point and they ascend (rows
-    // come out of the analysis in bin order) -> the candidate window is found by binary search
-    bool okasc = true;
-    for (int p = lane; p < phi; p += 32) {
-      const bool vp = pm[p] > 0.0;
-      const float a = vp ? (float)pf[p] : -1.f;
-      pf32[p] = a;
-      okasc = okasc && vp && (p + 1 >= phi || (pm[p + 1] > 0.0 && a <= (float)pf[p + 1]));
-    }
-    const bool asc = __all_sync(FULL, okasc);
-    __syncwarp();
-    // ---- candidate lists: cheap window scan over the previous row, then exact distances
-    int ncand[S], cidx[S];
+    // ---- candidate masks: bit b of cmask[s] = previous column p0[s] + b is within maxpitchjmp
+    int p0[S], res[S];                                            // res: -3 unresolved, -2 new, -4 no peak, >= 0 matched column
+    unsigned cmask[S];
     bool overflow = false;
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-      const int t = lane + 32 * s;
-      ncand[s] = 0; cidx[s] = 0;
-      if (t < nc) {
-        const int c = ord[t];
-        cidx[s] = c;
-        const float fc32 = (float)cf[c];
-        int n = 0;
-        int p0 = 0, p1 = phi;
+      p0[s] = 0; cmask[s] = 0u;
+      res[s] = mine[s] > 0.0 ? -3 : -4;
+      if (mine[s] > 0.0 && phi > 0) {
+        const double fc = fmine[s];
+        const float fc32 = (float)fc;
         float fhi = 3.0e38f;
+        int q = 0;
         if (asc) {
           // every p passing the window test below has pf32[p] in [flo, fhi]
           const float flo = fc32 * (1.f - eps32);
           fhi = fc32 * (1.f + eps32 + 2.f * eps32 * eps32);
 #pragma unroll
           for (int step = KM / 2; step >= 1; step >>= 1) {
-            const int mid = p0 + step;
-            if (mid <= phi && pf32[mid - 1] < flo) p0 = mid;
+            const int mid = q + step;
+            if (mid <= phi && pf32[mid - 1] < flo) q = mid;
           }
         }
-        for (int p = p0; p < p1; ++p) {
+        p0[s] = q;
+        for (int p = q; p < phi; ++p) {
           const float pv = pf32[p];
           if (pv > fhi) break;
-          if (fabsf(fc32 - pv) < eps32 * pv) {
-            if (n < LINK_NC) cand_p[(n * S + s) * 32 + lane] = (short)p;
-            ++n;
+          if (fabsf(fc32 - pv) < eps32 * pv && stonediff(fc, pf[p]) < maxjump) {   // :923: only these can ever match
+            if (p - q < 32) cmask[s] |= 1u << (p - q); else overflow = true;
           }
         }
-        ncand[s] = n;
-        overflow = overflow || n > LINK_NC;
       }
     }
-    if (!__any_sync(FULL, overflow)) {
+    if (__any_sync(FULL, overflow)) {
+      // ---- rare: the reference's loop itself, with both rows ranked by a warp bitonic sort
+      double *skey = reinterpret_cast<double *>(claim_m);
+      int nc = 0;
 #pragma unroll
-      for (int s = 0; s < S; ++s) {
-        const double fc = cf[cidx[s]];
-        int keep = 0;
-        for (int n = 0; n < ncand[s]; ++n) {
-          const int p = cand_p[(n * S + s) * 32 + lane];
-          const double d = stonediff(fc, pf[p]);
-          if (d < maxjump) {                                      // :923: only these can ever match
-            const int o = (keep * S + s) * 32 + lane;
-            cand_p[o] = (short)p; cand_d[o] = d; cand_r[o] = prank[p];
-            ++keep;
-          }
-        }
-        ncand[s] = keep;
+      for (int s = 0; s < S; ++s) nc += __popc(__ballot_sync(FULL, mine[s] > 0.0));
+      for (int i = lane; i < KM; i += 32) { skey[i] = cm[i]; sidx[i] = (short)i; }
+      __syncwarp();
+      warp_sort_desc(skey, sidx, KM, true);
+      for (int t = lane; t < nc; t += 32) ord[t] = sidx[t];
+      __syncwarp();
+      for (int i = lane; i < KM; i += 32) { skey[i] = i < phi ? pm[i] : -1.0; sidx[i] = (short)i; }
+      __syncwarp();
+      warp_sort_desc(skey, sidx, KM, false);
+      for (int t = lane; t < KM; t += 32) {
+        const int i = sidx[t];
+        if (i < phi) prank[i] = (short)(skey[t] > 0.0 ? t : 0);
       }
-    }
-    if (__any_sync(FULL, overflow)) {                             // rare: keep exactness via the generic loop
+      __syncwarp();
       const int nnew = link_greedy_generic(cf, pf, pm, ord, prank, nc, phi, maxjump, lrow);
       if (lane == 0) newcount[row] = nnew;
       __syncwarp();
       continue;
     }
+
     // ---- propose / commit rounds
-    if (lane < 4) usedw[lane] = 0u;
-    int res[S];                                                   // -3 unresolved, -2 new, >= 0 matched column
+    int prop[S];
 #pragma unroll
-    for (int s = 0; s < S; ++s) res[s] = (lane + 32 * s < nc) ? -3 : -4;
-    __syncwarp();
+    for (int s = 0; s < S; ++s) prop[s] = -1;
     for (;;) {
-      for (int p = lane; p < phi; p += 32) winner[p] = 0x7fffffff;
+      bool pend = false;
+#pragma unroll
+      for (int s = 0; s < S; ++s) pend = pend || (res[s] == -3 && cmask[s] != 0u);
+      if (!__any_sync(FULL, pend)) break;
+      for (int p = lane; p < phi; p += 32) { claim_m[p] = 0ull; claim_c[p] = -1; }
       __syncwarp();
-      int prop[S];
 #pragma unroll
       for (int s = 0; s < S; ++s) {
-        prop[s] = -1;
-        if (res[s] == -3) {
-          double bd = 1e300;
-          int br = 0x7fffffff;
-          for (int n = 0; n < ncand[s]; ++n) {
-            const int o = (n * S + s) * 32 + lane;
-            const int p = cand_p[o];
-            if (!((usedw[p >> 5] >> (p & 31)) & 1u)) {
-              const double d = cand_d[o];
-              const int r = cand_r[o];
-              if (d < bd || (d == bd && r < br)) { bd = d; br = r; prop[s] = p; }
+        if (res[s] == -3 && cmask[s] != 0u) {
+          // a kept proposal stays the arg-min while its target is unused (the unused set only shrinks)
+          if (prop[s] < 0 || ((usedw[prop[s] >> 5] >> (prop[s] & 31)) & 1u)) {
+            // nearest unused candidate; distance ties: larger previous magnitude, then lower column
+            const double fc = fmine[s];
+            double bd = 1e300, bm = -1.0;
+            int bp = -1;
+            for (unsigned rem = cmask[s]; rem; rem &= rem - 1u) {
+              const int p = p0[s] + __ffs((int)rem) - 1;
+              if ((usedw[p >> 5] >> (p & 31)) & 1u) { cmask[s] &= ~(rem & (0u - rem)); continue; }   // taken: drop it
+              const double d = stonediff(fc, pf[p]);
+              const double m = pm[p];
+              if (d < bd || (d == bd && m > bm)) { bd = d; bm = m; bp = p; }
             }
+            prop[s] = bp;
           }
-          if (prop[s] >= 0) atomicMin(&winner[prop[s]], lane + 32 * s);
+          if (prop[s] >= 0) atomicMax(&claim_m[prop[s]], (unsigned long long)__double_as_longlong(mine[s]));
         }
       }
       __syncwarp();
-      // first loser in the order
-      int L = nc;
-#pragma unroll
-      for (int s = S - 1; s >= 0; --s) {
-        const bool lose = res[s] == -3 && prop[s] >= 0 && winner[prop[s]] != lane + 32 * s;
-        const unsigned m = __ballot_sync(FULL, lose);
-        if (m) L = 32 * s + __ffs((int)m) - 1;
-      }
-      bool pending = false;
 #pragma unroll
       for (int s = 0; s < S; ++s) {
-        if (res[s] == -3) {
-          if (lane + 32 * s < L) {
-            res[s] = prop[s] >= 0 ? prop[s] : -2;
-            if (prop[s] >= 0) atomicOr(&usedw[prop[s] >> 5], 1u << (prop[s] & 31));
-          } else {
-            pending = true;
+        if (res[s] == -3 && prop[s] >= 0 && cmask[s] != 0u &&
+            claim_m[prop[s]] == (unsigned long long)__double_as_longlong(mine[s]))
+          atomicMax(&claim_c[prop[s]], lane + 32 * s);
+      }
+      __syncwarp();
+      // the earliest loser in the order (magnitude descending, ties higher column first): everybody
+      // before it keeps what it proposed, the loser and everybody after it try again
+      unsigned long long lk = 0ull;
+      int lc = -1;
+      bool win[S];
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const bool act = res[s] == -3 && prop[s] >= 0 && cmask[s] != 0u;
+        const unsigned long long key = (unsigned long long)__double_as_longlong(mine[s]);
+        win[s] = act && claim_m[prop[s]] == key && claim_c[prop[s]] == lane + 32 * s;
+        if (act && !win[s] && (key > lk || (key == lk && lane + 32 * s > lc))) { lk = key; lc = lane + 32 * s; }
+      }
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        const unsigned long long ok = __shfl_xor_sync(FULL, lk, o);
+        const int oc = __shfl_xor_sync(FULL, lc, o);
+        if (ok > lk || (ok == lk && oc > lc)) { lk = ok; lc = oc; }
+      }
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        if (win[s]) {
+          const unsigned long long key = (unsigned long long)__double_as_longlong(mine[s]);
+          if (lc < 0 || key > lk || (key == lk && lane + 32 * s > lc)) {
+            res[s] = prop[s];
+            atomicOr(&usedw[prop[s] >> 5], 1u << (prop[s] & 31));
           }
         }
       }
       __syncwarp();
-      if (!__any_sync(FULL, pending)) break;
     }
-    // ---- new partials are numbered in processing order (:941)
+    // ---- links; new partials numbered by descending magnitude, ties higher column first (:874-875, :941)
+    unsigned newm[S];
     int nnew = 0;
 #pragma unroll
+    for (int s = 0; s < S; ++s) { newm[s] = __ballot_sync(FULL, res[s] == -3); nnew += __popc(newm[s]); }
+    int rk[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) rk[s] = 0;
+    if (nnew > 1) {
+#pragma unroll
+      for (int s2 = 0; s2 < S; ++s2) {
+        for (unsigned rem = newm[s2]; rem; rem &= rem - 1u) {
+          const int c2 = 32 * s2 + __ffs((int)rem) - 1;
+          const double m2 = cm[c2];
+#pragma unroll
+          for (int s = 0; s < S; ++s) rk[s] += (m2 > mine[s] || (m2 == mine[s] && c2 > lane + 32 * s)) ? 1 : 0;
+        }
+      }
+    }
+#pragma unroll
     for (int s = 0; s < S; ++s) {
-      const bool isnew = res[s] == -2;
-      const unsigned m = __ballot_sync(FULL, isnew);
-      if (res[s] >= 0) lrow[cidx[s]] = res[s];
-      else if (isnew) lrow[cidx[s]] = -2 - (nnew + __popc(m & lanemask_lt()));
-      nnew += __popc(m);
+      if (res[s] >= 0) lrow[lane + 32 * s] = res[s];
+      else if (res[s] == -3) lrow[lane + 32 * s] = -2 - rk[s];
     }
     if (lane == 0) newcount[row] = nnew;
     __syncwarp();
@@ -815,117 +617,128 @@ __host__ __device__ inline int track_tile_rows(int K) {
   return rt > 32 ? 32 : (rt < 1 ? 1 : rt);
 }
 
-// One warp per chunk of TRACK_CHUNK frames, W warps per CTA: link + base -> tid, tile by tile
-// (<= 32 rows): bulk copy of the link rows into shared memory, sequential pass, bulk copy out.
-__global__ void track_chunk_kernel(const int32_t *__restrict__ link, const int32_t *__restrict__ base,
-                                   int64_t F, int K, int64_t nchunks, int64_t total_chunks, int32_t *__restrict__ tid) {
-  PVK_SMEM(smem);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
-  const int RT = track_tile_rows(K);
+// Sequential pass of ONE warp over rows [r0, r1) of a reference table, tile by tile (<= 32 rows)
+// through shared memory: bulk copy in, row after row, bulk copy out.  LINK: the rows come from
+// link + base (new partials get their final ids here) and go to T; otherwise T is updated in place.
+// A continued entry of row r0 stays a reference (-2 - column) to the row before r0; every later row
+// copies what the row before it holds.  `last` (K ints, may be NULL) receives the final row.
+template <bool LINK>
+__device__ __forceinline__ void warp_chunk_pass(const int32_t *__restrict__ link, const int32_t *__restrict__ base,
+                                                int32_t *T, int64_t r0, int64_t r1, int K, int *tile, int RT,
+                                                int32_t *last) {
+  const int lane = threadIdx.x & 31;
   const int KP = (K + 3) & ~3;                                                  // keeps `rows` 16-byte aligned
-  int *tile = reinterpret_cast<int *>(smem) + (size_t)warp * ((KP + RT * K + 3) & ~3);
-  const int64_t cid = (int64_t)blockIdx.x * W + warp;
-  if (cid >= total_chunks) return;
-  const int64_t clip = cid / nchunks, ch = cid % nchunks;
-  const int64_t j0 = ch * TRACK_CHUNK, j1 = (j0 + TRACK_CHUNK < F) ? j0 + TRACK_CHUNK : F;
   int *rows = tile + KP;                                                        // tile[0..K) = carried row
-  for (int64_t t0 = j0; t0 < j1; t0 += RT) {
-    const int n = (int)((t0 + RT <= j1) ? RT : j1 - t0);
-    const int64_t row0 = clip * F + t0;
-    warp_copy_ints(rows, link + row0 * K, n * K);
-    const int mybase = lane < n ? base[row0 + lane] : 0;
+  for (int64_t t0 = r0; t0 < r1; t0 += RT) {
+    const int n = (int)((t0 + RT <= r1) ? RT : r1 - t0);
+    warp_copy_ints(rows, (LINK ? link : T) + t0 * K, n * K);
+    const int mybase = (LINK && lane < n) ? base[t0 + lane] : 0;
     __syncwarp();
     const int *prev = tile;
     for (int i = 0; i < n; ++i) {
       int *r = rows + i * K;
       const int bi = __shfl_sync(FULL, mybase, i);
-      const bool first = (t0 + i == j0);
+      const bool first = (t0 + i == r0);
       for (int c = lane; c < K; c += 32) {
-        const int lk = r[c];
-        int v;
-        if (lk == LINK_NONE) v = -1;
-        else if (lk <= -2) v = bi + (-2 - lk);
-        else if (first) v = -2 - c;                  // continued from the chunk before: unresolved
-        else v = prev[lk];                           // same id as column lk of the row before
+        int v = r[c];
+        if (LINK) {
+          if (v == LINK_NONE) v = -1;
+          else if (v <= -2) v = bi + (-2 - v);         // new partial: final id
+          else v = first ? -2 - v : prev[v];           // same id as column v of the row before
+        } else if (v <= -2 && !first) {
+          v = prev[-2 - v];
+        }
         r[c] = v;
       }
       __syncwarp();
       prev = r;
     }
-    warp_copy_ints(tid + row0 * K, rows, n * K);
+    warp_copy_ints(T + t0 * K, rows, n * K);
     for (int c = lane; c < K; c += 32) tile[c] = rows[(n - 1) * K + c];
     __syncwarp();
   }
+  if (last != nullptr) for (int c = lane; c < K; c += 32) last[c] = tile[c];
 }
 
-// G[ch][c] for the first row of chunk ch >= 1: what the continued peak points at in chunk ch-1
-__global__ void track_boundary_kernel(const int32_t *__restrict__ link, const int32_t *__restrict__ tid,
-                                      int64_t F, int K, int64_t nchunks, int64_t nclips,
-                                      int32_t *__restrict__ G) {
-  const int64_t n = nclips * nchunks * K;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(e % K);
-    const int64_t cc = e / K, ch = cc % nchunks, clip = cc / nchunks;
-    const int64_t row = clip * F + ch * TRACK_CHUNK;
-    int v = tid[row * K + c];
-    if (v <= -2) {                      // continued from the previous chunk's last row
-      const int lk = link[row * K + c];
-      v = tid[(row - 1) * K + lk];      // >= 0 final, or <= -2: first-row column of chunk ch-1
+// Chain resolution, hierarchical: every level cuts its table into chunks of RES_CHUNK rows, one warp
+// resolves a chunk relative to the row before it (all chunks at once) and hands the chunk's last row
+// to the next, RES_CHUNK times shorter level; the last level (<= RES_MID rows) is resolved by one CTA;
+// then every level replaces its remaining references by the resolved last row of the chunk before.
+constexpr int RES_CHUNK = 32;
+constexpr int RES_MID = 512;
+
+__host__ __device__ inline int resolve_tile_ints(int K, int RT) { return (((K + 3) & ~3) + RT * K + 3) & ~3; }
+
+// level 1 (LINK: link + base -> tid) or a higher level (in place); S = last rows of the chunks
+template <bool LINK>
+__global__ void resolve_chunk_kernel(const int32_t *__restrict__ link, const int32_t *__restrict__ base, int32_t *T,
+                                     int64_t n, int K, int RT, int32_t *__restrict__ S) {
+  PVK_SMEM(smem);
+  const int warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+  int *tile = reinterpret_cast<int *>(smem) + (size_t)warp * resolve_tile_ints(K, RT);
+  const int64_t ch = (int64_t)blockIdx.x * W + warp;
+  const int64_t r0 = ch * RES_CHUNK;
+  if (r0 >= n) return;
+  const int64_t r1 = r0 + RES_CHUNK < n ? r0 + RES_CHUNK : n;
+  warp_chunk_pass<LINK>(link, base, T, r0, r1, K, tile, RT, S + ch * K);
+}
+
+// last level: one CTA, warp w owns rows [w m, (w+1) m): chunk pass, then warp 0 walks the NW last rows,
+// then every warp resolves what is left in its rows
+__global__ void resolve_mid_kernel(int32_t *T, int64_t n, int K, int RT) {
+  PVK_SMEM(smem);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
+  int *last = reinterpret_cast<int *>(smem);                                    // [NW][K]
+  int *tile = last + (((size_t)NW * K + 3) & ~(size_t)3) + (size_t)warp * resolve_tile_ints(K, RT);
+  const int64_t m = (n + NW - 1) / NW;
+  const int64_t r0 = warp * m, r1 = r0 + m < n ? r0 + m : n;
+  if (r0 < n) warp_chunk_pass<false>(nullptr, nullptr, T, r0, r1, K, tile, RT, last + warp * K);
+  __syncthreads();
+  if (warp == 0) {
+    for (int w = 1; w < NW && (int64_t)w * m < n; ++w) {
+      for (int c = lane; c < K; c += 32) {
+        const int v = last[w * K + c];
+        if (v <= -2) last[w * K + c] = last[(w - 1) * K + (-2 - v)];
+      }
+      __syncwarp();
     }
-    G[e] = v;
+  }
+  __syncthreads();
+  if (warp > 0 && r0 < n) {
+    const int *pl = last + (warp - 1) * K;
+    int32_t *t = T + r0 * K;
+    const int64_t ne = (r1 - r0) * K;
+    for (int64_t e = lane; e < ne; e += 32) {
+      const int v = t[e];
+      if (v <= -2) t[e] = pl[-2 - v];
+    }
   }
 }
 
-// G becomes the final ids of every chunk's first row: an unresolved entry -2-c takes the (final)
-// id of column c of the chunk before.  One CTA per clip streams the table through shared memory in
-// tiles of R rows and resolves a tile by pointer jumping: in round r an unresolved entry of row i
-// names a column of row i - 2^r and takes what it finds there -- a final id, or that entry's own
-// reference, which then sits 2^(r+1) rows back.  Rows i < 2^(r+1) - 1 are final after round r (row
-// -1 = last row of the tile before, kept in `carry`), so ceil(log2(R + 1)) rounds do instead of R
-// sequential row steps.
-__global__ void __launch_bounds__(1024) track_stitch_kernel(int32_t *__restrict__ G, int K, int64_t nchunks, int R) {
-  PVK_SMEM(smem);
-  const int KP = (K + 3) & ~3;
-  int *carry = reinterpret_cast<int *>(smem);
-  int *A = carry + KP;
-  int *B = A + (size_t)R * K + ((4 - ((R * K) & 3)) & 3);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NWARP = blockDim.x >> 5, BD = blockDim.x;
-  int32_t *g = G + (int64_t)blockIdx.x * nchunks * K;
-  for (int c = tid; c < K; c += BD) carry[c] = -1;                 // chunk 0 has no references
-  for (int64_t c0 = 0; c0 < nchunks; c0 += R) {
-    const int n = (int)((c0 + R <= nchunks) ? R : nchunks - c0);
-    const int ne = n * K;
-    for (int e = tid; e < ne; e += BD) A[e] = g[c0 * K + e];
-    __syncthreads();
-    for (int d = 1;; d <<= 1) {
-      int pending = 0;
-      for (int i = warp; i < n; i += NWARP) {
-        const int j = i - d;
-        const int *srow = j < 0 ? carry : A + j * K;
-        for (int c = lane; c < K; c += 32) {
-          int v = A[i * K + c];
-          if (v <= -2) { v = srow[-2 - v]; pending |= (v <= -2) ? 1 : 0; }
-          B[i * K + c] = v;
+// remaining references of chunk i >= 1 -> resolved last row of chunk i - 1 (Sres); one CTA per chunk
+__global__ void resolve_fix_kernel(int32_t *__restrict__ T, int64_t n, int K, const int32_t *__restrict__ Sres) {
+  for (int64_t ch = 1 + blockIdx.x; ch * RES_CHUNK < n; ch += gridDim.x) {
+    const int64_t r0 = ch * RES_CHUNK, r1 = r0 + RES_CHUNK < n ? r0 + RES_CHUNK : n;
+    const int32_t *pl = Sres + (ch - 1) * K;
+    int32_t *t = T + r0 * K;
+    const int ne = (int)((r1 - r0) * K);
+    if ((((uintptr_t)t) & 15) == 0 && (ne & 3) == 0) {
+      int4 *t4 = reinterpret_cast<int4 *>(t);
+      for (int e = threadIdx.x; e < (ne >> 2); e += blockDim.x) {
+        int4 v = t4[e];
+        if (v.x <= -2 || v.y <= -2 || v.z <= -2 || v.w <= -2) {
+          if (v.x <= -2) v.x = pl[-2 - v.x];
+          if (v.y <= -2) v.y = pl[-2 - v.y];
+          if (v.z <= -2) v.z = pl[-2 - v.z];
+          if (v.w <= -2) v.w = pl[-2 - v.w];
+          t4[e] = v;
         }
       }
-      int *t = A; A = B; B = t;
-      if (__syncthreads_count(pending) == 0) break;
-    }
-    for (int e = tid; e < ne; e += BD) g[c0 * K + e] = A[e];
-    __syncthreads();
-    for (int c = tid; c < K; c += BD) carry[c] = A[(n - 1) * K + c];
-    __syncthreads();
-  }
-}
-
-__global__ void track_fix_kernel(int32_t *__restrict__ tid, const int32_t *__restrict__ G, int64_t F,
-                                 int K, int64_t nchunks, int64_t nclips) {
-  const int64_t n = nclips * F * K;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
-    const int v = tid[e];
-    if (v <= -2) {
-      const int64_t row = e / K, clip = row / F, ch = (row % F) / TRACK_CHUNK;
-      tid[e] = G[(clip * nchunks + ch) * K + (-2 - v)];
+    } else {
+      for (int e = threadIdx.x; e < ne; e += blockDim.x) {
+        const int v = t[e];
+        if (v <= -2) t[e] = pl[-2 - v];
+      }
     }
   }
 }
@@ -1073,11 +886,20 @@ static inline int grid_for(int64_t n, int block) {
 
 using namespace pvk;
 
+// last-row tables of all resolve levels: rows/32 + rows/32^2 + ... rows of npks ints
+static int64_t resolve_levels_bytes(int64_t rows, int npks) {
+  int64_t total = 0;
+  for (int64_t n = rows; n > 1;) {
+    n = (n + RES_CHUNK - 1) / RES_CHUNK;
+    total += align_up(n * npks * 4, 256);
+  }
+  return total + 256;
+}
+
 extern "C" int64_t pvk_track_workspace_bytes(int64_t nclips, int64_t nframes, int npks) {
   if (nclips < 0 || nframes < 0 || npks < 1) return -1;
   const int64_t rows = nclips * nframes;
-  const int64_t nchunks = (nframes + TRACK_CHUNK - 1) / TRACK_CHUNK;
-  return align_up(rows * 4, 256) * 2 + align_up(nclips * nchunks * npks * 4, 256) +
+  return align_up(rows * 4, 256) * 2 + resolve_levels_bytes(rows, npks) +
          align_up(nclips * scan_tiles(nframes) * 8, 256) + 256;
 }
 
@@ -1100,57 +922,38 @@ extern "C" int pvk_track(const double *f, const double *mag, int64_t nclips, int
               "pvk_track: nclips*nframes*npks must be < 2^31");
   const int K = npks;
   const int64_t rows = nclips * nframes;
-  const int64_t nchunks = (nframes + TRACK_CHUNK - 1) / TRACK_CHUNK;
   unsigned char *ws = reinterpret_cast<unsigned char *>(workspace);
   int32_t *newcount = reinterpret_cast<int32_t *>(ws);
   int32_t *base = reinterpret_cast<int32_t *>(ws + align_up(rows * 4, 256));
-  int32_t *G = reinterpret_cast<int32_t *>(ws + 2 * align_up(rows * 4, 256));
-  long long *tsum = reinterpret_cast<long long *>(ws + 2 * align_up(rows * 4, 256) + align_up(nclips * nchunks * npks * 4, 256));
+  unsigned char *levels = ws + 2 * align_up(rows * 4, 256);
+  long long *tsum = reinterpret_cast<long long *>(levels + resolve_levels_bytes(rows, npks));
 
   {  // link: one warp per frame pair
     int64_t g;
-    // rows of more than `wide_from - 1` peaks take the wide kernel (PVK_LINK_WIDE_FROM: tuning override)
-    static const int wide_from = []() { const char *e = getenv("PVK_LINK_WIDE_FROM"); return e ? atoi(e) : 129; }();
-    if (K <= 128 && K < wide_from) {
-      const int S = K <= 32 ? 1 : (K <= 64 ? 2 : 4);
-      const int per_warp = link_fast_smem_per_warp(S);
-      const int W = S == 4 ? 4 : 8;
+    // rows of `wide_from` or more peaks take the sequential loop kernel (PVK_LINK_GENERIC_FROM: test override)
+    static const int wide_from = []() { const char *e = getenv("PVK_LINK_GENERIC_FROM"); return e ? atoi(e) : 513; }();
+    if (K <= 512 && K < wide_from) {
+      const int S = K <= 32 ? 1 : (K <= 64 ? 2 : (K <= 128 ? 4 : (K <= 256 ? 8 : 16)));
+      const int per_warp = link_claim_smem_per_warp(S);
+      const int W = S <= 4 ? 8 : (S == 8 ? 4 : 2);
       const int smem = W * per_warp;
       g = (rows + W - 1) / W;
       if (g > 148 * 64) g = 148 * 64;
-#define PVK_LINK_FAST(SS)                                                                          \
+#define PVK_LINK_CLAIM(SS)                                                                         \
       do {                                                                                           \
-        if (smem > 48 * 1024 && PVK_SET_SMEM(track_link_fast_kernel<SS>, smem) != 0) {              \
+        if (smem > 48 * 1024 && PVK_SET_SMEM(track_link_claim_kernel<SS>, smem) != 0) {             \
           set_error("pvk_track: cannot reserve %d bytes of shared memory", smem);                    \
           return PVK_ERR_CUDA;                                                                       \
         }                                                                                            \
-        PVK_LAUNCH(track_link_fast_kernel<SS>, dim3((unsigned)g), dim3(W * 32), smem, stream, f, mag, rows, \
+        PVK_LAUNCH(track_link_claim_kernel<SS>, dim3((unsigned)g), dim3(W * 32), smem, stream, f, mag, rows, \
                    nframes, K, maxpitchjmp, link, newcount);                                         \
       } while (0)
-      if (S == 1) PVK_LINK_FAST(1);
-      else if (S == 2) PVK_LINK_FAST(2);
-      else PVK_LINK_FAST(4);
-#undef PVK_LINK_FAST
-    } else if (K <= 512) {
-      const int S = K <= 128 ? 4 : (K <= 256 ? 8 : 16);
-      const int per_warp = link_wide_smem_per_warp(S);
-      const int W = S == 4 ? 8 : (S == 8 ? 4 : 2);
-      const int smem = W * per_warp;
-      g = (rows + W - 1) / W;
-      if (g > 148 * 64) g = 148 * 64;
-#define PVK_LINK_WIDE(SS)                                                                          \
-      do {                                                                                           \
-        if (smem > 48 * 1024 && PVK_SET_SMEM(track_link_wide_kernel<SS>, smem) != 0) {              \
-          set_error("pvk_track: cannot reserve %d bytes of shared memory", smem);                    \
-          return PVK_ERR_CUDA;                                                                       \
-        }                                                                                            \
-        PVK_LAUNCH(track_link_wide_kernel<SS>, dim3((unsigned)g), dim3(W * 32), smem, stream, f, mag, rows, \
-                   nframes, K, maxpitchjmp, link, newcount);                                         \
-      } while (0)
-      if (S == 4) PVK_LINK_WIDE(4);
-      else if (S == 8) PVK_LINK_WIDE(8);
-      else PVK_LINK_WIDE(16);
-#undef PVK_LINK_WIDE
+      if (S == 1) PVK_LINK_CLAIM(1);
+      else if (S == 2) PVK_LINK_CLAIM(2);
+      else if (S == 4) PVK_LINK_CLAIM(4);
+      else if (S == 8) PVK_LINK_CLAIM(8);
+      else PVK_LINK_CLAIM(16);
+#undef PVK_LINK_CLAIM
     } else {
       const int per_warp = link_generic_smem_per_warp(K);
       int W = 96 * 1024 / per_warp;                               // two CTAs per SM
@@ -1180,41 +983,64 @@ extern "C" int pvk_track(const double *f, const double *mag, int64_t nclips, int
     PVK_CHECK_LAUNCH("pvk_track(scan)");
   }
   {
+    // ---- chain resolution: level 1 turns link + base into ids chunk by chunk, the chunks' last rows
+    //      form the next level, ... the last level is resolved by one CTA, then the references left in
+    //      every level are replaced top-down.  The first row of every clip holds no reference.
     const int RT = track_tile_rows(K);
-    const size_t per_warp = (size_t)((((K + 3) & ~3) + RT * K + 3) & ~3) * 4;
+    const size_t per_warp = (size_t)resolve_tile_ints(K, RT) * 4;
     int W = (int)((64 * 1024) / per_warp);
     if (W > 4) W = 4;
     if (W < 1) W = 1;
     const size_t csm = per_warp * W;
-    if (csm > 48 * 1024 && PVK_SET_SMEM(track_chunk_kernel, (int)csm) != 0) {
+    if (csm > 48 * 1024 && (PVK_SET_SMEM(resolve_chunk_kernel<true>, (int)csm) != 0 ||
+                            PVK_SET_SMEM(resolve_chunk_kernel<false>, (int)csm) != 0)) {
       set_error("pvk_track: cannot reserve %d bytes of shared memory", (int)csm);
       return PVK_ERR_CUDA;
     }
-    const int64_t total_chunks = nclips * nchunks;
-    PVK_LAUNCH(track_chunk_kernel, dim3((unsigned)((total_chunks + W - 1) / W)), dim3(W * 32), csm, stream, link, base,
-               nframes, K, nchunks, total_chunks, tid);
-    PVK_CHECK_LAUNCH("pvk_track(chunk)");
-  }
-  if (nchunks > 1) {
-    PVK_LAUNCH(track_boundary_kernel, dim3(grid_for(nclips * nchunks * K, 256)), dim3(256), 0, stream, link, tid,
-               nframes, K, nchunks, nclips, G);
-    PVK_CHECK_LAUNCH("pvk_track(boundary)");
-    int tile = (48 * 1024) / (K * 4);                           // two tile buffers, <= 96 KB of shared memory
-    if (tile > 256) tile = 256;
-    if (tile > nchunks) tile = (int)nchunks;
-    if (tile < 1) tile = 1;
-    const size_t ssm = (size_t)(2 * (tile * K + 4) + ((K + 3) & ~3)) * 4;
-    if (ssm > 48 * 1024 && PVK_SET_SMEM(track_stitch_kernel, (int)ssm) != 0) {
-      set_error("pvk_track: cannot reserve %d bytes of shared memory", (int)ssm);
-      return PVK_ERR_CUDA;
+    int32_t *tab[16];
+    int64_t len[16];
+    int nl = 0;
+    tab[0] = tid; len[0] = rows;
+    unsigned char *lp = levels;
+    {
+      const int64_t nch = (rows + RES_CHUNK - 1) / RES_CHUNK;
+      tab[1] = reinterpret_cast<int32_t *>(lp); len[1] = nch;
+      lp += align_up(nch * K * 4, 256);
+      PVK_LAUNCH(resolve_chunk_kernel<true>, dim3((unsigned)((nch + W - 1) / W)), dim3(W * 32), csm, stream, link, base,
+                 tid, rows, K, RT, tab[1]);
+      PVK_CHECK_LAUNCH("pvk_track(chunk)");
+      nl = 1;
     }
-    int sbd = (tile * K + 31) / 32 * 32;                        // one thread per entry of a tile, <= 1024
-    if (sbd > 1024) sbd = 1024;
-    PVK_LAUNCH(track_stitch_kernel, dim3((unsigned)nclips), dim3(sbd), ssm, stream, G, K, nchunks, tile);
-    PVK_CHECK_LAUNCH("pvk_track(stitch)");
-    PVK_LAUNCH(track_fix_kernel, dim3(grid_for(rows * K, 256)), dim3(256), 0, stream, tid, G, nframes, K, nchunks,
-               nclips);
-    PVK_CHECK_LAUNCH("pvk_track(fix)");
+    if (len[1] > 1) {
+      while (len[nl] > RES_MID) {
+        const int64_t nch = (len[nl] + RES_CHUNK - 1) / RES_CHUNK;
+        tab[nl + 1] = reinterpret_cast<int32_t *>(lp); len[nl + 1] = nch;
+        lp += align_up(nch * K * 4, 256);
+        PVK_LAUNCH(resolve_chunk_kernel<false>, dim3((unsigned)((nch + W - 1) / W)), dim3(W * 32), csm, stream,
+                   (const int32_t *)nullptr, (const int32_t *)nullptr, tab[nl], len[nl], K, RT, tab[nl + 1]);
+        PVK_CHECK_LAUNCH("pvk_track(chunk)");
+        ++nl;
+      }
+      {
+        int NW = K > 512 ? 8 : 16;
+        int RTm = RT;
+        while (RTm > 1 && ((size_t)NW * K + 4 + (size_t)NW * resolve_tile_ints(K, RTm)) * 4 > 160 * 1024) RTm >>= 1;
+        const size_t msm = ((((size_t)NW * K + 3) & ~(size_t)3) + (size_t)NW * resolve_tile_ints(K, RTm)) * 4;
+        if (msm > 48 * 1024 && PVK_SET_SMEM(resolve_mid_kernel, (int)msm) != 0) {
+          set_error("pvk_track: cannot reserve %d bytes of shared memory", (int)msm);
+          return PVK_ERR_CUDA;
+        }
+        PVK_LAUNCH(resolve_mid_kernel, dim3(1), dim3(NW * 32), msm, stream, tab[nl], len[nl], K, RTm);
+        PVK_CHECK_LAUNCH("pvk_track(mid)");
+      }
+      for (int l = nl - 1; l >= 0; --l) {
+        int64_t g = (len[l] + RES_CHUNK - 1) / RES_CHUNK - 1;
+        if (g < 1) continue;
+        if (g > 148 * 32) g = 148 * 32;
+        PVK_LAUNCH(resolve_fix_kernel, dim3((unsigned)g), dim3(128), 0, stream, tab[l], len[l], K, tab[l + 1]);
+        PVK_CHECK_LAUNCH("pvk_track(fix)");
+      }
+    }
   }
   return PVK_OK;
 }
