@@ -398,6 +398,19 @@ def gpu_main(args):
                 box.append(D.StitchHandle(tr["tid"], plan, plans))
             if ht: ht.append(time.perf_counter())
             if e: e[2].record()
+        if world == 1:
+            # link, id resolution, pack and resynthesis are queued back to back (pack and resynthesis sized
+            # by upper bounds, the real counts are read on the device); the step's one host read-back
+            # (24 bytes: partials, points, last frame) comes at the very end
+            tr, pk, w = P.track_pack_resynth_device(tab["f"], tab["mag"], tab["ph"], tab["realph"], sr, hop, nfft, hop,
+                                                    after_link=after_link,
+                                                    after_pack=(lambda tr_: e[3].record()) if e else None)
+            if e: e[4].record()
+            state.update(a=a, tr=tr, pk=pk, w=w, st=dict(ntracks=tr["ntracks"], max_end=tr["max_end"]), table=tr["tid"],
+                         spans=(pk["tstart"], pk["tlen"]), peer=None)
+            if timed is not None:
+                timed.append(e)
+            return
         # local link + ids, then the pack sized by upper bounds, then the step's one hot-path host
         # read-back (24 bytes: partials, points, last frame)
         tr, pk = P.track_pack_device(tab["f"], tab["mag"], tab["ph"], tab["realph"], after_link=after_link)

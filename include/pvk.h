@@ -240,6 +240,18 @@ int pvk_track_pack(const double *f, const double *mag, const double *ph, const d
                    double *pmag, double *pph, double *prealph, void *workspace,
                    int64_t workspace_bytes, void *stream);
 
+/* pvk_track_pack sized by an upper bound: `ntracks` is the CAPACITY of tstart / tlen / toff, the
+ * real number of partials is read on the device from ntracks_dev[0] (pvk_track's output; NULL =
+ * `ntracks` itself).  Lets a caller queue the pack -- and the resynthesis, pvk_resynth_dev --
+ * behind the link kernels before it has read any count back: no host round trip in the middle of
+ * the hot path.  Entries beyond the real count are left untouched; toff[real count] = number of
+ * points. */
+int pvk_track_pack_dev(const double *f, const double *mag, const double *ph, const double *realph,
+                       const int32_t *tid, int64_t nframes, int npks, int64_t ntracks,
+                       const int32_t *ntracks_dev, int32_t *tstart, int32_t *tlen, int64_t *toff,
+                       double *pf, double *pmag, double *pph, double *prealph, void *workspace,
+                       int64_t workspace_bytes, void *stream);
+
 /* ------------------------------------------------------------------ segment sharding
  * A long signal split into per-GPU frame ranges is linked per segment (pvk_track on the
  * segment's window of rows: `own0` halo rows, then `nown` own rows, then more halo rows); these
@@ -309,6 +321,18 @@ int pvk_resynth(const int32_t *tid, int64_t nframes, int npks, int64_t ntracks,
                 int hop_an, double edge, int minframes, double *out, int64_t nout,
                 int64_t block0, int64_t nblocks, void *workspace, int64_t workspace_bytes,
                 int reuse_tracks, void *stream);
+
+/* pvk_resynth with the number of partials on the device (see pvk_track_pack_dev): `ntracks` is the
+ * capacity the workspace was sized for, ntracks_dev[0] the real count (NULL = `ntracks`).  `nout`
+ * may then be an upper bound, (nframes + 1) * hop + edge samples: samples beyond the real signal
+ * length are rendered into the caller's (larger) buffer and cut by the caller once it has read
+ * max(end) back. */
+int pvk_resynth_dev(const int32_t *tid, int64_t nframes, int npks, int64_t ntracks,
+                    const int32_t *ntracks_dev, const int32_t *tstart, const int32_t *tlen,
+                    const int64_t *toff, const double *pf, const double *pmag, const double *prealph,
+                    double sr, int hop, int nfft, int hop_an, double edge, int minframes, double *out,
+                    int64_t nout, int64_t block0, int64_t nblocks, void *workspace,
+                    int64_t workspace_bytes, int reuse_tracks, void *stream);
 
 #ifdef __cplusplus
 }

@@ -39,6 +39,7 @@ SIGNATURES = {
     "pvk_clip_spans": (_i, [_p, _p, _i64, _i64, _i64, _p, _p, _p]),
     "pvk_track_pack_workspace_bytes": (_i64, [_i64]),
     "pvk_track_pack": (_i, [_p, _p, _p, _p, _p, _i64, _i, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
+    "pvk_track_pack_dev": (_i, [_p, _p, _p, _p, _p, _i64, _i, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "pvk_segment_summary": (_i, [_p, _i, _i64, _i64, _i64, _p, _p]),
     "pvk_segment_resolve": (_i, [_p, _i, _i, _i, _p, _i64, _p, _p, _p]),
     "pvk_segment_rename": (_i, [_p, _i64, _p, _p, _p, _p]),
@@ -46,6 +47,8 @@ SIGNATURES = {
     "pvk_resynth_workspace_bytes": (_i64, [_i64, _i, _i64, _i64]),
     "pvk_resynth": (_i, [_p, _i64, _i, _i64, _p, _p, _p, _p, _p, _p, _d, _i, _i, _i, _d, _i, _p, _i64, _i64,
                          _i64, _p, _i64, _i, _p]),
+    "pvk_resynth_dev": (_i, [_p, _i64, _i, _i64, _p, _p, _p, _p, _p, _p, _p, _d, _i, _i, _i, _d, _i, _p, _i64, _i64,
+                             _i64, _p, _i64, _i, _p]),
 }
 
 

@@ -23,6 +23,8 @@ struct RParams {
   const int64_t *toff;
   const double *pf, *pmag, *prealph;
   int64_t F;
+  int64_t ntcap;            // capacity of tstart / tlen / toff: ids at or beyond it are ignored (a caller that
+                            // sized them by an upper bound which turned out too small renders again, sized exactly)
   int K;
   double sr, fstep, dfr;
   int h;                    // synthesis hop
@@ -165,9 +167,11 @@ __device__ __forceinline__ void make_body(const RParams &p, int64_t b, int v, in
 // One warp per partial.  For the rendered ones (tlen >= minframes, :1061): find the slots of the
 // first and the last frame in the frame table, set their bits in the start / end masks and store
 // the fade-in / fade-out parameters.
-__global__ void __launch_bounds__(256) resynth_tracks_kernel(RParams p, int64_t ntracks, uint32_t *__restrict__ mask,
-                                                             TrackFade *__restrict__ tfade) {
+__global__ void __launch_bounds__(256) resynth_tracks_kernel(RParams p, int64_t ntracks,
+                                                             const int32_t *__restrict__ ntracks_dev,
+                                                             uint32_t *__restrict__ mask, TrackFade *__restrict__ tfade) {
   const int lane = threadIdx.x & 31;
+  if (ntracks_dev != nullptr) { const int64_t m = *ntracks_dev; ntracks = m < ntracks ? m : ntracks; }
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < ntracks; v += nw) {
     const int nfr = p.tlen[v];
@@ -218,7 +222,7 @@ __global__ void __launch_bounds__(128) resynth_prepare_kernel(RParams p, int64_t
       int v = -1, nfr = 0;
       if (c < p.K) {
         v = p.tid[b * p.K + c];
-        if (v >= 0) nfr = p.tlen[v];
+        if (v >= 0 && v < p.ntcap) nfr = p.tlen[v];
       }
       const bool on = v >= 0 && nfr >= p.minframes;                 // :1061
       const unsigned mk = __ballot_sync(FULL, on);
@@ -448,7 +452,7 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 8) resynth_tile_kernel(RParam
       const int v = vnext;
       const int cn = c0 + 32 + lane;
       vnext = cn < K ? trow[cn] : -1;
-      const int nfr = v >= 0 ? p.tlen[v] : 0;
+      const int nfr = (v >= 0 && v < p.ntcap) ? p.tlen[v] : 0;
       const bool on = v >= 0 && nfr >= p.minframes;               // :1061
       const unsigned mk = __ballot_sync(FULL, on);
       if (mk == 0u) continue;                                      // warp uniform
@@ -521,6 +525,16 @@ extern "C" int pvk_resynth(const int32_t *tid, int64_t nframes, int npks, int64_
                            const double *prealph, double sr, int hop, int nfft, int hop_an, double edge,
                            int minframes, double *out, int64_t nout, int64_t block0, int64_t nblocks,
                            void *workspace, int64_t workspace_bytes, int reuse_tracks, void *stream) {
+  return pvk_resynth_dev(tid, nframes, npks, ntracks, nullptr, tstart, tlen, toff, pf, pmag, prealph, sr, hop, nfft, hop_an,
+                         edge, minframes, out, nout, block0, nblocks, workspace, workspace_bytes, reuse_tracks, stream);
+}
+
+extern "C" int pvk_resynth_dev(const int32_t *tid, int64_t nframes, int npks, int64_t ntracks,
+                               const int32_t *ntracks_dev, const int32_t *tstart, const int32_t *tlen,
+                               const int64_t *toff, const double *pf, const double *pmag, const double *prealph,
+                               double sr, int hop, int nfft, int hop_an, double edge, int minframes, double *out,
+                               int64_t nout, int64_t block0, int64_t nblocks, void *workspace,
+                               int64_t workspace_bytes, int reuse_tracks, void *stream) {
   PVK_REQUIRE(hop >= 1 && nfft >= 1 && hop_an >= 1, "pvk_resynth: hop=%d nfft=%d hop_an=%d must be >= 1", hop, nfft, hop_an);
   PVK_REQUIRE(npks >= 1 && npks <= PVK_MAX_NPKS, "pvk_resynth: npks=%d must be in [1, %d]", npks, PVK_MAX_NPKS);
   PVK_REQUIRE(sr > 0.0 && edge >= 0.0, "pvk_resynth: sr and edge must be positive");
@@ -540,7 +554,7 @@ extern "C" int pvk_resynth(const int32_t *tid, int64_t nframes, int npks, int64_
   RParams p;
   p.tid = tid; p.tstart = tstart; p.tlen = tlen; p.toff = toff;
   p.pf = pf; p.pmag = pmag; p.prealph = prealph;
-  p.F = nframes; p.K = npks; p.sr = sr;
+  p.F = nframes; p.K = npks; p.sr = sr; p.ntcap = ntracks;
   p.fstep = sr / (double)nfft;                               // :825
   const double overlap = (double)hop_an / (double)nfft;      // :824
   p.dfr = 1.0 / overlap / 2.0;                               // :687
@@ -577,7 +591,7 @@ extern "C" int pvk_resynth(const int32_t *tid, int64_t nframes, int npks, int64_
     int64_t gsz = (ntracks * 32 + 255) / 256;
     if (gsz > 148 * 16) gsz = 148 * 16;
     p.chunk0 = 0;
-    PVK_LAUNCH(resynth_tracks_kernel, dim3((unsigned)gsz), dim3(256), 0, stream, p, ntracks, mask, tfade);
+    PVK_LAUNCH(resynth_tracks_kernel, dim3((unsigned)gsz), dim3(256), 0, stream, p, ntracks, ntracks_dev, mask, tfade);
     PVK_CHECK_LAUNCH("pvk_resynth(tracks)");
   }
   // thread layout of the render kernel: RS samples per thread, nchp chunk threads per item

@@ -256,7 +256,7 @@ __global__ void track_link_kernel(const double *__restrict__ f, const double *__
 // columns (previous row with holes / out of order and more than 32 columns) take the loop itself.
 __host__ __device__ constexpr int link_claim_smem_per_warp(int S) {
   // cf cm pf pm (double) | claim magnitudes = sort keys (8) | pf32 (4) | claim columns (4) | ord prank sidx (short) | usedw
-  return 32 * S * (4 * 8 + 8 + 4 + 4 + 3 * 2) + 32 * 4;
+  return 32 * S * (4 * 8 + 8 + 4 + 4 + 3 * 2) + 3 * 32 * 4;
 }
 
 template <int S>
@@ -278,6 +278,8 @@ __global__ void track_link_claim_kernel(const double *__restrict__ f, const doub
   short *prank = ord + KM;
   short *sidx = prank + KM;
   unsigned *usedw = reinterpret_cast<unsigned *>(sidx + KM);      // [32]
+  unsigned *propw = usedw + 32, *confw = propw + 32;              // [32] each
+  for (int p = lane; p < KM; p += 32) { claim_m[p] = 0ull; claim_c[p] = -1; }
   // fp32 pre-test window: |fc - fp| < eps32 * fp is implied by |17.312 (fc/fp - 1)| < maxjump
   // (slack 1e-4 relative + 1e-6 absolute >> fp32 rounding of fc and fp); the exact fp64 test decides
   const float eps32 = (float)(maxjump / 17.312 * (1.0 + 1e-4) + 1e-6);
@@ -372,10 +374,14 @@ __global__ void track_link_claim_kernel(const double *__restrict__ f, const doub
       const int nnew = link_greedy_generic(cf, pf, pm, ord, prank, nc, phi, maxjump, lrow);
       if (lane == 0) newcount[row] = nnew;
       __syncwarp();
+      for (int p = lane; p < KM; p += 32) claim_m[p] = 0ull;      // (was the sort's key array)
+      __syncwarp();
       continue;
     }
 
-    // ---- propose / commit rounds
+    // ---- propose / commit rounds.  propw / confw: previous columns proposed / proposed more than once
+    //      in this round; claim_m / claim_c are only touched for contested columns and are reset by
+    //      their users (all-zero / -1 between rounds and rows)
     int prop[S];
 #pragma unroll
     for (int s = 0; s < S; ++s) prop[s] = -1;
@@ -384,10 +390,13 @@ __global__ void track_link_claim_kernel(const double *__restrict__ f, const doub
 #pragma unroll
       for (int s = 0; s < S; ++s) pend = pend || (res[s] == -3 && cmask[s] != 0u);
       if (!__any_sync(FULL, pend)) break;
-      for (int p = lane; p < phi; p += 32) { claim_m[p] = 0ull; claim_c[p] = -1; }
+      propw[lane] = 0u; confw[lane] = 0u;
       __syncwarp();
+      bool act[S];
+      bool clash = false;
 #pragma unroll
       for (int s = 0; s < S; ++s) {
+        act[s] = false;
         if (res[s] == -3 && cmask[s] != 0u) {
           // a kept proposal stays the arg-min while its target is unused (the unused set only shrinks)
           if (prop[s] < 0 || ((usedw[prop[s] >> 5] >> (prop[s] & 31)) & 1u)) {
@@ -404,14 +413,34 @@ __global__ void track_link_claim_kernel(const double *__restrict__ f, const doub
             }
             prop[s] = bp;
           }
-          if (prop[s] >= 0) atomicMax(&claim_m[prop[s]], (unsigned long long)__double_as_longlong(mine[s]));
+          if (prop[s] >= 0) {
+            act[s] = true;
+            const unsigned bit = 1u << (prop[s] & 31);
+            if (atomicOr(&propw[prop[s] >> 5], bit) & bit) { atomicOr(&confw[prop[s] >> 5], bit); clash = true; }
+          }
         }
+      }
+      __syncwarp();
+      if (!__any_sync(FULL, clash)) {
+        // nobody shares a target: every proposal stands, whatever the order
+#pragma unroll
+        for (int s = 0; s < S; ++s) if (act[s]) res[s] = prop[s];
+        __syncwarp();
+        usedw[lane] |= propw[lane];
+        __syncwarp();
+        continue;
+      }
+      // contested targets go to the proposer that comes first in the order: magnitude, then column
+      bool cont[S];
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        cont[s] = act[s] && ((confw[prop[s] >> 5] >> (prop[s] & 31)) & 1u);
+        if (cont[s]) atomicMax(&claim_m[prop[s]], (unsigned long long)__double_as_longlong(mine[s]));
       }
       __syncwarp();
 #pragma unroll
       for (int s = 0; s < S; ++s) {
-        if (res[s] == -3 && prop[s] >= 0 && cmask[s] != 0u &&
-            claim_m[prop[s]] == (unsigned long long)__double_as_longlong(mine[s]))
+        if (cont[s] && claim_m[prop[s]] == (unsigned long long)__double_as_longlong(mine[s]))
           atomicMax(&claim_c[prop[s]], lane + 32 * s);
       }
       __syncwarp();
@@ -422,11 +451,13 @@ __global__ void track_link_claim_kernel(const double *__restrict__ f, const doub
       bool win[S];
 #pragma unroll
       for (int s = 0; s < S; ++s) {
-        const bool act = res[s] == -3 && prop[s] >= 0 && cmask[s] != 0u;
         const unsigned long long key = (unsigned long long)__double_as_longlong(mine[s]);
-        win[s] = act && claim_m[prop[s]] == key && claim_c[prop[s]] == lane + 32 * s;
-        if (act && !win[s] && (key > lk || (key == lk && lane + 32 * s > lc))) { lk = key; lc = lane + 32 * s; }
+        win[s] = act[s] && (!cont[s] || (claim_m[prop[s]] == key && claim_c[prop[s]] == lane + 32 * s));
+        if (act[s] && !win[s] && (key > lk || (key == lk && lane + 32 * s > lc))) { lk = key; lc = lane + 32 * s; }
       }
+      __syncwarp();
+#pragma unroll
+      for (int s = 0; s < S; ++s) if (cont[s]) { claim_m[prop[s]] = 0ull; claim_c[prop[s]] = -1; }   // (all users write the same)
 #pragma unroll
       for (int o = 16; o >= 1; o >>= 1) {
         const unsigned long long ok = __shfl_xor_sync(FULL, lk, o);
@@ -437,7 +468,7 @@ __global__ void track_link_claim_kernel(const double *__restrict__ f, const doub
       for (int s = 0; s < S; ++s) {
         if (win[s]) {
           const unsigned long long key = (unsigned long long)__double_as_longlong(mine[s]);
-          if (lc < 0 || key > lk || (key == lk && lane + 32 * s > lc)) {
+          if (key > lk || (key == lk && lane + 32 * s > lc)) {
             res[s] = prop[s];
             atomicOr(&usedw[prop[s] >> 5], 1u << (prop[s] & 31));
           }
@@ -518,6 +549,10 @@ __global__ void __launch_bounds__(SCAN_BD) scan_tile_sums_kernel(const int32_t *
   long long *sh = reinterpret_cast<long long *>(smem);
   n = scan_count(n, n_dev);
   const int64_t t = blockIdx.x, row = blockIdx.y;
+  if (t * SCAN_TILE >= n) {                                    // beyond a device-side count: nothing to read
+    if (threadIdx.x == 0) tsum[row * ntiles + t] = 0;
+    return;
+  }
   int v[SCAN_E];
   scan_load_tile(in + row * stride, t * SCAN_TILE + (int64_t)threadIdx.x * SCAN_E, n, v);
   long long loc = 0;
@@ -540,10 +575,12 @@ __global__ void __launch_bounds__(SCAN_BD) scan_tile_apply_kernel(const int32_t 
   long long *wsum = sh + SCAN_BD / 32;
   n = scan_count(n, n_dev);
   const int64_t t = blockIdx.x, row = blockIdx.y;
+  if (t * SCAN_TILE >= n && t != ntiles - 1) return;           // beyond a device-side count (the last tile writes the totals)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long *ts = tsum + row * ntiles;
   long long before = 0;
-  for (int64_t i = tid; i < t; i += SCAN_BD) before += ts[i];
+  const int64_t tlive = (n + SCAN_TILE - 1) / SCAN_TILE;      // tiles holding elements
+  for (int64_t i = tid; i < (t < tlive ? t : tlive); i += SCAN_BD) before += ts[i];
   before = scan_block_sum(before, sh);
   const int64_t i0 = t * SCAN_TILE + (int64_t)tid * SCAN_E;
   int v[SCAN_E];
@@ -1099,6 +1136,15 @@ extern "C" int pvk_track_pack(const double *f, const double *mag, const double *
                               int64_t ntracks, int32_t *tstart, int32_t *tlen, int64_t *toff, double *pf,
                               double *pmag, double *pph, double *prealph, void *workspace,
                               int64_t workspace_bytes, void *stream) {
+  return pvk_track_pack_dev(f, mag, ph, realph, tid, nframes, npks, ntracks, nullptr, tstart, tlen, toff, pf, pmag, pph,
+                            prealph, workspace, workspace_bytes, stream);
+}
+
+extern "C" int pvk_track_pack_dev(const double *f, const double *mag, const double *ph, const double *realph,
+                                  const int32_t *tid, int64_t nframes, int npks, int64_t ntracks,
+                                  const int32_t *ntracks_dev, int32_t *tstart, int32_t *tlen, int64_t *toff,
+                                  double *pf, double *pmag, double *pph, double *prealph, void *workspace,
+                                  int64_t workspace_bytes, void *stream) {
   PVK_REQUIRE(npks >= 1 && nframes >= 0 && ntracks >= 0, "pvk_track_pack: bad sizes");
   PVK_REQUIRE(toff != nullptr, "pvk_track_pack: toff is NULL");
   if (ntracks == 0 || nframes == 0) {
@@ -1120,9 +1166,9 @@ extern "C" int pvk_track_pack(const double *f, const double *mag, const double *
     const int64_t nt = scan_tiles(ntracks);
     long long *tsum = reinterpret_cast<long long *>(workspace);
     PVK_LAUNCH(scan_tile_sums_kernel, dim3((unsigned)nt), dim3(SCAN_BD), SCAN_SMEM, stream, tlen, ntracks, ntracks,
-               (const int32_t *)nullptr, nt, tsum);
+               ntracks_dev, nt, tsum);
     PVK_LAUNCH(scan_tile_apply_kernel<int64_t>, dim3((unsigned)nt), dim3(SCAN_BD), SCAN_SMEM, stream, tlen, ntracks, ntracks,
-               (const int32_t *)nullptr, nt, tsum, toff, ntracks + 1, (int32_t *)nullptr, 1);
+               ntracks_dev, nt, tsum, toff, ntracks + 1, (int32_t *)nullptr, 1);
     PVK_CHECK_LAUNCH("pvk_track_pack(scan)");
   }
   {

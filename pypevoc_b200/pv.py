@@ -309,6 +309,33 @@ def pack_device(fd, magd, phd, realphd, tid, link, ntracks, npts=None):   # link
 PACK_SPEC_CAP = 4 << 20      # most partials a speculative pack is sized for (larger tables are re-packed)
 
 
+def _pack_speculative(fd, magd, phd, realphd, tr):
+    """Launch pvk_track_pack_dev sized by upper bounds (the exact counts still sit on the device):
+    returns (capacity, tstart, tlen, toff, packed arrays)."""
+    L = _lib.lib()
+    dev = fd.device
+    F, K = fd.shape
+    nt_ub = min(F * K, PACK_SPEC_CAP)
+    tstart = torch.empty((nt_ub,), dtype=torch.int32, device=dev)
+    tlen = torch.empty((nt_ub,), dtype=torch.int32, device=dev)
+    toff = torch.empty((nt_ub + 1,), dtype=torch.int64, device=dev)
+    packed = [torch.empty((F * K,), dtype=torch.float64, device=dev) for _ in range(4)]
+    wsb = int(L.pvk_track_pack_workspace_bytes(nt_ub))
+    ws = torch.empty(max(wsb, 8), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.pvk_track_pack_dev(_ptr(fd), _ptr(magd), _ptr(phd), _ptr(realphd), _ptr(tr["tid"]), F, K, nt_ub,
+                                        _ptr(tr["ntracks"]), _ptr(tstart), _ptr(tlen), _ptr(toff), _ptr(packed[0]),
+                                        _ptr(packed[1]), _ptr(packed[2]), _ptr(packed[3]), _ptr(ws), wsb, _stream()),
+                   "pvk_track_pack")
+    return nt_ub, tstart, tlen, toff, packed
+
+
+def _pack_sliced(raw, nt, npts):
+    _, tstart, tlen, toff, packed = raw
+    return dict(tstart=tstart[:nt], tlen=tlen[:nt], toff=toff[:nt + 1], pf=packed[0][:npts], pmag=packed[1][:npts],
+                pph=packed[2][:npts], prealph=packed[3][:npts], npts=npts)
+
+
 def track_pack_device(fd, magd, phd, realphd, maxpitchjmp=0.5, after_link=None):
     """pvk_track + pvk_track_pack of one clip with ONE host read-back: the pack is launched with
     upper bounds for the number of partials / points (the exact counts still sit on the device)
@@ -316,37 +343,63 @@ def track_pack_device(fd, magd, phd, realphd, maxpitchjmp=0.5, after_link=None):
     launches it; the few KB of over-allocated index arrays are sliced afterwards.  ``after_link``
     (optional) is called with the track dict right after the link kernels are launched.
     Returns (tr, pk) as track_device() + track_counts() and pack_device() give them."""
-    L = _lib.lib()
     tr = track_device(fd, magd, maxpitchjmp)
     if after_link is not None:
         after_link(tr)
-    dev = fd.device
     F, K = fd.shape
-    raw = None
-    if F * K > 0:
-        nt_ub = min(F * K, PACK_SPEC_CAP)
-        tstart = torch.empty((nt_ub,), dtype=torch.int32, device=dev)
-        tlen = torch.empty((nt_ub,), dtype=torch.int32, device=dev)
-        toff = torch.empty((nt_ub + 1,), dtype=torch.int64, device=dev)
-        packed = [torch.empty((F * K,), dtype=torch.float64, device=dev) for _ in range(4)]
-        wsb = int(L.pvk_track_pack_workspace_bytes(nt_ub))
-        ws = torch.empty(max(wsb, 8), dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
-            _lib.check(L.pvk_track_pack(_ptr(fd), _ptr(magd), _ptr(phd), _ptr(realphd), _ptr(tr["tid"]), F, K, nt_ub,
-                                        _ptr(tstart), _ptr(tlen), _ptr(toff), _ptr(packed[0]), _ptr(packed[1]),
-                                        _ptr(packed[2]), _ptr(packed[3]), _ptr(ws), wsb, _stream()), "pvk_track_pack")
-        raw = (nt_ub, tstart, tlen, toff, packed)
+    raw = _pack_speculative(fd, magd, phd, realphd, tr) if F * K > 0 else None
     nt, npts, last = track_counts(tr)
+    tr["ntracks_dev"] = tr["ntracks"]
     tr["ntracks"], tr["npts"], tr["max_end"] = nt, npts, last
     if raw is not None and 0 < nt <= raw[0]:
-        _, tstart, tlen, toff, packed = raw
-        pk = dict(tstart=tstart[:nt], tlen=tlen[:nt], toff=toff[:nt + 1], pf=packed[0][:npts], pmag=packed[1][:npts],
-                  pph=packed[2][:npts], prealph=packed[3][:npts], npts=npts)
+        pk = _pack_sliced(raw, nt, npts)
     elif nt == 0:
         pk = None
     else:                                                       # more partials than the speculative cap
         pk = pack_device(fd, magd, phd, realphd, tr["tid"], None, nt, npts=npts)
     return tr, pk
+
+
+def track_pack_resynth_device(fd, magd, phd, realphd, sr, hop, nfft, hop_an, edge=1.0, minframes=3,
+                              maxpitchjmp=0.5, after_link=None, after_pack=None):
+    """The whole back half of the hot path of one clip -- link, id resolution, pack, resynthesis --
+    queued back to back with ONE host read-back at the very end: pack and resynthesis are launched
+    sized by upper bounds (capacity of the index arrays, (F + 1) * hop + edge output samples) and
+    read the real number of partials on the device (pvk_track_pack_dev / pvk_resynth_dev); the
+    host then reads the 24 bytes of counts and slices.  Returns (tr, pk, w): as track_pack_device()
+    plus the float64 device signal (None without partials)."""
+    L = _lib.lib()
+    F, K = fd.shape
+    if F * K == 0:
+        tr, pk = track_pack_device(fd, magd, phd, realphd, maxpitchjmp, after_link)
+        return tr, pk, None
+    tr = track_device(fd, magd, maxpitchjmp)
+    if after_link is not None:
+        after_link(tr)
+    dev = fd.device
+    raw = _pack_speculative(fd, magd, phd, realphd, tr)
+    if after_pack is not None:
+        after_pack(tr)
+    nt_ub, tstart, tlen, toff, packed = raw
+    nout_ub, _ = synth_geometry(F - 1, hop, nfft, hop_an, edge)
+    nblk = -(-nout_ub // hop)
+    out = torch.empty((nout_ub,), dtype=torch.float64, device=dev)
+    ws = resynth_workspace(F, K, nt_ub, nblk, dev, hop=hop)
+    with torch.cuda.device(dev):
+        _lib.check(L.pvk_resynth_dev(_ptr(tr["tid"]), F, K, nt_ub, _ptr(tr["ntracks"]), _ptr(tstart), _ptr(tlen), _ptr(toff),
+                                     _ptr(packed[0]), _ptr(packed[1]), _ptr(packed[3]), float(sr), int(hop), int(nfft),
+                                     int(hop_an), float(edge), int(minframes), _ptr(out), int(nout_ub), 0, -1, _ptr(ws),
+                                     int(ws.numel()), 0, _stream()), "pvk_resynth")
+    nt, npts, last = track_counts(tr)                           # the hot path's one read-back
+    tr["ntracks_dev"] = tr["ntracks"]
+    tr["ntracks"], tr["npts"], tr["max_end"] = nt, npts, last
+    if nt == 0:
+        return tr, None, None
+    if nt > nt_ub:                                              # more partials than the speculative cap: redo, sized exactly
+        pk = pack_device(fd, magd, phd, realphd, tr["tid"], None, nt, npts=npts)
+        return tr, pk, resynth_device(tr["tid"], pk, sr, hop, nfft, hop_an, edge=edge, minframes=minframes, max_end=last)
+    nout, _ = synth_geometry(last, hop, nfft, hop_an, edge)
+    return tr, _pack_sliced(raw, nt, npts), out[:nout]
 
 
 def spans_device(tid, ntracks):
@@ -397,7 +450,11 @@ def resynth_device(tid, pk, sr, hop, nfft, hop_an, edge=1.0, minframes=3, max_en
     return out
 
 
-def resynth_workspace(F, K, ntracks, nblocks, dev):
+def resynth_workspace(F, K, ntracks, nblocks, dev, hop=None):
+    """Scratch of pvk_resynth.  ``hop`` given and a multiple of 128: the tile kernels build the partial
+    bodies themselves and need no per-block staging area."""
+    if hop is not None and int(hop) % 128 == 0:
+        nblocks = 1
     wsb = int(_lib.lib().pvk_resynth_workspace_bytes(int(F), int(K), int(ntracks), max(int(nblocks), 0)))
     return torch.empty(max(wsb, 8), dtype=torch.uint8, device=dev)
 
@@ -1438,6 +1495,21 @@ class SinSum(object):
                                       "broken in the reference (PVAnalysis.py:665); not provided")
         if int(hop) != hop:
             raise TypeError("hop must be an integer number of samples")
+        if self._trk is None and hostbuf is None:
+            # first use of the partials: link, pack and resynthesis go to the device back to back,
+            # the counts are read once at the end (no host round trip between the stages)
+            self._ensure_tables()
+            t = self._tables
+            if t["f"].shape[0] * t["f"].shape[1] > 0:
+                tr, pk, out = track_pack_resynth_device(t["f"], t["mag"], t["ph"], t["realph"], sr, int(hop), self.nfft,
+                                                        self.hop, edge=edge, minframes=minframes,
+                                                        maxpitchjmp=self._maxpitchjmp, after_link=self._after_link)
+                self._trk = tr
+                if pk is not None:
+                    self._pk = pk
+                if tr["ntracks"] == 0:
+                    raise ValueError("max() arg is an empty sequence")     # what the reference raises (:1059)
+                return out.cpu().numpy() if to_host else out
         pk = self._ensure_packed()
         tr = self._trk
         if tr["ntracks"] == 0:

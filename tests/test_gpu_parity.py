@@ -476,3 +476,45 @@ def test_full_size_config_prefix_vs_oracle(pvmod, name, sr, sec, nfft, hop, npks
     assert ss.st == tr["st"].tolist() and ss.end == tr["end"].tolist()
     print("%s: %d frames, %d sub-margin frames (%d with different bins), %d partials, %s" % (
         name, pv.nframes, sub, rep["mismatched"], len(ss.st), rep))
+
+
+def test_fused_back_half_equals_staged_calls(pvmod):
+    """SinSum.synth on fresh partials queues link + pack + resynthesis with upper-bound sizes and ONE
+    read-back at the end (pvk_track_pack_dev / pvk_resynth_dev); the result must equal the staged calls
+    (counts read first, exact sizes) bit for bit -- also when the signal ends in silence (the rendered
+    upper-bound tail is cut) and when there is no partial at all."""
+    from pypevoc_b200 import signals
+    from pypevoc_b200 import pv as P
+    sr = 44100
+    x = signals.harm(sr, 3.0, 220, 60, 0.5, 0.02, 23)
+    x[int(2.2 * sr):] = 0.0
+    for hop_s, edge, minframes in ((512, 1.0, 3), (384, 0.5, 2), (256, 1.0, 3)):
+        pv = pvmod.PV(x, sr, nfft=2048, hop=512, npks=40, progress=False)
+        pv.run_pv()
+        ss1 = pv.toSinSum()
+        w1 = ss1.synth(sr, hop_s, edge=edge, minframes=minframes)          # fused
+        ss2 = pv.toSinSum()
+        ss2._ensure_packed()                                                # staged: counts first
+        w2 = ss2.synth(sr, hop_s, edge=edge, minframes=minframes)
+        assert w1.shape == w2.shape and np.array_equal(w1, w2)
+        assert np.array_equal(ss1.track_ids, ss2.track_ids) and ss1.st == ss2.st and ss1.end == ss2.end
+        d1, d2 = ss1.device_tracks, ss2.device_tracks
+        for k in ("toff", "pf", "pmag", "pph", "prealph"):
+            assert torch.equal(d1[k], d2[k]), k
+        assert np.array_equal(ss1.synth(sr, hop_s, edge=edge, minframes=minframes), w1)   # second call: staged path
+    pz = pvmod.PV(np.zeros(8192, dtype=np.float32), sr, nfft=2048, hop=512, npks=10, progress=False)
+    pz.run_pv()
+    with pytest.raises(ValueError):
+        pz.toSinSum().synth(sr, 512)
+    # more partials than the speculative capacity: sized exactly afterwards, same result
+    cap = P.PACK_SPEC_CAP
+    try:
+        P.PACK_SPEC_CAP = 16
+        pv = pvmod.PV(x, sr, nfft=2048, hop=512, npks=40, progress=False)
+        pv.run_pv()
+        w3 = pv.toSinSum().synth(sr, 512)
+    finally:
+        P.PACK_SPEC_CAP = cap
+    pv = pvmod.PV(x, sr, nfft=2048, hop=512, npks=40, progress=False)
+    pv.run_pv()
+    assert np.array_equal(w3, pv.toSinSum().synth(sr, 512))
