@@ -180,13 +180,14 @@ def sharded_selfcheck(rank, world, dev):
     p = plans[rank]
     xl = torch.from_numpy(np.ascontiguousarray(x[p["sample0"]:p["sample0"] + p["nsamp"]]))
     bad = []
-    peer = None
+    peer = mcast = None
     for rep in range(3):                               # both alternating peer tables + one reuse
         spv = D.ShardedPV(xl.to(dev), sr, len(x), nfft=nfft, hop=hop, npks=npks, rank=rank, world=world, device=dev)
         spv.run_pv()
         ss = spv.toSinSum()
         w, s0 = ss.synth_local(to_host=True)
         peer = bool(ss._h.peer_used)
+        mcast = bool(getattr(ss._h, "multicast_used", False))
         for k in ("f", "mag", "ph", "realph", "binno"):
             if not np.array_equal(np.asarray(getattr(spv.pv, k))[spv.own_rows], getattr(pv0, k)[p["j0"]:p["j1"]]):
                 bad.append("rep %d: own rows of %s" % (rep, k))
@@ -207,7 +208,7 @@ def sharded_selfcheck(rank, world, dev):
         os._exit(3)
     return {"sharded_vs_unsharded": "bit-exact (own rows f/mag/ph/realph/binno, gathered track table, st/end, "
                                     "rendered block ranges; 3 passes)", "frames": int(pv0.nframes),
-            "partials": len(ss0.st), "ranks": world, "peer_memory_gather": peer}
+            "partials": len(ss0.st), "ranks": world, "peer_memory_gather": peer, "nvswitch_multicast": mcast}
 
 
 # --------------------------------------------------------------------------- clip batch (configs[2])
@@ -411,28 +412,19 @@ def gpu_main(args):
             if timed is not None:
                 timed.append(e)
             return
-        # local link + ids, then the pack sized by upper bounds, then the step's one hot-path host
-        # read-back (24 bytes: partials, points, last frame)
-        tr, pk = P.track_pack_device(tab["f"], tab["mag"], tab["ph"], tab["realph"], after_link=after_link)
-        ntl, npts, last = tr["ntracks"], tr["npts"], tr["max_end"]
-        sh = box[0] if box else None
-        if e: e[3].record()
-        if ht: ht.append(time.perf_counter()); ht.append(ht[-1])
-        if world == 1:
-            st = dict(ntracks=ntl, max_end=last)
-            w = D.resynth_local(tr["tid"], pk, plan, plans, last, sr, hop, nfft, hop)
-            table, spans = tr["tid"], (pk["tstart"], pk["tlen"])
-        else:
-            ll = last + plan["w0"] if last >= 0 else -1
-            w = D.resynth_local(tr["tid"], pk, plan, plans, None, sr, hop, nfft, hop, local_last=ll)
-            b0 = D.render_range_local(plan, plans, ll, hop, nfft, hop)[0]
-            if ht: ht.append(time.perf_counter())
-            ntg, max_end = sh.counts()                   # 8 ints; the numbering finished long ago
-            if ht: ht.append(time.perf_counter())
-            st = dict(ntracks=ntg, max_end=max_end)
-            w = w[:D.trim_local(w.numel(), b0, plan, plans, max_end, hop, nfft, hop)[0]]
-            table = sh.table()                           # the gather overlapped pack + resynthesis
-            spans = P.spans_device(table, ntg)           # first frame / length of every partial
+        # N > 1: the same back half on this rank's window (dist.track_pack_resynth_local): link -> [numbering +
+        # gather of the track table on a side stream] -> pack -> rendering of the rank's own block range, all
+        # queued back to back; one 24-byte read-back at the end, then the 8 integers of the numbering pass
+        tr, pk, w, b0 = D.track_pack_resynth_local(tab, plan, plans, sr, hop, nfft, hop, after_link=after_link,
+                                                   after_pack=(lambda tr_: e[3].record()) if e else None)
+        sh = box[0]
+        if ht: ht.append(time.perf_counter())
+        ntg, max_end = sh.counts()                       # 8 ints; the numbering finished long ago
+        if ht: ht.append(time.perf_counter())
+        st = dict(ntracks=ntg, max_end=max_end)
+        w = w[:D.trim_local(w.numel(), b0, plan, plans, max_end, hop, nfft, hop)[0]]
+        table = sh.table()                               # the gather overlapped pack + resynthesis
+        spans = P.spans_device(table, ntg)               # first frame / length of every partial
         if e: e[4].record()
         if ht:
             ht.append(time.perf_counter())

@@ -289,6 +289,15 @@ int pvk_segment_rename(const int32_t *tid_own, int64_t n, const int32_t *gidlow,
 int pvk_segment_rename_push(const int32_t *tid_own, int64_t n, const int32_t *gidlow, const int32_t *params,
                             int32_t *const *dst_tables, int ndst, int64_t dst_offset, void *stream);
 
+/*
+ * pvk_segment_rename_push through NVSwitch multicast: `mc_table` is the MULTICAST address of the
+ * ranks' int32 [frames_total, npks] tables (one symmetric allocation of every rank bound to a
+ * multicast object).  Every 16 bytes of renamed ids leave this GPU once (multimem.st) and the switch
+ * writes them into the table of every rank, this one included.  Barriers as for the push variant.
+ */
+int pvk_segment_rename_mcast(const int32_t *tid_own, int64_t n, const int32_t *gidlow, const int32_t *params,
+                             int32_t *mc_table, int64_t dst_offset, void *stream);
+
 /* ------------------------------------------------------------------ resynthesis
  * Replaces SinSum.synth -> RegPartial.synth (PVAnalysis.py:1053-1070,684-756),
  * phase_preserve=True path, for ONE clip.

@@ -44,6 +44,7 @@ SIGNATURES = {
     "pvk_segment_resolve": (_i, [_p, _i, _i, _i, _p, _i64, _p, _p, _p]),
     "pvk_segment_rename": (_i, [_p, _i64, _p, _p, _p, _p]),
     "pvk_segment_rename_push": (_i, [_p, _i64, _p, _p, _p, _i, _i64, _p]),
+    "pvk_segment_rename_mcast": (_i, [_p, _i64, _p, _p, _p, _i64, _p]),
     "pvk_resynth_workspace_bytes": (_i64, [_i64, _i, _i64, _i64]),
     "pvk_resynth": (_i, [_p, _i64, _i, _i64, _p, _p, _p, _p, _p, _p, _d, _i, _i, _i, _d, _i, _p, _i64, _i64,
                          _i64, _p, _i64, _i, _p]),

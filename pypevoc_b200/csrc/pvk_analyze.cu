@@ -1373,10 +1373,15 @@ template <int LOGM> static int launch_analyze(AParams prm, int64_t nclips, int r
     // that every resident CTA slot is busy for the same time: size the runs so that the grid is a
     // whole number of waves, as few as possible (every run pays one warm-up frame), with runs of
     // 4..256 frames.
+    // Clip batches: every clip is cut into the same number of equally long runs, as many as keep the
+    // grid within those waves (a clip's last run is not a short straggler that opens another wave).
     const int64_t slots = resident_ctas<LOGM>(smem);
     const int64_t total = nclips * prm.nframes;
     const int64_t waves = (total + slots * 256 - 1) / (slots * 256);
-    run = (total + slots * waves - 1) / (slots * waves);
+    int64_t per_clip = slots * waves / nclips;                 // runs per clip
+    const int64_t min_runs = (prm.nframes + 255) / 256;        // runs of at most 256 frames
+    if (per_clip < min_runs) per_clip = min_runs;
+    run = (prm.nframes + per_clip - 1) / per_clip;
     if (run < 4) run = 4;
   }
   if (run > prm.nframes) run = prm.nframes;

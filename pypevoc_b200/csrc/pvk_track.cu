@@ -1198,6 +1198,13 @@ namespace pvk {
 // summary[0..K) local ids of the row before the first own row, [K..2K) of the last own row,
 // [2K] nb = partials born before the own rows, [2K+1] nb + n_own, [2K+2] global index of the last
 // own row holding a point, [2K+3] number of own rows.  Pre-set to -1 / 0 by the caller.
+// summary <- {-1 x 2K, 0, 0, -1, nown}: set on the device (no pageable host-to-device copy: nothing that
+// could synchronise the side stream the call sits on, and capturable in a CUDA graph)
+__global__ void segment_summary_init_kernel(int32_t *__restrict__ summary, int K, int32_t nown) {
+  for (int c = threadIdx.x; c < 2 * K + 4; c += blockDim.x)
+    summary[c] = c < 2 * K ? -1 : (c == 2 * K + 2 ? -1 : (c == 2 * K + 3 ? nown : 0));
+}
+
 __global__ void segment_summary_kernel(const int32_t *__restrict__ tid, int K, int64_t own0, int64_t nown,
                                        int64_t j0, int32_t *__restrict__ summary) {
   const int64_t n = (own0 + nown) * K;
@@ -1301,15 +1308,58 @@ __global__ void segment_rename_push_kernel(const int32_t *__restrict__ tid_own, 
   }
 }
 
+// The same through NVSwitch MULTICAST: `mc` is the multicast address of the ranks' tables (one
+// symmetric allocation bound to a multicast object); one multimem.st leaves the GPU once and the
+// switch replicates it into the table of every rank, this one included -- 1/N of the NVLink egress
+// of per-peer stores.
+__device__ __forceinline__ void mc_store4(int32_t *p, int4 o) {
+#ifdef PVK_EMU
+  *reinterpret_cast<int4 *>(p) = o;
+#else
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(__int_as_float(o.x)),
+               "f"(__int_as_float(o.y)), "f"(__int_as_float(o.z)), "f"(__int_as_float(o.w))
+               : "memory");
+#endif
+}
+__device__ __forceinline__ void mc_store1(int32_t *p, int o) {
+#ifdef PVK_EMU
+  *p = o;
+#else
+  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(__int_as_float(o)) : "memory");
+#endif
+}
+
+__global__ void segment_rename_mcast_kernel(const int32_t *__restrict__ tid_own, int64_t n,
+                                            const int32_t *__restrict__ gidlow, const int32_t *__restrict__ params,
+                                            int32_t *mc, int64_t offset) {
+  const int base = params[0], nb = params[1];
+  int32_t *t = mc + offset;
+  const bool vec = (reinterpret_cast<uintptr_t>(t) & 15) == 0 && (reinterpret_cast<uintptr_t>(tid_own) & 15) == 0;
+  const int64_t n4 = vec ? n >> 2 : 0;
+  const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, ts = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t q = t0; q < n4; q += ts) {
+    const int4 v = reinterpret_cast<const int4 *>(tid_own)[q];
+    int4 o;
+    o.x = v.x < 0 ? -1 : (v.x >= nb ? base + (v.x - nb) : gidlow[v.x]);
+    o.y = v.y < 0 ? -1 : (v.y >= nb ? base + (v.y - nb) : gidlow[v.y]);
+    o.z = v.z < 0 ? -1 : (v.z >= nb ? base + (v.z - nb) : gidlow[v.z]);
+    o.w = v.w < 0 ? -1 : (v.w >= nb ? base + (v.w - nb) : gidlow[v.w]);
+    mc_store4(t + 4 * q, o);
+  }
+  for (int64_t e = 4 * n4 + t0; e < n; e += ts) {
+    const int v = tid_own[e];
+    mc_store1(t + e, v < 0 ? -1 : (v >= nb ? base + (v - nb) : gidlow[v]));
+  }
+}
+
 }  // namespace pvk
 
 extern "C" int pvk_segment_summary(const int32_t *tid, int npks, int64_t own0, int64_t nown, int64_t j0,
                                    int32_t *summary, void *stream) {
   PVK_REQUIRE(npks >= 1 && own0 >= 0 && nown >= 0 && summary, "pvk_segment_summary: bad arguments");
   const int K = npks;
-  cudaMemsetAsync(summary, 0xff, (size_t)(2 * K) * 4, (cudaStream_t)stream);           // -1
-  const int32_t tail[4] = {0, 0, -1, (int32_t)nown};
-  cudaMemcpyAsync(summary + 2 * K, tail, sizeof(tail), cudaMemcpyHostToDevice, (cudaStream_t)stream);
+  PVK_LAUNCH(segment_summary_init_kernel, dim3(1), dim3(256), 0, stream, summary, K, (int32_t)nown);
+  PVK_CHECK_LAUNCH("pvk_segment_summary");
   if (nown == 0) return PVK_OK;
   PVK_REQUIRE(tid != nullptr, "pvk_segment_summary: tid is NULL");
   PVK_LAUNCH(segment_summary_kernel, dim3(grid_for((own0 + nown) * K, 256)), dim3(256), 0, stream, tid, K, own0, nown,
@@ -1348,5 +1398,16 @@ extern "C" int pvk_segment_rename_push(const int32_t *tid_own, int64_t n, const 
   PVK_LAUNCH(segment_rename_push_kernel, dim3(grid_for(n / 4 + 1, 256)), dim3(256), 0, stream, tid_own, n, gidlow, params,
              dst_tables, ndst, dst_offset);
   PVK_CHECK_LAUNCH("pvk_segment_rename_push");
+  return PVK_OK;
+}
+
+extern "C" int pvk_segment_rename_mcast(const int32_t *tid_own, int64_t n, const int32_t *gidlow, const int32_t *params,
+                                        int32_t *mc_table, int64_t dst_offset, void *stream) {
+  PVK_REQUIRE(n >= 0 && dst_offset >= 0, "pvk_segment_rename_mcast: bad sizes");
+  if (n == 0) return PVK_OK;
+  PVK_REQUIRE(tid_own && gidlow && params && mc_table, "pvk_segment_rename_mcast: NULL pointer argument");
+  PVK_LAUNCH(segment_rename_mcast_kernel, dim3(grid_for(n / 4 + 1, 256)), dim3(256), 0, stream, tid_own, n, gidlow, params,
+             mc_table, dst_offset);
+  PVK_CHECK_LAUNCH("pvk_segment_rename_mcast");
   return PVK_OK;
 }

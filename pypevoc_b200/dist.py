@@ -319,6 +319,7 @@ class StitchHandle(object):
             else:
                 allv = mine
             self.peer_used = False
+            self.multicast_used = False
             if world > 1 and os.environ.get("PVK_PEER_GATHER", "1") != "0" and self._peer_gather(tid_local, allv, group):
                 return
             r = segment_rename_device(tid_local, plan, world, allv, max(p["own0"] for p in plans), sync=False)
@@ -367,9 +368,21 @@ class StitchHandle(object):
             _lib.check(L.pvk_segment_resolve(ptr(allv), world, K, g, ptr(scratch[0]), cap, ptr(scratch[1]), ptr(params),
                                              stream), "pvk_segment_resolve")
             own = tid_local[own0:own0 + nown].contiguous()
-            _lib.check(L.pvk_segment_rename_push(ptr(own), own.numel(), ptr(scratch[1]), ptr(params),
-                                                 C.c_void_p(int(hdl.buffer_ptrs_dev)), world, plan["j0"] * K, stream),
-                       "pvk_segment_rename_push")
+            mc = 0
+            if os.environ.get("PVK_PEER_MULTICAST", "1") != "0":
+                try:
+                    mc = int(hdl.multicast_ptr or 0)                # 0: no multicast object behind this buffer
+                except Exception:
+                    mc = 0
+            if mc:
+                # ONE store per 16 bytes, replicated into every rank's table by the NVSwitch
+                _lib.check(L.pvk_segment_rename_mcast(ptr(own), own.numel(), ptr(scratch[1]), ptr(params),
+                                                      C.c_void_p(mc), plan["j0"] * K, stream), "pvk_segment_rename_mcast")
+            else:
+                _lib.check(L.pvk_segment_rename_push(ptr(own), own.numel(), ptr(scratch[1]), ptr(params),
+                                                     C.c_void_p(int(hdl.buffer_ptrs_dev)), world, plan["j0"] * K, stream),
+                           "pvk_segment_rename_push")
+            self.multicast_used = bool(mc)
             hdl.barrier()                                 # all ranks' stores have landed
             table = buf.view(world * rows_max, K)[:F]
             self._keep = (own, scratch)
@@ -529,17 +542,56 @@ def resynth_local(tid_local, pk_local, plan, plans, max_end, sr, hop, nfft, hop_
                             reuse_tracks=reuse_tracks)
 
 
+def track_pack_resynth_local(tab, plan, plans, sr, hop, nfft, hop_an, edge=1.0, minframes=3, maxpitchjmp=0.5,
+                             after_link=None, after_pack=None):
+    """Back half of the path for one rank's window, queued without a host round trip
+    (pv.track_pack_resynth_device): link, pack and the rendering of the rank's block range.  No count
+    is needed to know the range: every rank but the one owning the last frames renders its own blocks
+    [j0, j1); the last one renders up to the bound its window allows (its last window row as "last
+    frame") -- cut with trim_local() once the global last frame is known.  ``tab``: device tables f mag
+    ph realph [window rows, K].  Returns (tr, pk, w, b0): w holds global samples [b0*hop, ...)."""
+    w1 = plan["w1"]
+    b0, b1, bound = render_range_local(plan, plans, (w1 - 1) if plan["nown"] > 0 else -1, hop, nfft, hop_an, edge)
+    w0 = plan["w0"]
+    rng = (b0 - w0, max(b1 - b0, 0), max(bound - w0 * hop, 0))
+    tr, pk, w = P.track_pack_resynth_device(tab["f"], tab["mag"], tab["ph"], tab["realph"], sr, hop, nfft, hop_an, edge=edge,
+                                            minframes=minframes, maxpitchjmp=maxpitchjmp, after_link=after_link,
+                                            after_pack=after_pack, block_range=rng)
+    if w is None:
+        w = torch.zeros((0,), dtype=torch.float64, device=tab["f"].device)
+    return tr, pk, w, b0
+
+
 # --------------------------------------------------------------------------- host API
 class ShardedSinSum(object):
     """Result of ShardedPV.toSinSum(): the global track table on every rank + this rank's local
     partials (window rows, local ids) for resynthesis."""
 
-    def __init__(self, spv, local_ss, handle):
+    def __init__(self, spv, local_ss, handle=None):
         self._spv = spv
         self.local = local_ss
-        self._h = handle                     # StitchHandle: numbering + gather in flight on a side stream
+        self._handle = handle                # StitchHandle: numbering + gather in flight on a side stream
         self._spans = None
+        self._first = None                   # (w, b0) rendered together with the first link / pack
         self.sr, self.nfft, self.hop = spv.sr, spv.nfft, spv.hop
+
+    def _hook(self, tr):
+        self._handle = StitchHandle(tr["tid"], self._spv.plan, self._spv.plans, self._spv.group)
+
+    @property
+    def _h(self):
+        """The stitch handle; created right behind the link kernels the first time the partials are
+        needed (by synth_local together with pack + rendering, or by any accessor)."""
+        if self._handle is None:
+            ss = self.local
+            ss._after_link = self._hook
+            try:
+                tr = ss._ensure_tracks()                             # link -> [numbering + gather] -> pack -> counts
+            finally:
+                ss._after_link = None
+            if self._handle is None:                                 # (no frames on this rank: nothing was launched)
+                self._handle = StitchHandle(tr["tid"], self._spv.plan, self._spv.plans, self._spv.group)
+        return self._handle
 
     @property
     def ntracks(self):
@@ -601,6 +653,19 @@ class ShardedSinSum(object):
         hop = spv.hop if hop is None else int(hop)
         if (edge, minframes) != (spv.edge, spv.minframes):
             raise ValueError("the segment halos were planned for edge=%r, minframes=%r" % (spv.edge, spv.minframes))
+        if self._handle is None and hostbuf is None and self.local._trk is None and spv.plan["nframes"] > 0:
+            # first use: link, numbering + gather (side stream), pack and rendering are queued back to back;
+            # the counts are read once at the end
+            t = self.local._tables
+            tr, pk, w, b0 = track_pack_resynth_local(t, spv.plan, spv.plans, sr, hop, self.nfft, self.hop, edge, minframes,
+                                                     maxpitchjmp=self.local._maxpitchjmp, after_link=self._hook)
+            self.local._trk = tr
+            if pk is not None:
+                self.local._pk = pk
+            n, s0 = trim_local(w.numel(), b0, spv.plan, spv.plans, self.max_end, hop, self.nfft, self.hop, edge)
+            w = w[:n]
+            return (w.cpu().numpy() if to_host else w), s0
+        self._h                                                      # (numbering + gather go out before the pack)
         pk = self.local._ensure_packed()
         tidl = self.local._trk["tid"]
         # block range from LOCAL knowledge (the numbering / gather may still be in flight); the
@@ -691,17 +756,11 @@ class ShardedPV(object):
         return slice(self.plan["own0"], self.plan["own0"] + self.plan["nown"])
 
     def toSinSum(self, async_gather=True):
-        """Local linking + global numbering + the all_gather of the track table."""
+        """Local linking + global numbering + the gather of the track table.  Nothing is launched
+        here: the work is queued the first time the result is used -- by ``synth_local`` in one go with
+        packing and rendering (one host read-back at the end), or by any accessor.  COLLECTIVE: every
+        rank must make the same first use (the numbering all_gather and the table gather need all ranks)."""
         d = self.pv.device_tables
         ss = P.SinSum(self.sr, nfft=self.nfft, hop=self.hop, device=self.pv._dev)
         ss._set_device_tables(d["f"], d["mag"], d["ph"], d["realph"])
-        if d["f"].shape[0] == 0:
-            tr = ss._ensure_tracks()
-            return ShardedSinSum(self, ss, StitchHandle(tr["tid"], self.plan, self.plans, self.group))
-        # queue the numbering + gather behind the link kernels BEFORE the host waits for their
-        # counts: the launch cost of the collectives hides behind analysis + linking
-        box = []
-        ss._after_link = lambda tr: box.append(StitchHandle(tr["tid"], self.plan, self.plans, self.group))
-        ss._ensure_tracks()                                  # link -> [numbering + gather] -> pack -> counts
-        ss._after_link = None
-        return ShardedSinSum(self, ss, box[0])
+        return ShardedSinSum(self, ss)

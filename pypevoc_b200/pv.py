@@ -361,13 +361,16 @@ def track_pack_device(fd, magd, phd, realphd, maxpitchjmp=0.5, after_link=None):
 
 
 def track_pack_resynth_device(fd, magd, phd, realphd, sr, hop, nfft, hop_an, edge=1.0, minframes=3,
-                              maxpitchjmp=0.5, after_link=None, after_pack=None):
+                              maxpitchjmp=0.5, after_link=None, after_pack=None, block_range=None):
     """The whole back half of the hot path of one clip -- link, id resolution, pack, resynthesis --
     queued back to back with ONE host read-back at the very end: pack and resynthesis are launched
     sized by upper bounds (capacity of the index arrays, (F + 1) * hop + edge output samples) and
     read the real number of partials on the device (pvk_track_pack_dev / pvk_resynth_dev); the
     host then reads the 24 bytes of counts and slices.  Returns (tr, pk, w): as track_pack_device()
-    plus the float64 device signal (None without partials)."""
+    plus the float64 device signal (None without partials).  ``block_range`` = (block0, nblocks,
+    nout): render only these output blocks of a signal of (at most) ``nout`` samples and return them
+    uncut (segment-sharded runs: the caller knows its block range without any count and trims once the
+    global last frame is known)."""
     L = _lib.lib()
     F, K = fd.shape
     if F * K == 0:
@@ -381,23 +384,33 @@ def track_pack_resynth_device(fd, magd, phd, realphd, sr, hop, nfft, hop_an, edg
     if after_pack is not None:
         after_pack(tr)
     nt_ub, tstart, tlen, toff, packed = raw
-    nout_ub, _ = synth_geometry(F - 1, hop, nfft, hop_an, edge)
-    nblk = -(-nout_ub // hop)
-    out = torch.empty((nout_ub,), dtype=torch.float64, device=dev)
-    ws = resynth_workspace(F, K, nt_ub, nblk, dev, hop=hop)
-    with torch.cuda.device(dev):
-        _lib.check(L.pvk_resynth_dev(_ptr(tr["tid"]), F, K, nt_ub, _ptr(tr["ntracks"]), _ptr(tstart), _ptr(tlen), _ptr(toff),
-                                     _ptr(packed[0]), _ptr(packed[1]), _ptr(packed[3]), float(sr), int(hop), int(nfft),
-                                     int(hop_an), float(edge), int(minframes), _ptr(out), int(nout_ub), 0, -1, _ptr(ws),
-                                     int(ws.numel()), 0, _stream()), "pvk_resynth")
+    if block_range is None:
+        nout_ub, _ = synth_geometry(F - 1, hop, nfft, hop_an, edge)
+        b0, nb = 0, -(-nout_ub // hop)
+    else:
+        b0, nb, nout_ub = (int(v) for v in block_range)
+    nsamp_out = max(min(nb * hop, nout_ub - b0 * hop), 0)
+    out = torch.empty((nsamp_out,), dtype=torch.float64, device=dev)
+    if nsamp_out > 0:
+        ws = resynth_workspace(F, K, nt_ub, nb, dev, hop=hop)
+        with torch.cuda.device(dev):
+            _lib.check(L.pvk_resynth_dev(_ptr(tr["tid"]), F, K, nt_ub, _ptr(tr["ntracks"]), _ptr(tstart), _ptr(tlen),
+                                         _ptr(toff), _ptr(packed[0]), _ptr(packed[1]), _ptr(packed[3]), float(sr), int(hop),
+                                         int(nfft), int(hop_an), float(edge), int(minframes), _ptr(out), int(nout_ub), b0, nb,
+                                         _ptr(ws), int(ws.numel()), 0, _stream()), "pvk_resynth")
     nt, npts, last = track_counts(tr)                           # the hot path's one read-back
     tr["ntracks_dev"] = tr["ntracks"]
     tr["ntracks"], tr["npts"], tr["max_end"] = nt, npts, last
     if nt == 0:
-        return tr, None, None
+        return tr, None, (None if block_range is None else out.zero_())
     if nt > nt_ub:                                              # more partials than the speculative cap: redo, sized exactly
         pk = pack_device(fd, magd, phd, realphd, tr["tid"], None, nt, npts=npts)
-        return tr, pk, resynth_device(tr["tid"], pk, sr, hop, nfft, hop_an, edge=edge, minframes=minframes, max_end=last)
+        if block_range is None:
+            return tr, pk, resynth_device(tr["tid"], pk, sr, hop, nfft, hop_an, edge=edge, minframes=minframes, max_end=last)
+        return tr, pk, resynth_device(tr["tid"], pk, sr, hop, nfft, hop_an, edge=edge, minframes=minframes, block0=b0,
+                                      nblocks=nb, nout=nout_ub, out=out)
+    if block_range is not None:
+        return tr, _pack_sliced(raw, nt, npts), out
     nout, _ = synth_geometry(last, hop, nfft, hop_an, edge)
     return tr, _pack_sliced(raw, nt, npts), out[:nout]
 

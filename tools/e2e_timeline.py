@@ -22,7 +22,7 @@ T = lambda: time.perf_counter()
 for it in range(5):
     torch.cuda.synchronize(); t0 = T()
     pv = PV(xh, sr, nfft=nfft, hop=hop, npks=npks, progress=False, device=dev); t1 = T()
-    pv.run_pv(hostbuf=hb); t2 = T()
+    pv.run_pv(hostbuf=hb, stream_tables=bench.E2E_TABLES); t2 = T()
     ss = pv.toSinSum(); ss._ensure_tracks(); t3 = T()
     ss._ensure_packed(); t4 = T()
     w = ss.synth(sr, hop, hostbuf=hb); t5 = T()
@@ -35,7 +35,7 @@ from pypevoc_b200 import pv as P
 P.TRACE = []
 torch.cuda.synchronize()
 pv = PV(xh, sr, nfft=nfft, hop=hop, npks=npks, progress=False, device=dev)
-pv.run_pv(hostbuf=hb)
+pv.run_pv(hostbuf=hb, stream_tables=bench.E2E_TABLES)
 ss = pv.toSinSum(); ss._ensure_tracks()
 P._mark("track done", torch.cuda.current_stream())
 w = ss.synth(sr, hop, hostbuf=hb)
