@@ -415,16 +415,24 @@ def gpu_main(args):
         # N > 1: the same back half on this rank's window (dist.track_pack_resynth_local): link -> [numbering +
         # gather of the track table on a side stream] -> pack -> rendering of the rank's own block range, all
         # queued back to back; one 24-byte read-back at the end, then the 8 integers of the numbering pass
+        def after_pack(tr_):
+            if e: e[3].record()
+            box[0].join_before_render()                  # (only with PVK_GATHER_JOIN=pack; default: joined at the end)
+        glob = {}
+
+        def before_sync(tr_):
+            # queued behind the rendering, before the host waits for anything on the main stream: the 8
+            # integers of the numbering pass (the side stream finished long ago), the join of the gathered
+            # table and the spans pass over it
+            glob["ntg"], glob["max_end"] = box[0].counts()
+            glob["table"] = box[0].table()
+            glob["spans"] = P.spans_device(glob["table"], glob["ntg"])     # first frame / length of every partial
         tr, pk, w, b0 = D.track_pack_resynth_local(tab, plan, plans, sr, hop, nfft, hop, after_link=after_link,
-                                                   after_pack=(lambda tr_: e[3].record()) if e else None)
+                                                   after_pack=after_pack, before_sync=before_sync)
         sh = box[0]
-        if ht: ht.append(time.perf_counter())
-        ntg, max_end = sh.counts()                       # 8 ints; the numbering finished long ago
-        if ht: ht.append(time.perf_counter())
+        ntg, max_end, table, spans = glob["ntg"], glob["max_end"], glob["table"], glob["spans"]
         st = dict(ntracks=ntg, max_end=max_end)
         w = w[:D.trim_local(w.numel(), b0, plan, plans, max_end, hop, nfft, hop)[0]]
-        table = sh.table()                               # the gather overlapped pack + resynthesis
-        spans = P.spans_device(table, ntg)               # first frame / length of every partial
         if e: e[4].record()
         if ht:
             ht.append(time.perf_counter())

@@ -283,12 +283,26 @@ _STITCH_STREAMS = {}
 _PEER_TABLES = {}            # (device, world, rows, K) -> symmetric-memory track tables (PVK_PEER_GATHER=1)
 
 
+def _peer_gather_wanted(world):
+    """PVK_PEER_GATHER=1 / 0 forces the fused rename + peer-store gather / the NCCL all_gather.  Unset:
+    chosen by measurement (profiles/r2u_*, r2w_*: B200 x 2 / x 8, NVSwitch): equal within noise on 2 GPUs
+    (1.375 vs 1.393 ms per step), NCCL -- which uses the switch's multicast itself -- 4 % ahead on 8
+    (1.441 vs 1.499 ms), so the peer-store kernel is the default up to 4 ranks and NCCL beyond."""
+    v = os.environ.get("PVK_PEER_GATHER")
+    if v is not None:
+        return v != "0"
+    return world <= 4
+
+
 def _stitch_stream(dev):
     """The side stream the numbering + gather run on (one per device; not the copy streams of
     pv._side_streams: the collectives must not queue behind table downloads)."""
     key = (dev.type, dev.index)
     if key not in _STITCH_STREAMS:
-        _STITCH_STREAMS[key] = torch.cuda.Stream(device=dev)
+        # high priority: its kernels are tiny (summary, resolve, rename + stores, barriers, the collective's
+        # copy CTAs) and must not queue behind the thousands of CTAs of the rendering kernel they overlap
+        prio = -1 if os.environ.get("PVK_STITCH_PRIORITY", "1") != "0" else 0
+        _STITCH_STREAMS[key] = torch.cuda.Stream(device=dev, priority=prio)
     return _STITCH_STREAMS[key]
 
 
@@ -320,7 +334,7 @@ class StitchHandle(object):
                 allv = mine
             self.peer_used = False
             self.multicast_used = False
-            if world > 1 and os.environ.get("PVK_PEER_GATHER", "1") != "0" and self._peer_gather(tid_local, allv, group):
+            if world > 1 and _peer_gather_wanted(world) and self._peer_gather(tid_local, allv, group):
                 return
             r = segment_rename_device(tid_local, plan, world, allv, max(p["own0"] for p in plans), sync=False)
             self._tid_own, self._params = r["tid_own"], r["params"]
@@ -328,7 +342,7 @@ class StitchHandle(object):
             self._table = finish()                        # queued behind the gather on the side stream
 
     def _peer_gather(self, tid_local, allv, group):
-        """Default path (PVK_PEER_GATHER=0 selects the NCCL all_gather): rename fused with the gather --
+        """(Default up to 4 ranks, see _peer_gather_wanted.)  Rename fused with the gather --
         pvk_segment_rename_push stores the renamed rows straight into the track tables of all ranks,
         which are symmetric-memory buffers mapped over NVLink; two signal-pad barriers replace the
         NCCL all_gather (verified bit for bit against the unsharded run on 2 GPUs, profiles/r2a_*).  Two buffers alternate, so a returned table stays valid until the second
@@ -397,6 +411,14 @@ class StitchHandle(object):
                 sys.stderr.write("pypevoc_b200: the peer-memory gather is unavailable (%r); "
                                  "using the NCCL all_gather\n" % (e,))
             return False
+
+    def join_before_render(self):
+        """PVK_GATHER_JOIN=pack: make the current stream wait for the numbering + gather before the
+        rendering kernels are queued on it.  Default ("end"): the gather runs beside the rendering on the
+        high-priority stitch stream and is joined when the table is needed -- measured on 8 GPUs
+        (profiles/r2w_*): 1.44 - 1.50 ms per step against 1.58 with the early join."""
+        if os.environ.get("PVK_GATHER_JOIN", "end") != "end":
+            torch.cuda.current_stream(self.dev).wait_stream(self.side)
 
     def counts(self):
         """(total number of partials, global index of the last frame holding a point)."""
@@ -543,7 +565,7 @@ def resynth_local(tid_local, pk_local, plan, plans, max_end, sr, hop, nfft, hop_
 
 
 def track_pack_resynth_local(tab, plan, plans, sr, hop, nfft, hop_an, edge=1.0, minframes=3, maxpitchjmp=0.5,
-                             after_link=None, after_pack=None):
+                             after_link=None, after_pack=None, before_sync=None):
     """Back half of the path for one rank's window, queued without a host round trip
     (pv.track_pack_resynth_device): link, pack and the rendering of the rank's block range.  No count
     is needed to know the range: every rank but the one owning the last frames renders its own blocks
@@ -556,7 +578,7 @@ def track_pack_resynth_local(tab, plan, plans, sr, hop, nfft, hop_an, edge=1.0, 
     rng = (b0 - w0, max(b1 - b0, 0), max(bound - w0 * hop, 0))
     tr, pk, w = P.track_pack_resynth_device(tab["f"], tab["mag"], tab["ph"], tab["realph"], sr, hop, nfft, hop_an, edge=edge,
                                             minframes=minframes, maxpitchjmp=maxpitchjmp, after_link=after_link,
-                                            after_pack=after_pack, block_range=rng)
+                                            after_pack=after_pack, block_range=rng, before_sync=before_sync)
     if w is None:
         w = torch.zeros((0,), dtype=torch.float64, device=tab["f"].device)
     return tr, pk, w, b0
@@ -658,7 +680,8 @@ class ShardedSinSum(object):
             # the counts are read once at the end
             t = self.local._tables
             tr, pk, w, b0 = track_pack_resynth_local(t, spv.plan, spv.plans, sr, hop, self.nfft, self.hop, edge, minframes,
-                                                     maxpitchjmp=self.local._maxpitchjmp, after_link=self._hook)
+                                                     maxpitchjmp=self.local._maxpitchjmp, after_link=self._hook,
+                                                     after_pack=lambda tr_: self._handle.join_before_render())
             self.local._trk = tr
             if pk is not None:
                 self.local._pk = pk

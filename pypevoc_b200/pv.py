@@ -361,7 +361,7 @@ def track_pack_device(fd, magd, phd, realphd, maxpitchjmp=0.5, after_link=None):
 
 
 def track_pack_resynth_device(fd, magd, phd, realphd, sr, hop, nfft, hop_an, edge=1.0, minframes=3,
-                              maxpitchjmp=0.5, after_link=None, after_pack=None, block_range=None):
+                              maxpitchjmp=0.5, after_link=None, after_pack=None, block_range=None, before_sync=None):
     """The whole back half of the hot path of one clip -- link, id resolution, pack, resynthesis --
     queued back to back with ONE host read-back at the very end: pack and resynthesis are launched
     sized by upper bounds (capacity of the index arrays, (F + 1) * hop + edge output samples) and
@@ -370,7 +370,8 @@ def track_pack_resynth_device(fd, magd, phd, realphd, sr, hop, nfft, hop_an, edg
     plus the float64 device signal (None without partials).  ``block_range`` = (block0, nblocks,
     nout): render only these output blocks of a signal of (at most) ``nout`` samples and return them
     uncut (segment-sharded runs: the caller knows its block range without any count and trims once the
-    global last frame is known)."""
+    global last frame is known).  ``before_sync`` (optional) is called once everything is queued,
+    before the host waits: work launched there runs behind the rendering instead of after the wait."""
     L = _lib.lib()
     F, K = fd.shape
     if F * K == 0:
@@ -398,6 +399,8 @@ def track_pack_resynth_device(fd, magd, phd, realphd, sr, hop, nfft, hop_an, edg
                                          _ptr(toff), _ptr(packed[0]), _ptr(packed[1]), _ptr(packed[3]), float(sr), int(hop),
                                          int(nfft), int(hop_an), float(edge), int(minframes), _ptr(out), int(nout_ub), b0, nb,
                                          _ptr(ws), int(ws.numel()), 0, _stream()), "pvk_resynth")
+    if before_sync is not None:
+        before_sync(tr)
     nt, npts, last = track_counts(tr)                           # the hot path's one read-back
     tr["ntracks_dev"] = tr["ntracks"]
     tr["ntracks"], tr["npts"], tr["max_end"] = nt, npts, last
