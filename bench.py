@@ -553,14 +553,14 @@ def gpu_main(args):
     roof_an = {"kernel": "analyze_kernel<10>", "bound": "hbm", "achieved": alg_an / (ms_an * 1e-3) / 1e9, "peak": hbm,
                "unit": "GB/s", "frac": alg_an / (ms_an * 1e-3) / 1e9 / hbm, "traffic": _traffic("analyze"),
                "ms": ms_an, "alg_bytes_per_launch": alg_an, "peak_source": how,
-               "note": "fused framing+FFT+peak-pick+IF: issue / latency bound at 16 resident warps per SM (ncu: issue "
-                       "slots 53 % busy, DRAM 4 %), see DESIGN.md 4.1"}
-    roof_syn = {"kernel": "resynth stage (resynth_tracks + 2 x (resynth_prepare + resynth_tile_kernel<16>))", "bound": "hbm", "achieved": alg_syn / (ms_syn * 1e-3) / 1e9, "peak": hbm,
+               "note": "fused framing+FFT+peak-pick+IF: issue / latency bound at 16 resident warps per SM (ncu r2x: issue "
+                       "slots 57 % busy, DRAM 5 %), see DESIGN.md 4.1"}
+    roof_syn = {"kernel": "resynth stage (resynth_tracks_kernel + resynth_tile_kernel, partial bodies built in-kernel)", "bound": "hbm", "achieved": alg_syn / (ms_syn * 1e-3) / 1e9, "peak": hbm,
                 "unit": "GB/s", "frac": alg_syn / (ms_syn * 1e-3) / 1e9 / hbm, "traffic": _traffic("resynth"),
                 "ms": ms_syn, "alg_bytes_per_launch": alg_syn, "peak_source": how,
                 "partial_samples_per_s": psamp_local / (ms_syn * 1e-3),
-                "note": "compute bound by construction (one MUFU cosine per partial-sample; ncu: XU pipe 79 % busy), "
-                        "see DESIGN.md 4.3"}
+                "note": "compute bound by construction (one MUFU cosine per partial-sample; ncu r2x: XU pipe 76 % busy, issue "
+                        "slots 76 %), see DESIGN.md 4.3"}
     # dominant KERNEL of the step: the analysis stage is one launch of analyze_kernel; the resynthesis
     # stage is resynth_tracks + 2 x (resynth_prepare + resynth_tile), of which the tile kernel takes
     # ~72 % (ncu launch lists under profiles/), so analysis dominates unless the tile kernel alone is longer
