@@ -561,10 +561,10 @@ def gpu_main(args):
                 "partial_samples_per_s": psamp_local / (ms_syn * 1e-3),
                 "note": "compute bound by construction (one MUFU cosine per partial-sample; ncu r2x: XU pipe 76 % busy, issue "
                         "slots 76 %), see DESIGN.md 4.3"}
-    # dominant KERNEL of the step: the analysis stage is one launch of analyze_kernel; the resynthesis
-    # stage is resynth_tracks + 2 x (resynth_prepare + resynth_tile), of which the tile kernel takes
-    # ~72 % (ncu launch lists under profiles/), so analysis dominates unless the tile kernel alone is longer
-    # reported on the same kernel at every N
+    # `roofline` is reported on the same kernel at every N: analyze_kernel, the one launch of the analysis stage
+    # (the metric's frames/s; ncu launch list r2x: 439 us).  The other long kernel, resynth_tile_kernel (472 us
+    # of the resynthesis stage, which also holds resynth_tracks_kernel and the step's read-back), is reported
+    # beside it as `roofline_resynth`.
     dominant = roof_an
     line = {
         "metric": METRIC, "value": frames_total / (ms_step * 1e-3), "unit": "frames/s",
