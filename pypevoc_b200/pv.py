@@ -1511,6 +1511,12 @@ class SinSum(object):
                                       "broken in the reference (PVAnalysis.py:665); not provided")
         if int(hop) != hop:
             raise TypeError("hop must be an integer number of samples")
+        if self._trk is None and hostbuf is not None:
+            self._ensure_tables()
+            if self._tables["f"].shape[0] * self._tables["f"].shape[1] > 0:
+                w = self._synth_streamed_fused(sr, int(hop), edge, minframes, hostbuf, int(chunks))
+                if w is not None:
+                    return w
         if self._trk is None and hostbuf is None:
             # first use of the partials: link, pack and resynthesis go to the device back to back,
             # the counts are read once at the end (no host round trip between the stages)
@@ -1535,6 +1541,62 @@ class SinSum(object):
         out = resynth_device(tr["tid"], pk, sr, int(hop), self.nfft, self.hop, edge=edge, minframes=minframes,
                              max_end=tr.get("max_end"))
         return out.cpu().numpy() if to_host else out
+
+    def _synth_streamed_fused(self, sr, hop, edge, minframes, hostbuf, chunks):
+        """synth(hostbuf=...) on fresh partials: link, pack, the chunked rendering and the downloads of
+        the finished chunks are all queued before the host reads any count (sizes are upper bounds,
+        pvk_track_pack_dev / pvk_resynth_dev); the signal is cut to its real length at the end.  Returns
+        None (after setting the tracks) when the staged path has to take over: no partial at all, or
+        more partials than the speculative capacity."""
+        L = _lib.lib()
+        dev = self._dev
+        t = self._tables
+        F, K = t["f"].shape
+        tr = track_device(t["f"], t["mag"], self._maxpitchjmp)
+        if self._after_link is not None:
+            self._after_link(tr)
+        raw = _pack_speculative(t["f"], t["mag"], t["ph"], t["realph"], tr)
+        nt_ub, tstart, tlen, toff, packed = raw
+        nout_ub, _ = synth_geometry(F - 1, hop, self.nfft, self.hop, edge)
+        nblk = -(-nout_ub // hop)
+        cur = torch.cuda.current_stream(dev)
+        _, d2h = _side_streams(dev)
+        with torch.cuda.device(dev):
+            out = torch.empty((nout_ub,), dtype=torch.float64, device=dev)
+            hw = _pinned(hostbuf, "w", (nout_ub,), torch.float64)
+            d2h.wait_stream(cur)
+            chunks = max(1, min(chunks, nblk // 64 if nblk >= 64 else 1))
+            ws = resynth_workspace(F, K, nt_ub, -(-nblk // chunks), dev, hop=hop)
+            _mark("pack queued", cur)
+            for i in range(chunks):
+                b0, b1 = (nblk * i) // chunks, (nblk * (i + 1)) // chunks
+                n0, n1 = b0 * hop, min(b1 * hop, nout_ub)
+                _lib.check(L.pvk_resynth_dev(_ptr(tr["tid"]), F, K, nt_ub, _ptr(tr["ntracks"]), _ptr(tstart), _ptr(tlen),
+                                             _ptr(toff), _ptr(packed[0]), _ptr(packed[1]), _ptr(packed[3]), float(sr),
+                                             int(hop), int(self.nfft), int(self.hop), float(edge), int(minframes),
+                                             _ptr(out[n0:n1]), int(nout_ub), b0, b1 - b0, _ptr(ws), int(ws.numel()),
+                                             1 if i > 0 else 0, _stream()), "pvk_resynth")
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                _mark("resynth %d" % i, cur)
+                with torch.cuda.stream(d2h):
+                    d2h.wait_event(ev)
+                    hw[n0:n1].copy_(out[n0:n1], non_blocking=True)
+                    _mark("w d2h %d" % i, d2h)
+            out.record_stream(d2h)
+            nt, npts, last = track_counts(tr)                    # the one read-back; the downloads keep running
+            tr["ntracks_dev"] = tr["ntracks"]
+            tr["ntracks"], tr["npts"], tr["max_end"] = nt, npts, last
+            self._trk = tr
+            if nt == 0 or nt > nt_ub:
+                d2h.synchronize()
+                return None
+            self._pk = _pack_sliced(raw, nt, npts)
+            d2h.synchronize()
+        nout, _ = synth_geometry(last, hop, self.nfft, self.hop, edge)
+        self.d2h_bytes = nout_ub * 8
+        self._last_out = out
+        return hw[:nout].numpy()
 
     def _synth_streamed(self, pk, tr, sr, hop, edge, minframes, hostbuf, chunks):
         dev = self._dev

@@ -252,3 +252,92 @@ def test_emu_clip_batch_flattened_with_guard_rows():
         assert not wb[s0 + len(w):(c + 1) * (F + G) * hop - E].any()     # (the next clip's fade-in heads come after)
         base += nt
     assert base == ntb
+
+
+def _many_births_table(seed=5, F=70, K=12):
+    rng = np.random.RandomState(seed)
+    f = np.zeros((F, K)); mag = np.zeros((F, K))
+    for j in range(F):                                        # many short partials: births in most frames
+        n = rng.randint(3, K + 1)
+        cols = np.sort(rng.choice(K, n, replace=False))
+        f[j, cols] = np.sort(rng.uniform(100, 8000, n)); mag[j, cols] = rng.uniform(0.1, 1.0, n)
+    return f, mag, rng.uniform(-3, 3, (F, K)), rng.uniform(-3, 3, (F, K))
+
+
+def test_emu_pack_and_resynth_with_device_side_counts():
+    """pvk_track_pack_dev / pvk_resynth_dev (index arrays sized by an upper bound, the real number of
+    partials read on the device): same packed tracks and the same signal as the exact-size calls; with
+    a capacity BELOW the real count nothing is read or written out of bounds (ids beyond the capacity
+    are ignored by every kernel that indexes with them)."""
+    import ctypes as C
+    f, mag, ph, rph = _many_births_table()
+    F, K = f.shape
+    tr = eh.track(f, mag)
+    tid = np.ascontiguousarray(tr["tid"][0])
+    nt = int(tr["ntracks"][0])
+    full = eh.track_pack(f, mag, ph, rph, tid, None, nt)
+    sr, nfft, hop = 16000, 512, 128
+    wfull = eh.resynth(tid, full, sr, hop, nfft, hop)
+    L = eh.lib()
+    ntd = np.array([nt], dtype=np.int32)
+    arrs = [np.ascontiguousarray(a) for a in (f, mag, ph, rph)]
+    G = 64
+    at = lambda a: C.c_void_p(a.ctypes.data + G * a.itemsize)  # noqa: E731
+    for cap in (F * K, nt, nt // 3):
+        tstart = np.full(cap + 2 * G, -77, dtype=np.int32); tlen = np.full(cap + 2 * G, -77, dtype=np.int32)
+        toff = np.full(cap + 1 + 2 * G, -77, dtype=np.int64)
+        packed = [np.full(F * K + 2 * G, -77.0) for _ in range(4)]
+        wsb = L.pvk_track_pack_workspace_bytes(cap)
+        ws = np.zeros(max(wsb, 8), dtype=np.uint8)
+        eh.check(L.pvk_track_pack_dev(eh.ptr(arrs[0]), eh.ptr(arrs[1]), eh.ptr(arrs[2]), eh.ptr(arrs[3]), eh.ptr(tid), F, K,
+                                      cap, eh.ptr(ntd), at(tstart), at(tlen), at(toff), at(packed[0]), at(packed[1]),
+                                      at(packed[2]), at(packed[3]), eh.ptr(ws), int(wsb), None))
+        for a in (tstart, tlen, toff) + tuple(packed):
+            assert np.all(a[:G] == -77) and np.all(a[-G:] == -77)
+        m = min(cap, nt)
+        assert np.array_equal(tstart[G:G + m], full["tstart"][:m]) and np.array_equal(tlen[G:G + m], full["tlen"][:m])
+        assert np.array_equal(toff[G:G + m + 1], full["toff"][:m + 1])
+        n = int(full["toff"][m])
+        for q, k in enumerate(("pf", "pmag", "pph", "prealph")):
+            assert np.array_equal(packed[q][G:G + n], full[k][:n])
+        # rendering with the upper-bound sizes: (F + 1) * hop + E samples, cut afterwards
+        E = int(nfft / hop / 2.0 * hop)
+        nout_ub = (F + 1) * hop + E
+        out = np.full(nout_ub + 2 * G, -77.0)
+        rwsb = int(L.pvk_resynth_workspace_bytes(F, K, cap, -(-nout_ub // hop)))
+        rws = np.zeros(max(rwsb, 8), dtype=np.uint8)
+        eh.check(L.pvk_resynth_dev(eh.ptr(tid), F, K, cap, eh.ptr(ntd), at(tstart), at(tlen), at(toff), at(packed[0]),
+                                   at(packed[1]), at(packed[3]), float(sr), hop, nfft, hop, 1.0, 3, at(out), nout_ub, 0, -1,
+                                   eh.ptr(rws), rwsb, 0, None))
+        assert np.all(out[:G] == -77) and np.all(out[-G:] == -77)
+        if cap >= nt:
+            assert np.array_equal(out[G:G + len(wfull)], wfull)
+            assert not out[G + len(wfull):G + nout_ub].any()       # beyond the real length: silence
+
+
+def test_emu_segment_rename_mcast_equals_push():
+    """pvk_segment_rename_mcast (one store per id to the multicast address of all ranks' tables; in
+    the emulator a plain table) writes what pvk_segment_rename_push writes into every table."""
+    from pypevoc_b200 import dist as D
+    f, mag, _, _ = _many_births_table(seed=9, F=90, K=10)
+    F, K = f.shape
+    world = 3
+    plans = D.plan_segments(512 + (F - 1) * 128 + 1, 512, 128, world)
+    assert plans[-1]["frames_total"] == F
+    tids = [np.ascontiguousarray(eh.track(f[p["w0"]:p["w1"]], mag[p["w0"]:p["w1"]])["tid"][0]) for p in plans]
+    tables = eh.segment_stitch_push(tids, plans)
+    L = eh.lib()
+    summ = np.zeros((world, 2 * K + 4), dtype=np.int32)
+    for r, p in enumerate(plans):
+        eh.check(L.pvk_segment_summary(eh.ptr(tids[r]), K, p["own0"], p["nown"], p["j0"], eh.ptr(summ[r]), None))
+    mc = np.full((F, K), -7, dtype=np.int32)
+    for r, p in enumerate(plans):
+        cap = max(max(q["own0"] for q in plans) * K, 1)
+        scratch = np.zeros(cap, dtype=np.int32); gidlow = np.zeros(cap, dtype=np.int32); params = np.zeros(8, dtype=np.int32)
+        eh.check(L.pvk_segment_resolve(eh.ptr(summ), world, K, r, eh.ptr(scratch), cap, eh.ptr(gidlow), eh.ptr(params), None))
+        own = np.ascontiguousarray(tids[r][p["own0"]:p["own0"] + p["nown"]])
+        eh.check(L.pvk_segment_rename_mcast(eh.ptr(own), own.size, eh.ptr(gidlow), eh.ptr(params), eh.ptr(mc), p["j0"] * K, None))
+    full = eh.track(f, mag)["tid"][0]
+    assert np.array_equal(mc, full)
+    for t in tables:
+        assert np.array_equal(t, mc)

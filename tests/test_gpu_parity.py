@@ -502,6 +502,11 @@ def test_fused_back_half_equals_staged_calls(pvmod):
         for k in ("toff", "pf", "pmag", "pph", "prealph"):
             assert torch.equal(d1[k], d2[k]), k
         assert np.array_equal(ss1.synth(sr, hop_s, edge=edge, minframes=minframes), w1)   # second call: staged path
+        hb = {}
+        ss3 = pv.toSinSum()
+        w3 = np.array(ss3.synth(sr, hop_s, edge=edge, minframes=minframes, hostbuf=hb))     # fused + streamed download
+        assert w3.shape == w1.shape and np.array_equal(w3, w1) and ss3.st == ss1.st
+        assert np.array_equal(np.array(ss3.synth(sr, hop_s, edge=edge, minframes=minframes, hostbuf=hb)), w1)  # staged + streamed
     pz = pvmod.PV(np.zeros(8192, dtype=np.float32), sr, nfft=2048, hop=512, npks=10, progress=False)
     pz.run_pv()
     with pytest.raises(ValueError):
