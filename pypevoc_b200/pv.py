@@ -72,6 +72,21 @@ def _pinned(hostbuf, key, shape, dtype):
     return hb
 
 
+def _chunk_bounds(n, chunks):
+    """Boundaries of ``chunks`` consecutive pieces of ``n`` items for a copy-bound pipeline: a short first
+    piece (the kernels start early), a short last one (little is left to do once the last upload has
+    landed), the rest in the middle -- weights 1 2 ... 2 1."""
+    if chunks <= 2:
+        return [(n * i) // chunks for i in range(chunks + 1)]
+    w = [1] + [2] * (chunks - 2) + [1]
+    tot, acc, out = float(sum(w)), 0, [0]
+    for v in w:
+        acc += v
+        out.append(int(round(n * acc / tot)))
+    out[-1] = n
+    return out
+
+
 class Progress(object):
     """Minimal stand-in for pypevoc.ProgressDisplay.Progress (ProgressDisplay.py:58-117):
     the GPU path finishes in one launch, so only completion is reported."""
@@ -728,10 +743,11 @@ class PV(object):
                 xd = self._xd_t
             d2h.wait_stream(cur)
             chunks = max(1, min(chunks, F // 64 if F >= 64 else 1))
+            bounds = _chunk_bounds(F, chunks)
             s_done = 0
             _mark("start", cur)
             for i in range(chunks if F else 0):
-                j0, j1 = (F * i) // chunks, (F * (i + 1)) // chunks
+                j0, j1 = bounds[i], bounds[i + 1]
                 if upload:
                     s_end = self.nsamp if i == chunks - 1 else (frame_lo + j1 - 1) * self.hop + self.nfft
                     with torch.cuda.stream(h2d):
@@ -1566,10 +1582,11 @@ class SinSum(object):
             hw = _pinned(hostbuf, "w", (nout_ub,), torch.float64)
             d2h.wait_stream(cur)
             chunks = max(1, min(chunks, nblk // 64 if nblk >= 64 else 1))
-            ws = resynth_workspace(F, K, nt_ub, -(-nblk // chunks), dev, hop=hop)
+            bounds = _chunk_bounds(nblk, chunks)
+            ws = resynth_workspace(F, K, nt_ub, max(b - a for a, b in zip(bounds, bounds[1:])), dev, hop=hop)
             _mark("pack queued", cur)
             for i in range(chunks):
-                b0, b1 = (nblk * i) // chunks, (nblk * (i + 1)) // chunks
+                b0, b1 = bounds[i], bounds[i + 1]
                 n0, n1 = b0 * hop, min(b1 * hop, nout_ub)
                 _lib.check(L.pvk_resynth_dev(_ptr(tr["tid"]), F, K, nt_ub, _ptr(tr["ntracks"]), _ptr(tstart), _ptr(tlen),
                                              _ptr(toff), _ptr(packed[0]), _ptr(packed[1]), _ptr(packed[3]), float(sr),
@@ -1613,10 +1630,12 @@ class SinSum(object):
             hw = _pinned(hostbuf, "w", (nout,), torch.float64)
             d2h.wait_stream(cur)
             chunks = max(1, min(chunks, nblk // 64 if nblk >= 64 else 1))
-            ws = resynth_workspace(F, K, int(pk["tstart"].shape[0]), -(-nblk // chunks), dev)
+            bounds = _chunk_bounds(nblk, chunks)
+            ws = resynth_workspace(F, K, int(pk["tstart"].shape[0]), max(b - a for a, b in zip(bounds, bounds[1:])), dev,
+                                   hop=hop)
             _mark("pack done", cur)
             for i in range(chunks):
-                b0, b1 = (nblk * i) // chunks, (nblk * (i + 1)) // chunks
+                b0, b1 = bounds[i], bounds[i + 1]
                 n0, n1 = b0 * hop, min(b1 * hop, nout)
                 resynth_device(tr["tid"], pk, sr, hop, self.nfft, self.hop, edge=edge, minframes=minframes,
                                max_end=max_end, block0=b0, nblocks=b1 - b0, out=out[n0:n1], ws=ws, reuse_tracks=i > 0)
