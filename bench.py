@@ -425,8 +425,9 @@ def gpu_main(args):
             # integers of the numbering pass (the side stream finished long ago), the join of the gathered
             # table and the spans pass over it
             glob["ntg"], glob["max_end"] = box[0].counts()
-            glob["table"] = box[0].table()
-            glob["spans"] = P.spans_device(glob["table"], glob["ntg"])     # first frame / length of every partial
+            with torch.cuda.stream(box[0].side):         # the spans pass over the N x longer table runs beside the
+                glob["spans"] = P.spans_device(box[0].table_on_side(), glob["ntg"])   # rendering, not after it
+            glob["table"] = box[0].table()               # (joins the side stream into the main one)
         tr, pk, w, b0 = D.track_pack_resynth_local(tab, plan, plans, sr, hop, nfft, hop, after_link=after_link,
                                                    after_pack=after_pack, before_sync=before_sync)
         sh = box[0]

@@ -440,6 +440,11 @@ class StitchHandle(object):
             self._tid_own.record_stream(cur)
         return self._tid_own
 
+    def table_on_side(self):
+        """The gathered table for work queued on the stitch stream itself (``with
+        torch.cuda.stream(handle.side)``): no join, the consumer runs beside the main stream's kernels."""
+        return self._table
+
     def table(self):
         """int32 [F, K] global ids of every frame (the main stream waits for the gather)."""
         if not self._joined:
