@@ -505,6 +505,265 @@ __global__ void track_link_claim_kernel(const double *__restrict__ f, const doub
   }
 }
 
+// ---- wide rows (K > 128): the same rank-free schedule with one CTA per frame pair.  A row of a few
+// hundred peaks on ONE warp is a long serial chain (16 slots per lane, a dozen rounds on dense rows);
+// spread over T = 128 / 256 threads with two columns each, a row takes 1/4 - 1/8 of the time, which is
+// what matters when there are few rows (60 s at hop 1024 are 2 800 rows for 148 SMs).  Thread t owns
+// columns t and t + T; warp collectives become block barriers / counts, the earliest loser is reduced
+// through shared memory.  Same result as track_link_claim_kernel and the loop, bit for bit.
+__host__ __device__ constexpr int link_cta_smem(int KM) {
+  // cf cm pf pm (double) | claim magnitudes = sort keys (8) | pf32 (4) | claim columns (4) | ord prank sidx (short)
+  // | usedw propw confw newbits (KM/32 words each) | 32 loser keys + 32 loser columns + 4 ints
+  return KM * (4 * 8 + 8 + 4 + 4 + 3 * 2) + 4 * (KM / 32) * 4 + 32 * 8 + 32 * 4 + 16;
+}
+
+__global__ void __launch_bounds__(256) track_link_cta_kernel(const double *__restrict__ f, const double *__restrict__ mag,
+                                                             int64_t nrows, int64_t F, int K, double maxjump,
+                                                             int32_t *__restrict__ link, int32_t *__restrict__ newcount) {
+  PVK_SMEM(smem);
+  constexpr int S = 2;
+  const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = T >> 5;
+  const int KM = T * S, NWORD = KM / 32;
+  double *cf = reinterpret_cast<double *>(smem);
+  double *cm = cf + KM;
+  double *pf = cm + KM;
+  double *pm = pf + KM;
+  unsigned long long *claim_m = reinterpret_cast<unsigned long long *>(pm + KM);
+  unsigned long long *redk = claim_m + KM;                        // [32]
+  float *pf32 = reinterpret_cast<float *>(redk + 32);
+  int *claim_c = reinterpret_cast<int *>(pf32 + KM);
+  int *redc = claim_c + KM;                                       // [32]
+  int *bc = redc + 32;                                            // [4]
+  unsigned *usedw = reinterpret_cast<unsigned *>(bc + 4);
+  unsigned *propw = usedw + NWORD, *confw = propw + NWORD, *newbits = confw + NWORD;
+  short *ord = reinterpret_cast<short *>(newbits + NWORD);
+  short *prank = ord + KM;
+  short *sidx = prank + KM;
+  for (int p = tid; p < KM; p += T) { claim_m[p] = 0ull; claim_c[p] = -1; }
+  const float eps32 = (float)(maxjump / 17.312 * (1.0 + 1e-4) + 1e-6);   // guard band as in the warp kernel
+
+  for (int64_t row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const bool has_prev = (row % F) > 0;
+    int32_t *lrow = link + row * K;
+    if (tid == 0) bc[0] = 0;
+    for (int w = tid; w < NWORD; w += T) usedw[w] = 0u;
+    __syncthreads();
+    int phil = 0;
+    double mine[S], fmine[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const int i = tid + T * s;
+      double cmv = -1.0, pmv = -1.0, cfv = 0.0, pfv = 0.0;
+      float p32 = -1.f;
+      if (i < K) {
+        const double a = f[row * K + i], b = mag[row * K + i];
+        const bool v = a > 0.0 && b > 0.0;                        // :876
+        cfv = a; cmv = v ? b : -1.0;
+        if (!v) lrow[i] = LINK_NONE;
+        if (has_prev) {
+          const double c = f[(row - 1) * K + i], d = mag[(row - 1) * K + i];
+          const bool vp = c > 0.0 && d > 0.0;
+          pfv = c; pmv = vp ? d : -1.0;
+          p32 = vp ? (float)c : -1.f;
+          if (vp) phil = i + 1;
+        }
+      }
+      cf[i] = cfv; cm[i] = cmv; pf[i] = pfv; pm[i] = pmv; pf32[i] = p32;
+      mine[s] = cmv; fmine[s] = cfv;
+    }
+    if (phil > 0) atomicMax(&bc[0], phil);
+    __syncthreads();
+    const int phi = bc[0];
+    bool okasc = true;
+    for (int p = tid; p < phi; p += T)
+      okasc = okasc && pm[p] > 0.0 && (p + 1 >= phi || (pm[p + 1] > 0.0 && pf32[p] <= pf32[p + 1]));
+    const bool asc = __syncthreads_count(okasc ? 0 : 1) == 0;
+
+    // ---- candidate masks (as in track_link_claim_kernel)
+    int p0[S], res[S];
+    unsigned cmask[S];
+    bool overflow = false;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      p0[s] = 0; cmask[s] = 0u;
+      res[s] = mine[s] > 0.0 ? -3 : -4;
+      if (mine[s] > 0.0 && phi > 0) {
+        const double fc = fmine[s];
+        const float fc32 = (float)fc;
+        float fhi = 3.0e38f;
+        int q = 0;
+        if (asc) {
+          const float flo = fc32 * (1.f - eps32);
+          fhi = fc32 * (1.f + eps32 + 2.f * eps32 * eps32);
+          for (int step = KM / 2; step >= 1; step >>= 1) {
+            const int mid = q + step;
+            if (mid <= phi && pf32[mid - 1] < flo) q = mid;
+          }
+        }
+        p0[s] = q;
+        for (int p = q; p < phi; ++p) {
+          const float pv = pf32[p];
+          if (pv > fhi) break;
+          if (fabsf(fc32 - pv) < eps32 * pv && stonediff(fc, pf[p]) < maxjump) {   // :923
+            if (p - q < 32) cmask[s] |= 1u << (p - q); else overflow = true;
+          }
+        }
+      }
+    }
+    if (__syncthreads_count(overflow ? 1 : 0) != 0) {
+      // ---- rare: the reference's loop itself, run by warp 0 with both rows ranked by a bitonic sort
+      if (warp == 0) {
+        double *skey = reinterpret_cast<double *>(claim_m);
+        int nc = 0;
+        for (int i0 = 0; i0 < KM; i0 += 32) nc += __popc(__ballot_sync(FULL, cm[i0 + lane] > 0.0));
+        for (int i = lane; i < KM; i += 32) { skey[i] = cm[i]; sidx[i] = (short)i; }
+        __syncwarp();
+        warp_sort_desc(skey, sidx, KM, true);
+        for (int t = lane; t < nc; t += 32) ord[t] = sidx[t];
+        __syncwarp();
+        for (int i = lane; i < KM; i += 32) { skey[i] = i < phi ? pm[i] : -1.0; sidx[i] = (short)i; }
+        __syncwarp();
+        warp_sort_desc(skey, sidx, KM, false);
+        for (int t = lane; t < KM; t += 32) {
+          const int i = sidx[t];
+          if (i < phi) prank[i] = (short)(skey[t] > 0.0 ? t : 0);
+        }
+        __syncwarp();
+        const int nnew = link_greedy_generic(cf, pf, pm, ord, prank, nc, phi, maxjump, lrow);
+        if (lane == 0) newcount[row] = nnew;
+      }
+      __syncthreads();
+      for (int p = tid; p < KM; p += T) claim_m[p] = 0ull;        // (was the sort's key array)
+      __syncthreads();
+      continue;
+    }
+
+    // ---- propose / commit rounds
+    int prop[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) prop[s] = -1;
+    for (;;) {
+      bool pend = false;
+#pragma unroll
+      for (int s = 0; s < S; ++s) pend = pend || (res[s] == -3 && cmask[s] != 0u);
+      if (__syncthreads_count(pend ? 1 : 0) == 0) break;
+      for (int w = tid; w < NWORD; w += T) { propw[w] = 0u; confw[w] = 0u; }
+      __syncthreads();
+      bool act[S];
+      bool clash = false;
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        act[s] = false;
+        if (res[s] == -3 && cmask[s] != 0u) {
+          if (prop[s] < 0 || ((usedw[prop[s] >> 5] >> (prop[s] & 31)) & 1u)) {
+            const double fc = fmine[s];
+            double bd = 1e300, bm = -1.0;
+            int bp = -1;
+            for (unsigned rem = cmask[s]; rem; rem &= rem - 1u) {
+              const int p = p0[s] + __ffs((int)rem) - 1;
+              if ((usedw[p >> 5] >> (p & 31)) & 1u) { cmask[s] &= ~(rem & (0u - rem)); continue; }
+              const double d = stonediff(fc, pf[p]);
+              const double m = pm[p];
+              if (d < bd || (d == bd && m > bm)) { bd = d; bm = m; bp = p; }
+            }
+            prop[s] = bp;
+          }
+          if (prop[s] >= 0) {
+            act[s] = true;
+            const unsigned bit = 1u << (prop[s] & 31);
+            if (atomicOr(&propw[prop[s] >> 5], bit) & bit) { atomicOr(&confw[prop[s] >> 5], bit); clash = true; }
+          }
+        }
+      }
+      if (__syncthreads_count(clash ? 1 : 0) == 0) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) if (act[s]) res[s] = prop[s];
+        for (int w = tid; w < NWORD; w += T) usedw[w] |= propw[w];
+        __syncthreads();
+        continue;
+      }
+      bool cont[S];
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        cont[s] = act[s] && ((confw[prop[s] >> 5] >> (prop[s] & 31)) & 1u);
+        if (cont[s]) atomicMax(&claim_m[prop[s]], (unsigned long long)__double_as_longlong(mine[s]));
+      }
+      __syncthreads();
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        if (cont[s] && claim_m[prop[s]] == (unsigned long long)__double_as_longlong(mine[s]))
+          atomicMax(&claim_c[prop[s]], tid + T * s);
+      }
+      __syncthreads();
+      unsigned long long lk = 0ull;
+      int lc = -1;
+      bool win[S];
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const unsigned long long key = (unsigned long long)__double_as_longlong(mine[s]);
+        win[s] = act[s] && (!cont[s] || (claim_m[prop[s]] == key && claim_c[prop[s]] == tid + T * s));
+        if (act[s] && !win[s] && (key > lk || (key == lk && tid + T * s > lc))) { lk = key; lc = tid + T * s; }
+      }
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        const unsigned long long ok = __shfl_xor_sync(FULL, lk, o);
+        const int oc = __shfl_xor_sync(FULL, lc, o);
+        if (ok > lk || (ok == lk && oc > lc)) { lk = ok; lc = oc; }
+      }
+      if (lane == 0) { redk[warp] = lk; redc[warp] = lc; }
+      __syncthreads();                                            // (every claim has been read by now)
+#pragma unroll
+      for (int s = 0; s < S; ++s) if (cont[s]) { claim_m[prop[s]] = 0ull; claim_c[prop[s]] = -1; }
+      lk = 0ull; lc = -1;
+      for (int w = 0; w < NW; ++w) {
+        const unsigned long long ok = redk[w];
+        const int oc = redc[w];
+        if (ok > lk || (ok == lk && oc > lc)) { lk = ok; lc = oc; }
+      }
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        if (win[s]) {
+          const unsigned long long key = (unsigned long long)__double_as_longlong(mine[s]);
+          if (key > lk || (key == lk && tid + T * s > lc)) {
+            res[s] = prop[s];
+            atomicOr(&usedw[prop[s] >> 5], 1u << (prop[s] & 31));
+          }
+        }
+      }
+      __syncthreads();
+    }
+    // ---- links; new partials numbered by descending magnitude, ties higher column first (:874-875, :941)
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const unsigned m = __ballot_sync(FULL, res[s] == -3);
+      if (lane == 0) newbits[NW * s + warp] = m;                  // columns 32 (NW s + warp) ... + 31
+    }
+    __syncthreads();
+    int nnew = 0;
+    for (int w = 0; w < NWORD; ++w) nnew += __popc(newbits[w]);
+    int rk[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) rk[s] = 0;
+    if (nnew > 1) {
+      for (int w = 0; w < NWORD; ++w) {
+        for (unsigned rem = newbits[w]; rem; rem &= rem - 1u) {
+          const int c2 = 32 * w + __ffs((int)rem) - 1;
+          const double m2 = cm[c2];
+#pragma unroll
+          for (int s = 0; s < S; ++s) rk[s] += (m2 > mine[s] || (m2 == mine[s] && c2 > tid + T * s)) ? 1 : 0;
+        }
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      if (res[s] >= 0) lrow[tid + T * s] = res[s];
+      else if (res[s] == -3) lrow[tid + T * s] = -2 - rk[s];
+    }
+    if (tid == 0) newcount[row] = nnew;
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------ exclusive scans
 // Tiled exclusive scan of int32 counts in two launches, every CTA independent: (1) per-tile sums,
 // (2) each tile adds up the sums of the tiles before it (a few hundred values even for an 8 hour
@@ -969,7 +1228,19 @@ extern "C" int pvk_track(const double *f, const double *mag, int64_t nclips, int
     int64_t g;
     // rows of `wide_from` or more peaks take the sequential loop kernel (PVK_LINK_GENERIC_FROM: test override)
     static const int wide_from = []() { const char *e = getenv("PVK_LINK_GENERIC_FROM"); return e ? atoi(e) : 513; }();
-    if (K <= 512 && K < wide_from) {
+    static const int cta_from = []() { const char *e = getenv("PVK_LINK_CTA_FROM"); return e ? atoi(e) : 129; }();
+    if (K <= 512 && K < wide_from && K >= cta_from) {
+      // one CTA per row: 128 threads up to 256 columns, 256 threads up to 512
+      const int T = K <= 256 ? 128 : 256;
+      const int smem = link_cta_smem(2 * T);
+      if (smem > 48 * 1024 && PVK_SET_SMEM(track_link_cta_kernel, smem) != 0) {
+        set_error("pvk_track: cannot reserve %d bytes of shared memory", smem);
+        return PVK_ERR_CUDA;
+      }
+      g = rows < 148 * 16 ? rows : 148 * 16;
+      PVK_LAUNCH(track_link_cta_kernel, dim3((unsigned)g), dim3(T), smem, stream, f, mag, rows, nframes, K, maxpitchjmp,
+                 link, newcount);
+    } else if (K <= 512 && K < wide_from) {
       const int S = K <= 32 ? 1 : (K <= 64 ? 2 : (K <= 128 ? 4 : (K <= 256 ? 8 : 16)));
       const int per_warp = link_claim_smem_per_warp(S);
       const int W = S <= 4 ? 8 : (S == 8 ? 4 : 2);

@@ -20,7 +20,7 @@ sys.path.insert(0, os.path.join(HERE, "emu"))
 
 
 def track_case(rng):
-    K = int(rng.choice([1, 2, 3, 5, 8, 16, 31, 32, 33, 50, 63, 64, 65, 100, 127, 128, 129, 140, 200]))
+    K = int(rng.choice([1, 2, 3, 5, 8, 16, 31, 32, 33, 50, 63, 64, 65, 100, 127, 128, 129, 140, 200, 256, 257, 300, 400, 512]))
     F = int(rng.randint(2, 10))
     f = np.zeros((F, K))
     mag = np.zeros((F, K))
