@@ -320,12 +320,12 @@ __global__ void track_link_claim_kernel(const double *__restrict__ f, const doub
     const bool asc = __all_sync(FULL, okasc);
 
     // ---- candidate masks: bit b of cmask[s] = previous column p0[s] + b is within maxpitchjmp
-    int p0[S], res[S];                                            // res: -3 unresolved, -2 new, -4 no peak, >= 0 matched column
+    int p0[S], res[S], prop[S];                                   // res: -3 unresolved, -2 new, -4 no peak, >= 0 matched column
     unsigned cmask[S];
     bool overflow = false;
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-      p0[s] = 0; cmask[s] = 0u;
+      p0[s] = 0; cmask[s] = 0u; prop[s] = -1;
       res[s] = mine[s] > 0.0 ? -3 : -4;
       if (mine[s] > 0.0 && phi > 0) {
         const double fc = fmine[s];
@@ -343,11 +343,19 @@ __global__ void track_link_claim_kernel(const double *__restrict__ f, const doub
           }
         }
         p0[s] = q;
+        // the first proposal falls out of the same pass: nearest candidate; distance ties: larger previous
+        // magnitude, then lower column (ascending scan + strict comparisons)
+        double bd = 1e300, bm = -1.0;
         for (int p = q; p < phi; ++p) {
           const float pv = pf32[p];
           if (pv > fhi) break;
-          if (fabsf(fc32 - pv) < eps32 * pv && stonediff(fc, pf[p]) < maxjump) {   // :923: only these can ever match
-            if (p - q < 32) cmask[s] |= 1u << (p - q); else overflow = true;
+          if (fabsf(fc32 - pv) < eps32 * pv) {
+            const double d = stonediff(fc, pf[p]);
+            if (d < maxjump) {                                    // :923: only these can ever match
+              if (p - q < 32) cmask[s] |= 1u << (p - q); else overflow = true;
+              const double m = pm[p];
+              if (d < bd || (d == bd && m > bm)) { bd = d; bm = m; prop[s] = p; }
+            }
           }
         }
       }
@@ -382,9 +390,6 @@ __global__ void track_link_claim_kernel(const double *__restrict__ f, const doub
     // ---- propose / commit rounds.  propw / confw: previous columns proposed / proposed more than once
     //      in this round; claim_m / claim_c are only touched for contested columns and are reset by
     //      their users (all-zero / -1 between rounds and rows)
-    int prop[S];
-#pragma unroll
-    for (int s = 0; s < S; ++s) prop[s] = -1;
     for (;;) {
       bool pend = false;
 #pragma unroll
@@ -580,12 +585,12 @@ __global__ void __launch_bounds__(256) track_link_cta_kernel(const double *__res
     const bool asc = __syncthreads_count(okasc ? 0 : 1) == 0;
 
     // ---- candidate masks (as in track_link_claim_kernel)
-    int p0[S], res[S];
+    int p0[S], res[S], prop[S];
     unsigned cmask[S];
     bool overflow = false;
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-      p0[s] = 0; cmask[s] = 0u;
+      p0[s] = 0; cmask[s] = 0u; prop[s] = -1;
       res[s] = mine[s] > 0.0 ? -3 : -4;
       if (mine[s] > 0.0 && phi > 0) {
         const double fc = fmine[s];
@@ -601,11 +606,17 @@ __global__ void __launch_bounds__(256) track_link_cta_kernel(const double *__res
           }
         }
         p0[s] = q;
+        double bd = 1e300, bm = -1.0;                             // (the first proposal falls out of the same pass)
         for (int p = q; p < phi; ++p) {
           const float pv = pf32[p];
           if (pv > fhi) break;
-          if (fabsf(fc32 - pv) < eps32 * pv && stonediff(fc, pf[p]) < maxjump) {   // :923
-            if (p - q < 32) cmask[s] |= 1u << (p - q); else overflow = true;
+          if (fabsf(fc32 - pv) < eps32 * pv) {
+            const double d = stonediff(fc, pf[p]);
+            if (d < maxjump) {                                    // :923
+              if (p - q < 32) cmask[s] |= 1u << (p - q); else overflow = true;
+              const double m = pm[p];
+              if (d < bd || (d == bd && m > bm)) { bd = d; bm = m; prop[s] = p; }
+            }
           }
         }
       }
@@ -639,9 +650,6 @@ __global__ void __launch_bounds__(256) track_link_cta_kernel(const double *__res
     }
 
     // ---- propose / commit rounds
-    int prop[S];
-#pragma unroll
-    for (int s = 0; s < S; ++s) prop[s] = -1;
     for (;;) {
       bool pend = false;
 #pragma unroll
