@@ -92,3 +92,30 @@ def test_host_tables_match_reference_expressions():
         assert n_frames(nsamp, nfft, hop) == orc.n_frames(nsamp, nfft, hop)
     assert n_frames(2048 + 3 * 512, 2048, 512) == 3
     assert synth_geometry(84, 512, 1024, 512) == (86 * 512 + 512, 512)
+
+
+def test_ctypes_signatures_match_the_header_types():
+    """Every prototype of include/pvk.h against the ctypes signature of pypevoc_b200/_lib.py: same
+    number of parameters, same classes (pointer / int64_t / int / double) in the same order, same
+    return type.  A drifted hand-written binding would corrupt the call frame, not fail cleanly."""
+    from pypevoc_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "pvk.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = re.findall(r"^\s*((?:const\s+)?[A-Za-z_0-9]+\s*\*?)\s*(pvk_[a-z_0-9]+)\s*\(([^;]*?)\)\s*;", src, flags=re.M | re.S)
+    assert len(protos) == len(_lib.SIGNATURES)
+
+    def cls(decl):
+        decl = decl.strip()
+        if "*" in decl:
+            return ctypes.c_char_p if decl.replace(" ", "").startswith("constchar*") else ctypes.c_void_p
+        base = decl.split()[-2] if len(decl.split()) > 1 else decl
+        base = decl.rsplit(None, 1)[0] if len(decl.split()) > 1 else decl
+        base = base.replace("const", "").strip()
+        return {"int64_t": ctypes.c_int64, "int": ctypes.c_int, "double": ctypes.c_double}[base]
+    for ret, name, params in protos:
+        res, args = _lib.SIGNATURES[name]
+        plist = [p for p in (q.strip() for q in params.replace("\n", " ").split(",")) if p and p != "void"]
+        got = [cls(p) for p in plist]
+        assert got == list(args), (name, [g.__name__ for g in got], [a.__name__ for a in args])
+        rcls = ctypes.c_char_p if "char" in ret else cls(ret + " x")
+        assert rcls == res, name
