@@ -119,3 +119,41 @@ def test_ctypes_signatures_match_the_header_types():
         assert got == list(args), (name, [g.__name__ for g in got], [a.__name__ for a in args])
         rcls = ctypes.c_char_p if "char" in ret else cls(ret + " x")
         assert rcls == res, name
+
+
+def test_host_pipeline_helpers():
+    """Pure host helpers of the streamed / sharded paths."""
+    from pypevoc_b200.pv import _chunk_bounds
+    from pypevoc_b200 import dist as D
+    for n in (0, 1, 63, 64, 1000, 51676):
+        for chunks in (1, 2, 3, 8):
+            b = _chunk_bounds(n, chunks)
+            assert len(b) == chunks + 1 and b[0] == 0 and b[-1] == n and all(x <= y for x, y in zip(b, b[1:]))
+    b = _chunk_bounds(51676, 8)
+    assert b[1] - b[0] < b[2] - b[1] and b[-1] - b[-2] < b[-2] - b[-3]          # short first and last piece
+    saved = os.environ.pop("PVK_PEER_GATHER", None)
+    try:
+        assert D._peer_gather_wanted(2) and D._peer_gather_wanted(4) and not D._peer_gather_wanted(8)
+        os.environ["PVK_PEER_GATHER"] = "1"
+        assert D._peer_gather_wanted(8)
+        os.environ["PVK_PEER_GATHER"] = "0"
+        assert not D._peer_gather_wanted(2)
+    finally:
+        os.environ.pop("PVK_PEER_GATHER", None)
+        if saved is not None:
+            os.environ["PVK_PEER_GATHER"] = saved
+    # every rank's block range is known without any count, and trimming it gives render_range()
+    nfft, hop = 2048, 512
+    for world in (2, 3, 8):
+        F = 400
+        plans = D.plan_segments(nfft + (F - 1) * hop + 1, nfft, hop, world)
+        for max_end in (F - 1, F - 40, 120, 5):
+            total = 0
+            for p in plans:
+                b0, b1, bound = D.render_range_local(p, plans, p["w1"] - 1 if p["nown"] else -1, hop, nfft, hop)
+                nrender = max(min(b1 * hop, bound) - b0 * hop, 0)
+                n, s0 = D.trim_local(nrender, b0, p, plans, max_end, hop, nfft, hop)
+                g0, g1, nout = D.render_range(p, plans, max_end, hop, nfft, hop)
+                assert n == max(min(g1 * hop, nout) - g0 * hop, 0)
+                total += n
+            assert total == D.render_range(plans[0], plans, max_end, hop, nfft, hop)[2]
