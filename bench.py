@@ -13,12 +13,16 @@ path (PV.run_pv -> toSinSum -> SinSum.synth) over that signal.
   e2e        same metric through the public API with HOST buffers: pinned host signal -> H2D
              -> PV.run_pv -> toSinSum -> synth -> D2H of the peak tables and the signal
   roofline   the step's dominant kernel against the measured HBM copy peak
-  cpu_baseline  the numpy oracle (port of the reference's algorithm) on one host core, on a
-             bounded prefix of the same samples
+  cpu_baseline  the unmodified reference (baseline/_ref; the numpy oracle port where it is absent) on
+             one host core, on a bounded prefix of the same samples
 N > 1 is weak scaling: every rank owns its own hop-aligned 10-minute segment of an N x 10
 minute signal (plus a few halo frames either side), analyses, links and resynthesises it from
-local data; a 2K+4-integer all_gather makes the partial numbering global and ONE all_gather
-collects the int32 track table (overlapped with pack + resynthesis).
+local data with one 24-byte read-back at the end of the step; a 2K+4-integer all_gather makes the
+partial numbering global and ONE gather collects the int32 track table on a high-priority side
+stream (NVSwitch multicast stores of the rename kernel up to 4 ranks, NCCL beyond -- dist.py).
+Before any N > 1 measurement a short sharded run is compared bit for bit with the unsharded one
+(exit status 3 on a mismatch).  `--workload cfg4 / cfg3`: the 8-hour signal (strong scaling) and the
+4096-clip batch of BASELINE.json as auxiliary lines.
 """
 import argparse
 import json
