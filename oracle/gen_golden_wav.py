@@ -27,7 +27,36 @@ START, COUNT = 22050, 33075                    # 1.0 s ... 2.5 s
 PVKW = dict(nfft=4096, hop=1024, npks=100)
 
 
+# more recordings of the reference's examples/ (round 2), each with parameters of a BASELINE config:
+# (output file, wav, first sample, samples, PV kwargs)
+EXTRA = [
+    ("real_guitar.npz", "SoloGuitarArpegi.wav", 44100, 44100, dict(nfft=2048, hop=512, npks=50)),       # the metric's parameters
+    ("real_speech.npz", "ProtectMarraigeInAmerica.wav", 22050, 33075, dict(nfft=512, hop=128, npks=20)),  # cfg3's (clip batches)
+]
+
+
+def one(outname, wavname, start, count, pvkw):
+    w = wave.open(os.path.join(ref_loader.REF_ROOT, "examples", wavname), "r")
+    sr = w.getframerate()
+    w.setpos(start)
+    pcm = np.frombuffer(w.readframes(count), dtype="<i2").copy()
+    w.close()
+    x = (pcm / float(np.iinfo(np.int16).max)).astype(np.float32).astype(np.float64)
+    pv = ref_loader.ref_run_pv(x, sr, **pvkw)
+    ss = pv.toSinSum()
+    out = dict(pcm=pcm, sr=np.int64(sr), f=pv.f, mag=pv.mag, ph=pv.ph, realph=pv.realph, binno=pv.binno,
+               totalmag=np.array(pv.totalmag), tid=tid_table(pv, ss), st=np.array(ss.st, dtype=np.int64),
+               end=np.array(ss.end, dtype=np.int64), synth=ref_loader.ref_sinsum_synth(ss, sr, pvkw["hop"]),
+               nfft=np.int64(pvkw["nfft"]), hop=np.int64(pvkw["hop"]), npks=np.int64(pvkw["npks"]))
+    print(outname, "frames", pv.nframes, "partials", len(ss.partial), "peaks/frame %.1f" % (pv.f > 0).sum(1).mean())
+    np.savez_compressed(os.path.join(GOLD, outname), **out)
+
+
 def main():
+    if "--extra-only" in sys.argv:
+        for case in EXTRA:
+            one(*case)
+        return
     w = wave.open(WAV, "r")
     sr = w.getframerate()
     w.setpos(START)
@@ -41,6 +70,8 @@ def main():
                end=np.array(ss.end, dtype=np.int64), synth=ref_loader.ref_sinsum_synth(ss, sr, PVKW["hop"]))
     print("frames", pv.nframes, "partials", len(ss.partial), "peaks/frame %.1f" % (pv.f > 0).sum(1).mean())
     np.savez_compressed(os.path.join(GOLD, "real_wav.npz"), **out)
+    for case in EXTRA:
+        one(*case)
 
 
 if __name__ == "__main__":

@@ -15,16 +15,21 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu
 from oracle import pv_oracle as orc
 import parity_util as pu
 
-G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "real_wav.npz"))
-PVKW = dict(nfft=4096, hop=1024, npks=100)
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+# saxophone @ WavResynth.py's parameters; guitar @ the metric's (nfft 2048 / hop 512 / npks 50); speech @ cfg3's
+CASES = {"sax": ("real_wav.npz", dict(nfft=4096, hop=1024, npks=100)),
+         "guitar": ("real_guitar.npz", dict(nfft=2048, hop=512, npks=50)),
+         "speech": ("real_speech.npz", dict(nfft=512, hop=128, npks=20))}
 
 
-def signal():
-    return (G["pcm"] / float(np.iinfo(np.int16).max)).astype(np.float32), int(G["sr"])
+def load(case):
+    G = np.load(os.path.join(GOLD, CASES[case][0]))
+    return G, CASES[case][1], (G["pcm"] / float(np.iinfo(np.int16).max)).astype(np.float32), int(G["sr"])
 
 
-def test_oracle_on_real_signal():
-    x, sr = signal()
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_oracle_on_real_signal(case):
+    G, PVKW, x, sr = load(case)
     o = orc.analyze(x, sr, **PVKW)
     for k in ("f", "mag", "ph", "realph", "binno"):
         assert np.array_equal(o[k], G[k], equal_nan=True), k
@@ -36,10 +41,11 @@ def test_oracle_on_real_signal():
     assert w.shape == G["synth"].shape and np.max(np.abs(w - G["synth"])) == 0.0
 
 
-def test_emu_kernels_on_real_signal():
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_emu_kernels_on_real_signal(case):
     eh = pytest.importorskip("emu_harness")
     eh.build()
-    x, sr = signal()
+    G, PVKW, x, sr = load(case)
     o = eh.analyze(x, sr, PVKW["nfft"], PVKW["hop"], PVKW["npks"], spectra=True)
     got = {k: o[k][0] for k in ("f", "mag", "ph", "realph", "binno", "totalmag", "npk")}
     ref = {k: G[k] for k in ("f", "mag", "ph", "realph", "binno", "totalmag")}
